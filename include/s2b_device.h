@@ -1,0 +1,262 @@
+// solver2d-b200 — the C ABI between the host C library and the CUDA (sm_100a) step pipeline.
+//
+// This is the inner drop-in boundary: everything s2World_Step does to simulation state happens
+// behind these entry points, on the GPU. They are plain `extern "C"` functions over an opaque handle, POD rows and
+// raw pointers + sizes — no C++ or torch types — so the reference's own host C (or any FFI: cgo, JNI, ctypes) can
+// bind them. Each entry point cites the reference interface it replaces.
+//
+// Memory model: the device owns the simulation state in SoA columns (DESIGN.md "data layout"). The host pushes
+// changed objects as rows (`s2b_upload_*`), runs stages, and pulls rows back on demand (`s2b_download_*`).
+// All calls on one world are ordered on that world's CUDA stream; downloads synchronise, uploads and stages do not.
+// A missing/failed CUDA runtime is fatal (message + abort): there is no CPU fallback.
+#pragma once
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+typedef struct s2bWorld s2bWorld;
+
+#if defined(__GNUC__)
+	#define S2B_API __attribute__((visibility("default")))
+#else
+	#define S2B_API
+#endif
+
+// ---- rows -----------------------------------------------------------------------------------------------------
+
+// flags shared by all rows
+#define S2B_ROW_VALID 0x1
+
+// One rigid body; mirrors the solver-relevant fields of s2Body (reference src/body.h:16-76).
+typedef struct s2bBodyRow
+{
+	int32_t index;	 // body pool slot
+	int32_t flags;	 // S2B_ROW_VALID | (s2BodyType << 1)
+	float origin[2]; // body origin
+	float position[2]; // centre of mass, world
+	float rot[2];	   // (sin, cos)
+	float linearVelocity[2];
+	float angularVelocity;
+	float localCenter[2];
+	float mass, invMass;
+	float I, invI;
+	float force[2];
+	float torque;
+	float linearDamping, angularDamping, gravityScale;
+} s2bBodyRow;
+
+// shape kinds, numeric values of s2ShapeType (reference src/shape.h:14-21)
+enum
+{
+	S2B_SHAPE_CAPSULE = 0,
+	S2B_SHAPE_CIRCLE = 1,
+	S2B_SHAPE_POLYGON = 2,
+	S2B_SHAPE_SEGMENT = 3,
+};
+
+// One collision shape; mirrors s2Shape (reference src/shape.h:23-48). Geometry is always given in "polygon form":
+// circle = 1 vertex + radius, capsule / segment = 2 vertices + the two side normals of s2MakeCapsule + radius,
+// polygon = count vertices + normals + radius.
+typedef struct s2bShapeRow
+{
+	int32_t index; // shape pool slot
+	int32_t flags; // S2B_ROW_VALID | (type << 1) | (moved << 4)
+	int32_t body;
+	int32_t proxyKey; // reference broad-phase proxy key (decides which shape of a pair is "A", broad_phase.c:196-205)
+	uint32_t categoryBits, maskBits;
+	int32_t groupIndex;
+	float friction;
+	float aabb[4];	  // tight AABB + speculative margin
+	float fatAABB[4]; // broad-phase AABB
+	float radius;
+	int32_t count;
+	float vertices[16];
+	float normals[16];
+} s2bShapeRow;
+
+#define S2B_SHAPE_MOVED 0x10
+
+enum
+{
+	S2B_JOINT_REVOLUTE = 0,
+	S2B_JOINT_MOUSE = 1,
+};
+
+#define S2B_JOINT_ENABLE_LIMIT 0x10
+#define S2B_JOINT_ENABLE_MOTOR 0x20
+#define S2B_JOINT_COLLIDE_CONNECTED 0x40
+
+// One joint; mirrors s2Joint / s2RevoluteJoint / s2MouseJoint (reference src/joint.h:28-102).
+typedef struct s2bJointRow
+{
+	int32_t index; // joint pool slot
+	int32_t flags; // S2B_ROW_VALID | (type << 1) | S2B_JOINT_*
+	int32_t bodyA, bodyB;
+	float localOriginAnchorA[2], localOriginAnchorB[2];
+	// revolute
+	float referenceAngle, lowerAngle, upperAngle;
+	float maxMotorTorque, motorSpeed;
+	// mouse
+	float hertz, dampingRatio;
+	float target[2];
+	// accumulated impulses (simulation state)
+	float impulse[2];
+	float motorImpulse, lowerImpulse, upperImpulse;
+} s2bJointRow;
+
+// One contact (shape pair) with its persistent manifold; mirrors s2Contact + s2Manifold + s2DistanceCache
+// (reference src/contact.h:44-61, include/solver2d/manifold.h:19-46, distance.h:37-43).
+typedef struct s2bContactPoint
+{
+	float localAnchorA[2], localAnchorB[2];
+	float separation, normalImpulse, tangentImpulse;
+	float frictionAnchorA[2], frictionAnchorB[2];
+	float frictionNormalA[2], frictionNormalB[2];
+	int32_t id;
+	int32_t persisted;
+} s2bContactPoint;
+
+typedef struct s2bContactRow
+{
+	int32_t shapeA, shapeB;
+	int32_t bodyA, bodyB;
+	int32_t pointCount;
+	int32_t frictionPersisted;
+	float friction;
+	float normal[2];
+	s2bContactPoint points[2];
+	int32_t cacheCount;
+	uint8_t cacheIndexA[4], cacheIndexB[4];
+	float cacheMetric;
+} s2bContactRow;
+
+// ---- step context ---------------------------------------------------------------------------------------------
+
+// Mirrors s2StepContext (reference src/solvers.h:13-24) without the host body pointer.
+typedef struct s2bStepContext
+{
+	float dt, inv_dt;
+	float h, inv_h; // sub-step for the sub-stepping variants, else dt
+	int32_t iterations;
+	int32_t extraIterations;
+	int32_t warmStart;
+} s2bStepContext;
+
+// How constraints are grouped into conflict-free sets (DESIGN.md "schedules").
+enum
+{
+	// Graph colouring on the device: few large groups, the production path. Gauss-Seidel order = colour-major.
+	S2B_SCHEDULE_COLOR = 0,
+	// Order-preserving wavefront levels: reproduces the sequential constraint order exactly (joints, then contacts,
+	// each in slot order, or in the order given by s2b_set_contact_order). Validation path — thousands of groups.
+	S2B_SCHEDULE_WAVEFRONT = 1,
+};
+
+typedef struct s2bCounters
+{
+	int32_t bodyCapacity, shapeCapacity, jointCapacity;
+	int32_t contactCount;	 // shape pairs with overlapping fat AABBs
+	int32_t constraintCount; // manifolds with >= 1 point in the last solve
+	int32_t jointCount;		 // live joints in the last solve
+	int32_t groupCount;		 // colours (or wavefront levels) in the last solve
+	int32_t overflowCount;	 // constraints solved serially after the coloured groups
+	int32_t treeHeight;		 // depth of the last BVH
+	int32_t movedCount;		 // proxies whose fat AABB changed in the last finalize
+	int32_t pairPassCount;	 // number of broad-phase passes run so far
+	int32_t kernelLaunches;	 // CUDA kernels launched by this world since creation
+	int64_t scratchBytes;	 // device bytes of per-step scratch currently reserved
+} s2bCounters;
+
+// ---- lifecycle ------------------------------------------------------------------------------------------------
+
+// Replaces the device-less pools/arena of s2CreateWorld (reference src/world.c:47-103). `cudaDevice` < 0 selects the
+// current device. `solverType` is the s2SolverType the world will be stepped with (selects optional columns).
+S2B_API s2bWorld* s2b_world_create(int cudaDevice, int solverType);
+S2B_API void s2b_world_destroy(s2bWorld* world);
+
+S2B_API void s2b_set_gravity(s2bWorld* world, float gx, float gy);
+S2B_API void s2b_set_schedule(s2bWorld* world, int schedule);
+// Colour-schedule tuning: maximum number of colours (<= 64) before a constraint spills to the serial overflow set.
+S2B_API void s2b_set_max_colors(s2bWorld* world, int maxColors);
+// Use the single persistent cooperative kernel for the solver stage (1, default where supported) or one launch
+// per group and pass (0; used for per-kernel profiling and as a cross-check).
+S2B_API void s2b_set_persistent(s2bWorld* world, int enable);
+
+// ---- host -> device -------------------------------------------------------------------------------------------
+
+// Scatter rows into the SoA columns; capacities grow on demand (replaces pool growth, reference src/pool.c:108-159).
+S2B_API void s2b_upload_bodies(s2bWorld* world, const s2bBodyRow* rows, int count, int bodyCapacity);
+S2B_API void s2b_upload_shapes(s2bWorld* world, const s2bShapeRow* rows, int count, int shapeCapacity);
+S2B_API void s2b_upload_joints(s2bWorld* world, const s2bJointRow* rows, int count, int jointCapacity);
+// Replace the whole contact table (rows in solve order). Test / checkpoint-restore hook: on the normal path contacts
+// are created and destroyed on the device by s2b_update_pairs.
+S2B_API void s2b_upload_contacts(s2bWorld* world, const s2bContactRow* rows, int count);
+// Sorted (bodyLo << 32 | bodyHi) keys of joints with collideConnected == false; consulted by the pair filter
+// (replaces s2ShouldBodiesCollide, reference src/body.c:386-417).
+S2B_API void s2b_upload_joint_pairs(s2bWorld* world, const uint64_t* sortedKeys, int count);
+// Force a broad-phase pass on the next s2b_update_pairs (creation/destruction of shapes or joints).
+S2B_API void s2b_mark_pairs_dirty(s2bWorld* world);
+// Validation hook: impose the sequential contact order for S2B_SCHEDULE_WAVEFRONT as a list of shape-pair keys
+// (lo << 32 | hi), earliest first; contacts not listed follow in slot order. count == 0 clears it.
+S2B_API void s2b_set_contact_order(s2bWorld* world, const uint64_t* pairKeys, int count);
+
+// ---- the step, stage by stage (reference src/world.c:120-306) -------------------------------------------------
+
+// Stages 1+2 and the destroy half of stage 3: s2UpdateBroadPhasePairs + s2BroadPhase_RebuildTrees (reference
+// src/broad_phase.c:309-367, :381-385) and the fat-AABB overlap test of world.c:149-166. No-op when no proxy moved.
+S2B_API void s2b_update_pairs(s2bWorld* world);
+// Stage 3: s2UpdateContact for every contact (reference src/contact.c:296-359 -> manifold.c, distance.c).
+S2B_API void s2b_update_contacts(s2bWorld* world);
+// Solver dispatch: s2Solve_<variant>(world, context) (reference src/solvers.h:70-79, src/world.c:206-256).
+S2B_API void s2b_solve(s2bWorld* world, int solverType, const s2bStepContext* context);
+// Stage 4: transforms, force reset, AABB refit, proxy enlarge + move buffering (reference src/world.c:258-301).
+S2B_API void s2b_finalize(s2bWorld* world);
+// All four in order.
+S2B_API void s2b_step(s2bWorld* world, int solverType, const s2bStepContext* context);
+
+// ---- device -> host (synchronising) ---------------------------------------------------------------------------
+
+S2B_API void s2b_sync(s2bWorld* world);
+// rows[i].index selects the slot to read for i < count (flags are filled in).
+S2B_API void s2b_download_bodies(s2bWorld* world, s2bBodyRow* rows, int count);
+// every slot 0..capacity-1 in order
+S2B_API void s2b_download_all_bodies(s2bWorld* world, s2bBodyRow* rows, int capacity);
+S2B_API void s2b_download_shape_boxes(s2bWorld* world, float* aabb4, float* fat4, int32_t* flags, int capacity);
+S2B_API void s2b_download_joints(s2bWorld* world, s2bJointRow* rows, int capacity);
+// returns the number of contacts written (<= maxCount), in device order (sorted by shape-pair key)
+S2B_API int s2b_download_contacts(s2bWorld* world, s2bContactRow* rows, int maxCount);
+// The solve order of the last s2b_solve: for each constraint, in Gauss-Seidel order, its contact slot; and the
+// group boundaries. Returns the constraint count. (Feeds the permuted oracle in the parity tests.)
+S2B_API int s2b_download_solve_order(s2bWorld* world, int32_t* contactSlots, int maxCount, int32_t* groupOffsets, int maxGroups,
+							 int32_t* groupCount);
+S2B_API void s2b_get_counters(s2bWorld* world, s2bCounters* out);
+
+// Packed per-body state {origin.x, origin.y, rot.s, rot.c, v.x, v.y, w, 0} for slots [first, first+count) written to
+// a DEVICE buffer (32 B/body) — the payload of the per-step NCCL all-gather in the multi-world configuration.
+S2B_API void s2b_pack_body_state(s2bWorld* world, int first, int count, void* deviceOut);
+
+// ---- measurement ----------------------------------------------------------------------------------------------
+
+// Run `steps` full steps back to back and return the elapsed device time in milliseconds measured with CUDA events
+// on the world's stream (sync on both sides).
+S2B_API float s2b_timed_steps(s2bWorld* world, int solverType, const s2bStepContext* context, int steps);
+// Per-stage device time of the last s2b_step in milliseconds: {pairs, contacts, solve, finalize}.
+S2B_API void s2b_last_stage_ms(s2bWorld* world, float out[4]);
+// Evict L2: overwrite a scratch buffer larger than the 126 MB L2 (bench hygiene between timed iterations).
+S2B_API void s2b_flush_l2(s2bWorld* world);
+// Standalone timing of the per-colour contact impulse kernel on the current constraint set (roofline probe):
+// launches the largest colour's solve kernel `reps` times, returns mean ms; *constraints receives its size.
+S2B_API float s2b_time_color_kernel(s2bWorld* world, const s2bStepContext* context, int reps, int* constraints);
+
+S2B_API const char* s2b_version(void);
+// sizeof of {s2bBodyRow, s2bShapeRow, s2bJointRow, s2bContactRow, s2bStepContext, s2bCounters}: lets an FFI binding
+// verify its struct mirrors at load time.
+S2B_API void s2b_abi_sizes(int32_t out[6]);
+
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,391 @@
+// solver2d-b200 — device-side world: SoA columns, scratch arena, launch helpers. Internal to the CUDA library.
+#pragma once
+
+#include "s2b_device.h"
+#include "solver2d/constants.h"
+#include "solver2d/aabb.h"
+#include "solver2d/math.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#define S2B_CHECK(call)                                                                                                \
+	do                                                                                                                 \
+	{                                                                                                                  \
+		cudaError_t err__ = (call);                                                                                    \
+		if (err__ != cudaSuccess)                                                                                      \
+		{                                                                                                              \
+			fprintf(stderr, "solver2d-b200: CUDA error %s at %s:%d (%s) — no CPU fallback, aborting\n",                 \
+					cudaGetErrorString(err__), __FILE__, __LINE__, #call);                                             \
+			abort();                                                                                                   \
+		}                                                                                                              \
+	} while (0)
+
+// ---- body flags (bflags column) -------------------------------------------------------------------------------
+#define S2B_BODY_VALID 0x1u
+#define S2B_BODY_TYPE(f) (((f) >> 1) & 0x3u)
+// a body takes part in conflict detection / write-back only if it can move in the solver
+#define S2B_BODY_STATIC 0u
+#define S2B_BODY_KINEMATIC 1u
+#define S2B_BODY_DYNAMIC 2u
+
+// ---- contact info word (cInfo.x) ------------------------------------------------------------------------------
+// bits 0-1 pointCount, bit 2 frictionPersisted, bit 3 persisted0, bit 4 persisted1
+#define S2B_CI_COUNT(x) ((x) & 0x3)
+#define S2B_CI_FRICTION_PERSISTED 0x4
+#define S2B_CI_PERSISTED0 0x8
+#define S2B_CI_PERSISTED1 0x10
+
+// A growable device array. grow() keeps the old contents (device-to-device copy on the world's stream).
+template <typename T> struct DevArray
+{
+	T* p = nullptr;
+	size_t cap = 0;
+
+	void reserve(size_t n, cudaStream_t stream, bool keep = true, bool zero = true)
+	{
+		if (n <= cap)
+		{
+			return;
+		}
+		size_t newCap = cap ? cap : 64;
+		while (newCap < n)
+		{
+			newCap += newCap / 2 + 64;
+		}
+		T* q = nullptr;
+		S2B_CHECK(cudaMalloc((void**)&q, newCap * sizeof(T)));
+		if (zero)
+		{
+			S2B_CHECK(cudaMemsetAsync(q, 0, newCap * sizeof(T), stream));
+		}
+		if (p != nullptr)
+		{
+			if (keep && cap > 0)
+			{
+				S2B_CHECK(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+			}
+			// stream-ordered release so in-flight kernels reading the old buffer stay valid
+			S2B_CHECK(cudaFreeAsync(p, stream));
+		}
+		p = q;
+		cap = newCap;
+	}
+
+	void release()
+	{
+		if (p)
+		{
+			cudaFree(p);
+		}
+		p = nullptr;
+		cap = 0;
+	}
+};
+
+// per-contact persistent columns; two sets (ping-pong) so a broad-phase pass can re-sort into the other one
+struct ContactColumns
+{
+	DevArray<unsigned long long> key; // lo shape << 32 | hi shape
+	DevArray<int2> shapes;			  // (A, B) in manifold order
+	DevArray<int2> bodies;			  // (A, B)
+	DevArray<int4> info;			  // x: count/flags, y: id0 | id1 << 16, z: GJK cache (count | iA<<2.. ), w: cache metric bits
+	DevArray<float4> nf;			  // normal.x normal.y friction 0
+	DevArray<float4> anchor[2];		  // localAnchorA.xy localAnchorB.xy   (body-origin relative, body frame)
+	DevArray<float4> impulse[2];	  // separation normalImpulse tangentImpulse 0
+	DevArray<float4> fanchor[2];	  // frictionAnchorA.xy frictionAnchorB.xy   (sticky only)
+	DevArray<float4> fnormal[2];	  // frictionNormalA.xy frictionNormalB.xy   (sticky only)
+
+	void reserve(size_t n, cudaStream_t s, bool sticky, bool keep)
+	{
+		key.reserve(n, s, keep);
+		shapes.reserve(n, s, keep);
+		bodies.reserve(n, s, keep);
+		info.reserve(n, s, keep);
+		nf.reserve(n, s, keep);
+		for (int p = 0; p < 2; ++p)
+		{
+			anchor[p].reserve(n, s, keep);
+			impulse[p].reserve(n, s, keep);
+			if (sticky)
+			{
+				fanchor[p].reserve(n, s, keep);
+				fnormal[p].reserve(n, s, keep);
+			}
+		}
+	}
+
+	void release()
+	{
+		key.release();
+		shapes.release();
+		bodies.release();
+		info.release();
+		nf.release();
+		for (int p = 0; p < 2; ++p)
+		{
+			anchor[p].release();
+			impulse[p].release();
+			fanchor[p].release();
+			fnormal[p].release();
+		}
+	}
+};
+
+// raw-pointer view of the contact columns handed to kernels
+struct ContactView
+{
+	unsigned long long* key;
+	int2* shapes;
+	int2* bodies;
+	int4* info;
+	float4* nf;
+	float4* anchor[2];
+	float4* impulse[2];
+	float4* fanchor[2];
+	float4* fnormal[2];
+};
+
+inline ContactView makeView(ContactColumns& c)
+{
+	ContactView v;
+	v.key = c.key.p;
+	v.shapes = c.shapes.p;
+	v.bodies = c.bodies.p;
+	v.info = c.info.p;
+	v.nf = c.nf.p;
+	for (int p = 0; p < 2; ++p)
+	{
+		v.anchor[p] = c.anchor[p].p;
+		v.impulse[p] = c.impulse[p].p;
+		v.fanchor[p] = c.fanchor[p].p;
+		v.fnormal[p] = c.fnormal[p].p;
+	}
+	return v;
+}
+
+// per-step contact-constraint columns in solve order (group-major). Which optional columns are live depends on the
+// solver variant (DESIGN.md "constraint stream").
+struct ConstraintView
+{
+	int2* idx;		  // bodyA, bodyB | flags in the two top bits of y (see S2B_CF_*)
+	float4* nf;		  // normal.x normal.y friction invI_A
+	float4* anchor[2]; // COM-relative local anchors: A.xy B.xy
+	float4* pm[2];	  // adjustedSeparation normalMass tangentMass invI_B(point 0) / spare(point 1)
+	float2* lambda[2]; // normalImpulse tangentImpulse (read-modify-write every pass)
+	float4* r0[2];	  // prepare-time world anchors rA0.xy rB0.xy (fixed-anchor variants, XPBD)
+	float* sep[2];	  // prepare-time separation (PGS family, NGS)
+	int* src;		  // contact slot this constraint came from
+	// sticky extras
+	float4* fanchor[2]; // COM-relative local friction anchors A.xy B.xy
+	float2* tsep[2];	// tangentSeparation, spare
+};
+
+#define S2B_CF_TWO_POINTS 0x40000000
+#define S2B_CF_STATIC_SOFT 0x80000000u
+#define S2B_CF_INDEX_MASK 0x3FFFFFFF
+
+// view of the body columns
+struct BodyView
+{
+	float4* vel;  // v.x v.y w invMass
+	float4* pose; // dp.x dp.y q.s q.c
+	float4* pos;  // p.x p.y invI I      (centre of mass)
+	float4* org;  // origin.x origin.y localCenter.x localCenter.y
+	float4* frc;  // force.x force.y torque mass
+	float4* prm;  // linearDamping angularDamping gravityScale invI
+	float4* aux0; // Jacobi: dv.x dv.y dw 0 ; XPBD: dp0.x dp0.y q0.s q0.c
+	float4* aux1; // XPBD: v0.x v0.y w0 0
+	uint8_t* flags;
+	int capacity;
+};
+
+// view of the shape columns
+struct ShapeView
+{
+	int4* head;		 // flags(valid|type<<1|moved<<4), body, proxyKey, vertex count
+	int4* filter;	 // categoryBits maskBits groupIndex 0
+	float4* aabb;	 // tight + speculative
+	float4* fat;	 // broad-phase box
+	float2* fr;		 // friction, radius
+	float2* verts;	 // [shape * 8 + i]
+	float2* normals; // [shape * 8 + i]
+	int capacity;
+};
+
+// per-joint columns (slot order)
+struct JointView
+{
+	int4* head;		// flags, bodyA, bodyB, 0
+	float4* anchors; // localOriginAnchorA.xy localOriginAnchorB.xy
+	float4* lim;	// referenceAngle lowerAngle upperAngle 0
+	float4* motor;	// maxMotorTorque motorSpeed hertz dampingRatio
+	float4* target; // mouse target.xy 0 0
+	float4* imp;	// impulse.x impulse.y motorImpulse 0
+	float4* limp;	// lowerImpulse upperImpulse 0 0
+	int capacity;
+};
+
+// per-step joint-constraint columns in solve order
+struct JointConstraintView
+{
+	int4* head;		// flags(type, limit, motor), bodyA, bodyB, source joint slot
+	float4* anchor; // COM-relative local anchors A.xy B.xy
+	float4* mass;	// invMassA invIA invMassB invIB
+	float4* d0ax;	// centerDiff0.xy axialMass 0
+	float4* lim;	// referenceAngle lowerAngle upperAngle 0
+	float4* motor;	// maxMotorTorque motorSpeed 0 0
+	float4* coef;	// biasCoefficient massCoefficient impulseCoefficient 0
+	float4* pivot;	// pivotMass cx.x cx.y cy.x cy.y (mouse, non-fresh revolute)
+	float4* imp;	// impulse.x impulse.y motorImpulse 0        (r/w)
+	float4* limp;	// lowerImpulse upperImpulse 0 0              (r/w)
+};
+
+struct StageTimer
+{
+	cudaEvent_t ev[5];
+	bool recorded = false;
+};
+
+struct s2bWorld
+{
+	int device = 0;
+	int solverType = 0;
+	cudaStream_t stream = nullptr;
+	float2 gravity = {0.0f, -10.0f};
+	int schedule = S2B_SCHEDULE_COLOR;
+	int maxColors = 24;
+	int persistent = 1;
+	int smCount = 148;
+	int coopSupported = 0;
+
+	// bodies
+	int bodyCap = 0;
+	DevArray<float4> bVel, bPose, bPos, bOrg, bFrc, bPrm, bAux0, bAux1;
+	DevArray<uint8_t> bFlags;
+
+	// shapes
+	int shapeCap = 0;
+	DevArray<int4> sHead, sFilter;
+	DevArray<float4> sAabb, sFat;
+	DevArray<float2> sFr, sVerts, sNormals;
+
+	// joints
+	int jointCap = 0;
+	DevArray<int4> jHead;
+	DevArray<float4> jAnchors, jLim, jMotor, jTarget, jImp, jLimp;
+	DevArray<unsigned long long> jointPairKeys;
+	int jointPairCount = 0;
+
+	// contacts
+	ContactColumns contacts[2];
+	int cur = 0;		  // which column set is live
+	int contactCount = 0; // host mirror (valid after a pair pass or upload)
+	bool sticky = false;
+
+	// broad phase
+	bool pairsDirty = true; // host-side structural change
+	DevArray<int> dMovedFlag; // [0] = number of proxies moved in last finalize (device counter)
+	int pairPassCount = 0;
+	int treeHeight = 0;
+
+	// solve-order hint (validation)
+	std::vector<unsigned long long> orderHint;
+
+	// scratch + bookkeeping for the solver stage live in solver_state.cuh (opaque here)
+	struct SolverScratch* scratch = nullptr;
+	struct BroadScratch* broad = nullptr;
+
+	// pinned host mailbox for small device->host counters
+	int* hostMail = nullptr; // pinned, 64 ints
+	int* devMail = nullptr;	 // device, 64 ints
+
+	int kernelLaunches = 0;
+	StageTimer timer;
+	float stageMs[4] = {0, 0, 0, 0};
+
+	DevArray<char> l2Flush;
+};
+
+inline BodyView bodyView(s2bWorld* w)
+{
+	BodyView v;
+	v.vel = w->bVel.p;
+	v.pose = w->bPose.p;
+	v.pos = w->bPos.p;
+	v.org = w->bOrg.p;
+	v.frc = w->bFrc.p;
+	v.prm = w->bPrm.p;
+	v.aux0 = w->bAux0.p;
+	v.aux1 = w->bAux1.p;
+	v.flags = w->bFlags.p;
+	v.capacity = w->bodyCap;
+	return v;
+}
+
+inline ShapeView shapeView(s2bWorld* w)
+{
+	ShapeView v;
+	v.head = w->sHead.p;
+	v.filter = w->sFilter.p;
+	v.aabb = w->sAabb.p;
+	v.fat = w->sFat.p;
+	v.fr = w->sFr.p;
+	v.verts = w->sVerts.p;
+	v.normals = w->sNormals.p;
+	v.capacity = w->shapeCap;
+	return v;
+}
+
+inline JointView jointView(s2bWorld* w)
+{
+	JointView v;
+	v.head = w->jHead.p;
+	v.anchors = w->jAnchors.p;
+	v.lim = w->jLim.p;
+	v.motor = w->jMotor.p;
+	v.target = w->jTarget.p;
+	v.imp = w->jImp.p;
+	v.limp = w->jLimp.p;
+	v.capacity = w->jointCap;
+	return v;
+}
+
+// mailbox slots
+enum
+{
+	MAIL_MOVED = 0,
+	MAIL_CONSTRAINTS = 1,
+	MAIL_GROUPS = 2,
+	MAIL_OVERFLOW = 3,
+	MAIL_NEW_PAIRS = 4,
+	MAIL_KEPT = 5,
+	MAIL_JOINTS = 6,
+	MAIL_UNCOLORED = 7,
+	MAIL_PAIR_OVERFLOW = 8,
+	MAIL_COUNT = 64
+};
+
+inline int gridFor(int n, int block)
+{
+	return (n + block - 1) / block;
+}
+
+#define S2B_LAUNCH(world, kernel, grid, block, smem, ...)                                                              \
+	do                                                                                                                 \
+	{                                                                                                                  \
+		kernel<<<(grid), (block), (smem), (world)->stream>>>(__VA_ARGS__);                                             \
+		(world)->kernelLaunches += 1;                                                                                  \
+	} while (0)
+
+// stage entry points implemented in the other translation units
+void s2bBroadphaseUpdatePairs(s2bWorld* w);
+void s2bNarrowphaseUpdate(s2bWorld* w);
+void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctx);
+void s2bFinalize(s2bWorld* w);
+void s2bFreeSolverScratch(s2bWorld* w);
+void s2bFreeBroadScratch(s2bWorld* w);

@@ -1,0 +1,88 @@
+// solver2d-b200 — per-step solver scratch (constraint streams, colouring, group tables) and the argument block
+// every solver kernel receives by value.
+#pragma once
+
+#include "s2b_internal.cuh"
+
+// soft-constraint coefficients (reference src/solve_common.c:264-271)
+struct SoftCoef
+{
+	float bias, mass, impulse;
+};
+
+// device-resident counters of the current solve (written by the set-up kernels, read by every later kernel, so the
+// host never has to synchronise to learn them)
+enum
+{
+	CNT_CONTACTS = 0,  // contact constraints (manifolds with >= 1 point)
+	CNT_JOINTS = 1,	   // live joints
+	CNT_GROUPS = 2,	   // parallel groups (colours / wavefront levels), excluding the serial overflow group
+	CNT_OVERFLOW_C = 3, // contact constraints in the overflow group
+	CNT_OVERFLOW_J = 4, // joints in the overflow group
+	CNT_REMAINING = 5, // colouring work counters (three rotating slots: 5, 6, 7)
+	CNT_ROUNDS = 8,
+	CNT_SIZE = 16
+};
+
+struct SolveArgs
+{
+	BodyView bodies;
+	ContactView contacts;
+	JointView joints;
+	ConstraintView cc;
+	JointConstraintView jc;
+	const int* counts;	  // CNT_*
+	const int* cGroupOff; // contact-constraint group offsets, CNT_GROUPS + 2 entries (last group = overflow)
+	const int* jGroupOff; // joint-constraint group offsets, same shape
+	s2bStepContext ctx;
+	float2 gravity;
+	SoftCoef softDynamic; // contact, both bodies movable
+	SoftCoef softStatic;  // contact against a body with zero inverse mass (doubled hertz)
+	SoftCoef softJoint;
+	float contactHertz;
+	float jointHertz;
+	int solverType;
+	int sticky;
+};
+
+struct SolverScratch
+{
+	// set-up
+	DevArray<int> counts;		  // CNT_SIZE
+	DevArray<int> activeFlag;	  // per contact slot: manifold has points
+	DevArray<int> activeSlots;	  // compacted contact slots, natural order
+	DevArray<int> jointFlag;	  // per joint slot: live
+	DevArray<int> jointSlots;	  // compacted joint slots, natural order
+	DevArray<int2> itemBodies;	  // per item (joints first, then contacts): conflict endpoints or -1
+	DevArray<int> degree;		  // per body
+	DevArray<int> adjStart;		  // per body + 1
+	DevArray<int> adjCursor;	  // per body
+	DevArray<int> adj;			  // 2 * items
+	DevArray<int> colorA, colorB; // per item, ping-pong
+	DevArray<unsigned char> sortKeyIn, sortKeyOut;
+	DevArray<int> sortValIn, sortValOut;
+	DevArray<int> cGroupOff, jGroupOff; // maxGroups + 2
+	DevArray<int> cPerm;				// solve position -> natural contact-constraint index
+	DevArray<int> jPerm;
+	DevArray<char> cubTemp;
+	int maxGroups = 0;
+
+	// contact constraint columns
+	DevArray<int2> idx;
+	DevArray<float4> nf;
+	DevArray<float4> anchor[2], pm[2], r0[2], fanchor[2];
+	DevArray<float2> lambda[2], tsep[2];
+	DevArray<float> sep[2];
+	DevArray<int> src;
+
+	// joint constraint columns
+	DevArray<int4> jhead;
+	DevArray<float4> janchor, jmass, jd0ax, jlim, jmotor, jcoef, jpivot, jimp, jlimp;
+
+	// host mirrors (valid when the last solve synchronised: multi-launch and wavefront modes)
+	int hostContacts = 0, hostJoints = 0, hostGroups = 0, hostOverflowC = 0, hostOverflowJ = 0;
+	bool hostCountsValid = false;
+	std::vector<int> hostCGroupOff, hostJGroupOff;
+};
+
+SolverScratch* s2bGetSolverScratch(s2bWorld* w);

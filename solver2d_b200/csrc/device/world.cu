@@ -1,0 +1,751 @@
+// solver2d-b200 — device world lifecycle, row scatter (host -> SoA) and row gather (SoA -> host).
+//
+// Replaces the reference's AoS pools (s2Body 184 B, s2Shape 240 B, s2Joint 188 B, s2Contact 216 B; reference
+// src/body.h, shape.h, joint.h, contact.h) with 128-bit aligned SoA columns resident in HBM. The host only ever
+// moves *rows that changed*; a scatter kernel writes them into the columns, so a stale host copy of an untouched
+// neighbour can never overwrite device state.
+#include "s2b_internal.cuh"
+
+// ---------------------------------------------------------------------------------------------------------------
+// scatter kernels
+// ---------------------------------------------------------------------------------------------------------------
+
+__global__ void s2bScatterBodies(const s2bBodyRow* __restrict__ rows, int count, BodyView b)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= count)
+	{
+		return;
+	}
+	s2bBodyRow r = rows[t];
+	int i = r.index;
+	b.vel[i] = make_float4(r.linearVelocity[0], r.linearVelocity[1], r.angularVelocity, r.invMass);
+	b.pose[i] = make_float4(0.0f, 0.0f, r.rot[0], r.rot[1]);
+	b.pos[i] = make_float4(r.position[0], r.position[1], r.invI, r.I);
+	b.org[i] = make_float4(r.origin[0], r.origin[1], r.localCenter[0], r.localCenter[1]);
+	b.frc[i] = make_float4(r.force[0], r.force[1], r.torque, r.mass);
+	b.prm[i] = make_float4(r.linearDamping, r.angularDamping, r.gravityScale, r.invI);
+	b.flags[i] = (uint8_t)(r.flags & 0x7);
+}
+
+__global__ void s2bScatterShapes(const s2bShapeRow* __restrict__ rows, int count, ShapeView s)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= count)
+	{
+		return;
+	}
+	const s2bShapeRow* r = rows + t;
+	int i = r->index;
+	s.head[i] = make_int4(r->flags, r->body, r->proxyKey, r->count);
+	s.filter[i] = make_int4((int)r->categoryBits, (int)r->maskBits, r->groupIndex, 0);
+	s.aabb[i] = make_float4(r->aabb[0], r->aabb[1], r->aabb[2], r->aabb[3]);
+	s.fat[i] = make_float4(r->fatAABB[0], r->fatAABB[1], r->fatAABB[2], r->fatAABB[3]);
+	s.fr[i] = make_float2(r->friction, r->radius);
+	for (int k = 0; k < 8; ++k)
+	{
+		s.verts[i * 8 + k] = make_float2(r->vertices[2 * k], r->vertices[2 * k + 1]);
+		s.normals[i * 8 + k] = make_float2(r->normals[2 * k], r->normals[2 * k + 1]);
+	}
+}
+
+__global__ void s2bScatterJoints(const s2bJointRow* __restrict__ rows, int count, JointView j)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= count)
+	{
+		return;
+	}
+	const s2bJointRow* r = rows + t;
+	int i = r->index;
+	j.head[i] = make_int4(r->flags, r->bodyA, r->bodyB, 0);
+	j.anchors[i] = make_float4(r->localOriginAnchorA[0], r->localOriginAnchorA[1], r->localOriginAnchorB[0],
+							   r->localOriginAnchorB[1]);
+	j.lim[i] = make_float4(r->referenceAngle, r->lowerAngle, r->upperAngle, 0.0f);
+	j.motor[i] = make_float4(r->maxMotorTorque, r->motorSpeed, r->hertz, r->dampingRatio);
+	j.target[i] = make_float4(r->target[0], r->target[1], 0.0f, 0.0f);
+	j.imp[i] = make_float4(r->impulse[0], r->impulse[1], r->motorImpulse, 0.0f);
+	j.limp[i] = make_float4(r->lowerImpulse, r->upperImpulse, 0.0f, 0.0f);
+}
+
+__device__ __forceinline__ int s2bPackCache(const s2bContactRow* r)
+{
+	// count (2 bits) | indexA[0..2] (3 bits each) | indexB[0..2] (3 bits each)
+	int bits = r->cacheCount & 0x3;
+	for (int k = 0; k < 3; ++k)
+	{
+		bits |= (r->cacheIndexA[k] & 0x7) << (2 + 3 * k);
+		bits |= (r->cacheIndexB[k] & 0x7) << (11 + 3 * k);
+	}
+	return bits;
+}
+
+__global__ void s2bScatterContacts(const s2bContactRow* __restrict__ rows, int count, ContactView c, int sticky)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= count)
+	{
+		return;
+	}
+	const s2bContactRow* r = rows + t;
+	unsigned long long lo = (unsigned long long)(r->shapeA < r->shapeB ? r->shapeA : r->shapeB);
+	unsigned long long hi = (unsigned long long)(r->shapeA < r->shapeB ? r->shapeB : r->shapeA);
+	c.key[t] = (lo << 32) | hi;
+	c.shapes[t] = make_int2(r->shapeA, r->shapeB);
+	c.bodies[t] = make_int2(r->bodyA, r->bodyB);
+	int flags = (r->pointCount & 0x3) | (r->frictionPersisted ? S2B_CI_FRICTION_PERSISTED : 0) |
+				(r->points[0].persisted ? S2B_CI_PERSISTED0 : 0) | (r->points[1].persisted ? S2B_CI_PERSISTED1 : 0);
+	int ids = (r->points[0].id & 0xFFFF) | ((r->points[1].id & 0xFFFF) << 16);
+	c.info[t] = make_int4(flags, ids, s2bPackCache(r), __float_as_int(r->cacheMetric));
+	c.nf[t] = make_float4(r->normal[0], r->normal[1], r->friction, 0.0f);
+	for (int p = 0; p < 2; ++p)
+	{
+		const s2bContactPoint* q = r->points + p;
+		c.anchor[p][t] = make_float4(q->localAnchorA[0], q->localAnchorA[1], q->localAnchorB[0], q->localAnchorB[1]);
+		c.impulse[p][t] = make_float4(q->separation, q->normalImpulse, q->tangentImpulse, 0.0f);
+		if (sticky)
+		{
+			c.fanchor[p][t] =
+				make_float4(q->frictionAnchorA[0], q->frictionAnchorA[1], q->frictionAnchorB[0], q->frictionAnchorB[1]);
+			c.fnormal[p][t] =
+				make_float4(q->frictionNormalA[0], q->frictionNormalA[1], q->frictionNormalB[0], q->frictionNormalB[1]);
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// gather kernels
+// ---------------------------------------------------------------------------------------------------------------
+
+__global__ void s2bGatherBodies(s2bBodyRow* rows, int count, BodyView b, int useRowIndex)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= count)
+	{
+		return;
+	}
+	int i = useRowIndex ? rows[t].index : t;
+	s2bBodyRow r;
+	float4 vel = b.vel[i], pose = b.pose[i], pos = b.pos[i], org = b.org[i], frc = b.frc[i], prm = b.prm[i];
+	r.index = i;
+	r.flags = b.flags[i];
+	r.origin[0] = org.x;
+	r.origin[1] = org.y;
+	r.position[0] = pos.x;
+	r.position[1] = pos.y;
+	r.rot[0] = pose.z;
+	r.rot[1] = pose.w;
+	r.linearVelocity[0] = vel.x;
+	r.linearVelocity[1] = vel.y;
+	r.angularVelocity = vel.z;
+	r.localCenter[0] = org.z;
+	r.localCenter[1] = org.w;
+	r.mass = frc.w;
+	r.invMass = vel.w;
+	r.I = pos.w;
+	r.invI = pos.z;
+	r.force[0] = frc.x;
+	r.force[1] = frc.y;
+	r.torque = frc.z;
+	r.linearDamping = prm.x;
+	r.angularDamping = prm.y;
+	r.gravityScale = prm.z;
+	rows[t] = r;
+}
+
+__global__ void s2bGatherJoints(s2bJointRow* rows, int count, JointView j)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count)
+	{
+		return;
+	}
+	s2bJointRow r;
+	int4 head = j.head[i];
+	float4 a = j.anchors[i], lim = j.lim[i], motor = j.motor[i], target = j.target[i], imp = j.imp[i], limp = j.limp[i];
+	r.index = i;
+	r.flags = head.x;
+	r.bodyA = head.y;
+	r.bodyB = head.z;
+	r.localOriginAnchorA[0] = a.x;
+	r.localOriginAnchorA[1] = a.y;
+	r.localOriginAnchorB[0] = a.z;
+	r.localOriginAnchorB[1] = a.w;
+	r.referenceAngle = lim.x;
+	r.lowerAngle = lim.y;
+	r.upperAngle = lim.z;
+	r.maxMotorTorque = motor.x;
+	r.motorSpeed = motor.y;
+	r.hertz = motor.z;
+	r.dampingRatio = motor.w;
+	r.target[0] = target.x;
+	r.target[1] = target.y;
+	r.impulse[0] = imp.x;
+	r.impulse[1] = imp.y;
+	r.motorImpulse = imp.z;
+	r.lowerImpulse = limp.x;
+	r.upperImpulse = limp.y;
+	rows[i] = r;
+}
+
+__global__ void s2bGatherContacts(s2bContactRow* rows, int count, ContactView c, int sticky)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= count)
+	{
+		return;
+	}
+	s2bContactRow r;
+	memset(&r, 0, sizeof(r));
+	int2 sh = c.shapes[t], bo = c.bodies[t];
+	int4 info = c.info[t];
+	float4 nf = c.nf[t];
+	r.shapeA = sh.x;
+	r.shapeB = sh.y;
+	r.bodyA = bo.x;
+	r.bodyB = bo.y;
+	r.pointCount = S2B_CI_COUNT(info.x);
+	r.frictionPersisted = (info.x & S2B_CI_FRICTION_PERSISTED) ? 1 : 0;
+	r.friction = nf.z;
+	r.normal[0] = nf.x;
+	r.normal[1] = nf.y;
+	for (int p = 0; p < 2; ++p)
+	{
+		s2bContactPoint* q = r.points + p;
+		float4 a = c.anchor[p][t], m = c.impulse[p][t];
+		q->localAnchorA[0] = a.x;
+		q->localAnchorA[1] = a.y;
+		q->localAnchorB[0] = a.z;
+		q->localAnchorB[1] = a.w;
+		q->separation = m.x;
+		q->normalImpulse = m.y;
+		q->tangentImpulse = m.z;
+		q->id = (info.y >> (16 * p)) & 0xFFFF;
+		q->persisted = (info.x & (p == 0 ? S2B_CI_PERSISTED0 : S2B_CI_PERSISTED1)) ? 1 : 0;
+		if (sticky)
+		{
+			float4 fa = c.fanchor[p][t], fn = c.fnormal[p][t];
+			q->frictionAnchorA[0] = fa.x;
+			q->frictionAnchorA[1] = fa.y;
+			q->frictionAnchorB[0] = fa.z;
+			q->frictionAnchorB[1] = fa.w;
+			q->frictionNormalA[0] = fn.x;
+			q->frictionNormalA[1] = fn.y;
+			q->frictionNormalB[0] = fn.z;
+			q->frictionNormalB[1] = fn.w;
+		}
+	}
+	r.cacheCount = info.z & 0x3;
+	for (int k = 0; k < 3; ++k)
+	{
+		r.cacheIndexA[k] = (uint8_t)((info.z >> (2 + 3 * k)) & 0x7);
+		r.cacheIndexB[k] = (uint8_t)((info.z >> (11 + 3 * k)) & 0x7);
+	}
+	r.cacheMetric = __int_as_float(info.w);
+	rows[t] = r;
+}
+
+__global__ void s2bPackBodyState(BodyView b, int first, int count, float4* out)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= count)
+	{
+		return;
+	}
+	int i = first + t;
+	float4 org = b.org[i], pose = b.pose[i], vel = b.vel[i];
+	out[2 * t + 0] = make_float4(org.x, org.y, pose.z, pose.w);
+	out[2 * t + 1] = make_float4(vel.x, vel.y, vel.z, 0.0f);
+}
+
+__global__ void s2bFlushKernel(char* buf, size_t n, int value)
+{
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	size_t stride = (size_t)gridDim.x * blockDim.x;
+	int4* p = (int4*)buf;
+	size_t n4 = n / sizeof(int4);
+	for (; i < n4; i += stride)
+	{
+		p[i] = make_int4(value, value, value, value);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------
+
+static void* stageRows(s2bWorld* w, const void* hostRows, size_t bytes)
+{
+	// stream-ordered staging buffer: allocate, copy, free after the scatter kernel
+	void* d = nullptr;
+	S2B_CHECK(cudaMallocAsync(&d, bytes, w->stream));
+	S2B_CHECK(cudaMemcpyAsync(d, hostRows, bytes, cudaMemcpyHostToDevice, w->stream));
+	return d;
+}
+
+extern "C" s2bWorld* s2b_world_create(int cudaDevice, int solverType)
+{
+	int deviceCount = 0;
+	cudaError_t err = cudaGetDeviceCount(&deviceCount);
+	if (err != cudaSuccess || deviceCount == 0)
+	{
+		fprintf(stderr, "solver2d-b200: no CUDA device available (%s) — this library has no CPU fallback\n",
+				cudaGetErrorString(err));
+		abort();
+	}
+	s2bWorld* w = new s2bWorld();
+	if (cudaDevice < 0)
+	{
+		S2B_CHECK(cudaGetDevice(&cudaDevice));
+	}
+	w->device = cudaDevice;
+	S2B_CHECK(cudaSetDevice(cudaDevice));
+	S2B_CHECK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+	cudaDeviceProp prop;
+	S2B_CHECK(cudaGetDeviceProperties(&prop, cudaDevice));
+	w->smCount = prop.multiProcessorCount;
+	w->coopSupported = prop.cooperativeLaunch;
+	w->solverType = solverType;
+	w->sticky = (solverType == 6); // s2_solverTGS_Sticky
+	S2B_CHECK(cudaMallocHost((void**)&w->hostMail, MAIL_COUNT * sizeof(int)));
+	memset(w->hostMail, 0, MAIL_COUNT * sizeof(int));
+	S2B_CHECK(cudaMalloc((void**)&w->devMail, MAIL_COUNT * sizeof(int)));
+	S2B_CHECK(cudaMemset(w->devMail, 0, MAIL_COUNT * sizeof(int)));
+	for (int i = 0; i < 5; ++i)
+	{
+		S2B_CHECK(cudaEventCreate(&w->timer.ev[i]));
+	}
+	// keep freed stream-ordered allocations cached in the pool (per-step scratch is recycled, not re-malloc'ed)
+	cudaMemPool_t pool;
+	S2B_CHECK(cudaDeviceGetDefaultMemPool(&pool, cudaDevice));
+	unsigned long long threshold = ~0ull;
+	S2B_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+	return w;
+}
+
+extern "C" void s2b_world_destroy(s2bWorld* w)
+{
+	if (w == nullptr)
+	{
+		return;
+	}
+	S2B_CHECK(cudaSetDevice(w->device));
+	S2B_CHECK(cudaStreamSynchronize(w->stream));
+	s2bFreeSolverScratch(w);
+	s2bFreeBroadScratch(w);
+	w->bVel.release();
+	w->bPose.release();
+	w->bPos.release();
+	w->bOrg.release();
+	w->bFrc.release();
+	w->bPrm.release();
+	w->bAux0.release();
+	w->bAux1.release();
+	w->bFlags.release();
+	w->sHead.release();
+	w->sFilter.release();
+	w->sAabb.release();
+	w->sFat.release();
+	w->sFr.release();
+	w->sVerts.release();
+	w->sNormals.release();
+	w->jHead.release();
+	w->jAnchors.release();
+	w->jLim.release();
+	w->jMotor.release();
+	w->jTarget.release();
+	w->jImp.release();
+	w->jLimp.release();
+	w->jointPairKeys.release();
+	w->contacts[0].release();
+	w->contacts[1].release();
+	w->dMovedFlag.release();
+	w->l2Flush.release();
+	cudaFreeHost(w->hostMail);
+	cudaFree(w->devMail);
+	for (int i = 0; i < 5; ++i)
+	{
+		cudaEventDestroy(w->timer.ev[i]);
+	}
+	cudaStreamDestroy(w->stream);
+	delete w;
+}
+
+extern "C" void s2b_set_gravity(s2bWorld* w, float gx, float gy)
+{
+	w->gravity = make_float2(gx, gy);
+}
+
+extern "C" void s2b_set_schedule(s2bWorld* w, int schedule)
+{
+	w->schedule = schedule;
+}
+
+extern "C" void s2b_set_max_colors(s2bWorld* w, int maxColors)
+{
+	w->maxColors = maxColors < 1 ? 1 : (maxColors > 64 ? 64 : maxColors);
+}
+
+extern "C" void s2b_set_persistent(s2bWorld* w, int enable)
+{
+	w->persistent = enable;
+}
+
+static void reserveBodies(s2bWorld* w, int cap)
+{
+	if (cap <= w->bodyCap)
+	{
+		return;
+	}
+	cudaStream_t s = w->stream;
+	w->bVel.reserve(cap, s);
+	w->bPose.reserve(cap, s);
+	w->bPos.reserve(cap, s);
+	w->bOrg.reserve(cap, s);
+	w->bFrc.reserve(cap, s);
+	w->bPrm.reserve(cap, s);
+	w->bAux0.reserve(cap, s);
+	w->bAux1.reserve(cap, s);
+	w->bFlags.reserve(cap, s);
+	w->bodyCap = (int)w->bVel.cap;
+}
+
+static void reserveShapes(s2bWorld* w, int cap)
+{
+	if (cap <= w->shapeCap)
+	{
+		return;
+	}
+	cudaStream_t s = w->stream;
+	w->sHead.reserve(cap, s);
+	w->sFilter.reserve(cap, s);
+	w->sAabb.reserve(cap, s);
+	w->sFat.reserve(cap, s);
+	w->sFr.reserve(cap, s);
+	w->shapeCap = (int)w->sHead.cap;
+	w->sVerts.reserve((size_t)w->shapeCap * 8, s);
+	w->sNormals.reserve((size_t)w->shapeCap * 8, s);
+}
+
+static void reserveJoints(s2bWorld* w, int cap)
+{
+	if (cap <= w->jointCap)
+	{
+		return;
+	}
+	cudaStream_t s = w->stream;
+	w->jHead.reserve(cap, s);
+	w->jAnchors.reserve(cap, s);
+	w->jLim.reserve(cap, s);
+	w->jMotor.reserve(cap, s);
+	w->jTarget.reserve(cap, s);
+	w->jImp.reserve(cap, s);
+	w->jLimp.reserve(cap, s);
+	w->jointCap = (int)w->jHead.cap;
+}
+
+extern "C" void s2b_upload_bodies(s2bWorld* w, const s2bBodyRow* rows, int count, int bodyCapacity)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	reserveBodies(w, bodyCapacity);
+	if (count <= 0)
+	{
+		return;
+	}
+	s2bBodyRow* d = (s2bBodyRow*)stageRows(w, rows, sizeof(s2bBodyRow) * (size_t)count);
+	S2B_LAUNCH(w, s2bScatterBodies, gridFor(count, 128), 128, 0, d, count, bodyView(w));
+	S2B_CHECK(cudaFreeAsync(d, w->stream));
+	// the staging copy reads pageable host memory: make sure it is consumed before the caller reuses the buffer
+	S2B_CHECK(cudaStreamSynchronize(w->stream));
+}
+
+extern "C" void s2b_upload_shapes(s2bWorld* w, const s2bShapeRow* rows, int count, int shapeCapacity)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	reserveShapes(w, shapeCapacity);
+	if (count <= 0)
+	{
+		return;
+	}
+	s2bShapeRow* d = (s2bShapeRow*)stageRows(w, rows, sizeof(s2bShapeRow) * (size_t)count);
+	S2B_LAUNCH(w, s2bScatterShapes, gridFor(count, 128), 128, 0, d, count, shapeView(w));
+	S2B_CHECK(cudaFreeAsync(d, w->stream));
+	S2B_CHECK(cudaStreamSynchronize(w->stream));
+	w->pairsDirty = true;
+}
+
+extern "C" void s2b_upload_joints(s2bWorld* w, const s2bJointRow* rows, int count, int jointCapacity)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	reserveJoints(w, jointCapacity);
+	if (count <= 0)
+	{
+		return;
+	}
+	s2bJointRow* d = (s2bJointRow*)stageRows(w, rows, sizeof(s2bJointRow) * (size_t)count);
+	S2B_LAUNCH(w, s2bScatterJoints, gridFor(count, 128), 128, 0, d, count, jointView(w));
+	S2B_CHECK(cudaFreeAsync(d, w->stream));
+	S2B_CHECK(cudaStreamSynchronize(w->stream));
+}
+
+extern "C" void s2b_upload_contacts(s2bWorld* w, const s2bContactRow* rows, int count)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	ContactColumns& c = w->contacts[w->cur];
+	c.reserve((size_t)(count > 0 ? count : 1), w->stream, w->sticky, false);
+	w->contactCount = count;
+	if (count <= 0)
+	{
+		return;
+	}
+	s2bContactRow* d = (s2bContactRow*)stageRows(w, rows, sizeof(s2bContactRow) * (size_t)count);
+	S2B_LAUNCH(w, s2bScatterContacts, gridFor(count, 128), 128, 0, d, count, makeView(c), w->sticky ? 1 : 0);
+	S2B_CHECK(cudaFreeAsync(d, w->stream));
+	S2B_CHECK(cudaStreamSynchronize(w->stream));
+}
+
+extern "C" void s2b_upload_joint_pairs(s2bWorld* w, const uint64_t* sortedKeys, int count)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	w->jointPairKeys.reserve((size_t)(count > 0 ? count : 1), w->stream, false);
+	w->jointPairCount = count;
+	if (count > 0)
+	{
+		S2B_CHECK(cudaMemcpyAsync(w->jointPairKeys.p, sortedKeys, sizeof(uint64_t) * (size_t)count, cudaMemcpyHostToDevice,
+								  w->stream));
+		S2B_CHECK(cudaStreamSynchronize(w->stream));
+	}
+	w->pairsDirty = true;
+}
+
+extern "C" void s2b_mark_pairs_dirty(s2bWorld* w)
+{
+	w->pairsDirty = true;
+}
+
+extern "C" void s2b_set_contact_order(s2bWorld* w, const uint64_t* pairKeys, int count)
+{
+	w->orderHint.assign(pairKeys, pairKeys + (count > 0 ? count : 0));
+}
+
+extern "C" void s2b_sync(s2bWorld* w)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	S2B_CHECK(cudaStreamSynchronize(w->stream));
+}
+
+extern "C" void s2b_download_bodies(s2bWorld* w, s2bBodyRow* rows, int count)
+{
+	if (count <= 0)
+	{
+		return;
+	}
+	S2B_CHECK(cudaSetDevice(w->device));
+	s2bBodyRow* d = (s2bBodyRow*)stageRows(w, rows, sizeof(s2bBodyRow) * (size_t)count);
+	S2B_LAUNCH(w, s2bGatherBodies, gridFor(count, 128), 128, 0, d, count, bodyView(w), 1);
+	S2B_CHECK(cudaMemcpyAsync(rows, d, sizeof(s2bBodyRow) * (size_t)count, cudaMemcpyDeviceToHost, w->stream));
+	S2B_CHECK(cudaFreeAsync(d, w->stream));
+	S2B_CHECK(cudaStreamSynchronize(w->stream));
+}
+
+extern "C" void s2b_download_all_bodies(s2bWorld* w, s2bBodyRow* rows, int capacity)
+{
+	if (capacity <= 0)
+	{
+		return;
+	}
+	S2B_CHECK(cudaSetDevice(w->device));
+	if (capacity > w->bodyCap)
+	{
+		capacity = w->bodyCap;
+	}
+	s2bBodyRow* d = nullptr;
+	S2B_CHECK(cudaMallocAsync((void**)&d, sizeof(s2bBodyRow) * (size_t)capacity, w->stream));
+	S2B_LAUNCH(w, s2bGatherBodies, gridFor(capacity, 128), 128, 0, d, capacity, bodyView(w), 0);
+	S2B_CHECK(cudaMemcpyAsync(rows, d, sizeof(s2bBodyRow) * (size_t)capacity, cudaMemcpyDeviceToHost, w->stream));
+	S2B_CHECK(cudaFreeAsync(d, w->stream));
+	S2B_CHECK(cudaStreamSynchronize(w->stream));
+}
+
+extern "C" void s2b_download_shape_boxes(s2bWorld* w, float* aabb4, float* fat4, int32_t* flags, int capacity)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	if (capacity > w->shapeCap)
+	{
+		capacity = w->shapeCap;
+	}
+	if (capacity <= 0)
+	{
+		return;
+	}
+	S2B_CHECK(cudaStreamSynchronize(w->stream));
+	if (aabb4)
+	{
+		S2B_CHECK(cudaMemcpy(aabb4, w->sAabb.p, sizeof(float4) * (size_t)capacity, cudaMemcpyDeviceToHost));
+	}
+	if (fat4)
+	{
+		S2B_CHECK(cudaMemcpy(fat4, w->sFat.p, sizeof(float4) * (size_t)capacity, cudaMemcpyDeviceToHost));
+	}
+	if (flags)
+	{
+		std::vector<int4> head((size_t)capacity);
+		S2B_CHECK(cudaMemcpy(head.data(), w->sHead.p, sizeof(int4) * (size_t)capacity, cudaMemcpyDeviceToHost));
+		for (int i = 0; i < capacity; ++i)
+		{
+			flags[i] = head[i].x;
+		}
+	}
+}
+
+extern "C" void s2b_download_joints(s2bWorld* w, s2bJointRow* rows, int capacity)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	if (capacity > w->jointCap)
+	{
+		capacity = w->jointCap;
+	}
+	if (capacity <= 0)
+	{
+		return;
+	}
+	s2bJointRow* d = nullptr;
+	S2B_CHECK(cudaMallocAsync((void**)&d, sizeof(s2bJointRow) * (size_t)capacity, w->stream));
+	S2B_LAUNCH(w, s2bGatherJoints, gridFor(capacity, 128), 128, 0, d, capacity, jointView(w));
+	S2B_CHECK(cudaMemcpyAsync(rows, d, sizeof(s2bJointRow) * (size_t)capacity, cudaMemcpyDeviceToHost, w->stream));
+	S2B_CHECK(cudaFreeAsync(d, w->stream));
+	S2B_CHECK(cudaStreamSynchronize(w->stream));
+}
+
+extern "C" int s2b_download_contacts(s2bWorld* w, s2bContactRow* rows, int maxCount)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	S2B_CHECK(cudaStreamSynchronize(w->stream));
+	int count = w->contactCount < maxCount ? w->contactCount : maxCount;
+	if (count <= 0)
+	{
+		return 0;
+	}
+	s2bContactRow* d = nullptr;
+	S2B_CHECK(cudaMallocAsync((void**)&d, sizeof(s2bContactRow) * (size_t)count, w->stream));
+	S2B_LAUNCH(w, s2bGatherContacts, gridFor(count, 128), 128, 0, d, count, makeView(w->contacts[w->cur]),
+			   w->sticky ? 1 : 0);
+	S2B_CHECK(cudaMemcpyAsync(rows, d, sizeof(s2bContactRow) * (size_t)count, cudaMemcpyDeviceToHost, w->stream));
+	S2B_CHECK(cudaFreeAsync(d, w->stream));
+	S2B_CHECK(cudaStreamSynchronize(w->stream));
+	return count;
+}
+
+extern "C" void s2b_pack_body_state(s2bWorld* w, int first, int count, void* deviceOut)
+{
+	if (count <= 0)
+	{
+		return;
+	}
+	S2B_CHECK(cudaSetDevice(w->device));
+	S2B_LAUNCH(w, s2bPackBodyState, gridFor(count, 128), 128, 0, bodyView(w), first, count, (float4*)deviceOut);
+}
+
+extern "C" void s2b_flush_l2(s2bWorld* w)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	const size_t bytes = (size_t)256 << 20; // 2x the 126 MB L2
+	w->l2Flush.reserve(bytes, w->stream, false, false);
+	static int value = 0;
+	value += 1;
+	S2B_LAUNCH(w, s2bFlushKernel, w->smCount * 8, 256, 0, w->l2Flush.p, bytes, value);
+}
+
+extern "C" void s2b_update_pairs(s2bWorld* w)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	s2bBroadphaseUpdatePairs(w);
+}
+
+extern "C" void s2b_update_contacts(s2bWorld* w)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	s2bNarrowphaseUpdate(w);
+}
+
+extern "C" void s2b_solve(s2bWorld* w, int solverType, const s2bStepContext* context)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	s2bSolve(w, solverType, context);
+}
+
+extern "C" void s2b_finalize(s2bWorld* w)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	s2bFinalize(w);
+}
+
+extern "C" void s2b_step(s2bWorld* w, int solverType, const s2bStepContext* context)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	cudaStream_t s = w->stream;
+	S2B_CHECK(cudaEventRecord(w->timer.ev[0], s));
+	s2bBroadphaseUpdatePairs(w);
+	S2B_CHECK(cudaEventRecord(w->timer.ev[1], s));
+	s2bNarrowphaseUpdate(w);
+	S2B_CHECK(cudaEventRecord(w->timer.ev[2], s));
+	s2bSolve(w, solverType, context);
+	S2B_CHECK(cudaEventRecord(w->timer.ev[3], s));
+	s2bFinalize(w);
+	S2B_CHECK(cudaEventRecord(w->timer.ev[4], s));
+	w->timer.recorded = true;
+}
+
+extern "C" void s2b_last_stage_ms(s2bWorld* w, float out[4])
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	for (int i = 0; i < 4; ++i)
+	{
+		out[i] = 0.0f;
+	}
+	if (w->timer.recorded == false)
+	{
+		return;
+	}
+	S2B_CHECK(cudaEventSynchronize(w->timer.ev[4]));
+	for (int i = 0; i < 4; ++i)
+	{
+		S2B_CHECK(cudaEventElapsedTime(out + i, w->timer.ev[i], w->timer.ev[i + 1]));
+	}
+}
+
+extern "C" float s2b_timed_steps(s2bWorld* w, int solverType, const s2bStepContext* context, int steps)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	cudaEvent_t e0, e1;
+	S2B_CHECK(cudaEventCreate(&e0));
+	S2B_CHECK(cudaEventCreate(&e1));
+	S2B_CHECK(cudaStreamSynchronize(w->stream));
+	S2B_CHECK(cudaEventRecord(e0, w->stream));
+	for (int i = 0; i < steps; ++i)
+	{
+		s2b_step(w, solverType, context);
+	}
+	S2B_CHECK(cudaEventRecord(e1, w->stream));
+	S2B_CHECK(cudaEventSynchronize(e1));
+	float ms = 0.0f;
+	S2B_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	return ms;
+}
+
+extern "C" void s2b_abi_sizes(int32_t out[6])
+{
+	out[0] = (int32_t)sizeof(s2bBodyRow);
+	out[1] = (int32_t)sizeof(s2bShapeRow);
+	out[2] = (int32_t)sizeof(s2bJointRow);
+	out[3] = (int32_t)sizeof(s2bContactRow);
+	out[4] = (int32_t)sizeof(s2bStepContext);
+	out[5] = (int32_t)sizeof(s2bCounters);
+}
+
+extern "C" const char* s2b_version(void)
+{
+	return "solver2d-b200 0.1 (sm_100a)";
+}

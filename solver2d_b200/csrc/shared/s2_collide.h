@@ -1,0 +1,963 @@
+// solver2d-b200 — narrow-phase geometry: GJK closest features, SAT, edge clipping and the per-shape-pair manifold
+// functions, written once as plain-C inline functions that compile for the host (public s2Collide* / s2ShapeDistance
+// API, csrc/host/collide.c) and for the device (one thread per contact, csrc/device/narrowphase.cu).
+//
+// Behaviour contract = the reference narrow phase (src/manifold.c, src/distance.c): same feature ids, same
+// contact points, and — because both sides are compiled without FMA contraction — the same float results
+// bit for bit on the same inputs. Citations on each function.
+#pragma once
+
+#include "solver2d/distance.h"
+#include "solver2d/geometry.h"
+#include "solver2d/manifold.h"
+#include "solver2d/math.h"
+
+#include <float.h>
+
+#if defined(__CUDACC__)
+	#define S2C_FN static inline __host__ __device__
+#else
+	#define S2C_FN static inline
+#endif
+
+// ---- small helpers ----------------------------------------------------------------------------------------------
+
+S2C_FN s2Vec2 s2cVec(float x, float y)
+{
+	s2Vec2 v;
+	v.x = x;
+	v.y = y;
+	return v;
+}
+
+// s2Normalize (reference src/math.c:40-51)
+S2C_FN s2Vec2 s2cNormalize(s2Vec2 v)
+{
+	float length = s2Length(v);
+	if (length < 0.001f * FLT_EPSILON)
+	{
+		return s2cVec(0.0f, 0.0f);
+	}
+	float invLength = 1.0f / length;
+	return s2cVec(invLength * v.x, invLength * v.y);
+}
+
+// s2NormalizeChecked (reference src/math.c:53-65)
+S2C_FN s2Vec2 s2cNormalizeChecked(s2Vec2 v)
+{
+	float length = s2Length(v);
+	if (length < FLT_EPSILON)
+	{
+		return s2cVec(0.0f, 0.0f);
+	}
+	float invLength = 1.0f / length;
+	return s2cVec(invLength * v.x, invLength * v.y);
+}
+
+// s2GetLengthAndNormalize (reference src/math.c:67-79)
+S2C_FN s2Vec2 s2cGetLengthAndNormalize(float* length, s2Vec2 v)
+{
+	*length = s2Length(v);
+	if (*length < FLT_EPSILON)
+	{
+		return s2cVec(0.0f, 0.0f);
+	}
+	float invLength = 1.0f / *length;
+	return s2cVec(invLength * v.x, invLength * v.y);
+}
+
+S2C_FN void s2cClearManifold(s2Manifold* m)
+{
+	// every byte zero, like the reference's `s2Manifold manifold = {0}`
+	unsigned char* p = (unsigned char*)m;
+	for (unsigned i = 0; i < sizeof(s2Manifold); ++i)
+	{
+		p[i] = 0;
+	}
+}
+
+// s2MakeCapsule (reference src/geometry.c:96-111): a 2-gon with the two side normals
+S2C_FN void s2cMakeCapsule(s2Polygon* shape, s2Vec2 p1, s2Vec2 p2, float radius)
+{
+	for (int i = 0; i < s2_maxPolygonVertices; ++i)
+	{
+		shape->vertices[i] = s2cVec(0.0f, 0.0f);
+		shape->normals[i] = s2cVec(0.0f, 0.0f);
+	}
+	shape->vertices[0] = p1;
+	shape->vertices[1] = p2;
+	s2Vec2 axis = s2cNormalizeChecked(s2Sub(p2, p1));
+	s2Vec2 normal = s2RightPerp(axis);
+	shape->normals[0] = normal;
+	shape->normals[1] = s2Neg(normal);
+	shape->count = 2;
+	shape->radius = radius;
+}
+
+// ---- GJK (reference src/distance.c) -----------------------------------------------------------------------------
+
+typedef struct s2cSimplexVertex
+{
+	s2Vec2 wA, wB, w; // support points and their difference wB - wA
+	float a;		  // barycentric weight
+	int indexA, indexB;
+} s2cSimplexVertex;
+
+typedef struct s2cSimplex
+{
+	s2cSimplexVertex v[3];
+	int count;
+} s2cSimplex;
+
+// s2FindSupport (reference src/distance.c:117-132)
+S2C_FN int s2cFindSupport(const s2Vec2* vertices, int count, s2Vec2 direction)
+{
+	int bestIndex = 0;
+	float bestValue = s2Dot(vertices[0], direction);
+	for (int i = 1; i < count; ++i)
+	{
+		float value = s2Dot(vertices[i], direction);
+		if (value > bestValue)
+		{
+			bestIndex = i;
+			bestValue = value;
+		}
+	}
+	return bestIndex;
+}
+
+S2C_FN s2Vec2 s2cWeight2(float a1, s2Vec2 w1, float a2, s2Vec2 w2)
+{
+	return s2cVec(a1 * w1.x + a2 * w2.x, a1 * w1.y + a2 * w2.y);
+}
+
+S2C_FN s2Vec2 s2cWeight3(float a1, s2Vec2 w1, float a2, s2Vec2 w2, float a3, s2Vec2 w3)
+{
+	return s2cVec(a1 * w1.x + a2 * w2.x + a3 * w3.x, a1 * w1.y + a2 * w2.y + a3 * w3.y);
+}
+
+// s2SolveSimplex2 (reference src/distance.c:304-334): closest point of a segment to the origin
+S2C_FN void s2cSolveSimplex2(s2cSimplex* s)
+{
+	s2Vec2 w1 = s->v[0].w;
+	s2Vec2 w2 = s->v[1].w;
+	s2Vec2 e12 = s2Sub(w2, w1);
+
+	float d12_2 = -s2Dot(w1, e12);
+	if (d12_2 <= 0.0f)
+	{
+		s->v[0].a = 1.0f;
+		s->count = 1;
+		return;
+	}
+
+	float d12_1 = s2Dot(w2, e12);
+	if (d12_1 <= 0.0f)
+	{
+		s->v[1].a = 1.0f;
+		s->count = 1;
+		s->v[0] = s->v[1];
+		return;
+	}
+
+	float inv_d12 = 1.0f / (d12_1 + d12_2);
+	s->v[0].a = d12_1 * inv_d12;
+	s->v[1].a = d12_2 * inv_d12;
+	s->count = 2;
+}
+
+// s2SolveSimplex3 (reference src/distance.c:336-446): closest point of a triangle to the origin (Voronoi regions)
+S2C_FN void s2cSolveSimplex3(s2cSimplex* s)
+{
+	s2Vec2 w1 = s->v[0].w;
+	s2Vec2 w2 = s->v[1].w;
+	s2Vec2 w3 = s->v[2].w;
+
+	s2Vec2 e12 = s2Sub(w2, w1);
+	float w1e12 = s2Dot(w1, e12);
+	float w2e12 = s2Dot(w2, e12);
+	float d12_1 = w2e12;
+	float d12_2 = -w1e12;
+
+	s2Vec2 e13 = s2Sub(w3, w1);
+	float w1e13 = s2Dot(w1, e13);
+	float w3e13 = s2Dot(w3, e13);
+	float d13_1 = w3e13;
+	float d13_2 = -w1e13;
+
+	s2Vec2 e23 = s2Sub(w3, w2);
+	float w2e23 = s2Dot(w2, e23);
+	float w3e23 = s2Dot(w3, e23);
+	float d23_1 = w3e23;
+	float d23_2 = -w2e23;
+
+	float n123 = s2Cross(e12, e13);
+
+	float d123_1 = n123 * s2Cross(w2, w3);
+	float d123_2 = n123 * s2Cross(w3, w1);
+	float d123_3 = n123 * s2Cross(w1, w2);
+
+	// vertex 1
+	if (d12_2 <= 0.0f && d13_2 <= 0.0f)
+	{
+		s->v[0].a = 1.0f;
+		s->count = 1;
+		return;
+	}
+
+	// edge 12
+	if (d12_1 > 0.0f && d12_2 > 0.0f && d123_3 <= 0.0f)
+	{
+		float inv_d12 = 1.0f / (d12_1 + d12_2);
+		s->v[0].a = d12_1 * inv_d12;
+		s->v[1].a = d12_2 * inv_d12;
+		s->count = 2;
+		return;
+	}
+
+	// edge 13
+	if (d13_1 > 0.0f && d13_2 > 0.0f && d123_2 <= 0.0f)
+	{
+		float inv_d13 = 1.0f / (d13_1 + d13_2);
+		s->v[0].a = d13_1 * inv_d13;
+		s->v[2].a = d13_2 * inv_d13;
+		s->count = 2;
+		s->v[1] = s->v[2];
+		return;
+	}
+
+	// vertex 2
+	if (d12_1 <= 0.0f && d23_2 <= 0.0f)
+	{
+		s->v[1].a = 1.0f;
+		s->count = 1;
+		s->v[0] = s->v[1];
+		return;
+	}
+
+	// vertex 3
+	if (d13_1 <= 0.0f && d23_1 <= 0.0f)
+	{
+		s->v[2].a = 1.0f;
+		s->count = 1;
+		s->v[0] = s->v[2];
+		return;
+	}
+
+	// edge 23
+	if (d23_1 > 0.0f && d23_2 > 0.0f && d123_1 <= 0.0f)
+	{
+		float inv_d23 = 1.0f / (d23_1 + d23_2);
+		s->v[1].a = d23_1 * inv_d23;
+		s->v[2].a = d23_2 * inv_d23;
+		s->count = 2;
+		s->v[0] = s->v[2];
+		return;
+	}
+
+	// interior
+	float inv_d123 = 1.0f / (d123_1 + d123_2 + d123_3);
+	s->v[0].a = d123_1 * inv_d123;
+	s->v[1].a = d123_2 * inv_d123;
+	s->v[2].a = d123_3 * inv_d123;
+	s->count = 3;
+}
+
+// s2ShapeDistance (reference src/distance.c:485-636) over raw vertex arrays. The simplex cache is input/output.
+S2C_FN s2DistanceOutput s2cShapeDistance(s2DistanceCache* cache, const s2Vec2* vertsA, int countA, float radiusA,
+										 s2Transform xfA, const s2Vec2* vertsB, int countB, float radiusB, s2Transform xfB,
+										 bool useRadii)
+{
+	s2DistanceOutput output;
+	output.pointA = s2cVec(0.0f, 0.0f);
+	output.pointB = s2cVec(0.0f, 0.0f);
+	output.distance = 0.0f;
+	output.iterations = 0;
+
+	// simplex from the cache (reference s2MakeSimplexFromCache, distance.c:174-218)
+	s2cSimplex simplex;
+	simplex.count = cache->count;
+	for (int i = 0; i < simplex.count; ++i)
+	{
+		s2cSimplexVertex* v = simplex.v + i;
+		v->indexA = cache->indexA[i];
+		v->indexB = cache->indexB[i];
+		v->wA = s2TransformPoint(xfA, vertsA[v->indexA]);
+		v->wB = s2TransformPoint(xfB, vertsB[v->indexB]);
+		v->w = s2Sub(v->wB, v->wA);
+		v->a = -1.0f;
+	}
+	if (simplex.count == 0)
+	{
+		s2cSimplexVertex* v = simplex.v + 0;
+		v->indexA = 0;
+		v->indexB = 0;
+		v->wA = s2TransformPoint(xfA, vertsA[0]);
+		v->wB = s2TransformPoint(xfB, vertsB[0]);
+		v->w = s2Sub(v->wB, v->wA);
+		v->a = 1.0f;
+		simplex.count = 1;
+	}
+
+	const int maxIters = 20;
+	int saveA[3], saveB[3];
+	int iter = 0;
+	while (iter < maxIters)
+	{
+		int saveCount = simplex.count;
+		for (int i = 0; i < saveCount; ++i)
+		{
+			saveA[i] = simplex.v[i].indexA;
+			saveB[i] = simplex.v[i].indexB;
+		}
+
+		if (simplex.count == 2)
+		{
+			s2cSolveSimplex2(&simplex);
+		}
+		else if (simplex.count == 3)
+		{
+			s2cSolveSimplex3(&simplex);
+		}
+
+		// the origin is inside the triangle: overlap
+		if (simplex.count == 3)
+		{
+			break;
+		}
+
+		// search direction (reference s2ComputeSimplexSearchDirection, distance.c:232-258)
+		s2Vec2 d;
+		if (simplex.count == 1)
+		{
+			d = s2Neg(simplex.v[0].w);
+		}
+		else
+		{
+			s2Vec2 e12 = s2Sub(simplex.v[1].w, simplex.v[0].w);
+			float sgn = s2Cross(e12, s2Neg(simplex.v[0].w));
+			if (sgn > 0.0f)
+			{
+				d = s2CrossSV(1.0f, e12);
+			}
+			else
+			{
+				d = s2CrossVS(e12, 1.0f);
+			}
+		}
+
+		if (s2Dot(d, d) < FLT_EPSILON * FLT_EPSILON)
+		{
+			// the origin is (numerically) on the simplex: overlap, stop here
+			break;
+		}
+
+		s2cSimplexVertex* vertex = simplex.v + simplex.count;
+		vertex->indexA = s2cFindSupport(vertsA, countA, s2InvRotateVector(xfA.q, s2Neg(d)));
+		vertex->wA = s2TransformPoint(xfA, vertsA[vertex->indexA]);
+		vertex->indexB = s2cFindSupport(vertsB, countB, s2InvRotateVector(xfB.q, d));
+		vertex->wB = s2TransformPoint(xfB, vertsB[vertex->indexB]);
+		vertex->w = s2Sub(vertex->wB, vertex->wA);
+
+		++iter;
+
+		// a repeated support point terminates the iteration
+		bool duplicate = false;
+		for (int i = 0; i < saveCount; ++i)
+		{
+			if (vertex->indexA == saveA[i] && vertex->indexB == saveB[i])
+			{
+				duplicate = true;
+				break;
+			}
+		}
+		if (duplicate)
+		{
+			break;
+		}
+
+		++simplex.count;
+	}
+
+	// witness points (reference s2ComputeSimplexWitnessPoints, distance.c:284-316)
+	if (simplex.count == 1)
+	{
+		output.pointA = simplex.v[0].wA;
+		output.pointB = simplex.v[0].wB;
+	}
+	else if (simplex.count == 2)
+	{
+		output.pointA = s2cWeight2(simplex.v[0].a, simplex.v[0].wA, simplex.v[1].a, simplex.v[1].wA);
+		output.pointB = s2cWeight2(simplex.v[0].a, simplex.v[0].wB, simplex.v[1].a, simplex.v[1].wB);
+	}
+	else
+	{
+		output.pointA = s2cWeight3(simplex.v[0].a, simplex.v[0].wA, simplex.v[1].a, simplex.v[1].wA, simplex.v[2].a,
+								   simplex.v[2].wA);
+		output.pointB = output.pointA;
+	}
+	output.distance = s2Distance(output.pointA, output.pointB);
+	output.iterations = iter;
+
+	// cache the simplex (reference s2MakeSimplexCache + s2Simplex_Metric, distance.c:148-172, 220-230)
+	if (simplex.count == 1)
+	{
+		cache->metric = 0.0f;
+	}
+	else if (simplex.count == 2)
+	{
+		cache->metric = s2Distance(simplex.v[0].w, simplex.v[1].w);
+	}
+	else
+	{
+		cache->metric = s2Cross(s2Sub(simplex.v[1].w, simplex.v[0].w), s2Sub(simplex.v[2].w, simplex.v[0].w));
+	}
+	cache->count = (uint16_t)simplex.count;
+	for (int i = 0; i < simplex.count; ++i)
+	{
+		cache->indexA[i] = (uint8_t)simplex.v[i].indexA;
+		cache->indexB[i] = (uint8_t)simplex.v[i].indexB;
+	}
+
+	if (useRadii)
+	{
+		if (output.distance < FLT_EPSILON)
+		{
+			s2Vec2 p = s2cVec(0.5f * (output.pointA.x + output.pointB.x), 0.5f * (output.pointA.y + output.pointB.y));
+			output.pointA = p;
+			output.pointB = p;
+			output.distance = 0.0f;
+		}
+		else
+		{
+			float rA = radiusA;
+			float rB = radiusB;
+			output.distance = S2_MAX(0.0f, output.distance - rA - rB);
+			s2Vec2 normal = s2cNormalize(s2Sub(output.pointB, output.pointA));
+			s2Vec2 offsetA = s2cVec(rA * normal.x, rA * normal.y);
+			s2Vec2 offsetB = s2cVec(rB * normal.x, rB * normal.y);
+			output.pointA = s2Add(output.pointA, offsetA);
+			output.pointB = s2Sub(output.pointB, offsetB);
+		}
+	}
+
+	return output;
+}
+
+// s2SegmentDistance (reference src/distance.c:14-98, Ericson 5.1.9)
+S2C_FN s2SegmentDistanceResult s2cSegmentDistance(s2Vec2 p1, s2Vec2 q1, s2Vec2 p2, s2Vec2 q2)
+{
+	s2SegmentDistanceResult result;
+	result.fraction1 = 0.0f;
+	result.fraction2 = 0.0f;
+
+	s2Vec2 d1 = s2Sub(q1, p1);
+	s2Vec2 d2 = s2Sub(q2, p2);
+	s2Vec2 r = s2Sub(p1, p2);
+	float dd1 = s2Dot(d1, d1);
+	float dd2 = s2Dot(d2, d2);
+	float rd2 = s2Dot(r, d2);
+	float rd1 = s2Dot(r, d1);
+
+	const float epsSqr = FLT_EPSILON * FLT_EPSILON;
+
+	if (dd1 < epsSqr || dd2 < epsSqr)
+	{
+		if (dd1 >= epsSqr)
+		{
+			result.fraction1 = S2_CLAMP(-rd1 / dd1, 0.0f, 1.0f);
+			result.fraction2 = 0.0f;
+		}
+		else if (dd2 >= epsSqr)
+		{
+			result.fraction1 = 0.0f;
+			result.fraction2 = S2_CLAMP(rd2 / dd2, 0.0f, 1.0f);
+		}
+	}
+	else
+	{
+		float d12 = s2Dot(d1, d2);
+		float denom = dd1 * dd2 - d12 * d12;
+		float f1 = 0.0f;
+		if (denom != 0.0f)
+		{
+			f1 = S2_CLAMP((d12 * rd2 - rd1 * dd2) / denom, 0.0f, 1.0f);
+		}
+		float f2 = (d12 * f1 + rd2) / dd2;
+		if (f2 < 0.0f)
+		{
+			f2 = 0.0f;
+			f1 = S2_CLAMP(-rd1 / dd1, 0.0f, 1.0f);
+		}
+		else if (f2 > 1.0f)
+		{
+			f2 = 1.0f;
+			f1 = S2_CLAMP((d12 - rd1) / dd1, 0.0f, 1.0f);
+		}
+		result.fraction1 = f1;
+		result.fraction2 = f2;
+	}
+
+	result.closest1 = s2MulAdd(p1, result.fraction1, d1);
+	result.closest2 = s2MulAdd(p2, result.fraction2, d2);
+	result.distanceSquared = s2DistanceSquared(result.closest1, result.closest2);
+	return result;
+}
+
+// ---- manifolds (reference src/manifold.c) -----------------------------------------------------------------------
+
+// s2CollideCircles (reference src/manifold.c:16-49)
+S2C_FN void s2cCollideCircles(s2Manifold* manifold, s2Vec2 centerA, float radiusA, s2Transform xfA, s2Vec2 centerB,
+							  float radiusB, s2Transform xfB)
+{
+	s2cClearManifold(manifold);
+	s2Transform xf = s2InvMulTransforms(xfA, xfB);
+	s2Vec2 pointA = centerA;
+	s2Vec2 pointB = s2TransformPoint(xf, centerB);
+
+	float distance;
+	s2Vec2 normal = s2cGetLengthAndNormalize(&distance, s2Sub(pointB, pointA));
+
+	float separation = distance - radiusA - radiusB;
+	if (separation > s2_speculativeDistance)
+	{
+		return;
+	}
+
+	s2Vec2 cA = s2MulAdd(pointA, radiusA, normal);
+	s2Vec2 cB = s2MulAdd(pointB, -radiusB, normal);
+	s2Vec2 contactPointA = s2Lerp(cA, cB, 0.5f);
+
+	manifold->normal = s2RotateVector(xfA.q, normal);
+	manifold->points[0].localAnchorA = contactPointA;
+	manifold->points[0].localAnchorB = s2InvTransformPoint(xf, contactPointA);
+	manifold->points[0].separation = separation;
+	manifold->points[0].id = 0;
+	manifold->pointCount = 1;
+}
+
+// s2CollideCapsuleAndCircle (reference src/manifold.c:52-112); a segment is a capsule of radius 0 (:656-660)
+S2C_FN void s2cCollideCapsuleAndCircle(s2Manifold* manifold, s2Vec2 p1, s2Vec2 p2, float radiusA, s2Transform xfA,
+									   s2Vec2 centerB, float radiusB, s2Transform xfB)
+{
+	s2cClearManifold(manifold);
+	s2Transform xf = s2InvMulTransforms(xfA, xfB);
+	s2Vec2 pB = s2TransformPoint(xf, centerB);
+
+	s2Vec2 e = s2Sub(p2, p1);
+	s2Vec2 pA;
+	float s1 = s2Dot(s2Sub(pB, p1), e);
+	float s2 = s2Dot(s2Sub(p2, pB), e);
+	if (s1 < 0.0f)
+	{
+		pA = p1;
+	}
+	else if (s2 < 0.0f)
+	{
+		pA = p2;
+	}
+	else
+	{
+		float s = s1 / s2Dot(e, e);
+		pA = s2MulAdd(p1, s, e);
+	}
+
+	float distance;
+	s2Vec2 normal = s2cGetLengthAndNormalize(&distance, s2Sub(pB, pA));
+
+	float separation = distance - radiusA - radiusB;
+	if (separation > s2_speculativeDistance)
+	{
+		return;
+	}
+
+	s2Vec2 cA = s2MulAdd(pA, radiusA, normal);
+	s2Vec2 cB = s2MulAdd(pB, -radiusB, normal);
+	s2Vec2 contactPointA = s2Lerp(cA, cB, 0.5f);
+
+	manifold->normal = s2RotateVector(xfA.q, normal);
+	manifold->points[0].localAnchorA = contactPointA;
+	manifold->points[0].localAnchorB = s2InvTransformPoint(xf, contactPointA);
+	manifold->points[0].separation = separation;
+	manifold->points[0].id = 0;
+	manifold->pointCount = 1;
+}
+
+// s2CollidePolygonAndCircle (reference src/manifold.c:114-222)
+S2C_FN void s2cCollidePolygonAndCircle(s2Manifold* manifold, const s2Vec2* vertices, const s2Vec2* normals, int vertexCount,
+									   float radiusA, s2Transform xfA, s2Vec2 centerB, float radiusB, s2Transform xfB)
+{
+	s2cClearManifold(manifold);
+	s2Transform xf = s2InvMulTransforms(xfA, xfB);
+	s2Vec2 c = s2TransformPoint(xf, centerB);
+	float radius = radiusA + radiusB;
+
+	int normalIndex = 0;
+	float separation = -FLT_MAX;
+	for (int i = 0; i < vertexCount; ++i)
+	{
+		float s = s2Dot(normals[i], s2Sub(c, vertices[i]));
+		if (s > separation)
+		{
+			separation = s;
+			normalIndex = i;
+		}
+	}
+
+	if (separation > radius + s2_speculativeDistance)
+	{
+		return;
+	}
+
+	int vertIndex1 = normalIndex;
+	int vertIndex2 = vertIndex1 + 1 < vertexCount ? vertIndex1 + 1 : 0;
+	s2Vec2 v1 = vertices[vertIndex1];
+	s2Vec2 v2 = vertices[vertIndex2];
+
+	float u1 = s2Dot(s2Sub(c, v1), s2Sub(v2, v1));
+	float u2 = s2Dot(s2Sub(c, v2), s2Sub(v1, v2));
+
+	if (u1 < 0.0f && separation > FLT_EPSILON)
+	{
+		// closest to v1, outside
+		s2Vec2 normal = s2cNormalize(s2Sub(c, v1));
+		separation = s2Dot(s2Sub(c, v1), normal);
+		if (separation > radius + s2_speculativeDistance)
+		{
+			return;
+		}
+		s2Vec2 cA = s2MulAdd(v1, radiusA, normal);
+		s2Vec2 cB = s2MulSub(c, radiusB, normal);
+		s2Vec2 contactPointA = s2Lerp(cA, cB, 0.5f);
+		manifold->normal = s2RotateVector(xfA.q, normal);
+		manifold->points[0].localAnchorA = contactPointA;
+		manifold->points[0].localAnchorB = s2InvTransformPoint(xf, contactPointA);
+		manifold->points[0].separation = s2Dot(s2Sub(cB, cA), normal);
+		manifold->points[0].id = 0;
+		manifold->pointCount = 1;
+	}
+	else if (u2 < 0.0f && separation > FLT_EPSILON)
+	{
+		// closest to v2, outside
+		s2Vec2 normal = s2cNormalize(s2Sub(c, v2));
+		separation = s2Dot(s2Sub(c, v2), normal);
+		if (separation > radius + s2_speculativeDistance)
+		{
+			return;
+		}
+		s2Vec2 cA = s2MulAdd(v2, radiusA, normal);
+		s2Vec2 cB = s2MulSub(c, radiusB, normal);
+		s2Vec2 contactPointA = s2Lerp(cA, cB, 0.5f);
+		manifold->normal = s2RotateVector(xfA.q, normal);
+		manifold->points[0].localAnchorA = contactPointA;
+		manifold->points[0].localAnchorB = s2InvTransformPoint(xf, contactPointA);
+		manifold->points[0].separation = s2Dot(s2Sub(cB, cA), normal);
+		manifold->points[0].id = 0;
+		manifold->pointCount = 1;
+	}
+	else
+	{
+		// face region (the centre may be inside)
+		s2Vec2 normal = normals[normalIndex];
+		manifold->normal = s2RotateVector(xfA.q, normal);
+		s2Vec2 cA = s2MulAdd(c, radiusA - s2Dot(s2Sub(c, v1), normal), normal);
+		s2Vec2 cB = s2MulSub(c, radiusB, normal);
+		s2Vec2 contactPointA = s2Lerp(cA, cB, 0.5f);
+		manifold->points[0].localAnchorA = contactPointA;
+		manifold->points[0].localAnchorB = s2InvTransformPoint(xf, contactPointA);
+		manifold->points[0].separation = separation - radius;
+		manifold->points[0].id = 0;
+		manifold->pointCount = 1;
+	}
+}
+
+// s2ClipPolygons (reference src/manifold.c:248-399): clip the incident edge against the side planes of the reference
+// edge; two points with feature ids. Everything is in polyA's frame.
+S2C_FN void s2cClipPolygons(s2Manifold* manifold, const s2Polygon* polyA, const s2Polygon* polyB, int edgeA, int edgeB, bool flip)
+{
+	s2cClearManifold(manifold);
+
+	const s2Polygon* poly1;
+	const s2Polygon* poly2;
+	int i11, i12, i21, i22;
+	if (flip)
+	{
+		poly1 = polyB;
+		poly2 = polyA;
+		i11 = edgeB;
+		i12 = edgeB + 1 < polyB->count ? edgeB + 1 : 0;
+		i21 = edgeA;
+		i22 = edgeA + 1 < polyA->count ? edgeA + 1 : 0;
+	}
+	else
+	{
+		poly1 = polyA;
+		poly2 = polyB;
+		i11 = edgeA;
+		i12 = edgeA + 1 < polyA->count ? edgeA + 1 : 0;
+		i21 = edgeB;
+		i22 = edgeB + 1 < polyB->count ? edgeB + 1 : 0;
+	}
+
+	s2Vec2 normal = poly1->normals[i11];
+	s2Vec2 v11 = poly1->vertices[i11];
+	s2Vec2 v12 = poly1->vertices[i12];
+	s2Vec2 v21 = poly2->vertices[i21];
+	s2Vec2 v22 = poly2->vertices[i22];
+
+	s2Vec2 tangent = s2CrossSV(1.0f, normal);
+
+	float lower1 = 0.0f;
+	float upper1 = s2Dot(s2Sub(v12, v11), tangent);
+	float upper2 = s2Dot(s2Sub(v21, v11), tangent);
+	float lower2 = s2Dot(s2Sub(v22, v11), tangent);
+
+	s2Vec2 vLower;
+	if (lower2 < lower1 && upper2 - lower2 > FLT_EPSILON)
+	{
+		vLower = s2Lerp(v22, v21, (lower1 - lower2) / (upper2 - lower2));
+	}
+	else
+	{
+		vLower = v22;
+	}
+
+	s2Vec2 vUpper;
+	if (upper2 > upper1 && upper2 - lower2 > FLT_EPSILON)
+	{
+		vUpper = s2Lerp(v22, v21, (upper1 - lower2) / (upper2 - lower2));
+	}
+	else
+	{
+		vUpper = v21;
+	}
+
+	float separationLower = s2Dot(s2Sub(vLower, v11), normal);
+	float separationUpper = s2Dot(s2Sub(vUpper, v11), normal);
+
+	float r1 = poly1->radius;
+	float r2 = poly2->radius;
+
+	// contact points at the mid surface
+	vLower = s2MulAdd(vLower, 0.5f * (r1 - r2 - separationLower), normal);
+	vUpper = s2MulAdd(vUpper, 0.5f * (r1 - r2 - separationUpper), normal);
+
+	float radius = r1 + r2;
+
+	if (flip == false)
+	{
+		manifold->normal = normal;
+		manifold->points[0].localAnchorA = vLower;
+		manifold->points[0].separation = separationLower - radius;
+		manifold->points[0].id = (uint16_t)S2_MAKE_ID(i11, i22);
+		manifold->points[1].localAnchorA = vUpper;
+		manifold->points[1].separation = separationUpper - radius;
+		manifold->points[1].id = (uint16_t)S2_MAKE_ID(i12, i21);
+		manifold->pointCount = 2;
+	}
+	else
+	{
+		manifold->normal = s2Neg(normal);
+		manifold->points[0].localAnchorA = vUpper;
+		manifold->points[0].separation = separationUpper - radius;
+		manifold->points[0].id = (uint16_t)S2_MAKE_ID(i21, i12);
+		manifold->points[1].localAnchorA = vLower;
+		manifold->points[1].separation = separationLower - radius;
+		manifold->points[1].id = (uint16_t)S2_MAKE_ID(i22, i11);
+		manifold->pointCount = 2;
+	}
+}
+
+// s2FindMaxSeparation (reference src/manifold.c:402-438)
+S2C_FN float s2cFindMaxSeparation(int* edgeIndex, const s2Polygon* poly1, const s2Polygon* poly2)
+{
+	int count1 = poly1->count;
+	int count2 = poly2->count;
+	int bestIndex = 0;
+	float maxSeparation = -FLT_MAX;
+	for (int i = 0; i < count1; ++i)
+	{
+		s2Vec2 n = poly1->normals[i];
+		s2Vec2 v1 = poly1->vertices[i];
+		float si = FLT_MAX;
+		for (int j = 0; j < count2; ++j)
+		{
+			float sij = s2Dot(n, s2Sub(poly2->vertices[j], v1));
+			if (sij < si)
+			{
+				si = sij;
+			}
+		}
+		if (si > maxSeparation)
+		{
+			maxSeparation = si;
+			bestIndex = i;
+		}
+	}
+	*edgeIndex = bestIndex;
+	return maxSeparation;
+}
+
+// s2PolygonSAT (reference src/manifold.c:441-493): overlap assumed
+S2C_FN void s2cPolygonSAT(s2Manifold* manifold, const s2Polygon* polyA, const s2Polygon* polyB)
+{
+	int edgeA = 0;
+	float separationA = s2cFindMaxSeparation(&edgeA, polyA, polyB);
+	int edgeB = 0;
+	float separationB = s2cFindMaxSeparation(&edgeB, polyB, polyA);
+
+	bool flip;
+	if (separationB > separationA)
+	{
+		flip = true;
+		s2Vec2 searchDirection = polyB->normals[edgeB];
+		int count = polyA->count;
+		edgeA = 0;
+		float minDot = FLT_MAX;
+		for (int i = 0; i < count; ++i)
+		{
+			float dot = s2Dot(searchDirection, polyA->normals[i]);
+			if (dot < minDot)
+			{
+				minDot = dot;
+				edgeA = i;
+			}
+		}
+	}
+	else
+	{
+		flip = false;
+		s2Vec2 searchDirection = polyA->normals[edgeA];
+		int count = polyB->count;
+		edgeB = 0;
+		float minDot = FLT_MAX;
+		for (int i = 0; i < count; ++i)
+		{
+			float dot = s2Dot(searchDirection, polyB->normals[i]);
+			if (dot < minDot)
+			{
+				minDot = dot;
+				edgeB = i;
+			}
+		}
+	}
+
+	s2cClipPolygons(manifold, polyA, polyB, edgeA, edgeB, flip);
+}
+
+// s2CollidePolygons (reference src/manifold.c:509-650): GJK closest features, SAT when (nearly) overlapping,
+// vertex-vertex or edge clipping otherwise. Capsules and segments arrive here as 2-gons.
+S2C_FN void s2cCollidePolygons(s2Manifold* manifold, const s2Polygon* polyA, s2Transform xfA, const s2Polygon* polyB,
+							   s2Transform xfB, s2DistanceCache* cache)
+{
+	s2cClearManifold(manifold);
+	float radius = polyA->radius + polyB->radius;
+
+	s2Transform xf = s2InvMulTransforms(xfA, xfB);
+
+	// polyB in polyA's frame
+	s2Polygon localPolyB;
+	localPolyB.count = polyB->count;
+	localPolyB.radius = polyB->radius;
+	for (int i = 0; i < localPolyB.count; ++i)
+	{
+		localPolyB.vertices[i] = s2TransformPoint(xf, polyB->vertices[i]);
+		localPolyB.normals[i] = s2RotateVector(xf.q, polyB->normals[i]);
+	}
+
+	s2Transform identity;
+	identity.p = s2cVec(0.0f, 0.0f);
+	identity.q.s = 0.0f;
+	identity.q.c = 1.0f;
+	int countA = S2_MIN(polyA->count, s2_maxPolygonVertices);
+	int countB = S2_MIN(localPolyB.count, s2_maxPolygonVertices);
+	s2DistanceOutput output =
+		s2cShapeDistance(cache, polyA->vertices, countA, 0.0f, identity, localPolyB.vertices, countB, 0.0f, identity, false);
+
+	if (output.distance > radius + s2_speculativeDistance)
+	{
+		return;
+	}
+
+	if (output.distance < 0.1f * s2_linearSlop)
+	{
+		s2cPolygonSAT(manifold, polyA, &localPolyB);
+		if (manifold->pointCount > 0)
+		{
+			manifold->normal = s2RotateVector(xfA.q, manifold->normal);
+			for (int i = 0; i < manifold->pointCount; ++i)
+			{
+				manifold->points[i].localAnchorB = s2InvTransformPoint(xf, manifold->points[i].localAnchorA);
+			}
+		}
+		return;
+	}
+
+	if (cache->count == 1)
+	{
+		// vertex-vertex
+		s2Vec2 pA = output.pointA;
+		s2Vec2 pB = output.pointB;
+		float distance = output.distance;
+		s2Vec2 normal = s2cNormalize(s2Sub(pB, pA));
+		s2Vec2 contactPointA = s2MulAdd(pB, 0.5f * (polyA->radius - localPolyB.radius - distance), normal);
+
+		manifold->normal = s2RotateVector(xfA.q, normal);
+		manifold->points[0].localAnchorA = contactPointA;
+		manifold->points[0].localAnchorB = s2InvTransformPoint(xf, contactPointA);
+		manifold->points[0].separation = distance - radius;
+		manifold->points[0].id = (uint16_t)S2_MAKE_ID(cache->indexA[0], cache->indexB[0]);
+		manifold->pointCount = 1;
+		return;
+	}
+
+	// vertex-edge: pick reference and incident edges around the closest features
+	bool flip;
+	int edgeA, edgeB;
+	int a1 = cache->indexA[0];
+	int a2 = cache->indexA[1];
+	int b1 = cache->indexB[0];
+	int b2 = cache->indexB[1];
+
+	if (a1 == a2)
+	{
+		// one vertex of A against an edge of B
+		s2Vec2 axis = s2Sub(output.pointA, output.pointB);
+		float dot1 = s2Dot(axis, localPolyB.normals[b1]);
+		float dot2 = s2Dot(axis, localPolyB.normals[b2]);
+		edgeB = dot1 > dot2 ? b1 : b2;
+		flip = true;
+
+		axis = localPolyB.normals[edgeB];
+		int edgeA1 = a1;
+		int edgeA2 = edgeA1 == 0 ? polyA->count - 1 : edgeA1 - 1;
+		dot1 = s2Dot(axis, polyA->normals[edgeA1]);
+		dot2 = s2Dot(axis, polyA->normals[edgeA2]);
+		edgeA = dot1 < dot2 ? edgeA1 : edgeA2;
+	}
+	else
+	{
+		s2Vec2 axis = s2Sub(output.pointB, output.pointA);
+		float dot1 = s2Dot(axis, polyA->normals[a1]);
+		float dot2 = s2Dot(axis, polyA->normals[a2]);
+		edgeA = dot1 > dot2 ? a1 : a2;
+		flip = false;
+
+		axis = polyA->normals[edgeA];
+		int edgeB1 = b1;
+		int edgeB2 = edgeB1 == 0 ? localPolyB.count - 1 : edgeB1 - 1;
+		dot1 = s2Dot(axis, localPolyB.normals[edgeB1]);
+		dot2 = s2Dot(axis, localPolyB.normals[edgeB2]);
+		edgeB = dot1 < dot2 ? edgeB1 : edgeB2;
+	}
+
+	s2cClipPolygons(manifold, polyA, &localPolyB, edgeA, edgeB, flip);
+	if (manifold->pointCount > 0)
+	{
+		manifold->normal = s2RotateVector(xfA.q, manifold->normal);
+		for (int i = 0; i < manifold->pointCount; ++i)
+		{
+			manifold->points[i].localAnchorB = s2InvTransformPoint(xf, manifold->points[i].localAnchorA);
+		}
+	}
+}
