@@ -11,6 +11,7 @@
 // A missing/failed CUDA runtime is fatal (message + abort): there is no CPU fallback.
 #pragma once
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -64,7 +65,7 @@ enum
 typedef struct s2bShapeRow
 {
 	int32_t index; // shape pool slot
-	int32_t flags; // S2B_ROW_VALID | (type << 1) | (moved << 4)
+	int32_t flags; // S2B_ROW_VALID | (type << 1) | S2B_SHAPE_MOVED | S2B_SHAPE_FRESH
 	int32_t body;
 	int32_t proxyKey; // reference broad-phase proxy key (decides which shape of a pair is "A", broad_phase.c:196-205)
 	uint32_t categoryBits, maskBits;
@@ -79,6 +80,8 @@ typedef struct s2bShapeRow
 } s2bShapeRow;
 
 #define S2B_SHAPE_MOVED 0x10
+// set by the host on every (re)created shape: a contact that references such a slot belongs to a destroyed shape
+#define S2B_SHAPE_FRESH 0x20
 
 enum
 {
@@ -195,9 +198,24 @@ S2B_API void s2b_upload_joints(s2bWorld* world, const s2bJointRow* rows, int cou
 // Replace the whole contact table (rows in solve order). Test / checkpoint-restore hook: on the normal path contacts
 // are created and destroyed on the device by s2b_update_pairs.
 S2B_API void s2b_upload_contacts(s2bWorld* world, const s2bContactRow* rows, int count);
-// Sorted (bodyLo << 32 | bodyHi) keys of joints with collideConnected == false; consulted by the pair filter
-// (replaces s2ShouldBodiesCollide, reference src/body.c:386-417).
-S2B_API void s2b_upload_joint_pairs(s2bWorld* world, const uint64_t* sortedKeys, int count);
+// Sorted (bodyLo << 32 | bodyHi) keys of jointed body pairs, consulted by the pair pass:
+//   blockKeys   — every live joint; no NEW contact is created between such bodies (replaces the joint-list walk of
+//                 s2ShouldBodiesCollide, reference src/body.c:386-417, which ignores collideConnected);
+//   destroyKeys — joints created with collideConnected == false; EXISTING contacts between such bodies are removed
+//                 (replaces s2DestroyContactsBetweenBodies, reference src/joint.c:120-152, 214-217).
+S2B_API void s2b_upload_joint_pairs(s2bWorld* world, const uint64_t* blockKeys, int blockCount, const uint64_t* destroyKeys,
+									int destroyCount);
+// Only force / torque of the listed bodies (the per-frame input of s2Body_ApplyForceToCenter).
+typedef struct s2bForceRow
+{
+	int32_t index;
+	float force[2];
+	float torque;
+} s2bForceRow;
+S2B_API void s2b_upload_forces(s2bWorld* world, const s2bForceRow* rows, int count);
+// Page-locked host memory for row staging (uploads from it are asynchronous DMA).
+S2B_API void* s2b_host_alloc(size_t bytes);
+S2B_API void s2b_host_free(void* p);
 // Force a broad-phase pass on the next s2b_update_pairs (creation/destruction of shapes or joints).
 S2B_API void s2b_mark_pairs_dirty(s2bWorld* world);
 // Validation hook: impose the sequential contact order for S2B_SCHEDULE_WAVEFRONT as a list of shape-pair keys
@@ -225,6 +243,10 @@ S2B_API void s2b_sync(s2bWorld* world);
 S2B_API void s2b_download_bodies(s2bWorld* world, s2bBodyRow* rows, int count);
 // every slot 0..capacity-1 in order
 S2B_API void s2b_download_all_bodies(s2bWorld* world, s2bBodyRow* rows, int capacity);
+// The lazy read-back behind s2Body_GetPosition & co: 12 floats per body slot {origin.xy, position.xy, rot.sc, v.xy, w,
+// force.xy, torque} gathered on the device and copied into a pinned buffer owned by the world. The pointer stays valid
+// until the next call. Synchronises.
+S2B_API const float* s2b_sync_body_state(s2bWorld* world, int capacity);
 S2B_API void s2b_download_shape_boxes(s2bWorld* world, float* aabb4, float* fat4, int32_t* flags, int capacity);
 S2B_API void s2b_download_joints(s2bWorld* world, s2bJointRow* rows, int capacity);
 // returns the number of contacts written (<= maxCount), in device order (sorted by shape-pair key)

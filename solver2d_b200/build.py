@@ -85,7 +85,8 @@ def build(verbose: bool = False, force: bool = False) -> str:
     newest = max(os.path.getmtime(o) for o in objs)
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
-                                                     "-Xcompiler", "-fPIC", "-Xlinker", "--no-undefined", "-lm"]
+                                                     "-Xcompiler", "-fPIC", "-Xlinker", "--no-undefined",
+                                                     "-Xlinker", "-Bsymbolic", "-lm"]
         if verbose:
             print(" ".join(cmd), flush=True)
         res = subprocess.run(cmd, capture_output=True, text=True)

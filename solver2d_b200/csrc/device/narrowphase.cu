@@ -1,7 +1,189 @@
-// solver2d-b200 — narrow phase on the device (placeholder until the manifold kernels land).
+// solver2d-b200 — stage 3 of s2World_Step on the device: one thread per contact recomputes the manifold of its shape
+// pair and carries the accumulated impulses over by feature id.
+//
+// Replaces the contact loop of s2World_Step (reference src/world.c:138-168) + s2UpdateContact (reference
+// src/contact.c:296-359) + the manifold functions it dispatches to (src/manifold.c via the table at contact.c:139-154).
+// The geometry itself lives in csrc/shared/s2_collide.h and is shared with the host-callable s2Collide* API.
+//
+// Traffic per polygon-polygon contact: 2 shape headers + 2 x (count x 16 B) geometry + 2 x 32 B body transform read,
+// ~112 B of manifold columns read and written. Arithmetic (GJK + clip) dominates; the kernel is latency/ALU bound,
+// not bandwidth bound.
 #include "s2b_internal.cuh"
+
+#include "shared/s2_collide.h"
+
+__device__ __forceinline__ void s2bLoadPolygon(s2Polygon* poly, const ShapeView& s, int shape, int count, float radius)
+{
+	for (int k = 0; k < count; ++k)
+	{
+		float2 v = s.verts[shape * 8 + k];
+		float2 n = s.normals[shape * 8 + k];
+		poly->vertices[k].x = v.x;
+		poly->vertices[k].y = v.y;
+		poly->normals[k].x = n.x;
+		poly->normals[k].y = n.y;
+	}
+	poly->count = count;
+	poly->radius = radius;
+}
+
+__global__ void __launch_bounds__(128) s2bUpdateContactsKernel(ContactView c, int contactCount, ShapeView s, BodyView b, int sticky)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= contactCount)
+	{
+		return;
+	}
+
+	int2 shapes = c.shapes[i];
+	int4 headA = s.head[shapes.x], headB = s.head[shapes.y];
+	int typeA = (headA.x >> 1) & 0x7, typeB = (headB.x >> 1) & 0x7;
+	int bodyA = headA.y, bodyB = headB.y;
+	float radiusA = s.fr[shapes.x].y, radiusB = s.fr[shapes.y].y;
+
+	float4 orgA = b.org[bodyA], orgB = b.org[bodyB];
+	float4 poseA = b.pose[bodyA], poseB = b.pose[bodyB];
+	s2Transform xfA, xfB;
+	xfA.p.x = orgA.x;
+	xfA.p.y = orgA.y;
+	xfA.q.s = poseA.z;
+	xfA.q.c = poseA.w;
+	xfB.p.x = orgB.x;
+	xfB.p.y = orgB.y;
+	xfB.q.s = poseB.z;
+	xfB.q.c = poseB.w;
+
+	// previous manifold state
+	int4 info = c.info[i];
+	int oldCount = S2B_CI_COUNT(info.x);
+	int oldId[2] = {info.y & 0xFFFF, (info.y >> 16) & 0xFFFF};
+	float4 oldImp[2] = {c.impulse[0][i], c.impulse[1][i]};
+
+	s2DistanceCache cache;
+	cache.metric = __int_as_float(info.w);
+	cache.count = (uint16_t)(info.z & 0x3);
+	for (int k = 0; k < 3; ++k)
+	{
+		cache.indexA[k] = (uint8_t)((info.z >> (2 + 3 * k)) & 0x7);
+		cache.indexB[k] = (uint8_t)((info.z >> (11 + 3 * k)) & 0x7);
+	}
+
+	s2Manifold m;
+	if (typeB == S2B_SHAPE_CIRCLE)
+	{
+		float2 cB = s.verts[shapes.y * 8];
+		s2Vec2 centerB = {cB.x, cB.y};
+		if (typeA == S2B_SHAPE_CIRCLE)
+		{
+			float2 cA = s.verts[shapes.x * 8];
+			s2Vec2 centerA = {cA.x, cA.y};
+			s2cCollideCircles(&m, centerA, radiusA, xfA, centerB, radiusB, xfB);
+		}
+		else if (typeA == S2B_SHAPE_CAPSULE || typeA == S2B_SHAPE_SEGMENT)
+		{
+			float2 a1 = s.verts[shapes.x * 8], a2 = s.verts[shapes.x * 8 + 1];
+			s2Vec2 p1 = {a1.x, a1.y}, p2 = {a2.x, a2.y};
+			s2cCollideCapsuleAndCircle(&m, p1, p2, typeA == S2B_SHAPE_SEGMENT ? 0.0f : radiusA, xfA, centerB, radiusB, xfB);
+		}
+		else
+		{
+			s2Polygon polyA;
+			s2bLoadPolygon(&polyA, s, shapes.x, headA.w, radiusA);
+			s2cCollidePolygonAndCircle(&m, polyA.vertices, polyA.normals, polyA.count, polyA.radius, xfA, centerB, radiusB, xfB);
+		}
+	}
+	else
+	{
+		// polygon / capsule / segment pairs all go through the polygon path (capsules and segments are 2-gons)
+		s2Polygon polyA, polyB;
+		s2bLoadPolygon(&polyA, s, shapes.x, headA.w, typeA == S2B_SHAPE_SEGMENT ? 0.0f : radiusA);
+		s2bLoadPolygon(&polyB, s, shapes.y, headB.w, typeB == S2B_SHAPE_SEGMENT ? 0.0f : radiusB);
+		s2cCollidePolygons(&m, &polyA, xfA, &polyB, xfB, &cache);
+	}
+
+	// s2UpdateContact: match old ids to new ids and carry the impulses (reference src/contact.c:317-358)
+	int pointCount = m.pointCount;
+	bool frictionPersisted = pointCount == oldCount;
+	int flags = pointCount & 0x3;
+	float4 newImp[2];
+	int newId[2] = {0, 0};
+	int matched[2] = {-1, -1};
+	for (int p = 0; p < 2; ++p)
+	{
+		newImp[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		if (p < pointCount)
+		{
+			int id2 = m.points[p].id;
+			newId[p] = id2;
+			newImp[p].x = m.points[p].separation;
+			bool persisted = false;
+			for (int j = 0; j < oldCount; ++j)
+			{
+				if (oldId[j] == id2)
+				{
+					newImp[p].y = oldImp[j].y;
+					newImp[p].z = oldImp[j].z;
+					matched[p] = j;
+					persisted = true;
+					break;
+				}
+			}
+			if (persisted)
+			{
+				flags |= (p == 0 ? S2B_CI_PERSISTED0 : S2B_CI_PERSISTED1);
+			}
+			else
+			{
+				frictionPersisted = false;
+			}
+		}
+	}
+	if (frictionPersisted)
+	{
+		flags |= S2B_CI_FRICTION_PERSISTED;
+	}
+
+	if (sticky)
+	{
+		// friction anchors / normals follow their point (reference src/contact.c:339-342); unmatched points start at 0
+		float4 oldFA[2] = {c.fanchor[0][i], c.fanchor[1][i]};
+		float4 oldFN[2] = {c.fnormal[0][i], c.fnormal[1][i]};
+		for (int p = 0; p < 2; ++p)
+		{
+			float4 fa = make_float4(0.0f, 0.0f, 0.0f, 0.0f), fn = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			if (p < pointCount && matched[p] >= 0)
+			{
+				fa = oldFA[matched[p]];
+				fn = oldFN[matched[p]];
+			}
+			c.fanchor[p][i] = fa;
+			c.fnormal[p][i] = fn;
+		}
+	}
+
+	int cacheBits = cache.count & 0x3;
+	for (int k = 0; k < 3; ++k)
+	{
+		cacheBits |= (cache.indexA[k] & 0x7) << (2 + 3 * k);
+		cacheBits |= (cache.indexB[k] & 0x7) << (11 + 3 * k);
+	}
+	c.info[i] = make_int4(flags, (newId[0] & 0xFFFF) | ((newId[1] & 0xFFFF) << 16), cacheBits, __float_as_int(cache.metric));
+	float4 nf = c.nf[i];
+	c.nf[i] = make_float4(m.normal.x, m.normal.y, nf.z, nf.w);
+	for (int p = 0; p < 2; ++p)
+	{
+		c.anchor[p][i] = make_float4(m.points[p].localAnchorA.x, m.points[p].localAnchorA.y, m.points[p].localAnchorB.x,
+									 m.points[p].localAnchorB.y);
+		c.impulse[p][i] = newImp[p];
+	}
+}
 
 void s2bNarrowphaseUpdate(s2bWorld* w)
 {
-	(void)w;
+	if (w->contactCount <= 0)
+	{
+		return;
+	}
+	S2B_LAUNCH(w, s2bUpdateContactsKernel, gridFor(w->contactCount, 128), 128, 0, makeView(w->contacts[w->cur]), w->contactCount,
+			   shapeView(w), bodyView(w), w->sticky ? 1 : 0);
 }

@@ -278,8 +278,15 @@ struct s2bWorld
 	int jointCap = 0;
 	DevArray<int4> jHead;
 	DevArray<float4> jAnchors, jLim, jMotor, jTarget, jImp, jLimp;
-	DevArray<unsigned long long> jointPairKeys;
+	DevArray<unsigned long long> jointPairKeys; // every jointed body pair: blocks new contacts
 	int jointPairCount = 0;
+	DevArray<unsigned long long> jointDestroyKeys; // pairs whose existing contacts are removed
+	int jointDestroyCount = 0;
+
+	// pinned read-back buffer of s2b_sync_body_state
+	float* hostState = nullptr;
+	size_t hostStateFloats = 0;
+	DevArray<float4> dState;
 
 	// contacts
 	ContactColumns contacts[2];

@@ -357,6 +357,12 @@ extern "C" void s2b_world_destroy(s2bWorld* w)
 	w->jImp.release();
 	w->jLimp.release();
 	w->jointPairKeys.release();
+	w->jointDestroyKeys.release();
+	w->dState.release();
+	if (w->hostState != nullptr)
+	{
+		cudaFreeHost(w->hostState);
+	}
 	w->contacts[0].release();
 	w->contacts[1].release();
 	w->dMovedFlag.release();
@@ -504,18 +510,107 @@ extern "C" void s2b_upload_contacts(s2bWorld* w, const s2bContactRow* rows, int 
 	S2B_CHECK(cudaStreamSynchronize(w->stream));
 }
 
-extern "C" void s2b_upload_joint_pairs(s2bWorld* w, const uint64_t* sortedKeys, int count)
+extern "C" void s2b_upload_joint_pairs(s2bWorld* w, const uint64_t* blockKeys, int blockCount, const uint64_t* destroyKeys,
+									   int destroyCount)
 {
 	S2B_CHECK(cudaSetDevice(w->device));
-	w->jointPairKeys.reserve((size_t)(count > 0 ? count : 1), w->stream, false);
-	w->jointPairCount = count;
-	if (count > 0)
+	w->jointPairKeys.reserve((size_t)(blockCount > 0 ? blockCount : 1), w->stream, false);
+	w->jointDestroyKeys.reserve((size_t)(destroyCount > 0 ? destroyCount : 1), w->stream, false);
+	w->jointPairCount = blockCount;
+	w->jointDestroyCount = destroyCount;
+	if (blockCount > 0)
 	{
-		S2B_CHECK(cudaMemcpyAsync(w->jointPairKeys.p, sortedKeys, sizeof(uint64_t) * (size_t)count, cudaMemcpyHostToDevice,
+		S2B_CHECK(cudaMemcpyAsync(w->jointPairKeys.p, blockKeys, sizeof(uint64_t) * (size_t)blockCount, cudaMemcpyHostToDevice,
 								  w->stream));
-		S2B_CHECK(cudaStreamSynchronize(w->stream));
 	}
+	if (destroyCount > 0)
+	{
+		S2B_CHECK(cudaMemcpyAsync(w->jointDestroyKeys.p, destroyKeys, sizeof(uint64_t) * (size_t)destroyCount,
+								  cudaMemcpyHostToDevice, w->stream));
+	}
+	S2B_CHECK(cudaStreamSynchronize(w->stream));
 	w->pairsDirty = true;
+}
+
+__global__ void s2bScatterForces(const s2bForceRow* __restrict__ rows, int count, BodyView b)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= count)
+	{
+		return;
+	}
+	s2bForceRow r = rows[t];
+	float4 f = b.frc[r.index];
+	b.frc[r.index] = make_float4(r.force[0], r.force[1], r.torque, f.w);
+}
+
+extern "C" void s2b_upload_forces(s2bWorld* w, const s2bForceRow* rows, int count)
+{
+	if (count <= 0)
+	{
+		return;
+	}
+	S2B_CHECK(cudaSetDevice(w->device));
+	s2bForceRow* d = (s2bForceRow*)stageRows(w, rows, sizeof(s2bForceRow) * (size_t)count);
+	S2B_LAUNCH(w, s2bScatterForces, gridFor(count, 128), 128, 0, d, count, bodyView(w));
+	S2B_CHECK(cudaFreeAsync(d, w->stream));
+	S2B_CHECK(cudaStreamSynchronize(w->stream));
+}
+
+extern "C" void* s2b_host_alloc(size_t bytes)
+{
+	void* p = nullptr;
+	S2B_CHECK(cudaMallocHost(&p, bytes));
+	return p;
+}
+
+extern "C" void s2b_host_free(void* p)
+{
+	if (p != nullptr)
+	{
+		cudaFreeHost(p);
+	}
+}
+
+__global__ void s2bGatherBodyState(BodyView b, int count, float4* out)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count)
+	{
+		return;
+	}
+	float4 org = b.org[i], pos = b.pos[i], pose = b.pose[i], vel = b.vel[i], frc = b.frc[i];
+	out[3 * i + 0] = make_float4(org.x, org.y, pos.x, pos.y);
+	out[3 * i + 1] = make_float4(pose.z, pose.w, vel.x, vel.y);
+	out[3 * i + 2] = make_float4(vel.z, frc.x, frc.y, frc.z);
+}
+
+extern "C" const float* s2b_sync_body_state(s2bWorld* w, int capacity)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	if (capacity > w->bodyCap)
+	{
+		capacity = w->bodyCap;
+	}
+	size_t floats = 12 * (size_t)(capacity > 0 ? capacity : 1);
+	if (floats > w->hostStateFloats)
+	{
+		if (w->hostState != nullptr)
+		{
+			cudaFreeHost(w->hostState);
+		}
+		w->hostStateFloats = floats + floats / 2;
+		S2B_CHECK(cudaMallocHost((void**)&w->hostState, sizeof(float) * w->hostStateFloats));
+	}
+	if (capacity > 0)
+	{
+		w->dState.reserve(3 * (size_t)capacity, w->stream, false, false);
+		S2B_LAUNCH(w, s2bGatherBodyState, gridFor(capacity, 256), 256, 0, bodyView(w), capacity, w->dState.p);
+		S2B_CHECK(cudaMemcpyAsync(w->hostState, w->dState.p, sizeof(float) * 12 * (size_t)capacity, cudaMemcpyDeviceToHost,
+								  w->stream));
+	}
+	S2B_CHECK(cudaStreamSynchronize(w->stream));
+	return w->hostState;
 }
 
 extern "C" void s2b_mark_pairs_dirty(s2bWorld* w)
@@ -656,44 +751,42 @@ extern "C" void s2b_flush_l2(s2bWorld* w)
 	S2B_LAUNCH(w, s2bFlushKernel, w->smCount * 8, 256, 0, w->l2Flush.p, bytes, value);
 }
 
+// Each stage stamps its start on the world's stream (ev[0..3]); finalize also stamps the end (ev[4]).
 extern "C" void s2b_update_pairs(s2bWorld* w)
 {
 	S2B_CHECK(cudaSetDevice(w->device));
-	s2bBroadphaseUpdatePairs(w);
+	s2bBroadphaseUpdatePairs(w); // may synchronise on the previous step before it enqueues anything
 }
 
 extern "C" void s2b_update_contacts(s2bWorld* w)
 {
 	S2B_CHECK(cudaSetDevice(w->device));
+	S2B_CHECK(cudaEventRecord(w->timer.ev[1], w->stream));
 	s2bNarrowphaseUpdate(w);
 }
 
 extern "C" void s2b_solve(s2bWorld* w, int solverType, const s2bStepContext* context)
 {
 	S2B_CHECK(cudaSetDevice(w->device));
+	S2B_CHECK(cudaEventRecord(w->timer.ev[2], w->stream));
 	s2bSolve(w, solverType, context);
 }
 
 extern "C" void s2b_finalize(s2bWorld* w)
 {
 	S2B_CHECK(cudaSetDevice(w->device));
+	S2B_CHECK(cudaEventRecord(w->timer.ev[3], w->stream));
 	s2bFinalize(w);
+	S2B_CHECK(cudaEventRecord(w->timer.ev[4], w->stream));
+	w->timer.recorded = true;
 }
 
 extern "C" void s2b_step(s2bWorld* w, int solverType, const s2bStepContext* context)
 {
-	S2B_CHECK(cudaSetDevice(w->device));
-	cudaStream_t s = w->stream;
-	S2B_CHECK(cudaEventRecord(w->timer.ev[0], s));
-	s2bBroadphaseUpdatePairs(w);
-	S2B_CHECK(cudaEventRecord(w->timer.ev[1], s));
-	s2bNarrowphaseUpdate(w);
-	S2B_CHECK(cudaEventRecord(w->timer.ev[2], s));
-	s2bSolve(w, solverType, context);
-	S2B_CHECK(cudaEventRecord(w->timer.ev[3], s));
-	s2bFinalize(w);
-	S2B_CHECK(cudaEventRecord(w->timer.ev[4], s));
-	w->timer.recorded = true;
+	s2b_update_pairs(w);
+	s2b_update_contacts(w);
+	s2b_solve(w, solverType, context);
+	s2b_finalize(w);
 }
 
 extern "C" void s2b_last_stage_ms(s2bWorld* w, float out[4])

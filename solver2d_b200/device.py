@@ -73,7 +73,8 @@ ABI_SYMBOLS = [
     "s2b_update_contacts", "s2b_solve", "s2b_finalize", "s2b_step", "s2b_sync", "s2b_download_bodies",
     "s2b_download_all_bodies", "s2b_download_shape_boxes", "s2b_download_joints", "s2b_download_contacts",
     "s2b_download_solve_order", "s2b_get_counters", "s2b_pack_body_state", "s2b_timed_steps", "s2b_last_stage_ms",
-    "s2b_flush_l2", "s2b_time_color_kernel", "s2b_version",
+    "s2b_flush_l2", "s2b_time_color_kernel", "s2b_version", "s2b_abi_sizes", "s2b_upload_forces", "s2b_host_alloc",
+    "s2b_host_free", "s2b_sync_body_state",
 ]
 
 
@@ -116,7 +117,7 @@ class Device:
         for name in ("s2b_upload_bodies", "s2b_upload_shapes", "s2b_upload_joints"):
             getattr(L, name).argtypes = [vp, vp, C.c_int, C.c_int]
         L.s2b_upload_contacts.argtypes = [vp, vp, C.c_int]
-        L.s2b_upload_joint_pairs.argtypes = [vp, vp, C.c_int]
+        L.s2b_upload_joint_pairs.argtypes = [vp, vp, C.c_int, vp, C.c_int]
         L.s2b_set_contact_order.argtypes = [vp, vp, C.c_int]
         for name in ("s2b_mark_pairs_dirty", "s2b_update_pairs", "s2b_update_contacts", "s2b_finalize", "s2b_sync",
                      "s2b_flush_l2"):
@@ -152,10 +153,28 @@ class DeviceWorld:
         self.h = self.L.s2b_world_create(device, solver_type)
         self.body_cap = self.shape_cap = self.joint_cap = 0
 
+    @classmethod
+    def attach(cls, dev: Device, world_id) -> "DeviceWorld":
+        """Device view of a world created through the public API (s2World_GetDevice, include/solver2d_b200.h)."""
+        fn = dev.lib.s2World_GetDevice
+        fn.restype = C.c_void_p
+        from .capi import WorldId
+        fn.argtypes = [WorldId]
+        self = cls.__new__(cls)
+        self.dev = dev
+        self.L = dev.lib
+        self.solver_type = -1
+        self.h = fn(world_id)
+        self.owned = False
+        c = Counters()
+        self.L.s2b_get_counters(self.h, C.byref(c))
+        self.body_cap, self.shape_cap, self.joint_cap = c.bodyCapacity, c.shapeCapacity, c.jointCapacity
+        return self
+
     def destroy(self):
-        if self.h:
+        if self.h and getattr(self, "owned", True):
             self.L.s2b_world_destroy(self.h)
-            self.h = None
+        self.h = None
 
     # -- uploads ------------------------------------------------------------------------------------------------
     def upload_bodies(self, rows: np.ndarray, capacity: int):
@@ -177,9 +196,10 @@ class DeviceWorld:
         rows = np.ascontiguousarray(rows, dtype=CONTACT_ROW)
         self.L.s2b_upload_contacts(self.h, rows.ctypes.data, len(rows))
 
-    def upload_joint_pairs(self, keys: np.ndarray):
-        keys = np.ascontiguousarray(np.sort(keys.astype(np.uint64)))
-        self.L.s2b_upload_joint_pairs(self.h, keys.ctypes.data, len(keys))
+    def upload_joint_pairs(self, block_keys: np.ndarray, destroy_keys: np.ndarray | None = None):
+        block = np.ascontiguousarray(np.sort(block_keys.astype(np.uint64)))
+        destroy = block if destroy_keys is None else np.ascontiguousarray(np.sort(destroy_keys.astype(np.uint64)))
+        self.L.s2b_upload_joint_pairs(self.h, block.ctypes.data, len(block), destroy.ctypes.data, len(destroy))
 
     def set_contact_order(self, keys: np.ndarray):
         keys = np.ascontiguousarray(keys.astype(np.uint64))

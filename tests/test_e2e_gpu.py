@@ -1,0 +1,160 @@
+"""GPU end-to-end parity through the public C API: the SAME scene script drives the reference library and the product
+library (solver2d_b200/capi.py binds both).
+
+What is compared, stage by stage:
+* broad phase : the contact (shape-pair) set and the (A, B) order of every pair            -> must be identical
+* narrow phase: every manifold after the first step (ids, anchors, separations, normal)   -> bit-exact
+* full step, reference Gauss-Seidel order imposed (wavefront schedule + per-step order)   -> |dpos| <= 1e-4 m after
+  600 steps on config 1 (north_star), in practice bit-exact
+* full step, production colour schedule, free running                                       -> deviation is the order
+  sensitivity of Gauss-Seidel itself (2.5e-3 m after 600 steps when the *reference* is re-ordered);
+  bounded loosely here and reported.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import ref as refmod
+from solver2d_b200 import capi, device, scenes
+
+pytestmark = pytest.mark.gpu
+
+DT = 1.0 / 60.0
+
+
+@pytest.fixture(scope="module")
+def product():
+    return capi.Solver2D(device.LIB_PATH)
+
+
+def _ref_pair_table(R, wid):
+    cf, ci = R.contacts(wid)
+    I = refmod.CONTACT_I
+    slots = np.nonzero(ci[:, I["valid"]] == 1)[0]
+    a, b = ci[slots, I["shapeA"]], ci[slots, I["shapeB"]]
+    keys = (np.minimum(a, b).astype(np.uint64) << np.uint64(32)) | np.maximum(a, b).astype(np.uint64)
+    return keys, a, b, slots, cf, ci
+
+
+def _positions(lib, sc):
+    return np.array([tuple(lib.s2Body_GetPosition(b)) for b in sc.bodies], dtype=np.float64)
+
+
+def _angles(lib, sc):
+    return np.array([lib.s2Body_GetAngle(b) for b in sc.bodies], dtype=np.float64)
+
+
+@pytest.mark.parametrize("recipe,kw", [(scenes.pyramid, dict(base_count=10)), (scenes.pyramid, dict(base_count=30)),
+                                        (scenes.vertical_stack, dict(count=6, columns=3))])
+def test_pairs_and_manifolds_first_step(reference, product, dev, recipe, kw):
+    R, P = reference, product
+    sr = recipe(R, "TGS_Soft", **kw)
+    sp = recipe(P, "TGS_Soft", **kw)
+    sr.step(DT, 4, 2, True)
+    sp.step(DT, 4, 2, True)
+    keys, a, b, slots, cf, ci = _ref_pair_table(R, sr.world)
+    dw = device.DeviceWorld.attach(dev, sp.world)
+    rows = dw.download_contacts(len(keys) + 16)
+    assert len(rows) == len(keys), "contact count differs"
+    order = np.argsort(keys)
+    dev_keys = (np.minimum(rows["shapeA"], rows["shapeB"]).astype(np.uint64) << np.uint64(32)) | \
+        np.maximum(rows["shapeA"], rows["shapeB"]).astype(np.uint64)
+    assert np.array_equal(dev_keys, keys[order]), "pair sets differ"
+    assert np.array_equal(rows["shapeA"], a[order]) and np.array_equal(rows["shapeB"], b[order]), "(A,B) order differs"
+    # manifolds (geometry is computed before the solver runs, so it is comparable after the full step)
+    I = refmod.CONTACT_I
+    assert np.array_equal(rows["pointCount"], ci[slots[order], I["pointCount"]])
+    two = rows["pointCount"] == 2
+    assert np.array_equal(rows["points"]["id"][:, 0], ci[slots[order], I["id0"]])
+    assert np.array_equal(rows["points"]["id"][two, 1], ci[slots[order], I["id1"]][two])
+    ref_normal = cf[slots[order], 1:3]
+    assert np.array_equal(rows["normal"].view(np.uint32), ref_normal.view(np.uint32)), "normals not bit-exact"
+    for j in range(2):
+        base = refmod.CONTACT_F["points"] + refmod.POINT_STRIDE * j
+        live = rows["pointCount"] > j
+        for name, off, width in (("localAnchorA", 0, 2), ("localAnchorB", 2, 2), ("separation", 4, 1)):
+            ref_v = cf[slots[order], base + off:base + off + width][live]
+            dev_v = rows["points"][name][:, j][live].reshape(ref_v.shape)
+            assert np.array_equal(np.ascontiguousarray(dev_v).view(np.uint32), np.ascontiguousarray(ref_v).view(np.uint32)), \
+                f"{name}[{j}] not bit-exact"
+    sr.destroy()
+    sp.destroy()
+
+
+def test_config1_600_steps_reference_order(reference, product, dev):
+    """north_star criterion: per-body |dpos| <= 1e-4 m vs the reference after 600 steps on config 1 (Pyramid, 55 boxes,
+    TGS_Soft, 4 sub-steps), with the reference's Gauss-Seidel order imposed through the validation schedule."""
+    R, P = reference, product
+    sr = scenes.pyramid(R, "TGS_Soft", base_count=10)
+    sp = scenes.pyramid(P, "TGS_Soft", base_count=10)
+    dw = device.DeviceWorld.attach(dev, sp.world)
+    dw.set_schedule(device.SCHEDULE_WAVEFRONT)
+    worst = 0.0
+    for step in range(600):
+        R.step_collide(sr.world)
+        keys, *_ = _ref_pair_table(R, sr.world)
+        dw.set_contact_order(keys)  # pool order of the reference = its sequential solve order
+        R.step_solve(sr.world, DT, 4, 2, True)
+        R.step_finalize(sr.world)
+        sp.step(DT, 4, 2, True)
+        if step in (0, 9, 59, 599):
+            d = np.abs(_positions(R, sr) - _positions(P, sp)).max()
+            worst = max(worst, d)
+    dpos = np.abs(_positions(R, sr) - _positions(P, sp)).max()
+    dang = np.abs(_angles(R, sr) - _angles(P, sp)).max()
+    print(f"config1 reference-order: max|dpos| = {dpos:.3e} m, max|dangle| = {dang:.3e} rad, worst sampled {worst:.3e}")
+    assert dpos <= 1e-4 and dang <= 1e-4
+    sr.destroy()
+    sp.destroy()
+
+
+def test_config1_600_steps_color_schedule(reference, product):
+    R, P = reference, product
+    sr = scenes.pyramid(R, "TGS_Soft", base_count=10)
+    sp = scenes.pyramid(P, "TGS_Soft", base_count=10)
+    for _ in range(600):
+        sr.step(DT, 4, 2, True)
+        sp.step(DT, 4, 2, True)
+    dpos = np.abs(_positions(R, sr) - _positions(P, sp)).max()
+    print(f"config1 colour schedule, free running: max|dpos| = {dpos:.3e} m")
+    # order sensitivity of Gauss-Seidel (the reference re-ordered against itself: 2.5e-3 m)
+    assert dpos < 2e-2
+    assert R.s2World_GetStatistics(sr.world).contactCount == P.s2World_GetStatistics(sp.world).contactCount
+    sr.destroy()
+    sp.destroy()
+
+
+def test_falling_boxes_pair_set_tracks_reference(reference, product, dev):
+    """Proxies leave their fat AABBs while falling: the device pair pass must create / destroy the same contacts."""
+    R, P = reference, product
+
+    def build(lib):
+        sc = scenes.vertical_stack(lib, "TGS_Soft", count=5, columns=4)
+        # throw the top boxes sideways so pairs are created and destroyed
+        for k, bid in enumerate(sc.bodies[1:]):
+            if k % 5 >= 3:
+                lib.s2Body_SetLinearVelocity(bid, capi.Vec2(3.0 if k % 2 else -3.0, 1.0))
+        return sc
+
+    sr, sp = build(R), build(P)
+    dw = device.DeviceWorld.attach(dev, sp.world)
+    dw.set_schedule(device.SCHEDULE_WAVEFRONT)
+    passes = 0
+    for step in range(120):
+        R.step_collide(sr.world)
+        keys, *_ = _ref_pair_table(R, sr.world)
+        dw.set_contact_order(keys)
+        R.step_solve(sr.world, DT, 4, 2, True)
+        R.step_finalize(sr.world)
+        sp.step(DT, 4, 2, True)
+        rows = dw.download_contacts(len(keys) + 64)
+        dev_keys = (np.minimum(rows["shapeA"], rows["shapeB"]).astype(np.uint64) << np.uint64(32)) | \
+            np.maximum(rows["shapeA"], rows["shapeB"]).astype(np.uint64)
+        assert np.array_equal(np.sort(keys), dev_keys), f"pair set differs at step {step}"
+    passes = dw.counters().pairPassCount
+    assert passes > 3
+    dpos = np.abs(_positions(R, sr) - _positions(P, sp)).max()
+    assert dpos <= 1e-4, dpos
+    sr.destroy()
+    sp.destroy()
