@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py — the headline benchmark of solver2d-b200 (contract: see the task statement and DESIGN.md §measurement).
+
+Metric (BASELINE.json): constraint-iterations / second on the 100k-box TGS_Soft pyramid.
+  * workload  : Pyramid recipe (reference samples/collection/sample_contact.cpp:499-561), baseCount = 447
+                -> 100 128 boxes, ~299 490 contact constraints; s2_solverTGS_Soft, dt = 1/60, 4 sub-steps, 2 relax
+                iterations, warm starting on. Deterministic lattice ("data": "synthetic").
+  * a "step"  : one s2World_Step (pair update, narrow phase, solver, finalize), all of it inside the timed region.
+  * unit of work: constraint-iteration = one execution of the per-constraint solve body on one manifold or joint
+                (SURVEY.md §8d): per step (manifolds with >= 1 point + joints) x sub-steps x (1 + [relax > 0]); counted
+                by a device-side meter inside the solver stage.
+  * value     : constraint-iterations / device time, state resident in HBM, whole step timed with CUDA events on the
+                world's stream, L2 evicted between timed steps.
+  * e2e       : same metric through the public C API with host buffers: every step applies a force to every box
+                (host -> device), steps, and reads every body transform back (device -> host), wall clock.
+  * roofline  : persistent solver kernel (the dominant kernel): algorithmic bytes of SURVEY.md §8d / its device time,
+                against the measured HBM copy bandwidth of MEASURED_PEAKS.json.
+  * cpu_baseline: the unmodified reference (oracle/_ref, compiled from /root/reference) on one host core, bounded sample.
+
+`--impl reference` times the reference's own CPU implementation on the same workload (bounded sample per step).
+N > 1 (`torchrun`): the 100k-box pyramid is ONE island and does not shard -> one replica per GPU
+("replicas only", weak scaling) with the per-step NCCL all-gather of packed body state north_star asks for.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DT = 1.0 / 60.0
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi SM clock / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu_index), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes_per_step(constraints: int, bodies: int, substeps: int, relax: bool) -> float:
+    """S*[C*(152 + 208*(1+[E>0])) + Nb*100] + C*(250 + 16) + Nb*32 for one TGS_Soft solver stage."""
+    passes = 1 + (1 if relax else 0)
+    return substeps * (constraints * (152.0 + 208.0 * passes) + bodies * 100.0) + constraints * (250.0 + 16.0) + bodies * 32.0
+
+
+def build_scene(lib, base_count: int):
+    from solver2d_b200 import scenes
+    return scenes.pyramid(lib, "TGS_Soft", base_count=base_count)
+
+
+def run_reference(args, rank: int, world_size: int):
+    """The reference's own CPU implementation of the path (oracle/_ref), one host thread (it is single-threaded)."""
+    if rank != 0:
+        return
+    from oracle import ref
+    if not ref.available():
+        ref.build_ref()
+    R = ref.load()
+    sc = build_scene(R, args.base)
+    nb = len(sc.bodies)
+    idx = np.array([b.index for b in sc.bodies[1:]], dtype=np.int32)
+    forces = np.zeros((len(idx), 2), dtype=np.float32)
+    forces[:, 0] = 0.01
+    caps = R.capacities(sc.world)
+    transforms = np.zeros((caps["bodyCap"], 4), dtype=np.float32)
+    t0 = time.perf_counter()
+    sc.step(DT, args.substeps, args.relax, True)  # first step: all-pairs broad phase, reported apart
+    first = time.perf_counter() - t0
+    for _ in range(max(args.warmup - 1, 0)):
+        sc.step(DT, args.substeps, args.relax, True)
+    work = 0
+    total = 0.0
+    for _ in range(args.steps):
+        # constraints of this step are those of the manifolds as they stand after the step's own narrow phase; the
+        # count after the step is the same set (manifold geometry is fixed before the solver runs)
+        total += R.timed_e2e_steps(sc.world, 1, DT, args.substeps, args.relax, True, idx, forces, transforms)
+        c, j = R.constraint_counts(sc.world)
+        work += (c + j) * args.substeps * (1 + (1 if args.relax > 0 else 0))
+    value = work / total
+    line = {
+        "impl": "reference", "metric": "constraint_iters_per_sec", "value": value, "unit": "constraint-iters/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"pyramid{args.base}_tgs_soft_s{args.substeps}_e{args.relax}", "boxes": nb - 1,
+                   "dt": DT, "note": "reference CPU path, 1 thread (the reference is single-threaded)"},
+        "cpu_baseline": {"value": value, "unit": "constraint-iters/s", "cores": 1, "kind": "reference",
+                         "sample": f"{args.steps} steps after {args.warmup} warm-up; first step {first:.3f} s"},
+        "e2e": {"value": value, "unit": "constraint-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank: int, world_size: int, local_rank: int):
+    os.environ["S2B_DEVICE"] = str(local_rank)  # worlds of this process live on its own GPU
+    import torch
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(local_rank)
+
+    from solver2d_b200 import capi, device
+    P = capi.Solver2D(device.LIB_PATH)
+    dev = device.Device()
+    L = P.lib
+    L.s2World_TimedSteps.restype = C.c_float
+    L.s2World_TimedSteps.argtypes = [capi.WorldId, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_bool, C.c_int32]
+    L.s2World_ApplyForcesToCenters.argtypes = [capi.WorldId, C.c_void_p, C.c_void_p, C.c_int32]
+    L.s2World_GetBodyTransforms.restype = C.c_int32
+    L.s2World_GetBodyTransforms.argtypes = [capi.WorldId, C.c_void_p, C.c_int32]
+    L.s2b_get_work.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.s2b_last_solve_kernel_ms.restype = C.c_float
+    L.s2b_last_solve_kernel_ms.argtypes = [C.c_void_p]
+
+    sc = build_scene(P, args.base)
+    dw = device.DeviceWorld.attach(dev, sc.world)
+    nb = len(sc.bodies)
+
+    def get_work(reset=False):
+        out = (C.c_uint64 * 2)()
+        L.s2b_get_work(dw.h, out, 1 if reset else 0)
+        return int(out[0]), int(out[1])
+
+    # per-step NCCL all-gather of packed body state (north_star) when several GPUs run replicas
+    gather_in = gather_out = None
+    if dist is not None:
+        gather_in = torch.empty((nb + 8) * 8, dtype=torch.float32, device="cuda")
+        gather_out = torch.empty(world_size * (nb + 8) * 8, dtype=torch.float32, device="cuda")
+
+    def exchange():
+        if dist is None:
+            return
+        L.s2b_pack_body_state(dw.h, 0, nb, C.c_void_p(gather_in.data_ptr()))
+        dw.sync()
+        dist.all_gather_into_tensor(gather_out, gather_in)
+
+    # ---- warm-up (includes the first-step all-pairs broad phase) ----
+    for _ in range(args.warmup):
+        sc.step(DT, args.substeps, args.relax, True)
+        exchange()
+    dw.sync()
+    get_work(reset=True)
+    launches0 = dw.counters().kernelLaunches
+
+    # ---- value: device-resident, CUDA events per step, L2 flushed between steps ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    solve_kernel_ms = []
+    total_ms = 0.0
+    if dist is None:
+        for _ in range(args.steps):
+            total_ms += float(L.s2World_TimedSteps(sc.world, 1, DT, args.substeps, args.relax, True, 1 if args.flush_l2 else 0))
+            solve_kernel_ms.append(float(L.s2b_last_solve_kernel_ms(dw.h)))
+    else:
+        for _ in range(args.steps):
+            total_ms += float(L.s2World_TimedSteps(sc.world, 1, DT, args.substeps, args.relax, True, 1 if args.flush_l2 else 0))
+            solve_kernel_ms.append(float(L.s2b_last_solve_kernel_ms(dw.h)))
+            t0 = torch.cuda.Event(enable_timing=True)
+            t1 = torch.cuda.Event(enable_timing=True)
+            t0.record()
+            exchange()
+            t1.record()
+            t1.synchronize()
+            total_ms += t0.elapsed_time(t1)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    work, solves = get_work(reset=True)
+    launches = dw.counters().kernelLaunches - launches0
+    counters = dw.counters()
+    stage_ms = dw.stage_ms()
+
+    # ---- e2e: public API with host buffers, H2D + D2H inside the timed region ----
+    idx = np.array([b.index for b in sc.bodies[1:]], dtype=np.int32)
+    forces = np.zeros((len(idx), 2), dtype=np.float32)
+    forces[:, 0] = 0.01
+    transforms = np.zeros((counters.bodyCapacity, 4), dtype=np.float32)
+    e2e_steps = max(args.steps // 2, 3)
+    for _ in range(2):
+        L.s2World_ApplyForcesToCenters(sc.world, idx.ctypes.data, forces.ctypes.data, len(idx))
+        sc.step(DT, args.substeps, args.relax, True)
+        L.s2World_GetBodyTransforms(sc.world, transforms.ctypes.data, counters.bodyCapacity)
+    get_work(reset=True)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        f = forces if (s & 1) == 0 else -forces
+        L.s2World_ApplyForcesToCenters(sc.world, idx.ctypes.data, f.ctypes.data, len(idx))
+        sc.step(DT, args.substeps, args.relax, True)
+        L.s2World_GetBodyTransforms(sc.world, transforms.ctypes.data, counters.bodyCapacity)
+        exchange()
+    torch.cuda.synchronize()
+    e2e_time = time.perf_counter() - t0
+    e2e_work, _ = get_work(reset=True)
+
+    # ---- aggregate over ranks: whole-job work / max time ----
+    t_vals = torch.tensor([total_ms, e2e_time], dtype=torch.float64, device="cuda")
+    w_vals = torch.tensor([float(work), float(e2e_work)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w_vals, op=dist.ReduceOp.SUM)
+    total_ms_max, e2e_time_max = t_vals.tolist()
+    work_all, e2e_work_all = w_vals.tolist()
+
+    if rank == 0:
+        value = work_all / (total_ms_max * 1e-3)
+        e2e_value = e2e_work_all / e2e_time_max
+        peak, peak_src = _peaks()
+        constraints = counters.constraintCount
+        alg = algorithmic_bytes_per_step(constraints, nb, args.substeps, args.relax > 0)
+        k_ms = float(np.mean(solve_kernel_ms)) if solve_kernel_ms else 0.0
+        achieved = (alg / (k_ms * 1e-3)) / 1e9 if k_ms > 0 else 0.0
+        line = {
+            "metric": "constraint_iters_per_sec", "value": value, "unit": "constraint-iters/s", "n_gpus": world_size,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"pyramid{args.base}_tgs_soft_s{args.substeps}_e{args.relax}", "boxes": nb - 1,
+                       "contact_constraints": constraints, "colours": counters.groupCount, "dt": DT,
+                       "l2": "flushed between timed steps" if args.flush_l2 else "not flushed (working set < L2)",
+                       "parallelism": "single island: replicas only" + ("" if world_size == 1 else
+                                                                        f", x{world_size} + NCCL all-gather of body state"),
+                       "schedule": "graph colouring, persistent cooperative solver kernel"},
+            "stage_ms_last_step": {"pairs": stage_ms[0], "contacts": stage_ms[1], "solve": stage_ms[2], "finalize": stage_ms[3]},
+            "e2e": {"value": e2e_value, "unit": "constraint-iters/s", "ms_per_step": 1e3 * e2e_time_max / e2e_steps,
+                    "h2d_bytes_per_step": int(len(idx) * 16), "d2h_bytes_per_step": int(counters.bodyCapacity * 48),
+                    "steps": e2e_steps, "clock": "host wall clock, synchronised on both sides"},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "s2bPersistentTgsSoft (whole solver stage of one step)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                         "traffic": None, "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms, "peak_source": peak_src},
+            "clocks": clocks,
+            "wall_s_timed_region": wall,
+        }
+        if not args.no_cpu_baseline and world_size == 1:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    sc.destroy()
+
+
+def cpu_baseline(args) -> dict:
+    """Bounded sample of the same workload on the unmodified reference, one host core."""
+    from oracle import ref
+    if not ref.available() and not ref.build_ref():
+        return {"value": None, "unit": "constraint-iters/s", "cores": 1, "kind": "reference", "sample": "oracle/_ref missing"}
+    R = ref.load()
+    sc = build_scene(R, args.base)
+    t0 = time.perf_counter()
+    sc.step(DT, args.substeps, args.relax, True)
+    first = time.perf_counter() - t0
+    for _ in range(2):
+        sc.step(DT, args.substeps, args.relax, True)
+    steps = args.cpu_steps
+    total = R.timed_steps(sc.world, steps, DT, args.substeps, args.relax, True)
+    c, j = R.constraint_counts(sc.world)
+    work = (c + j) * args.substeps * (1 + (1 if args.relax > 0 else 0)) * steps
+    sc.destroy()
+    return {"value": work / total, "unit": "constraint-iters/s", "cores": 1, "kind": "reference",
+            "ms_per_step": 1e3 * total / steps,
+            "sample": f"{steps} steady steps of the same workload after 3 warm-up steps (first step {first:.2f} s); host has "
+                      f"{os.cpu_count()} cores, the reference uses 1"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--base", type=int, default=447, help="pyramid base count (447 -> 100 128 boxes)")
+    ap.add_argument("--substeps", type=int, default=4)
+    ap.add_argument("--relax", type=int, default=2)
+    ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=20)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world_size)
+    else:
+        run_ours(args, rank, world_size, local_rank)
+
+
+if __name__ == "__main__":
+    main()

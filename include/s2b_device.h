@@ -251,9 +251,10 @@ S2B_API void s2b_download_shape_boxes(s2bWorld* world, float* aabb4, float* fat4
 S2B_API void s2b_download_joints(s2bWorld* world, s2bJointRow* rows, int capacity);
 // returns the number of contacts written (<= maxCount), in device order (sorted by shape-pair key)
 S2B_API int s2b_download_contacts(s2bWorld* world, s2bContactRow* rows, int maxCount);
-// The solve order of the last s2b_solve: for each constraint, in Gauss-Seidel order, its contact slot; and the
-// group boundaries. Returns the constraint count. (Feeds the permuted oracle in the parity tests.)
-S2B_API int s2b_download_solve_order(s2bWorld* world, int32_t* contactSlots, int maxCount, int32_t* groupOffsets, int maxGroups,
+// The Gauss-Seidel visiting order of the last s2b_solve, group by group: items[k] >= 0 is a contact slot, items[k] < 0
+// is joint slot (-1 - items[k]); groupSizes[g] items belong to group g (the serial overflow group, if any, is last).
+// Returns the item count. (Feeds the order-permuted oracle in the parity tests.)
+S2B_API int s2b_download_solve_order(s2bWorld* world, int32_t* items, int maxItems, int32_t* groupSizes, int maxGroups,
 							 int32_t* groupCount);
 S2B_API void s2b_get_counters(s2bWorld* world, s2bCounters* out);
 
@@ -270,6 +271,15 @@ S2B_API float s2b_timed_steps(s2bWorld* world, int solverType, const s2bStepCont
 S2B_API void s2b_last_stage_ms(s2bWorld* world, float out[4]);
 // Evict L2: overwrite a scratch buffer larger than the 126 MB L2 (bench hygiene between timed iterations).
 S2B_API void s2b_flush_l2(s2bWorld* world);
+// Device-side work meter, accumulated by every s2b_solve: out[0] = constraint-iterations ((contact
+// constraints + joints) x solve passes of the variant), out[1] = solver stages run. Synchronises.
+S2B_API void s2b_get_work(s2bWorld* world, uint64_t out[2], int reset);
+// Device time of the last persistent solver kernel in milliseconds (CUDA events on the world's stream); 0 if the last
+// solve used the multi-launch path.
+S2B_API float s2b_last_solve_kernel_ms(s2bWorld* world);
+// Stop-watch on the world's stream: s2b_mark_time(w, 0) ... s2b_mark_time(w, 1); s2b_elapsed_ms waits for mark 1.
+S2B_API void s2b_mark_time(s2bWorld* world, int slot);
+S2B_API float s2b_elapsed_ms(s2bWorld* world);
 // Standalone timing of the per-colour contact impulse kernel on the current constraint set (roofline probe):
 // launches the largest colour's solve kernel `reps` times, returns mean ms; *constraints receives its size.
 S2B_API float s2b_time_color_kernel(s2bWorld* world, const s2bStepContext* context, int reps, int* constraints);

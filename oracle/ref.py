@@ -81,6 +81,11 @@ class Reference(capi.Solver2D):
         L.s2ref_set_contact_impulses.argtypes = [C.c_int, C.c_int] + [C.c_float] * 4
         L.s2ref_timed_steps.restype = C.c_double
         L.s2ref_timed_steps.argtypes = [capi.WorldId, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.s2ref_timed_e2e_steps.restype = C.c_double
+        L.s2ref_timed_e2e_steps.argtypes = [capi.WorldId, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                            C.c_void_p, C.c_int, C.c_void_p]
+        L.s2ref_constraint_counts.restype = None
+        L.s2ref_constraint_counts.argtypes = [C.c_int, ip]
 
     # -- taps ---------------------------------------------------------------------------------------------------
     def capacities(self, wid) -> dict:
@@ -125,6 +130,16 @@ class Reference(capi.Solver2D):
         self.step_collide(wid)
         self.step_solve(wid, dt, vel_iters, pos_iters, warm_start)
         self.step_finalize(wid)
+
+    def constraint_counts(self, wid):
+        out = (C.c_int * 2)()
+        self.lib.s2ref_constraint_counts(wid.index, out)
+        return out[0], out[1]
+
+    def timed_e2e_steps(self, wid, steps, dt, vel_iters, pos_iters, warm_start, body_indices, forces_xy, transforms) -> float:
+        return float(self.lib.s2ref_timed_e2e_steps(wid, steps, dt, vel_iters, pos_iters, 1 if warm_start else 0,
+                                                    body_indices.ctypes.data, forces_xy.ctypes.data, len(body_indices),
+                                                    transforms.ctypes.data))
 
     def timed_steps(self, wid, steps, dt, vel_iters, pos_iters, warm_start=True) -> float:
         return float(self.lib.s2ref_timed_steps(wid, steps, dt, vel_iters, pos_iters, 1 if warm_start else 0))

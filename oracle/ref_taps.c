@@ -443,3 +443,53 @@ TAP_EXPORT double s2ref_timed_steps(s2WorldId worldId, int steps, float timeStep
 	clock_gettime(CLOCK_MONOTONIC, &t1);
 	return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+// The reference-side "end to end" step used by bench.py's reference arm: apply a force to every listed body through the
+// reference's own API, step, read every transform back — the same client pattern the product's e2e number measures.
+TAP_EXPORT double s2ref_timed_e2e_steps(s2WorldId worldId, int steps, float timeStep, int velIters, int posIters, int warmStart,
+										const int* bodyIndices, const float* forcesXY, int forceCount, float* transforms)
+{
+	s2World* world = s2GetWorldFromId(worldId);
+	struct timespec t0, t1;
+	clock_gettime(CLOCK_MONOTONIC, &t0);
+	for (int s = 0; s < steps; ++s)
+	{
+		float sign = (s & 1) ? -1.0f : 1.0f;
+		for (int i = 0; i < forceCount; ++i)
+		{
+			s2Body* b = world->bodies + bodyIndices[i];
+			s2BodyId id = {b->object.index, world->index, b->object.revision};
+			s2Body_ApplyForceToCenter(id, (s2Vec2){sign * forcesXY[2 * i], sign * forcesXY[2 * i + 1]});
+		}
+		s2World_Step(worldId, timeStep, velIters, posIters, warmStart != 0);
+		int cap = world->bodyPool.capacity;
+		for (int i = 0; i < cap; ++i)
+		{
+			const s2Body* b = world->bodies + i;
+			transforms[4 * i + 0] = b->origin.x;
+			transforms[4 * i + 1] = b->origin.y;
+			transforms[4 * i + 2] = b->rot.s;
+			transforms[4 * i + 3] = b->rot.c;
+		}
+	}
+	clock_gettime(CLOCK_MONOTONIC, &t1);
+	return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+// constraint count of the next solve: manifolds with >= 1 point (what every s2Solve_* gathers, e.g. reference
+// src/solve_tgs_soft.c:162-179) + live joints
+TAP_EXPORT void s2ref_constraint_counts(int worldIndex, int* out)
+{
+	s2World* w = s2GetWorldFromIndex((int16_t)worldIndex);
+	int manifolds = 0;
+	for (int i = 0; i < w->contactPool.capacity; ++i)
+	{
+		const s2Contact* c = w->contacts + i;
+		if (s2IsFree(&c->object) == false && c->manifold.pointCount > 0)
+		{
+			manifolds += 1;
+		}
+	}
+	out[0] = manifolds;
+	out[1] = w->jointPool.count;
+}

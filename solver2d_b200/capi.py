@@ -248,6 +248,51 @@ _API = {
     "s2ComputeHull": (Hull, [C.POINTER(Vec2), C.c_int32]),
 }
 
+class Transform(C.Structure):
+    _fields_ = [("p", Vec2), ("q", Rot)]
+
+
+class ManifoldPoint(C.Structure):
+    _fields_ = [("localAnchorA", Vec2), ("localAnchorB", Vec2), ("frictionAnchorA", Vec2), ("frictionAnchorB", Vec2),
+                ("frictionNormalA", Vec2), ("frictionNormalB", Vec2), ("separation", C.c_float),
+                ("normalImpulse", C.c_float), ("tangentImpulse", C.c_float), ("id", C.c_uint16), ("persisted", C.c_bool)]
+
+
+class Manifold(C.Structure):
+    _fields_ = [("points", ManifoldPoint * 2), ("normal", Vec2), ("pointCount", C.c_int32),
+                ("constraintIndex", C.c_int32), ("frictionPersisted", C.c_bool)]
+
+
+class DistanceCache(C.Structure):
+    _fields_ = [("metric", C.c_float), ("count", C.c_uint16), ("indexA", C.c_uint8 * 3), ("indexB", C.c_uint8 * 3)]
+
+
+class MassData(C.Structure):
+    _fields_ = [("mass", C.c_float), ("center", Vec2), ("I", C.c_float)]
+
+
+# host-callable geometry / narrow-phase API (reference include/solver2d/manifold.h, geometry.h)
+_API.update({
+    "s2CollideCircles": (Manifold, [C.POINTER(Circle), Transform, C.POINTER(Circle), Transform]),
+    "s2CollideCapsuleAndCircle": (Manifold, [C.POINTER(Capsule), Transform, C.POINTER(Circle), Transform]),
+    "s2CollideSegmentAndCircle": (Manifold, [C.POINTER(Segment), Transform, C.POINTER(Circle), Transform]),
+    "s2CollidePolygonAndCircle": (Manifold, [C.POINTER(Polygon), Transform, C.POINTER(Circle), Transform]),
+    "s2CollideCapsules": (Manifold, [C.POINTER(Capsule), Transform, C.POINTER(Capsule), Transform, C.POINTER(DistanceCache)]),
+    "s2CollideSegmentAndCapsule": (Manifold, [C.POINTER(Segment), Transform, C.POINTER(Capsule), Transform,
+                                              C.POINTER(DistanceCache)]),
+    "s2CollidePolygonAndCapsule": (Manifold, [C.POINTER(Polygon), Transform, C.POINTER(Capsule), Transform,
+                                              C.POINTER(DistanceCache)]),
+    "s2CollidePolygons": (Manifold, [C.POINTER(Polygon), Transform, C.POINTER(Polygon), Transform, C.POINTER(DistanceCache)]),
+    "s2CollideSegmentAndPolygon": (Manifold, [C.POINTER(Segment), Transform, C.POINTER(Polygon), Transform,
+                                              C.POINTER(DistanceCache)]),
+    "s2ComputePolygonMass": (MassData, [C.POINTER(Polygon), C.c_float]),
+    "s2ComputeCapsuleMass": (MassData, [C.POINTER(Capsule), C.c_float]),
+    "s2ComputeCircleMass": (MassData, [C.POINTER(Circle), C.c_float]),
+    "s2ComputePolygonAABB": (Box, [C.POINTER(Polygon), Transform]),
+    "s2PointInPolygon": (C.c_bool, [Vec2, C.POINTER(Polygon)]),
+    "s2MakeRoundedBox": (Polygon, [C.c_float, C.c_float, C.c_float]),
+})
+
 QUERY_CALLBACK = C.CFUNCTYPE(C.c_bool, ShapeId, C.c_void_p)
 
 

@@ -312,6 +312,12 @@ struct s2bWorld
 	int* devMail = nullptr;	 // device, 64 ints
 
 	int kernelLaunches = 0;
+	// device-side work meter: [0] constraint-iterations, [1] solver stages run (bench metric)
+	DevArray<unsigned long long> dWork;
+	// device time of the last persistent solver kernel (roofline probe)
+	cudaEvent_t solveKernelStart = nullptr, solveKernelEnd = nullptr;
+	bool solveKernelTimed = false;
+	cudaEvent_t markEvents[2] = {nullptr, nullptr};
 	StageTimer timer;
 	float stageMs[4] = {0, 0, 0, 0};
 

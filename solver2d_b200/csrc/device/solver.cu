@@ -711,6 +711,12 @@ __global__ void __launch_bounds__(S2B_BLOCK) s2bPersistentTgsSoft(SolveArgs a, P
 	s2bGridFlatPass<JOP_STORE, OP_STORE>(a, p);
 }
 
+__global__ void s2bMeterWork(const int* counts, int passes, unsigned long long* work)
+{
+	work[0] += (unsigned long long)(counts[CNT_CONTACTS] + counts[CNT_JOINTS]) * (unsigned long long)passes;
+	work[1] += 1ull;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------------------------
@@ -1231,16 +1237,59 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 		int wanted = std::max(gridFor(std::max(maxItems, bodyCap), S2B_BLOCK), 1);
 		int grid = std::min(w->smCount * blocksPerSm, wanted);
 		void* args[] = {&a, &pp};
+		if (w->solveKernelStart == nullptr)
+		{
+			S2B_CHECK(cudaEventCreate(&w->solveKernelStart));
+			S2B_CHECK(cudaEventCreate(&w->solveKernelEnd));
+		}
+		S2B_CHECK(cudaEventRecord(w->solveKernelStart, st));
 		S2B_CHECK(cudaLaunchCooperativeKernel((void*)s2bPersistentTgsSoft, dim3(grid), dim3(S2B_BLOCK), args, 0, st));
+		S2B_CHECK(cudaEventRecord(w->solveKernelEnd, st));
+		w->solveKernelTimed = true;
 		w->kernelLaunches += 1;
 	}
 	else
 	{
 		runTgsSoftMultiLaunch(w, a, pp, plan, hostNJ, hostNC);
 	}
+
+	// work meter: constraint-iterations of this step = (contact constraints + joints) x solve passes
+	{
+		w->dWork.reserve(4, st, true);
+		int passes = ctx.iterations * (1 + (ctx.extraIterations > 0 ? 1 : 0));
+		S2B_LAUNCH(w, s2bMeterWork, 1, 1, 0, s->counts.p, passes, w->dWork.p);
+	}
 }
 
-extern "C" int s2b_download_solve_order(s2bWorld* w, int32_t* contactSlots, int maxCount, int32_t* groupOffsets, int maxGroups,
+extern "C" void s2b_get_work(s2bWorld* w, uint64_t out[2], int reset)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	S2B_CHECK(cudaStreamSynchronize(w->stream));
+	out[0] = out[1] = 0;
+	if (w->dWork.p != nullptr)
+	{
+		S2B_CHECK(cudaMemcpy(out, w->dWork.p, sizeof(uint64_t) * 2, cudaMemcpyDeviceToHost));
+		if (reset)
+		{
+			S2B_CHECK(cudaMemset(w->dWork.p, 0, sizeof(uint64_t) * 2));
+		}
+	}
+}
+
+extern "C" float s2b_last_solve_kernel_ms(s2bWorld* w)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	if (w->solveKernelTimed == false)
+	{
+		return 0.0f;
+	}
+	S2B_CHECK(cudaEventSynchronize(w->solveKernelEnd));
+	float ms = 0.0f;
+	S2B_CHECK(cudaEventElapsedTime(&ms, w->solveKernelStart, w->solveKernelEnd));
+	return ms;
+}
+
+extern "C" int s2b_download_solve_order(s2bWorld* w, int32_t* items, int maxItems, int32_t* groupSizes, int maxGroups,
 										int32_t* groupCount)
 {
 	S2B_CHECK(cudaSetDevice(w->device));
@@ -1248,23 +1297,65 @@ extern "C" int s2b_download_solve_order(s2bWorld* w, int32_t* contactSlots, int 
 	S2B_CHECK(cudaStreamSynchronize(w->stream));
 	int counts[CNT_SIZE];
 	S2B_CHECK(cudaMemcpy(counts, s->counts.p, sizeof(counts), cudaMemcpyDeviceToHost));
-	int nC = counts[CNT_CONTACTS];
-	int n = nC < maxCount ? nC : maxCount;
-	if (n > 0 && contactSlots != nullptr)
+	int nC = counts[CNT_CONTACTS], nJ = counts[CNT_JOINTS], groups = counts[CNT_GROUPS];
+	bool wavefront = w->schedule == S2B_SCHEDULE_WAVEFRONT;
+	int tableLen = (wavefront ? groups : S2B_MAX_COLORS) + 2;
+	std::vector<int> cOff((size_t)tableLen), jOff((size_t)tableLen), src((size_t)std::max(nC, 1)), jPerm((size_t)std::max(nJ, 1)),
+		jointSlots((size_t)std::max(nJ, 1));
+	S2B_CHECK(cudaMemcpy(cOff.data(), s->cGroupOff.p, sizeof(int) * (size_t)tableLen, cudaMemcpyDeviceToHost));
+	S2B_CHECK(cudaMemcpy(jOff.data(), s->jGroupOff.p, sizeof(int) * (size_t)tableLen, cudaMemcpyDeviceToHost));
+	if (nC > 0)
 	{
-		S2B_CHECK(cudaMemcpy(contactSlots, s->src.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
+		S2B_CHECK(cudaMemcpy(src.data(), s->src.p, sizeof(int) * (size_t)nC, cudaMemcpyDeviceToHost));
 	}
-	int groups = counts[CNT_GROUPS];
+	if (nJ > 0)
+	{
+		S2B_CHECK(cudaMemcpy(jPerm.data(), s->jPerm.p, sizeof(int) * (size_t)nJ, cudaMemcpyDeviceToHost));
+		S2B_CHECK(cudaMemcpy(jointSlots.data(), s->jointSlots.p, sizeof(int) * (size_t)nJ, cudaMemcpyDeviceToHost));
+	}
+	// group g = joints [jOff[g], jOff[g+1]) then contacts [cOff[g], cOff[g+1]); the serial overflow group (colour
+	// schedule only) sits at table index S2B_MAX_COLORS and is visited last
+	int written = 0, groupsOut = 0;
+	auto emit = [&](int g) {
+		int size = 0;
+		for (int t = jOff[(size_t)g]; t < jOff[(size_t)g + 1]; ++t, ++size)
+		{
+			if (written < maxItems && items != nullptr)
+			{
+				items[written] = -1 - jointSlots[(size_t)jPerm[(size_t)t]];
+			}
+			written += 1;
+		}
+		for (int t = cOff[(size_t)g]; t < cOff[(size_t)g + 1]; ++t, ++size)
+		{
+			if (written < maxItems && items != nullptr)
+			{
+				items[written] = src[(size_t)t];
+			}
+			written += 1;
+		}
+		if (size > 0)
+		{
+			if (groupSizes != nullptr && groupsOut < maxGroups)
+			{
+				groupSizes[groupsOut] = size;
+			}
+			groupsOut += 1;
+		}
+	};
+	for (int g = 0; g < groups; ++g)
+	{
+		emit(g);
+	}
+	if (wavefront == false)
+	{
+		emit(S2B_MAX_COLORS);
+	}
 	if (groupCount != nullptr)
 	{
-		*groupCount = groups;
+		*groupCount = groupsOut;
 	}
-	if (groupOffsets != nullptr && maxGroups > 0)
-	{
-		int m = std::min(maxGroups, (w->schedule == S2B_SCHEDULE_WAVEFRONT ? groups : S2B_MAX_COLORS) + 2);
-		S2B_CHECK(cudaMemcpy(groupOffsets, s->cGroupOff.p, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost));
-	}
-	return nC;
+	return written;
 }
 
 extern "C" void s2b_get_counters(s2bWorld* w, s2bCounters* out)

@@ -367,6 +367,12 @@ extern "C" void s2b_world_destroy(s2bWorld* w)
 	w->contacts[1].release();
 	w->dMovedFlag.release();
 	w->l2Flush.release();
+	w->dWork.release();
+	if (w->solveKernelStart != nullptr)
+	{
+		cudaEventDestroy(w->solveKernelStart);
+		cudaEventDestroy(w->solveKernelEnd);
+	}
 	cudaFreeHost(w->hostMail);
 	cudaFree(w->devMail);
 	for (int i = 0; i < 5; ++i)
@@ -825,6 +831,32 @@ extern "C" float s2b_timed_steps(s2bWorld* w, int solverType, const s2bStepConte
 	S2B_CHECK(cudaEventElapsedTime(&ms, e0, e1));
 	cudaEventDestroy(e0);
 	cudaEventDestroy(e1);
+	return ms;
+}
+
+// user stop-watch on the world's stream: mark(0) ... mark(1), then elapsed
+static cudaEvent_t s2bMarkEvent(s2bWorld* w, int slot)
+{
+	static_assert(sizeof(cudaEvent_t) == sizeof(void*), "event handle size");
+	if (w->markEvents[slot] == nullptr)
+	{
+		S2B_CHECK(cudaEventCreate(&w->markEvents[slot]));
+	}
+	return w->markEvents[slot];
+}
+
+extern "C" void s2b_mark_time(s2bWorld* w, int slot)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	S2B_CHECK(cudaEventRecord(s2bMarkEvent(w, slot & 1), w->stream));
+}
+
+extern "C" float s2b_elapsed_ms(s2bWorld* w)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	S2B_CHECK(cudaEventSynchronize(s2bMarkEvent(w, 1)));
+	float ms = 0.0f;
+	S2B_CHECK(cudaEventElapsedTime(&ms, s2bMarkEvent(w, 0), s2bMarkEvent(w, 1)));
 	return ms;
 }
 

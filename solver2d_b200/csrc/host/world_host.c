@@ -507,7 +507,9 @@ s2WorldId s2CreateWorld(const s2WorldDef* def)
 	world->boxesFresh = true;
 
 	// no CUDA device -> s2b_world_create reports and aborts: there is no CPU path
-	world->device = s2b_world_create(-1, (int)def->solverType);
+	// S2B_DEVICE selects the CUDA device of new worlds (one process per GPU sets it to its local rank)
+	const char* deviceEnv = getenv("S2B_DEVICE");
+	world->device = s2b_world_create(deviceEnv != NULL ? atoi(deviceEnv) : -1, (int)def->solverType);
 	s2b_set_gravity(world->device, world->gravity.x, world->gravity.y);
 
 	const char* schedule = getenv("S2B_SCHEDULE");
@@ -749,6 +751,37 @@ s2bWorld* s2World_GetDevice(s2WorldId worldId)
 void s2World_Flush(s2WorldId worldId)
 {
 	s2FlushToDevice(s2GetWorldFromId(worldId));
+}
+
+void s2World_ApplyForcesToCenters(s2WorldId worldId, const int32_t* bodyIndices, const float* forcesXY, int32_t count)
+{
+	s2World* world = s2GetWorldFromId(worldId);
+	for (int32_t i = 0; i < count; ++i)
+	{
+		s2Body* body = world->bodies + bodyIndices[i];
+		body->force.x += forcesXY[2 * i];
+		body->force.y += forcesXY[2 * i + 1];
+		s2MarkBodyForceDirty(world, body);
+	}
+}
+
+float s2World_TimedSteps(s2WorldId worldId, int32_t steps, float timeStep, int32_t velIters, int32_t posIters, bool warmStart,
+						 int32_t flushL2)
+{
+	s2World* world = s2GetWorldFromId(worldId);
+	float total = 0.0f;
+	for (int32_t i = 0; i < steps; ++i)
+	{
+		if (flushL2)
+		{
+			s2b_flush_l2(world->device);
+		}
+		s2b_mark_time(world->device, 0);
+		s2World_Step(worldId, timeStep, velIters, posIters, warmStart);
+		s2b_mark_time(world->device, 1);
+		total += s2b_elapsed_ms(world->device);
+	}
+	return total;
 }
 
 int32_t s2World_GetBodyTransforms(s2WorldId worldId, float* out, int32_t capacity)

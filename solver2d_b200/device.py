@@ -270,13 +270,14 @@ class DeviceWorld:
         self.L.s2b_download_shape_boxes(self.h, aabb.ctypes.data, fat.ctypes.data, flags.ctypes.data, cap)
         return aabb, fat, flags
 
-    def solve_order(self, max_count: int, max_groups: int = 70000):
-        slots = np.zeros(max(max_count, 1), dtype=np.int32)
-        offs = np.zeros(max_groups, dtype=np.int32)
+    def solve_order(self, max_items: int, max_groups: int = 70000):
+        """(items, group_sizes): items >= 0 contact slot, < 0 joint slot (-1 - k), in the order the last solve visited them."""
+        items = np.zeros(max(max_items, 1), dtype=np.int32)
+        sizes = np.zeros(max_groups, dtype=np.int32)
         groups = C.c_int(0)
-        n = self.L.s2b_download_solve_order(self.h, slots.ctypes.data, max_count, offs.ctypes.data, max_groups,
+        n = self.L.s2b_download_solve_order(self.h, items.ctypes.data, max_items, sizes.ctypes.data, max_groups,
                                             C.byref(groups))
-        return slots[:n], offs, groups.value
+        return items[:n], sizes[:groups.value]
 
     def counters(self) -> Counters:
         c = Counters()

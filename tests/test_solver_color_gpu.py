@@ -1,0 +1,90 @@
+"""GPU: the PRODUCTION schedule (device graph colouring + persistent cooperative kernel) against the order-permuted
+oracle. The device reports the Gauss-Seidel order it used (colour-major); the plain-C oracle — pinned bit for bit to the
+unmodified reference in tests/test_oracle_cpu.py — replays the solver stage in exactly that order. Tolerance: 0 (bit-exact),
+because the kernels are compiled without FMA contraction."""
+import numpy as np
+import pytest
+
+from helpers import bit_equal, body_rows_from_ref, contact_rows_from_ref, joint_rows_from_ref
+from oracle import port
+from solver2d_b200 import capi, device, scenes
+
+pytestmark = pytest.mark.gpu
+DT = 1.0 / 60.0
+
+
+def _case(reference, dev, recipe, solver, warm, vel, pos, persistent, max_colors=None, **kw):
+    R = reference
+    O = port.load()
+    sc = recipe(R, solver, **kw)
+    for _ in range(warm):
+        sc.step(DT, vel, pos, True)
+    R.step_collide(sc.world)
+    bodies = body_rows_from_ref(*R.bodies(sc.world))
+    contacts, _ = contact_rows_from_ref(*R.contacts(sc.world))
+    joints = joint_rows_from_ref(*R.joints(sc.world))
+    ctx = device.make_context(solver, DT, vel, pos, True)
+
+    dw = dev.create_world(capi.SOLVER[solver])
+    dw.upload_bodies(bodies, len(bodies))
+    dw.upload_joints(joints, len(joints))
+    dw.upload_contacts(contacts)
+    dw.set_schedule(device.SCHEDULE_COLOR)
+    dw.set_persistent(persistent)
+    if max_colors is not None:
+        dw.set_max_colors(max_colors)
+    dw.solve(ctx)
+    got = dw.download_all_bodies(len(bodies))
+    got_contacts = dw.download_contacts(len(contacts))
+    order, group_sizes = dw.solve_order(len(contacts) + len(joints))
+    counters = dw.counters()
+    dw.destroy()
+
+    # validity of the colouring: within a parallel group no movable body appears twice
+    movable = (bodies["invMass"] != 0) | (bodies["invI"] != 0)
+    start = 0
+    parallel_groups = len(group_sizes) - (1 if counters.overflowCount > 0 else 0)
+    for g, size in enumerate(group_sizes):
+        seen = set()
+        for it in order[start:start + size]:
+            if it >= 0:
+                ends = [contacts["bodyA"][it], contacts["bodyB"][it]]
+            else:
+                j = joints[-1 - it]
+                ends = [j["bodyB"]] if ((j["flags"] >> 1) & 7) == 1 else [j["bodyA"], j["bodyB"]]
+            for b in ends:
+                if movable[b] and g < parallel_groups:
+                    assert b not in seen, f"body {b} twice in group {g}"
+                    seen.add(b)
+        start += size
+    assert start == len(order)
+
+    ob, oc, oj = O.solve(capi.SOLVER[solver], bodies, contacts, joints, ctx, order=order)
+    valid = (bodies["flags"] & 1) == 1
+    assert bit_equal(got["position"][valid], ob["position"][valid])
+    assert bit_equal(got["rot"][valid], ob["rot"][valid])
+    assert bit_equal(got["linearVelocity"][valid], ob["linearVelocity"][valid])
+    assert bit_equal(got["angularVelocity"][valid], ob["angularVelocity"][valid])
+    live = contacts["pointCount"] > 0
+    assert bit_equal(got_contacts["points"]["normalImpulse"][live], oc["points"]["normalImpulse"][live])
+    assert bit_equal(got_contacts["points"]["tangentImpulse"][live], oc["points"]["tangentImpulse"][live])
+    sc.destroy()
+    return counters
+
+
+@pytest.mark.parametrize("persistent", [True, False])
+@pytest.mark.parametrize("base,warm", [(10, 30), (40, 10)])
+def test_color_schedule_matches_permuted_oracle(reference, dev, base, warm, persistent):
+    c = _case(reference, dev, scenes.pyramid, "TGS_Soft", warm, 4, 2, persistent, base_count=base)
+    assert c.overflowCount == 0 and 2 <= c.groupCount <= 16
+
+
+def test_color_schedule_with_overflow_group(reference, dev):
+    # force constraints into the serial overflow group by allowing only 3 colours
+    c = _case(reference, dev, scenes.pyramid, "TGS_Soft", 20, 4, 2, True, max_colors=3, base_count=15)
+    assert c.overflowCount > 0 and c.groupCount <= 3
+
+
+def test_color_schedule_joints_and_contacts(reference, dev):
+    c = _case(reference, dev, scenes.joint_contact_stress, "TGS_Soft", 90, 4, 2, True, bridges=3, planks=24, grid=9)
+    assert c.jointCount == 75 and c.constraintCount > 20
