@@ -214,14 +214,17 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
     solve_kernel_ms = []
+    step_ms = []
     total_ms = 0.0
     if dist is None:
         for _ in range(args.steps):
-            total_ms += float(L.s2World_TimedSteps(sc.world, 1, DT, args.substeps, args.relax, True, 1 if args.flush_l2 else 0))
+            step_ms.append(float(L.s2World_TimedSteps(sc.world, 1, DT, args.substeps, args.relax, True, 1 if args.flush_l2 else 0)))
+            total_ms += step_ms[-1]
             solve_kernel_ms.append(float(L.s2b_last_solve_kernel_ms(dw.h)))
     else:
         for _ in range(args.steps):
-            total_ms += float(L.s2World_TimedSteps(sc.world, 1, DT, args.substeps, args.relax, True, 1 if args.flush_l2 else 0))
+            step_ms.append(float(L.s2World_TimedSteps(sc.world, 1, DT, args.substeps, args.relax, True, 1 if args.flush_l2 else 0)))
+            total_ms += step_ms[-1]
             solve_kernel_ms.append(float(L.s2b_last_solve_kernel_ms(dw.h)))
             t0 = torch.cuda.Event(enable_timing=True)
             t1 = torch.cuda.Event(enable_timing=True)
@@ -293,6 +296,8 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
                                                                         f", x{world_size} + NCCL all-gather of body state"),
                        "schedule": "graph colouring, persistent cooperative solver kernel"},
             "stage_ms_last_step": {"pairs": stage_ms[0], "contacts": stage_ms[1], "solve": stage_ms[2], "finalize": stage_ms[3]},
+            "step_ms_stats": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)), "max": float(np.max(step_ms)),
+                              "pair_passes_total": int(counters.pairPassCount)},
             "e2e": {"value": e2e_value, "unit": "constraint-iters/s", "ms_per_step": 1e3 * e2e_time_max / e2e_steps,
                     "h2d_bytes_per_step": int(len(idx) * 16), "d2h_bytes_per_step": int(counters.bodyCapacity * 48),
                     "steps": e2e_steps, "clock": "host wall clock, synchronised on both sides"},

@@ -12,7 +12,8 @@
 // It shares the row structs of include/s2b_device.h (types only) and the float inlines of include/solver2d/math.h; it is
 // compiled with the reference's flags (gcc -std=gnu17 -O2, no FMA contraction).
 //
-// Restated so far: s2Solve_TGS_Soft (src/solve_tgs_soft.c:138-280), with revolute (soft) and mouse joints.
+// Restated: the nine variants north_star names — s2Solve_PGS, _PGS_NGS, _PGS_Soft, _TGS_Soft, _TGS_NGS, _TGS_Sticky,
+// _SoftStep, _XPBD, _Jacobi — with revolute and mouse joints (s2Solve_PGS_NGS_Block is not restated: SURVEY §8f-2).
 
 #include "s2b_device.h"
 #include "solver2d/constants.h"
@@ -27,13 +28,18 @@ typedef struct s2oBody
 {
 	int valid, type;
 	s2Vec2 position, dp, v, localCenter, force;
-	s2Rot q;
+	s2Vec2 dv, dp0; // Jacobi accumulator; XPBD previous delta position
+	float dw;
+	s2Rot q, q0;
 	float w, mass, invMass, I, invI, torque, linearDamping, angularDamping, gravityScale;
 } s2oBody;
 
 typedef struct s2oPoint
 {
 	s2Vec2 localAnchorA, localAnchorB; // relative to the centres of mass, body frames
+	s2Vec2 rA0, rB0;				   // world anchors at prepare time
+	s2Vec2 localFrictionAnchorA, localFrictionAnchorB;
+	float separation, tangentSeparation;
 	float adjustedSeparation, normalImpulse, tangentImpulse, normalMass, tangentMass;
 	float biasCoefficient, massCoefficient, impulseCoefficient;
 } s2oPoint;
@@ -41,6 +47,7 @@ typedef struct s2oPoint
 typedef struct s2oConstraint
 {
 	int row, indexA, indexB, pointCount;
+	int unpersist; // TGS_Sticky: friction hit its limit in some pass
 	s2Vec2 normal;
 	float friction;
 	s2oPoint points[2];
@@ -142,6 +149,9 @@ static void s2oPrepareContactSoft(s2oConstraint* c, const s2bContactRow* row, in
 		cp->localAnchorB = s2Sub(s2MakeVec2(mp->localAnchorB[0], mp->localAnchorB[1]), bodyB->localCenter);
 		s2Vec2 rA = s2RotateVector(qA, cp->localAnchorA);
 		s2Vec2 rB = s2RotateVector(qB, cp->localAnchorB);
+		cp->rA0 = rA;
+		cp->rB0 = rB;
+		cp->separation = mp->separation;
 		cp->adjustedSeparation = mp->separation - s2Dot(s2Sub(rB, rA), normal);
 
 		float rnA = s2Cross(rA, normal);
@@ -546,186 +556,6 @@ static void s2oSolveJointSoft(s2oJoint* j, s2oBody* bodies, float contextH, floa
 	s2oSolveRevoluteSoft(j, bodies, h, inv_h, useBias);
 }
 
-// ---- driver ------------------------------------------------------------------------------------------------------
+#include "s2o_variants.inc"
 
-// order entries: k >= 0 -> contact row k ; k < 0 -> joint slot (-1 - k)
-S2O_EXPORT int s2o_solve(int solverType, s2bBodyRow* bodyRows, int bodyCapacity, s2bContactRow* contactRows, int contactCount,
-						 s2bJointRow* jointRows, int jointCapacity, const int* order, int orderCount, const s2bStepContext* ctx, float gx,
-						 float gy)
-{
-	if (solverType != 7)
-	{
-		return -1; // not restated yet
-	}
-	s2Vec2 gravity = {gx, gy};
-
-	s2oBody* bodies = (s2oBody*)calloc((size_t)(bodyCapacity > 0 ? bodyCapacity : 1), sizeof(s2oBody));
-	for (int i = 0; i < bodyCapacity; ++i)
-	{
-		const s2bBodyRow* r = bodyRows + i;
-		s2oBody* b = bodies + i;
-		b->valid = (r->flags & S2B_ROW_VALID) != 0;
-		b->type = (r->flags >> 1) & 0x3;
-		b->position = s2MakeVec2(r->position[0], r->position[1]);
-		b->dp = s2Vec2_zero;
-		b->q.s = r->rot[0];
-		b->q.c = r->rot[1];
-		b->v = s2MakeVec2(r->linearVelocity[0], r->linearVelocity[1]);
-		b->w = r->angularVelocity;
-		b->localCenter = s2MakeVec2(r->localCenter[0], r->localCenter[1]);
-		b->force = s2MakeVec2(r->force[0], r->force[1]);
-		b->torque = r->torque;
-		b->mass = r->mass;
-		b->invMass = r->invMass;
-		b->I = r->I;
-		b->invI = r->invI;
-		b->linearDamping = r->linearDamping;
-		b->angularDamping = r->angularDamping;
-		b->gravityScale = r->gravityScale;
-	}
-
-	// the visiting order: given, or the reference's (joints in slot order, then contact constraints in row order)
-	int* items = (int*)malloc(sizeof(int) * (size_t)(contactCount + jointCapacity + 1));
-	int itemCount = 0;
-	if (order != NULL)
-	{
-		for (int i = 0; i < orderCount; ++i)
-		{
-			items[itemCount++] = order[i];
-		}
-	}
-	else
-	{
-		for (int i = 0; i < jointCapacity; ++i)
-		{
-			if (jointRows[i].flags & S2B_ROW_VALID)
-			{
-				items[itemCount++] = -1 - i;
-			}
-		}
-		for (int i = 0; i < contactCount; ++i)
-		{
-			if (contactRows[i].pointCount > 0)
-			{
-				items[itemCount++] = i;
-			}
-		}
-	}
-
-	s2oConstraint* constraints = (s2oConstraint*)calloc((size_t)(contactCount > 0 ? contactCount : 1), sizeof(s2oConstraint));
-	s2oJoint* joints = (s2oJoint*)calloc((size_t)(jointCapacity > 0 ? jointCapacity : 1), sizeof(s2oJoint));
-
-	int substeps = ctx->iterations;
-	float h = ctx->h, inv_h = ctx->inv_h;
-	// reference src/solve_tgs_soft.c:185-186
-	float contactHertz = S2_MIN(s2_contactHertz, 0.25f * inv_h);
-	float jointHertz = S2_MIN(s2_jointHertz, 0.125f * inv_h);
-
-	// prepare (reference src/solve_tgs_soft.c:194-206; joints always warm start here)
-	for (int k = 0; k < itemCount; ++k)
-	{
-		int it = items[k];
-		if (it >= 0)
-		{
-			s2oPrepareContactSoft(constraints + it, contactRows + it, it, bodies, ctx->warmStart, h, contactHertz);
-		}
-		else
-		{
-			int slot = -1 - it;
-			s2oPrepareJointSoft(joints + slot, jointRows + slot, bodies, ctx->h, h, jointHertz, 1);
-		}
-	}
-
-	// sub-steps (reference src/solve_tgs_soft.c:211-269)
-	for (int s = 0; s < substeps; ++s)
-	{
-		s2oIntegrateVelocities(bodies, bodyCapacity, gravity, h);
-		if (ctx->warmStart)
-		{
-			for (int k = 0; k < itemCount; ++k)
-			{
-				int it = items[k];
-				if (it >= 0)
-				{
-					s2oWarmStartContact(constraints + it, bodies);
-				}
-				else
-				{
-					s2oWarmStartJoint(joints + (-1 - it), bodies);
-				}
-			}
-		}
-		for (int k = 0; k < itemCount; ++k)
-		{
-			int it = items[k];
-			if (it >= 0)
-			{
-				s2oSolveContactTgsSoft(constraints + it, bodies, inv_h, 1);
-			}
-			else
-			{
-				s2oSolveJointSoft(joints + (-1 - it), bodies, ctx->h, h, inv_h, 1);
-			}
-		}
-		s2oIntegratePositions(bodies, bodyCapacity, h);
-		if (ctx->extraIterations > 0)
-		{
-			for (int k = 0; k < itemCount; ++k)
-			{
-				int it = items[k];
-				if (it >= 0)
-				{
-					s2oSolveContactTgsSoft(constraints + it, bodies, inv_h, 0);
-				}
-				else
-				{
-					s2oSolveJointSoft(joints + (-1 - it), bodies, ctx->h, h, inv_h, 0);
-				}
-			}
-		}
-	}
-
-	s2oFinalizePositions(bodies, bodyCapacity);
-
-	// store (reference src/solve_common.c:396-410) and write the state back into the rows
-	for (int k = 0; k < itemCount; ++k)
-	{
-		int it = items[k];
-		if (it >= 0)
-		{
-			s2oConstraint* c = constraints + it;
-			for (int j = 0; j < c->pointCount; ++j)
-			{
-				contactRows[it].points[j].normalImpulse = c->points[j].normalImpulse;
-				contactRows[it].points[j].tangentImpulse = c->points[j].tangentImpulse;
-			}
-		}
-		else
-		{
-			int slot = -1 - it;
-			jointRows[slot].impulse[0] = joints[slot].impulse.x;
-			jointRows[slot].impulse[1] = joints[slot].impulse.y;
-			jointRows[slot].motorImpulse = joints[slot].motorImpulse;
-			jointRows[slot].lowerImpulse = joints[slot].lowerImpulse;
-			jointRows[slot].upperImpulse = joints[slot].upperImpulse;
-		}
-	}
-	for (int i = 0; i < bodyCapacity; ++i)
-	{
-		s2bBodyRow* r = bodyRows + i;
-		const s2oBody* b = bodies + i;
-		r->position[0] = b->position.x;
-		r->position[1] = b->position.y;
-		r->rot[0] = b->q.s;
-		r->rot[1] = b->q.c;
-		r->linearVelocity[0] = b->v.x;
-		r->linearVelocity[1] = b->v.y;
-		r->angularVelocity = b->w;
-	}
-
-	free(items);
-	free(constraints);
-	free(joints);
-	free(bodies);
-	return 0;
-}
+#include "s2o_driver.inc"

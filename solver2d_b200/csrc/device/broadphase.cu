@@ -540,8 +540,15 @@ __global__ void s2bFlagKeptContacts(ContactView c, int contactCount, ShapeView s
 	keepFlag[i] = keep ? 1 : 0;
 }
 
+// The sort key is the pair key squeezed to 2 x shapeBits bits (lo << shapeBits | hi) so the radix sort runs only over
+// significant digits.
+__device__ __forceinline__ unsigned long long s2bSqueezeKey(unsigned long long pairKey, int shapeBits)
+{
+	return ((pairKey >> 32) << shapeBits) | (pairKey & 0xFFFFFFFFull);
+}
+
 __global__ void s2bMergeKeys(const int* counters, const int* keepSlots, const unsigned long long* oldKeys,
-							 const unsigned long long* newKey, unsigned long long* mergeKey, int* mergeSrc, int capacity)
+							 const unsigned long long* newKey, unsigned long long* mergeKey, int* mergeSrc, int capacity, int shapeBits)
 {
 	int kept = counters[BC_KEPT], fresh = counters[BC_NEW_PAIRS];
 	int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -551,12 +558,12 @@ __global__ void s2bMergeKeys(const int* counters, const int* keepSlots, const un
 	}
 	if (t < kept)
 	{
-		mergeKey[t] = oldKeys[keepSlots[t]];
+		mergeKey[t] = s2bSqueezeKey(oldKeys[keepSlots[t]], shapeBits);
 		mergeSrc[t] = keepSlots[t]; // >= 0: old slot
 	}
 	else if (t < kept + fresh)
 	{
-		mergeKey[t] = newKey[t - kept];
+		mergeKey[t] = s2bSqueezeKey(newKey[t - kept], shapeBits);
 		mergeSrc[t] = -1 - (t - kept); // < 0: new pair index
 	}
 	else
@@ -569,7 +576,7 @@ __global__ void s2bMergeKeys(const int* counters, const int* keepSlots, const un
 // s2CreateContact for new pairs (reference src/contact.c:156-229: empty manifold, empty cache, mixed friction), plain
 // copy for survivors
 __global__ void s2bGatherContactsSorted(const int* counters, const unsigned long long* sortedKey, const int* sortedSrc, ContactView src,
-										ContactView dst, const int2* newShapes, ShapeView s, int sticky)
+										ContactView dst, const int2* newShapes, ShapeView s, int sticky, int shapeBits)
 {
 	int total = counters[BC_KEPT] + counters[BC_NEW_PAIRS];
 	int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -578,13 +585,15 @@ __global__ void s2bGatherContactsSorted(const int* counters, const unsigned long
 		return;
 	}
 	int from = sortedSrc[t];
-	dst.key[t] = sortedKey[t];
+	unsigned long long squeezed = sortedKey[t];
+	dst.key[t] = ((squeezed >> shapeBits) << 32) | (squeezed & ((1ull << shapeBits) - 1ull));
 	if (from >= 0)
 	{
 		dst.shapes[t] = src.shapes[from];
 		dst.bodies[t] = src.bodies[from];
 		dst.info[t] = src.info[from];
 		dst.nf[t] = src.nf[from];
+		dst.color[t] = src.color[from];
 		for (int p = 0; p < 2; ++p)
 		{
 			dst.anchor[p][t] = src.anchor[p][from];
@@ -605,6 +614,7 @@ __global__ void s2bGatherContactsSorted(const int* counters, const unsigned long
 		// s2MixFriction (reference src/contact.c:42-45)
 		float friction = sqrtf(s.fr[sh.x].x * s.fr[sh.y].x);
 		dst.nf[t] = make_float4(0.0f, 0.0f, friction, 0.0f);
+		dst.color[t] = -1;
 		for (int p = 0; p < 2; ++p)
 		{
 			dst.anchor[p][t] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -775,18 +785,28 @@ void s2bBroadphaseUpdatePairs(s2bWorld* w)
 		w->treeHeight = hostCounters[BC_HEIGHT];
 
 		int total = kept + fresh;
+		if (fresh == 0 && kept == oldCount)
+		{
+			// the moved proxies still overlap exactly the shapes they overlapped before: the contact table stands as it is
+			// (the usual outcome on a slowly settling pile)
+			break;
+		}
 		nxt.reserve((size_t)std::max(total, 1), st, w->sticky, false);
 		if (total > 0)
 		{
+			int shapeBits = 1;
+			while ((1 << shapeBits) < shapeCap && shapeBits < 31)
+			{
+				shapeBits += 1;
+			}
 			S2B_LAUNCH(w, s2bMergeKeys, gridFor(total, 256), 256, 0, B->counters.p, B->keepSlots.p, cur.key.p, B->newKey.p,
-					   B->mergeKeyIn.p, B->mergeSrcIn.p, total);
+					   B->mergeKeyIn.p, B->mergeSrcIn.p, total, shapeBits);
 			tb = B->cubTemp.cap;
-			// shape indices are < 2^31: 63 significant key bits
 			cub::DeviceRadixSort::SortPairs(B->cubTemp.p, tb, B->mergeKeyIn.p, B->mergeKeyOut.p, B->mergeSrcIn.p, B->mergeSrcOut.p,
-											total, 0, 64, st);
+											total, 0, 2 * shapeBits, st);
 			w->kernelLaunches += 9;
 			S2B_LAUNCH(w, s2bGatherContactsSorted, gridFor(total, 128), 128, 0, B->counters.p, B->mergeKeyOut.p, B->mergeSrcOut.p,
-					   makeView(cur), makeView(nxt), B->newShapes.p, sv, w->sticky ? 1 : 0);
+					   makeView(cur), makeView(nxt), B->newShapes.p, sv, w->sticky ? 1 : 0, shapeBits);
 		}
 		w->cur ^= 1;
 		w->contactCount = total;

@@ -89,6 +89,7 @@ enum PrepareKind
 {
 	PREPARE_PGS = 0,  // s2PrepareContacts_PGS  (reference src/solve_common.c:93-168)
 	PREPARE_SOFT = 1, // s2PrepareContacts_Soft (reference src/solve_common.c:188-274)
+	PREPARE_COLD = 2, // s2PrepareContacts_XPBD (reference src/solve_xpbd.c:18-86): never warm starts
 };
 
 // Builds row t of the constraint stream from contact slot src[t]. Writes are coalesced (row t), reads gather the
@@ -110,7 +111,7 @@ template <int KIND> __device__ __forceinline__ void s2bPrepareContact(const Solv
 	s2Rot qA = R2(poseA.z, poseA.w), qB = R2(poseB.z, poseB.w);
 	s2Vec2 normal = V2(mnf.x, mnf.y);
 	s2Vec2 tangent = s2RightPerp(normal);
-	bool warmStart = a.ctx.warmStart != 0;
+	bool warmStart = KIND == PREPARE_COLD ? false : a.ctx.warmStart != 0;
 
 	// contact stiffness is doubled against a body of infinite mass (reference solve_common.c:219)
 	unsigned flags = 0;
@@ -388,4 +389,938 @@ __device__ __forceinline__ void s2bSolveContactTgsSoft(const SolveArgs& a, int t
 	}
 	BodyPair bp = {ia, ib, velA, velB, (mA != 0.0f) || (iA != 0.0f), (mB != 0.0f) || (iB != 0.0f)};
 	s2bStoreVelocities(a, bp, vA, wA, vB, wB);
+}
+
+// ===============================================================================================================
+// The other variants. Every function keeps the structure "load both bodies - normal rows - friction rows - store" and
+// differs in the switches of SURVEY.md §8a: anchors (fixed r0 | current), separation (prepare-time | current), bias
+// law, row order, and what is written back (v,w | dv,dw | dp,q).
+// ===============================================================================================================
+
+struct ContactLoad
+{
+	int ia, ib, pointCount;
+	bool staticSoft;
+	float4 nf;
+	float4 velA, velB;
+	float mA, mB, iA, iB;
+};
+
+__device__ __forceinline__ ContactLoad s2bLoadContact(const SolveArgs& a, int t)
+{
+	ContactLoad c;
+	int2 idx = a.cc.idx[t];
+	c.ia = idx.x;
+	c.ib = idx.y & S2B_CF_INDEX_MASK;
+	c.pointCount = (idx.y & S2B_CF_TWO_POINTS) ? 2 : 1;
+	c.staticSoft = ((unsigned)idx.y & S2B_CF_STATIC_SOFT) != 0;
+	c.nf = a.cc.nf[t];
+	c.velA = a.bodies.vel[c.ia];
+	c.velB = a.bodies.vel[c.ib];
+	c.mA = c.velA.w;
+	c.mB = c.velB.w;
+	c.iA = c.nf.w;
+	c.iB = a.cc.pm[0][t].w;
+	return c;
+}
+
+__device__ __forceinline__ void s2bStoreContactVelocities(const SolveArgs& a, const ContactLoad& c, s2Vec2 vA, float wA, s2Vec2 vB, float wB)
+{
+	if ((c.mA != 0.0f) || (c.iA != 0.0f))
+	{
+		a.bodies.vel[c.ia] = make_float4(vA.x, vA.y, wA, c.velA.w);
+	}
+	if ((c.mB != 0.0f) || (c.iB != 0.0f))
+	{
+		a.bodies.vel[c.ib] = make_float4(vB.x, vB.y, wB, c.velB.w);
+	}
+}
+
+// s2WarmStartContacts_Fixed (reference src/solve_soft_step.c:16-63): prepare-time anchors
+__device__ __forceinline__ void s2bWarmStartContactFixed(const SolveArgs& a, int t)
+{
+	ContactLoad c = s2bLoadContact(a, t);
+	s2Vec2 vA = V2(c.velA.x, c.velA.y), vB = V2(c.velB.x, c.velB.y);
+	float wA = c.velA.z, wB = c.velB.z;
+	s2Vec2 normal = V2(c.nf.x, c.nf.y);
+	s2Vec2 tangent = s2RightPerp(normal);
+#pragma unroll
+	for (int j = 0; j < 2; ++j)
+	{
+		if (j < c.pointCount)
+		{
+			float4 r0 = a.cc.r0[j][t];
+			float2 l = a.cc.lambda[j][t];
+			s2Vec2 rA = V2(r0.x, r0.y), rB = V2(r0.z, r0.w);
+			s2Vec2 P = s2Add(s2MulSV(l.x, normal), s2MulSV(l.y, tangent));
+			wA -= c.iA * s2Cross(rA, P);
+			vA = s2MulAdd(vA, -c.mA, P);
+			wB += c.iB * s2Cross(rB, P);
+			vB = s2MulAdd(vB, c.mB, P);
+		}
+	}
+	s2bStoreContactVelocities(a, c, vA, wA, vB, wB);
+}
+
+// Velocity solves with FIXED anchors and the PREPARE-time separation:
+//   KIND 0  s2SolveContacts_PGS_Baumgarte (reference src/solve_pgs.c:17-122)
+//   KIND 1  s2SolveContacts_PGS_Soft      (reference src/solve_pgs_soft.c:16-125), bias clamp -0.5 * maxBaumgarteVelocity
+//   KIND 2  s2SolveContacts_Jacobi_Soft   (reference src/solve_jacobi.c:21-132), clamp -maxBaumgarteVelocity, writes dv/dw
+template <int KIND> __device__ __forceinline__ void s2bSolveContactFixed(const SolveArgs& a, int t, float inv_h, bool useBias)
+{
+	ContactLoad c = s2bLoadContact(a, t);
+	const SoftCoef soft = c.staticSoft ? a.softStatic : a.softDynamic;
+	s2Vec2 vA = V2(c.velA.x, c.velA.y), vB = V2(c.velB.x, c.velB.y);
+	float wA = c.velA.z, wB = c.velB.z;
+	s2Vec2 normal = V2(c.nf.x, c.nf.y);
+	s2Vec2 tangent = s2RightPerp(normal);
+	float friction = c.nf.z;
+	float2 lam[2] = {a.cc.lambda[0][t], a.cc.lambda[1][t]};
+	float4 r0[2] = {a.cc.r0[0][t], a.cc.r0[1][t]};
+	float4 pm[2] = {a.cc.pm[0][t], a.cc.pm[1][t]};
+	float sep[2] = {a.cc.sep[0][t], a.cc.sep[1][t]};
+
+#pragma unroll
+	for (int j = 0; j < 2; ++j)
+	{
+		if (j < c.pointCount)
+		{
+			float bias = 0.0f, massScale = 1.0f, impulseScale = 0.0f;
+			if (KIND == 0)
+			{
+				if (sep[j] > 0.0f)
+				{
+					bias = sep[j] * inv_h;
+				}
+				else
+				{
+					bias = S2_MAX(s2_baumgarte * inv_h * S2_MIN(0.0f, sep[j] + s2_linearSlop), -s2_maxBaumgarteVelocity);
+				}
+			}
+			else
+			{
+				if (sep[j] > 0.0f)
+				{
+					bias = sep[j] * inv_h;
+				}
+				else if (useBias)
+				{
+					bias = KIND == 1 ? S2_MAX(soft.bias * sep[j], -0.5f * s2_maxBaumgarteVelocity)
+									 : S2_MAX(soft.bias * sep[j], -s2_maxBaumgarteVelocity);
+					massScale = soft.mass;
+					impulseScale = soft.impulse;
+				}
+			}
+			s2Vec2 rA = V2(r0[j].x, r0[j].y), rB = V2(r0[j].z, r0[j].w);
+			s2Vec2 vrB = s2Add(vB, s2CrossSV(wB, rB));
+			s2Vec2 vrA = s2Add(vA, s2CrossSV(wA, rA));
+			float vn = s2Dot(s2Sub(vrB, vrA), normal);
+			float impulse = KIND == 0 ? -pm[j].y * (vn + bias) : -pm[j].y * massScale * (vn + bias) - impulseScale * lam[j].x;
+			float newImpulse = S2_MAX(lam[j].x + impulse, 0.0f);
+			impulse = newImpulse - lam[j].x;
+			lam[j].x = newImpulse;
+			s2Vec2 P = s2MulSV(impulse, normal);
+			vA = s2MulSub(vA, c.mA, P);
+			wA -= c.iA * s2Cross(rA, P);
+			vB = s2MulAdd(vB, c.mB, P);
+			wB += c.iB * s2Cross(rB, P);
+		}
+	}
+
+#pragma unroll
+	for (int j = 0; j < 2; ++j)
+	{
+		if (j < c.pointCount)
+		{
+			s2Vec2 rA = V2(r0[j].x, r0[j].y), rB = V2(r0[j].z, r0[j].w);
+			s2Vec2 vrB = s2Add(vB, s2CrossSV(wB, rB));
+			s2Vec2 vrA = s2Add(vA, s2CrossSV(wA, rA));
+			s2Vec2 dv = s2Sub(vrB, vrA);
+			float vt = s2Dot(dv, tangent);
+			float lambda = pm[j].z * (-vt);
+			float maxFriction = friction * lam[j].x;
+			float newImpulse = S2_CLAMP(lam[j].y + lambda, -maxFriction, maxFriction);
+			lambda = newImpulse - lam[j].y;
+			lam[j].y = newImpulse;
+			s2Vec2 P = s2MulSV(lambda, tangent);
+			vA = s2MulSub(vA, c.mA, P);
+			wA -= c.iA * s2Cross(rA, P);
+			vB = s2MulAdd(vB, c.mB, P);
+			wB += c.iB * s2Cross(rB, P);
+		}
+	}
+
+	a.cc.lambda[0][t] = lam[0];
+	if (c.pointCount == 2)
+	{
+		a.cc.lambda[1][t] = lam[1];
+	}
+	if (KIND == 2)
+	{
+		// Jacobi: accumulate the velocity change instead of applying it (reference src/solve_jacobi.c:126-130). Bodies of
+		// infinite mass receive an exact zero in the reference; they are skipped here.
+		if ((c.mA != 0.0f) || (c.iA != 0.0f))
+		{
+			float4 d = a.bodies.aux0[c.ia];
+			s2Vec2 dvA = s2Add(V2(d.x, d.y), s2Sub(vA, V2(c.velA.x, c.velA.y)));
+			a.bodies.aux0[c.ia] = make_float4(dvA.x, dvA.y, d.z + (wA - c.velA.z), 0.0f);
+		}
+		if ((c.mB != 0.0f) || (c.iB != 0.0f))
+		{
+			float4 d = a.bodies.aux0[c.ib];
+			s2Vec2 dvB = s2Add(V2(d.x, d.y), s2Sub(vB, V2(c.velB.x, c.velB.y)));
+			a.bodies.aux0[c.ib] = make_float4(dvB.x, dvB.y, d.z + (wB - c.velB.z), 0.0f);
+		}
+	}
+	else
+	{
+		s2bStoreContactVelocities(a, c, vA, wA, vB, wB);
+	}
+}
+
+// s2SolveContacts_PGS (reference src/solve_pgs_ngs.c:16-124): Box2D-2.4 order — friction rows first, then normal rows;
+// speculative points (prepare-time separation > 0) are skipped and their impulse zeroed.
+__device__ __forceinline__ void s2bSolveContactPgs(const SolveArgs& a, int t)
+{
+	ContactLoad c = s2bLoadContact(a, t);
+	s2Vec2 vA = V2(c.velA.x, c.velA.y), vB = V2(c.velB.x, c.velB.y);
+	float wA = c.velA.z, wB = c.velB.z;
+	s2Vec2 normal = V2(c.nf.x, c.nf.y);
+	s2Vec2 tangent = s2CrossVS(normal, 1.0f);
+	float friction = c.nf.z;
+	float2 lam[2] = {a.cc.lambda[0][t], a.cc.lambda[1][t]};
+	float4 r0[2] = {a.cc.r0[0][t], a.cc.r0[1][t]};
+	float4 pm[2] = {a.cc.pm[0][t], a.cc.pm[1][t]};
+	float sep[2] = {a.cc.sep[0][t], a.cc.sep[1][t]};
+
+#pragma unroll
+	for (int j = 0; j < 2; ++j)
+	{
+		if (j < c.pointCount)
+		{
+			if (sep[j] > 0.0f)
+			{
+				lam[j].y = 0.0f;
+				continue;
+			}
+			s2Vec2 rA = V2(r0[j].x, r0[j].y), rB = V2(r0[j].z, r0[j].w);
+			s2Vec2 vrB = s2Add(vB, s2CrossSV(wB, rB));
+			s2Vec2 vrA = s2Add(vA, s2CrossSV(wA, rA));
+			float vt = s2Dot(s2Sub(vrB, vrA), tangent);
+			float lambda = pm[j].z * (-vt);
+			float maxFriction = friction * lam[j].x;
+			float newImpulse = S2_CLAMP(lam[j].y + lambda, -maxFriction, maxFriction);
+			lambda = newImpulse - lam[j].y;
+			lam[j].y = newImpulse;
+			s2Vec2 P = s2MulSV(lambda, tangent);
+			vA = s2MulSub(vA, c.mA, P);
+			wA -= c.iA * s2Cross(rA, P);
+			vB = s2MulAdd(vB, c.mB, P);
+			wB += c.iB * s2Cross(rB, P);
+		}
+	}
+
+#pragma unroll
+	for (int j = 0; j < 2; ++j)
+	{
+		if (j < c.pointCount)
+		{
+			if (sep[j] > 0.0f)
+			{
+				lam[j].x = 0.0f;
+				continue;
+			}
+			s2Vec2 rA = V2(r0[j].x, r0[j].y), rB = V2(r0[j].z, r0[j].w);
+			s2Vec2 vrB = s2Add(vB, s2CrossSV(wB, rB));
+			s2Vec2 vrA = s2Add(vA, s2CrossSV(wA, rA));
+			float vn = s2Dot(s2Sub(vrB, vrA), normal);
+			float impulse = -pm[j].y * vn;
+			float newImpulse = S2_MAX(lam[j].x + impulse, 0.0f);
+			impulse = newImpulse - lam[j].x;
+			lam[j].x = newImpulse;
+			s2Vec2 P = s2MulSV(impulse, normal);
+			vA = s2MulSub(vA, c.mA, P);
+			wA -= c.iA * s2Cross(rA, P);
+			vB = s2MulAdd(vB, c.mB, P);
+			wB += c.iB * s2Cross(rB, P);
+		}
+	}
+
+	a.cc.lambda[0][t] = lam[0];
+	if (c.pointCount == 2)
+	{
+		a.cc.lambda[1][t] = lam[1];
+	}
+	s2bStoreContactVelocities(a, c, vA, wA, vB, wB);
+}
+
+// Velocity solves that evaluate the separation at the CURRENT sub-step pose:
+//   KIND 0  s2SolveContacts_TGS_Fixed (reference src/solve_soft_step.c:66-177): soft, clamp -0.5*maxBaumgarte, velocity
+//           and impulse applied at the FIXED prepare-time anchors
+//   KIND 1  s2SolveContacts_TGS       (reference src/solve_tgs_ngs.c:91-201): rigid, speculative bias only, current anchors
+template <int KIND> __device__ __forceinline__ void s2bSolveContactSubstep(const SolveArgs& a, int t, float inv_h, bool useBias)
+{
+	ContactLoad c = s2bLoadContact(a, t);
+	const SoftCoef soft = c.staticSoft ? a.softStatic : a.softDynamic;
+	float4 poseA = a.bodies.pose[c.ia], poseB = a.bodies.pose[c.ib];
+	s2Vec2 vA = V2(c.velA.x, c.velA.y), vB = V2(c.velB.x, c.velB.y);
+	float wA = c.velA.z, wB = c.velB.z;
+	s2Vec2 dcA = V2(poseA.x, poseA.y), dcB = V2(poseB.x, poseB.y);
+	s2Rot qA = R2(poseA.z, poseA.w), qB = R2(poseB.z, poseB.w);
+	s2Vec2 normal = V2(c.nf.x, c.nf.y);
+	s2Vec2 tangent = s2RightPerp(normal);
+	float friction = c.nf.z;
+	float2 lam[2] = {a.cc.lambda[0][t], a.cc.lambda[1][t]};
+	float4 la[2] = {a.cc.anchor[0][t], a.cc.anchor[1][t]};
+	float4 pm[2] = {a.cc.pm[0][t], a.cc.pm[1][t]};
+	float4 r0[2];
+	if (KIND == 0)
+	{
+		r0[0] = a.cc.r0[0][t];
+		r0[1] = a.cc.r0[1][t];
+	}
+
+#pragma unroll
+	for (int j = 0; j < 2; ++j)
+	{
+		if (j < c.pointCount)
+		{
+			s2Vec2 rAc = s2RotateVector(qA, V2(la[j].x, la[j].y));
+			s2Vec2 rBc = s2RotateVector(qB, V2(la[j].z, la[j].w));
+			s2Vec2 rA, rB;
+			float s;
+			float bias = 0.0f, massScale = 1.0f, impulseScale = 0.0f;
+			if (KIND == 0)
+			{
+				s2Vec2 ds = s2Add(s2Sub(dcB, dcA), s2Sub(rBc, rAc));
+				s = s2Dot(ds, normal) + pm[j].x;
+				if (s > 0.0f)
+				{
+					bias = s * inv_h;
+				}
+				else if (useBias)
+				{
+					bias = S2_MAX(soft.bias * s, -0.5f * s2_maxBaumgarteVelocity);
+					massScale = soft.mass;
+					impulseScale = soft.impulse;
+				}
+				rA = V2(r0[j].x, r0[j].y);
+				rB = V2(r0[j].z, r0[j].w);
+			}
+			else
+			{
+				s2Vec2 d = s2Add(s2Sub(dcB, dcA), s2Sub(rBc, rAc));
+				s = s2Dot(d, normal) + pm[j].x;
+				bias = s > 0.0f ? s * inv_h : 0.0f;
+				rA = rAc;
+				rB = rBc;
+			}
+			s2Vec2 vrB = s2Add(vB, s2CrossSV(wB, rB));
+			s2Vec2 vrA = s2Add(vA, s2CrossSV(wA, rA));
+			float vn = s2Dot(s2Sub(vrB, vrA), normal);
+			float impulse = KIND == 0 ? -pm[j].y * massScale * (vn + bias) - impulseScale * lam[j].x : -pm[j].y * (vn + bias);
+			float newImpulse = S2_MAX(lam[j].x + impulse, 0.0f);
+			impulse = newImpulse - lam[j].x;
+			lam[j].x = newImpulse;
+			s2Vec2 P = s2MulSV(impulse, normal);
+			vA = s2MulSub(vA, c.mA, P);
+			wA -= c.iA * s2Cross(rA, P);
+			vB = s2MulAdd(vB, c.mB, P);
+			wB += c.iB * s2Cross(rB, P);
+		}
+	}
+
+#pragma unroll
+	for (int j = 0; j < 2; ++j)
+	{
+		if (j < c.pointCount)
+		{
+			s2Vec2 rA, rB;
+			if (KIND == 0)
+			{
+				rA = V2(r0[j].x, r0[j].y);
+				rB = V2(r0[j].z, r0[j].w);
+			}
+			else
+			{
+				rA = s2RotateVector(qA, V2(la[j].x, la[j].y));
+				rB = s2RotateVector(qB, V2(la[j].z, la[j].w));
+			}
+			s2Vec2 vrB = s2Add(vB, s2CrossSV(wB, rB));
+			s2Vec2 vrA = s2Add(vA, s2CrossSV(wA, rA));
+			float vt = s2Dot(s2Sub(vrB, vrA), tangent);
+			float impulse = -pm[j].z * vt;
+			float maxFriction = friction * lam[j].x;
+			float newImpulse = S2_CLAMP(lam[j].y + impulse, -maxFriction, maxFriction);
+			impulse = newImpulse - lam[j].y;
+			lam[j].y = newImpulse;
+			s2Vec2 P = s2MulSV(impulse, tangent);
+			vA = s2MulSub(vA, c.mA, P);
+			wA -= c.iA * s2Cross(rA, P);
+			vB = s2MulAdd(vB, c.mB, P);
+			wB += c.iB * s2Cross(rB, P);
+		}
+	}
+
+	a.cc.lambda[0][t] = lam[0];
+	if (c.pointCount == 2)
+	{
+		a.cc.lambda[1][t] = lam[1];
+	}
+	s2bStoreContactVelocities(a, c, vA, wA, vB, wB);
+}
+
+// s2SolveContact_NGS (reference src/solve_common.c:328-394): non-linear Gauss-Seidel position pass. Reads and writes
+// deltaPosition and rotation of both bodies; points that were speculative at prepare time are skipped.
+__device__ __forceinline__ void s2bSolveContactNgs(const SolveArgs& a, int t)
+{
+	ContactLoad c = s2bLoadContact(a, t);
+	float4 poseA = a.bodies.pose[c.ia], poseB = a.bodies.pose[c.ib];
+	s2Vec2 dcA = V2(poseA.x, poseA.y), dcB = V2(poseB.x, poseB.y);
+	s2Rot qA = R2(poseA.z, poseA.w), qB = R2(poseB.z, poseB.w);
+	s2Vec2 normal = V2(c.nf.x, c.nf.y);
+
+#pragma unroll
+	for (int j = 0; j < 2; ++j)
+	{
+		if (j < c.pointCount)
+		{
+			if (a.cc.sep[j][t] > 0.0f)
+			{
+				continue;
+			}
+			float4 la = a.cc.anchor[j][t];
+			float adjustedSeparation = a.cc.pm[j][t].x;
+			s2Vec2 rA = s2RotateVector(qA, V2(la.x, la.y));
+			s2Vec2 rB = s2RotateVector(qB, V2(la.z, la.w));
+			s2Vec2 d = s2Add(s2Sub(dcB, dcA), s2Sub(rB, rA));
+			float separation = s2Dot(d, normal) + adjustedSeparation;
+			float C = S2_CLAMP(s2_baumgarte * (separation + s2_linearSlop), -s2_maxLinearCorrection, 0.0f);
+			float rnA = s2Cross(rA, normal);
+			float rnB = s2Cross(rB, normal);
+			float K = c.mA + c.mB + c.iA * rnA * rnA + c.iB * rnB * rnB;
+			float impulse = K > 0.0f ? -C / K : 0.0f;
+			s2Vec2 P = s2MulSV(impulse, normal);
+			dcA = s2MulSub(dcA, c.mA, P);
+			qA = s2IntegrateRot(qA, -c.iA * s2Cross(rA, P));
+			dcB = s2MulAdd(dcB, c.mB, P);
+			qB = s2IntegrateRot(qB, c.iB * s2Cross(rB, P));
+		}
+	}
+
+	if ((c.mA != 0.0f) || (c.iA != 0.0f))
+	{
+		a.bodies.pose[c.ia] = make_float4(dcA.x, dcA.y, qA.s, qA.c);
+	}
+	if ((c.mB != 0.0f) || (c.iB != 0.0f))
+	{
+		a.bodies.pose[c.ib] = make_float4(dcB.x, dcB.y, qB.s, qB.c);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TGS_Sticky (reference src/solve_tgs_sticky.c)
+// ---------------------------------------------------------------------------------------------------------------
+
+// s2PrepareContacts_Sticky (reference src/solve_tgs_sticky.c:19-165): no warm starting; friction acts at anchors that
+// persist across steps while the pair keeps its manifold and the bodies have not rotated / separated too far. Reads and
+// WRITES the persistent manifold (friction anchors, friction normals, frictionPersisted).
+__device__ __forceinline__ void s2bPrepareContactSticky(const SolveArgs& a, int t)
+{
+	const ConstraintView& cc = a.cc;
+	int slot = cc.src[t];
+	int2 bodies = a.contacts.bodies[slot];
+	int4 info = a.contacts.info[slot];
+	float4 mnf = a.contacts.nf[slot];
+	int pointCount = S2B_CI_COUNT(info.x);
+
+	float4 velA = a.bodies.vel[bodies.x], velB = a.bodies.vel[bodies.y];
+	float4 poseA = a.bodies.pose[bodies.x], poseB = a.bodies.pose[bodies.y];
+	float4 orgA = a.bodies.org[bodies.x], orgB = a.bodies.org[bodies.y];
+	float4 posA = a.bodies.pos[bodies.x], posB = a.bodies.pos[bodies.y];
+	float mA = velA.w, mB = velB.w, iA = posA.z, iB = posB.z;
+	s2Rot qA = R2(poseA.z, poseA.w), qB = R2(poseB.z, poseB.w);
+	s2Vec2 lcA = V2(orgA.z, orgA.w), lcB = V2(orgB.z, orgB.w);
+	s2Vec2 normal = V2(mnf.x, mnf.y);
+	s2Vec2 tangent = s2RightPerp(normal);
+
+	unsigned flags = pointCount == 2 ? S2B_CF_TWO_POINTS : 0;
+	cc.idx[t] = make_int2(bodies.x, (int)((unsigned)bodies.y | flags));
+	cc.nf[t] = make_float4(normal.x, normal.y, mnf.z, iA);
+
+	s2Vec2 lA[2], lB[2], rA0[2], rB0[2];
+	float adjSep[2], normalMass[2], tangentMass[2], tangentSeparation[2];
+	s2Vec2 lfA[2], lfB[2];
+	float4 manifoldAnchor[2];
+	for (int j = 0; j < 2; ++j)
+	{
+		lA[j] = lB[j] = rA0[j] = rB0[j] = lfA[j] = lfB[j] = V2(0.0f, 0.0f);
+		adjSep[j] = normalMass[j] = tangentMass[j] = tangentSeparation[j] = 0.0f;
+		manifoldAnchor[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		if (j < pointCount)
+		{
+			float4 la = a.contacts.anchor[j][slot];
+			manifoldAnchor[j] = la;
+			float separation = a.contacts.impulse[j][slot].x;
+			lA[j] = s2Sub(V2(la.x, la.y), lcA);
+			lB[j] = s2Sub(V2(la.z, la.w), lcB);
+			s2Vec2 rA = s2RotateVector(qA, lA[j]);
+			s2Vec2 rB = s2RotateVector(qB, lB[j]);
+			rA0[j] = rA;
+			rB0[j] = rB;
+			adjSep[j] = separation - s2Dot(s2Sub(rB, rA), normal);
+			float rtA = s2Cross(rA, tangent);
+			float rtB = s2Cross(rB, tangent);
+			float kTangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
+			tangentMass[j] = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
+			float rnA = s2Cross(rA, normal);
+			float rnB = s2Cross(rB, normal);
+			float kNormal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+			normalMass[j] = kNormal > 0.0f ? 1.0f / kNormal : 0.0f;
+		}
+	}
+
+	s2Vec2 cA = V2(posA.x, posA.y), cB = V2(posB.x, posB.y);
+	bool frictionConfirmed = false;
+	if (info.x & S2B_CI_FRICTION_PERSISTED)
+	{
+		int confirmCount = 0;
+		for (int j = 0; j < pointCount; ++j)
+		{
+			float4 fa = a.contacts.fanchor[j][slot];
+			float4 fn = a.contacts.fnormal[j][slot];
+			s2Vec2 normalA = s2RotateVector(qA, V2(fn.x, fn.y));
+			s2Vec2 normalB = s2RotateVector(qB, V2(fn.z, fn.w));
+			float nn = s2Dot(normalA, normalB);
+			if (nn < 0.98f)
+			{
+				break; // relative rotation invalidated the cached anchors
+			}
+			lfA[j] = s2Sub(V2(fa.x, fa.y), lcA);
+			lfB[j] = s2Sub(V2(fa.z, fa.w), lcB);
+			s2Vec2 rAf = s2RotateVector(qA, lfA[j]);
+			s2Vec2 rBf = s2RotateVector(qB, lfB[j]);
+			s2Vec2 offset = s2Add(s2Sub(cB, cA), s2Sub(rBf, rAf));
+			float normalSeparation = s2Dot(offset, normalA);
+			if (S2_ABS(normalSeparation) > 2.0f * s2_linearSlop)
+			{
+				break; // normal separation invalidated the cached anchors
+			}
+			tangentSeparation[j] = s2Dot(s2Sub(cB, cA), tangent);
+			float rtA = s2Cross(rAf, tangent);
+			float rtB = s2Cross(rBf, tangent);
+			float kTangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
+			tangentMass[j] = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
+			confirmCount += 1;
+		}
+		frictionConfirmed = confirmCount == pointCount;
+	}
+
+	if (frictionConfirmed == false)
+	{
+		for (int j = 0; j < pointCount; ++j)
+		{
+			s2Vec2 fnA = s2InvRotateVector(qA, normal);
+			s2Vec2 fnB = s2InvRotateVector(qB, normal);
+			a.contacts.fnormal[j][slot] = make_float4(fnA.x, fnA.y, fnB.x, fnB.y);
+			a.contacts.fanchor[j][slot] = manifoldAnchor[j];
+			lfA[j] = lA[j];
+			lfB[j] = lB[j];
+			tangentSeparation[j] = s2Dot(s2Sub(cB, cA), tangent);
+			float rtA = s2Cross(rA0[j], tangent);
+			float rtB = s2Cross(rB0[j], tangent);
+			float kTangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
+			tangentMass[j] = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
+		}
+	}
+	a.contacts.info[slot] = make_int4(info.x | S2B_CI_FRICTION_PERSISTED, info.y, info.z, info.w);
+
+	for (int j = 0; j < 2; ++j)
+	{
+		cc.anchor[j][t] = make_float4(lA[j].x, lA[j].y, lB[j].x, lB[j].y);
+		cc.pm[j][t] = make_float4(adjSep[j], normalMass[j], tangentMass[j], j == 0 ? iB : 0.0f);
+		cc.lambda[j][t] = make_float2(0.0f, 0.0f);
+		cc.fanchor[j][t] = make_float4(lfA[j].x, lfA[j].y, lfB[j].x, lfB[j].y);
+		cc.tsep[j][t] = make_float2(tangentSeparation[j], 0.0f);
+	}
+}
+
+// s2SolveContacts_TGS_Sticky (reference src/solve_tgs_sticky.c:167-310): Baumgarte normal rows at the current anchors
+// (factor 0.8), then friction as a *position-level* constraint at the persistent friction anchors (factor 0.5) limited by
+// half the friction coefficient times the sum of the normal impulses; hitting the limit un-persists the anchors.
+__device__ __forceinline__ void s2bSolveContactSticky(const SolveArgs& a, int t, float inv_h, bool useBias)
+{
+	ContactLoad c = s2bLoadContact(a, t);
+	const float contactBaumgarte = 0.8f;
+	const float frictionBaumgarte = 0.5f;
+	float4 poseA = a.bodies.pose[c.ia], poseB = a.bodies.pose[c.ib];
+	s2Vec2 vA = V2(c.velA.x, c.velA.y), vB = V2(c.velB.x, c.velB.y);
+	float wA = c.velA.z, wB = c.velB.z;
+	s2Vec2 dcA = V2(poseA.x, poseA.y), dcB = V2(poseB.x, poseB.y);
+	s2Rot qA = R2(poseA.z, poseA.w), qB = R2(poseB.z, poseB.w);
+	s2Vec2 normal = V2(c.nf.x, c.nf.y);
+	s2Vec2 tangent = s2RightPerp(normal);
+	float friction = c.nf.z;
+	float2 lam[2] = {a.cc.lambda[0][t], a.cc.lambda[1][t]};
+	float totalNormalImpulse = 0.0f;
+	bool unpersist = false;
+
+#pragma unroll
+	for (int j = 0; j < 2; ++j)
+	{
+		if (j < c.pointCount)
+		{
+			float4 la = a.cc.anchor[j][t];
+			float4 pm = a.cc.pm[j][t];
+			s2Vec2 rA = s2RotateVector(qA, V2(la.x, la.y));
+			s2Vec2 rB = s2RotateVector(qB, V2(la.z, la.w));
+			s2Vec2 d = s2Add(s2Sub(dcB, dcA), s2Sub(rB, rA));
+			float separation = s2Dot(d, normal) + pm.x;
+			float bias = 0.0f;
+			if (separation > 0.0f)
+			{
+				bias = separation * inv_h;
+			}
+			else if (useBias)
+			{
+				bias = S2_MAX(-s2_maxBaumgarteVelocity, contactBaumgarte * separation * inv_h);
+			}
+			s2Vec2 vrA = s2Add(vA, s2CrossSV(wA, rA));
+			s2Vec2 vrB = s2Add(vB, s2CrossSV(wB, rB));
+			float vn = s2Dot(s2Sub(vrB, vrA), normal);
+			float impulse = -pm.y * (vn + bias);
+			float newImpulse = S2_MAX(lam[j].x + impulse, 0.0f);
+			impulse = newImpulse - lam[j].x;
+			lam[j].x = newImpulse;
+			totalNormalImpulse += lam[j].x;
+			s2Vec2 P = s2MulSV(impulse, normal);
+			vA = s2MulSub(vA, c.mA, P);
+			wA -= c.iA * s2Cross(rA, P);
+			vB = s2MulAdd(vB, c.mB, P);
+			wB += c.iB * s2Cross(rB, P);
+		}
+	}
+
+#pragma unroll
+	for (int j = 0; j < 2; ++j)
+	{
+		if (j < c.pointCount)
+		{
+			float4 lf = a.cc.fanchor[j][t];
+			float tangentMass = a.cc.pm[j][t].z;
+			float tangentSeparation = a.cc.tsep[j][t].x;
+			s2Vec2 rAf = s2RotateVector(qA, V2(lf.x, lf.y));
+			s2Vec2 rBf = s2RotateVector(qB, V2(lf.z, lf.w));
+			s2Vec2 d = s2Add(s2Sub(dcB, dcA), s2Sub(rBf, rAf));
+			float separation = s2Dot(d, tangent) + tangentSeparation;
+			float bias = useBias ? frictionBaumgarte * separation * inv_h : 0.0f;
+			s2Vec2 vrA = s2Add(vA, s2CrossSV(wA, rAf));
+			s2Vec2 vrB = s2Add(vB, s2CrossSV(wB, rBf));
+			float vt = s2Dot(s2Sub(vrB, vrA), tangent);
+			float impulse = -tangentMass * (vt + bias);
+			float maxFriction = 0.5f * friction * totalNormalImpulse;
+			float newImpulse = lam[j].y + impulse;
+			if (newImpulse < -maxFriction)
+			{
+				newImpulse = -maxFriction;
+				unpersist = true;
+			}
+			else if (newImpulse > maxFriction)
+			{
+				newImpulse = maxFriction;
+				unpersist = true;
+			}
+			impulse = newImpulse - lam[j].y;
+			lam[j].y = newImpulse;
+			s2Vec2 P = s2MulSV(impulse, tangent);
+			vA = s2MulSub(vA, c.mA, P);
+			wA -= c.iA * s2Cross(rAf, P);
+			vB = s2MulAdd(vB, c.mB, P);
+			wB += c.iB * s2Cross(rBf, P);
+		}
+	}
+
+	a.cc.lambda[0][t] = lam[0];
+	if (c.pointCount == 2)
+	{
+		a.cc.lambda[1][t] = lam[1];
+	}
+	if (unpersist)
+	{
+		int slot = a.cc.src[t];
+		int4 info = a.contacts.info[slot];
+		a.contacts.info[slot] = make_int4(info.x & ~S2B_CI_FRICTION_PERSISTED, info.y, info.z, info.w);
+	}
+	s2bStoreContactVelocities(a, c, vA, wA, vB, wB);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// XPBD (reference src/solve_xpbd.c)
+// ---------------------------------------------------------------------------------------------------------------
+
+// s2SolveContactPositions_XPBD (reference src/solve_xpbd.c:88-216): position-level non-penetration and static friction.
+__device__ __forceinline__ void s2bSolveContactXpbdPositions(const SolveArgs& a, int t, float h)
+{
+	ContactLoad c = s2bLoadContact(a, t);
+	const float baseCompliance = 0.0f;
+	float compliance = (c.mA == 0.0f || c.mB == 0.0f) ? 0.25f * baseCompliance : baseCompliance;
+	float4 poseA = a.bodies.pose[c.ia], poseB = a.bodies.pose[c.ib];
+	s2Vec2 dcA = V2(poseA.x, poseA.y), dcB = V2(poseB.x, poseB.y);
+	s2Rot qA = R2(poseA.z, poseA.w), qB = R2(poseB.z, poseB.w);
+	s2Vec2 normal = V2(c.nf.x, c.nf.y);
+	s2Vec2 tangent = s2CrossVS(normal, 1.0f);
+	float friction = c.nf.z;
+	float2 lam[2] = {a.cc.lambda[0][t], a.cc.lambda[1][t]};
+
+#pragma unroll
+	for (int j = 0; j < 2; ++j)
+	{
+		if (j < c.pointCount)
+		{
+			float4 la = a.cc.anchor[j][t];
+			float4 r0 = a.cc.r0[j][t];
+			s2Vec2 rA = s2RotateVector(qA, V2(la.x, la.y));
+			s2Vec2 rB = s2RotateVector(qB, V2(la.z, la.w));
+			s2Vec2 drA = s2Sub(rA, V2(r0.x, r0.y));
+			s2Vec2 drB = s2Sub(rB, V2(r0.z, r0.w));
+			s2Vec2 ds = s2Add(s2Sub(dcB, dcA), s2Sub(drB, drA));
+			float C = s2Dot(ds, normal) + a.cc.sep[j][t];
+			if (C > 0)
+			{
+				lam[j].x = 0.0f;
+				continue;
+			}
+			C = S2_MAX(-s2_maxBaumgarteVelocity * h, C);
+			float rnA = s2Cross(rA, normal);
+			float rnB = s2Cross(rB, normal);
+			float kA = c.mA + c.iA * rnA * rnA;
+			float kB = c.mB + c.iB * rnB * rnB;
+			float lambda = -C / (kA + kB + compliance);
+			lam[j].x = lambda;
+			s2Vec2 P = s2MulSV(lambda, normal);
+			dcA = s2MulSub(dcA, c.mA, P);
+			qA = s2IntegrateRot(qA, -c.iA * s2Cross(rA, P));
+			dcB = s2MulAdd(dcB, c.mB, P);
+			qB = s2IntegrateRot(qB, c.iB * s2Cross(rB, P));
+		}
+	}
+
+#pragma unroll
+	for (int j = 0; j < 2; ++j)
+	{
+		if (j < c.pointCount)
+		{
+			float4 la = a.cc.anchor[j][t];
+			float4 r0 = a.cc.r0[j][t];
+			s2Vec2 rA = s2RotateVector(qA, V2(la.x, la.y));
+			s2Vec2 rB = s2RotateVector(qB, V2(la.z, la.w));
+			s2Vec2 drA = s2Sub(rA, V2(r0.x, r0.y));
+			s2Vec2 drB = s2Sub(rB, V2(r0.z, r0.w));
+			s2Vec2 dp = s2Add(s2Sub(dcB, dcA), s2Sub(drB, drA));
+			float C = s2Dot(dp, tangent);
+			float rtA = s2Cross(rA, tangent);
+			float rtB = s2Cross(rB, tangent);
+			float kA = c.mA + c.iA * rtA * rtA;
+			float kB = c.mB + c.iB * rtB * rtB;
+			float lambda = -C / (kA + kB);
+			float maxLambda = friction * lam[j].x;
+			if (lambda < -maxLambda || maxLambda < lambda)
+			{
+				lam[j].y = 0.0f; // beyond the static friction cone: skipped, not clamped (reference :190-194)
+				continue;
+			}
+			lam[j].y = lambda;
+			s2Vec2 P = s2MulSV(lambda, tangent);
+			dcA = s2MulSub(dcA, c.mA, P);
+			qA = s2IntegrateRot(qA, -c.iA * s2Cross(rA, P));
+			dcB = s2MulAdd(dcB, c.mB, P);
+			qB = s2IntegrateRot(qB, c.iB * s2Cross(rB, P));
+		}
+	}
+
+	a.cc.lambda[0][t] = lam[0];
+	if (c.pointCount == 2)
+	{
+		a.cc.lambda[1][t] = lam[1];
+	}
+	if ((c.mA != 0.0f) || (c.iA != 0.0f))
+	{
+		a.bodies.pose[c.ia] = make_float4(dcA.x, dcA.y, qA.s, qA.c);
+	}
+	if ((c.mB != 0.0f) || (c.iB != 0.0f))
+	{
+		a.bodies.pose[c.ib] = make_float4(dcB.x, dcB.y, qB.s, qB.c);
+	}
+}
+
+// s2SolveContactVelocities_XPBD (reference src/solve_xpbd.c:218-338): velocity relaxation + kinetic friction
+__device__ __forceinline__ void s2bSolveContactXpbdVelocities(const SolveArgs& a, int t, float h)
+{
+	ContactLoad c = s2bLoadContact(a, t);
+	float inv_h = h > 0.0f ? 1.0f / h : 0.0f;
+	float4 poseA = a.bodies.pose[c.ia], poseB = a.bodies.pose[c.ib];
+	s2Rot qA = R2(poseA.z, poseA.w), qB = R2(poseB.z, poseB.w);
+	s2Vec2 vA = V2(c.velA.x, c.velA.y), vB = V2(c.velB.x, c.velB.y);
+	float wA = c.velA.z, wB = c.velB.z;
+	s2Vec2 normal = V2(c.nf.x, c.nf.y);
+	s2Vec2 tangent = s2CrossVS(normal, 1.0f);
+	float friction = c.nf.z;
+	float2 lam[2] = {a.cc.lambda[0][t], a.cc.lambda[1][t]};
+
+#pragma unroll
+	for (int j = 0; j < 2; ++j)
+	{
+		if (j < c.pointCount)
+		{
+			if (lam[j].x == 0.0f)
+			{
+				continue;
+			}
+			float4 la = a.cc.anchor[j][t];
+			s2Vec2 rA = s2RotateVector(qA, V2(la.x, la.y));
+			s2Vec2 rB = s2RotateVector(qB, V2(la.z, la.w));
+			s2Vec2 vrB = s2Add(vB, s2CrossSV(wB, rB));
+			s2Vec2 vrA = s2Add(vA, s2CrossSV(wA, rA));
+			s2Vec2 dv = s2Sub(vrB, vrA);
+			float rnA = s2Cross(rA, normal);
+			float rnB = s2Cross(rB, normal);
+			float kA = c.mA + c.iA * rnA * rnA;
+			float kB = c.mB + c.iB * rnB * rnB;
+			float vn = s2Dot(dv, normal);
+			float lambda = -vn / (kA + kB);
+			s2Vec2 P = s2MulSV(lambda, normal);
+			vA = s2MulSub(vA, c.mA, P);
+			wA -= c.iA * s2Cross(rA, P);
+			vB = s2MulAdd(vB, c.mB, P);
+			wB += c.iB * s2Cross(rB, P);
+		}
+	}
+
+#pragma unroll
+	for (int j = 0; j < 2; ++j)
+	{
+		if (j < c.pointCount)
+		{
+			float4 la = a.cc.anchor[j][t];
+			s2Vec2 rA = s2RotateVector(qA, V2(la.x, la.y));
+			s2Vec2 rB = s2RotateVector(qB, V2(la.z, la.w));
+			s2Vec2 vrB = s2Add(vB, s2CrossSV(wB, rB));
+			s2Vec2 vrA = s2Add(vA, s2CrossSV(wA, rA));
+			s2Vec2 dv = s2Sub(vrB, vrA);
+			float vt = s2Dot(dv, tangent);
+			if (vt == 0.0f)
+			{
+				continue;
+			}
+			float rtA = s2Cross(rA, tangent);
+			float rtB = s2Cross(rB, tangent);
+			float kA = c.mA + c.iA * rtA * rtA;
+			float kB = c.mB + c.iB * rtB * rtB;
+			float maxFrictionImpulse = friction * lam[j].x;
+			float huf = (maxFrictionImpulse * inv_h) * (kA + kB);
+			float abs_vt = S2_ABS(vt);
+			float Cdot = (vt / abs_vt) * S2_MIN(huf, abs_vt);
+			float lambda = -Cdot / (kA + kB);
+			lam[j].y = lambda;
+			s2Vec2 P = s2MulSV(lambda, tangent);
+			vA = s2MulSub(vA, c.mA, P);
+			wA -= c.iA * s2Cross(rA, P);
+			vB = s2MulAdd(vB, c.mB, P);
+			wB += c.iB * s2Cross(rB, P);
+		}
+	}
+
+	a.cc.lambda[0][t] = lam[0];
+	if (c.pointCount == 2)
+	{
+		a.cc.lambda[1][t] = lam[1];
+	}
+	s2bStoreContactVelocities(a, c, vA, wA, vB, wB);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// body passes of the Jacobi and XPBD variants
+// ---------------------------------------------------------------------------------------------------------------
+
+// reset of dv / dw (reference src/solve_jacobi.c:176-186)
+__device__ __forceinline__ void s2bJacobiReset(const SolveArgs& a, int i)
+{
+	if (a.bodies.flags[i] & S2B_BODY_VALID)
+	{
+		a.bodies.aux0[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	}
+}
+
+// apply and clear the accumulated velocity change of one sweep (reference src/solve_jacobi.c:233-245)
+__device__ __forceinline__ void s2bJacobiApply(const SolveArgs& a, int i)
+{
+	if ((a.bodies.flags[i] & S2B_BODY_VALID) == 0)
+	{
+		return;
+	}
+	float4 vel = a.bodies.vel[i];
+	float4 d = a.bodies.aux0[i];
+	s2Vec2 v = s2Add(V2(vel.x, vel.y), V2(d.x, d.y));
+	float w = vel.z + d.z;
+	a.bodies.vel[i] = make_float4(v.x, v.y, w, vel.w);
+	a.bodies.aux0[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+// XPBD integrates velocities AND positions up front and remembers the previous pose (reference src/solve_xpbd.c:408-443);
+// every non-static body, kinematic ones included
+__device__ __forceinline__ void s2bXpbdIntegrate(const SolveArgs& a, int i, float h)
+{
+	unsigned f = a.bodies.flags[i];
+	if ((f & S2B_BODY_VALID) == 0 || S2B_BODY_TYPE(f) == S2B_BODY_STATIC)
+	{
+		return;
+	}
+	float4 vel = a.bodies.vel[i];
+	float4 frc = a.bodies.frc[i];
+	float4 prm = a.bodies.prm[i];
+	float4 pose = a.bodies.pose[i];
+	float invMass = vel.w, invI = prm.w, mass = frc.w;
+	s2Vec2 v = V2(vel.x, vel.y);
+	float w = vel.z;
+	s2Vec2 gravity = V2(a.gravity.x, a.gravity.y);
+	v = s2Add(v, s2MulSV(h * invMass, s2MulAdd(V2(frc.x, frc.y), mass * prm.z, gravity)));
+	w = w + h * invI * frc.z;
+	v = s2MulSV(1.0f / (1.0f + h * prm.x), v);
+	w *= 1.0f / (1.0f + h * prm.y);
+	a.bodies.vel[i] = make_float4(v.x, v.y, w, invMass);
+	a.bodies.aux0[i] = pose; // deltaPosition0, rot0
+	s2Vec2 dp = s2MulAdd(V2(pose.x, pose.y), h, v);
+	s2Rot q = s2IntegrateRot(R2(pose.z, pose.w), h * w);
+	a.bodies.pose[i] = make_float4(dp.x, dp.y, q.s, q.c);
+}
+
+// velocities from the position change of the sub-step (reference src/solve_xpbd.c:457-483); dynamic bodies only
+__device__ __forceinline__ void s2bXpbdProjectVelocity(const SolveArgs& a, int i, float inv_h)
+{
+	unsigned f = a.bodies.flags[i];
+	if ((f & S2B_BODY_VALID) == 0 || S2B_BODY_TYPE(f) != S2B_BODY_DYNAMIC)
+	{
+		return;
+	}
+	float4 vel = a.bodies.vel[i];
+	float4 pose = a.bodies.pose[i];
+	float4 pose0 = a.bodies.aux0[i];
+	s2Vec2 v = s2MulSV(inv_h, s2Sub(V2(pose.x, pose.y), V2(pose0.x, pose0.y)));
+	float w = s2ComputeAngularVelocity(R2(pose0.z, pose0.w), R2(pose.z, pose.w), inv_h);
+	a.bodies.vel[i] = make_float4(v.x, v.y, w, vel.w);
+}
+
+// XPBD finalises dynamic bodies only (reference src/solve_xpbd.c:497-511)
+__device__ __forceinline__ void s2bXpbdFinalize(const SolveArgs& a, int i)
+{
+	unsigned f = a.bodies.flags[i];
+	if ((f & S2B_BODY_VALID) == 0 || S2B_BODY_TYPE(f) != S2B_BODY_DYNAMIC)
+	{
+		return;
+	}
+	float4 pos = a.bodies.pos[i];
+	float4 pose = a.bodies.pose[i];
+	s2Vec2 p = s2Add(V2(pos.x, pos.y), V2(pose.x, pose.y));
+	a.bodies.pos[i] = make_float4(p.x, p.y, pos.z, pos.w);
+	a.bodies.pose[i] = make_float4(0.0f, 0.0f, pose.z, pose.w);
 }

@@ -483,3 +483,226 @@ __device__ __forceinline__ void s2bSolveJointBaumgarte(const SolveArgs& a, int t
 	}
 	s2bSolveRevoluteVelocity<JSOLVE_BAUMGARTE>(a, t, h, inv_h, useBias);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// s2SolveRevolute (reference src/revolute_joint.c:152-303): rigid velocity solve used by PGS_NGS and TGS_NGS — motor,
+// limits with a speculative max(C, 0)/h term, point-to-point with the pivot mass computed at prepare time.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void s2bSolveRevoluteRigid(const SolveArgs& a, int t, float h)
+{
+	const JointConstraintView& jc = a.jc;
+	int4 head = jc.head[t];
+	int ia = head.y, ib = head.z;
+	float4 anchor = jc.anchor[t];
+	float4 mass = jc.mass[t];
+	float4 d0 = jc.d0ax[t];
+	float4 lim = jc.lim[t];
+	float4 motor = jc.motor[t];
+	float4 pv = jc.pivot[t];
+	float4 imp = jc.imp[t];
+	float4 limp = jc.limp[t];
+	float4 velA = a.bodies.vel[ia], velB = a.bodies.vel[ib];
+	float4 poseA = a.bodies.pose[ia], poseB = a.bodies.pose[ib];
+	s2Vec2 vA = V2(velA.x, velA.y), vB = V2(velB.x, velB.y);
+	float wA = velA.z, wB = velB.z;
+	float mA = mass.x, iA = mass.y, mB = mass.z, iB = mass.w;
+	float axialMass = d0.z;
+	s2Rot qA = R2(poseA.z, poseA.w), qB = R2(poseB.z, poseB.w);
+	bool fixedRotation = (iA + iB == 0.0f);
+
+	if ((head.x & S2B_JOINT_ENABLE_MOTOR) && fixedRotation == false)
+	{
+		float Cdot = wB - wA - motor.y;
+		float impulse = -axialMass * Cdot;
+		float oldImpulse = imp.z;
+		float maxImpulse = h * motor.x;
+		imp.z = S2_CLAMP(imp.z + impulse, -maxImpulse, maxImpulse);
+		impulse = imp.z - oldImpulse;
+		wA -= iA * impulse;
+		wB += iB * impulse;
+	}
+
+	if ((head.x & S2B_JOINT_ENABLE_LIMIT) && fixedRotation == false)
+	{
+		float angle = s2RelativeAngle(qB, qA) - lim.x;
+		{
+			float C = angle - lim.y;
+			float Cdot = wB - wA;
+			float impulse = -axialMass * (Cdot + S2_MAX(C, 0.0f) / h);
+			float oldImpulse = limp.x;
+			limp.x = S2_MAX(limp.x + impulse, 0.0f);
+			impulse = limp.x - oldImpulse;
+			wA -= iA * impulse;
+			wB += iB * impulse;
+		}
+		{
+			float C = lim.z - angle;
+			float Cdot = wA - wB;
+			float impulse = -axialMass * (Cdot + S2_MAX(C, 0.0f) / h);
+			float oldImpulse = limp.y;
+			limp.y = S2_MAX(limp.y + impulse, 0.0f);
+			impulse = limp.y - oldImpulse;
+			wA += iA * impulse;
+			wB -= iB * impulse;
+		}
+	}
+
+	{
+		s2Vec2 rA = s2RotateVector(qA, V2(anchor.x, anchor.y));
+		s2Vec2 rB = s2RotateVector(qB, V2(anchor.z, anchor.w));
+		s2Vec2 Cdot = s2Sub(s2Add(vB, s2CrossSV(wB, rB)), s2Add(vA, s2CrossSV(wA, rA)));
+		s2Mat22 pivot;
+		pivot.cx = V2(pv.x, pv.y);
+		pivot.cy = V2(pv.z, pv.w);
+		s2Vec2 impulse = s2MulMV(pivot, s2Neg(Cdot));
+		imp.x += impulse.x;
+		imp.y += impulse.y;
+		vA = s2MulSub(vA, mA, impulse);
+		wA -= iA * s2Cross(rA, impulse);
+		vB = s2MulAdd(vB, mB, impulse);
+		wB += iB * s2Cross(rB, impulse);
+	}
+
+	jc.imp[t] = imp;
+	jc.limp[t] = limp;
+	s2bStoreJointVelocities(a, ia, ib, velA, velB, vA, wA, vB, wB, mA, iA, mB, iB);
+}
+
+// s2SolveJoint dispatch (reference src/joint.c:329-345)
+__device__ __forceinline__ void s2bSolveJointRigid(const SolveArgs& a, int t, float h)
+{
+	if (S2B_JOINT_TYPE(a.jc.head[t].x) == S2B_JOINT_MOUSE)
+	{
+		s2bSolveMouse(a, t);
+		return;
+	}
+	s2bSolveRevoluteRigid(a, t, h);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// s2SolveRevolutePosition (reference src/revolute_joint.c:305-419): NGS position pass for the revolute joint (angular
+// limit + point-to-point with a fresh 2x2 mass); s2SolveJointPosition does nothing for a mouse joint (joint.c:349-361).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void s2bSolveJointPosition(const SolveArgs& a, int t)
+{
+	const JointConstraintView& jc = a.jc;
+	int4 head = jc.head[t];
+	if (S2B_JOINT_TYPE(head.x) == S2B_JOINT_MOUSE)
+	{
+		return;
+	}
+	int ia = head.y, ib = head.z;
+	float4 anchor = jc.anchor[t];
+	float4 mass = jc.mass[t];
+	float4 d0 = jc.d0ax[t];
+	float4 lim = jc.lim[t];
+	float4 poseA = a.bodies.pose[ia], poseB = a.bodies.pose[ib];
+	s2Vec2 dcA = V2(poseA.x, poseA.y), dcB = V2(poseB.x, poseB.y);
+	s2Rot qA = R2(poseA.z, poseA.w), qB = R2(poseB.z, poseB.w);
+	float mA = mass.x, iA = mass.y, mB = mass.z, iB = mass.w;
+	float axialMass = d0.z;
+	bool fixedRotation = (iA + iB == 0.0f);
+
+	if ((head.x & S2B_JOINT_ENABLE_LIMIT) && fixedRotation == false)
+	{
+		float angle = s2RelativeAngle(qB, qA) - lim.x;
+		float C = 0.0f;
+		if (S2_ABS(lim.z - lim.y) < 2.0f * s2_angularSlop)
+		{
+			C = S2_CLAMP(angle - lim.y, -s2_maxAngularCorrection, s2_maxAngularCorrection);
+		}
+		else if (angle <= lim.y)
+		{
+			C = S2_CLAMP(angle - lim.y + s2_angularSlop, -s2_maxAngularCorrection, 0.0f);
+		}
+		else if (angle >= lim.z)
+		{
+			C = S2_CLAMP(angle - lim.z - s2_angularSlop, 0.0f, s2_maxAngularCorrection);
+		}
+		float limitImpulse = -axialMass * C;
+		qA = s2IntegrateRot(qA, -iA * limitImpulse);
+		qB = s2IntegrateRot(qB, iB * limitImpulse);
+	}
+
+	{
+		s2Vec2 rA = s2RotateVector(qA, V2(anchor.x, anchor.y));
+		s2Vec2 rB = s2RotateVector(qB, V2(anchor.z, anchor.w));
+		s2Vec2 C = s2Add(s2Add(s2Sub(dcB, dcA), s2Sub(rB, rA)), V2(d0.x, d0.y));
+		s2Mat22 K;
+		K.cx.x = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
+		K.cx.y = -iA * rA.x * rA.y - iB * rB.x * rB.y;
+		K.cy.x = K.cx.y;
+		K.cy.y = mA + mB + iA * rA.x * rA.x + iB * rB.x * rB.x;
+		s2Vec2 impulse = s2Solve22(K, s2Neg(C));
+		dcA = s2MulSub(dcA, mA, impulse);
+		qA = s2IntegrateRot(qA, -iA * s2Cross(rA, impulse));
+		dcB = s2MulAdd(dcB, mB, impulse);
+		qB = s2IntegrateRot(qB, iB * s2Cross(rB, impulse));
+	}
+
+	if ((mA != 0.0f) || (iA != 0.0f))
+	{
+		a.bodies.pose[ia] = make_float4(dcA.x, dcA.y, qA.s, qA.c);
+	}
+	if ((mB != 0.0f) || (iB != 0.0f))
+	{
+		a.bodies.pose[ib] = make_float4(dcB.x, dcB.y, qB.s, qB.c);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// s2SolveJoint_XPBD (reference src/joint.c:447-463): mouse -> s2SolveMouse; revolute -> s2SolveRevolute_XPBD
+// (src/revolute_joint.c:825-888): distance constraint along the current separation, zero compliance.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void s2bSolveJointXpbd(const SolveArgs& a, int t)
+{
+	const JointConstraintView& jc = a.jc;
+	int4 head = jc.head[t];
+	if (S2B_JOINT_TYPE(head.x) == S2B_JOINT_MOUSE)
+	{
+		s2bSolveMouse(a, t);
+		return;
+	}
+	const float compliance = 0.0f;
+	int ia = head.y, ib = head.z;
+	float4 anchor = jc.anchor[t];
+	float4 mass = jc.mass[t];
+	float4 d0 = jc.d0ax[t];
+	float4 poseA = a.bodies.pose[ia], poseB = a.bodies.pose[ib];
+	s2Vec2 dcA = V2(poseA.x, poseA.y), dcB = V2(poseB.x, poseB.y);
+	s2Rot qA = R2(poseA.z, poseA.w), qB = R2(poseB.z, poseB.w);
+	s2Vec2 rA = s2RotateVector(qA, V2(anchor.x, anchor.y));
+	s2Vec2 rB = s2RotateVector(qB, V2(anchor.z, anchor.w));
+	s2Vec2 separation = s2Add(s2Add(s2Sub(dcB, dcA), s2Sub(rB, rA)), V2(d0.x, d0.y));
+	float c = s2Length(separation);
+	// s2Normalize (reference src/math.c:40-51)
+	s2Vec2 n = V2(0.0f, 0.0f);
+	if (c >= 0.001f * 1.1920929e-07f)
+	{
+		float invLength = 1.0f / c;
+		n = V2(invLength * separation.x, invLength * separation.y);
+	}
+	float mA = mass.x, iA = mass.y, mB = mass.z, iB = mass.w;
+	if (mA == 0.0f && mB == 0.0f)
+	{
+		return;
+	}
+	float rnA = s2Cross(rA, n);
+	float rnB = s2Cross(rB, n);
+	float kA = mA + iA * rnA * rnA;
+	float kB = mB + iB * rnB * rnB;
+	float lambda = -c / (kA + kB + compliance);
+	s2Vec2 p = s2MulSV(lambda, n);
+	dcA = s2MulSub(dcA, mA, p);
+	qA = s2IntegrateRot(qA, -iA * s2Cross(rA, p));
+	dcB = s2MulAdd(dcB, mB, p);
+	qB = s2IntegrateRot(qB, iB * s2Cross(rB, p));
+	if ((mA != 0.0f) || (iA != 0.0f))
+	{
+		a.bodies.pose[ia] = make_float4(dcA.x, dcA.y, qA.s, qA.c);
+	}
+	if ((mB != 0.0f) || (iB != 0.0f))
+	{
+		a.bodies.pose[ib] = make_float4(dcB.x, dcB.y, qB.s, qB.c);
+	}
+}

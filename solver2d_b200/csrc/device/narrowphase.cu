@@ -170,6 +170,10 @@ __global__ void __launch_bounds__(128) s2bUpdateContactsKernel(ContactView c, in
 	c.info[i] = make_int4(flags, (newId[0] & 0xFFFF) | ((newId[1] & 0xFFFF) << 16), cacheBits, __float_as_int(cache.metric));
 	float4 nf = c.nf[i];
 	c.nf[i] = make_float4(m.normal.x, m.normal.y, nf.z, nf.w);
+	if (pointCount == 0)
+	{
+		c.color[i] = -1; // not a constraint this step: its colour is free again
+	}
 	for (int p = 0; p < 2; ++p)
 	{
 		c.anchor[p][i] = make_float4(m.points[p].localAnchorA.x, m.points[p].localAnchorA.y, m.points[p].localAnchorB.x,

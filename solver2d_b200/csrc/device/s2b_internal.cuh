@@ -95,6 +95,7 @@ struct ContactColumns
 	DevArray<int2> bodies;			  // (A, B)
 	DevArray<int4> info;			  // x: count/flags, y: id0 | id1 << 16, z: GJK cache (count | iA<<2.. ), w: cache metric bits
 	DevArray<float4> nf;			  // normal.x normal.y friction 0
+	DevArray<int> color;			  // colour the constraint was last solved with (-1: none)
 	DevArray<float4> anchor[2];		  // localAnchorA.xy localAnchorB.xy   (body-origin relative, body frame)
 	DevArray<float4> impulse[2];	  // separation normalImpulse tangentImpulse 0
 	DevArray<float4> fanchor[2];	  // frictionAnchorA.xy frictionAnchorB.xy   (sticky only)
@@ -107,6 +108,7 @@ struct ContactColumns
 		bodies.reserve(n, s, keep);
 		info.reserve(n, s, keep);
 		nf.reserve(n, s, keep);
+		color.reserve(n, s, keep);
 		for (int p = 0; p < 2; ++p)
 		{
 			anchor[p].reserve(n, s, keep);
@@ -126,6 +128,7 @@ struct ContactColumns
 		bodies.release();
 		info.release();
 		nf.release();
+		color.release();
 		for (int p = 0; p < 2; ++p)
 		{
 			anchor[p].release();
@@ -144,6 +147,7 @@ struct ContactView
 	int2* bodies;
 	int4* info;
 	float4* nf;
+	int* color;
 	float4* anchor[2];
 	float4* impulse[2];
 	float4* fanchor[2];
@@ -158,6 +162,7 @@ inline ContactView makeView(ContactColumns& c)
 	v.bodies = c.bodies.p;
 	v.info = c.info.p;
 	v.nf = c.nf.p;
+	v.color = c.color.p;
 	for (int p = 0; p < 2; ++p)
 	{
 		v.anchor[p] = c.anchor[p].p;
@@ -227,6 +232,7 @@ struct JointView
 	float4* target; // mouse target.xy 0 0
 	float4* imp;	// impulse.x impulse.y motorImpulse 0
 	float4* limp;	// lowerImpulse upperImpulse 0 0
+	int* color;		// colour the joint was last solved with (-1: none)
 	int capacity;
 };
 
@@ -262,6 +268,8 @@ struct s2bWorld
 	int persistent = 1;
 	int smCount = 148;
 	int coopSupported = 0;
+	int colorGrid = 0;	// cooperative grid sizes, computed once
+	int solveGrid = 0;
 
 	// bodies
 	int bodyCap = 0;
@@ -278,6 +286,7 @@ struct s2bWorld
 	int jointCap = 0;
 	DevArray<int4> jHead;
 	DevArray<float4> jAnchors, jLim, jMotor, jTarget, jImp, jLimp;
+	DevArray<int> jColor;
 	DevArray<unsigned long long> jointPairKeys; // every jointed body pair: blocks new contacts
 	int jointPairCount = 0;
 	DevArray<unsigned long long> jointDestroyKeys; // pairs whose existing contacts are removed
@@ -364,6 +373,7 @@ inline JointView jointView(s2bWorld* w)
 	v.target = w->jTarget.p;
 	v.imp = w->jImp.p;
 	v.limp = w->jLimp.p;
+	v.color = w->jColor.p;
 	v.capacity = w->jointCap;
 	return v;
 }

@@ -25,7 +25,7 @@ namespace cg = cooperative_groups;
 
 #define S2B_MAX_COLORS 64
 #define S2B_OVERFLOW_KEY 255
-#define S2B_BLOCK 128
+#define S2B_BLOCK 256
 
 // ---------------------------------------------------------------------------------------------------------------
 // scratch management
@@ -230,7 +230,17 @@ __global__ void s2bFillAdjacency(const int* counts, const int2* itemBodies, cons
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Jones-Plassmann colouring of the constraint graph (items = nodes, shared movable body = edge)
+// Colouring of the constraint graph (items = nodes; two items conflict when they share a movable body).
+//
+// Colours are PERSISTENT: every contact slot and joint slot remembers the colour it was solved with, so on a settled
+// scene nothing has to be coloured at all and only constraints that appeared this step (new pair, manifold that gained
+// its first point, re-uploaded joint) are uncoloured when the kernel starts.
+// Uncoloured items are coloured by speculative rounds (Gebremedhin-Manne): every uncoloured item tentatively takes the
+// smallest colour no *committed* neighbour holds; among neighbours that took the same tentative colour in the same
+// round only the one with the highest (hashed) priority commits, the others retry. Each round is two grid-wide phases;
+// a handful of rounds colours a whole scene from scratch. The outcome depends only on the item set and the persisted
+// colours, never on thread scheduling.
+// Colour codes: -1 uncoloured, 0..maxColors-1, S2B_OVERFLOW_KEY = no colour below maxColors was free (serial group).
 // ---------------------------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ unsigned s2bPriority(unsigned i)
@@ -251,83 +261,162 @@ __device__ __forceinline__ bool s2bHigherPriority(unsigned j, unsigned i)
 	return pj > pi || (pj == pi && j > i);
 }
 
-// One round for item i. colorIn is read-only in the round, colorOut is written (ping-pong) so the result does not
-// depend on thread scheduling. Colour codes: -1 uncoloured, 0..maxColors-1, S2B_OVERFLOW_KEY overflow.
-__device__ __forceinline__ int s2bColorRound(int i, const int2* itemBodies, const int* adjStart, const int* adj,
-											 const int* colorIn, int maxColors)
+// seed the working colours from the persistent columns (joints first, then contact constraints)
+__global__ void s2bSeedColors(const int* counts, const int* jointSlots, const int* activeSlots, const int* jointColor,
+							  const int* contactColor, int* color, int maxColors)
 {
-	int c = colorIn[i];
-	if (c != -1)
+	int nJ = counts[CNT_JOINTS], nC = counts[CNT_CONTACTS];
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nJ + nC)
 	{
-		return c;
+		return;
 	}
-	int2 e = itemBodies[i];
-	unsigned long long forbidden = 0ull;
-	bool isMax = true;
-#pragma unroll
-	for (int side = 0; side < 2; ++side)
-	{
-		int body = side == 0 ? e.x : e.y;
-		if (body < 0)
-		{
-			continue;
-		}
-		int begin = adjStart[body], end = adjStart[body + 1];
-		for (int k = begin; k < end; ++k)
-		{
-			int j = adj[k];
-			if (j == i)
-			{
-				continue;
-			}
-			int cj = colorIn[j];
-			if (cj == -1)
-			{
-				if (s2bHigherPriority((unsigned)j, (unsigned)i))
-				{
-					isMax = false;
-				}
-			}
-			else if (cj < S2B_MAX_COLORS)
-			{
-				forbidden |= 1ull << cj;
-			}
-		}
-	}
-	if (isMax == false)
-	{
-		return -1;
-	}
-	unsigned long long freeMask = ~forbidden;
-	int pick = freeMask == 0ull ? S2B_MAX_COLORS : (__ffsll((long long)freeMask) - 1);
-	return pick < maxColors ? pick : S2B_OVERFLOW_KEY;
+	int c = i < nJ ? jointColor[jointSlots[i]] : contactColor[activeSlots[i - nJ]];
+	// overflow is re-evaluated every step; a colour beyond the current limit is dropped
+	color[i] = (c >= 0 && c < maxColors) ? c : -1;
 }
 
-// Cooperative colouring: rounds separated by grid barriers until no item is left uncoloured.
-// The "remaining" counter rotates over three slots so that resetting a slot never races with the adds of a round.
-__global__ void s2bColorKernel(int* counts, const int2* itemBodies, const int* adjStart, const int* adj, int* colorA,
-							   int* colorB, int maxColors)
+__global__ void s2bStoreColors(const int* counts, const int* jointSlots, const int* activeSlots, int* jointColor,
+							   int* contactColor, const int* color)
+{
+	int nJ = counts[CNT_JOINTS], nC = counts[CNT_CONTACTS];
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nJ + nC)
+	{
+		return;
+	}
+	if (i < nJ)
+	{
+		jointColor[jointSlots[i]] = color[i];
+	}
+	else
+	{
+		contactColor[activeSlots[i - nJ]] = color[i];
+	}
+}
+
+// Cooperative kernel: speculative rounds until nothing is left uncoloured.
+// `tent` holds (round << 8 | colour) so a value written in an earlier round can never be mistaken for this round's.
+__global__ void __launch_bounds__(256) s2bColorKernel(int* counts, const int2* itemBodies, const int* adjStart, const int* adj, int* color,
+													  int* tent, int maxColors)
 {
 	cg::grid_group grid = cg::this_grid();
 	int n = counts[CNT_JOINTS] + counts[CNT_CONTACTS];
 	int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	int stride = gridDim.x * blockDim.x;
-	for (int i = tid; i < n; i += stride)
+
+	// nothing to colour (the common case on a settled scene): leave without a single grid barrier.
+	// Every thread evaluates the same predicate on data written by earlier kernels, so the exit is uniform.
 	{
-		colorA[i] = -1;
+		__shared__ int blockUncoloured;
+		if (threadIdx.x == 0)
+		{
+			blockUncoloured = 0;
+		}
+		__syncthreads();
+		int mine = 0;
+		for (int i = tid; i < n; i += stride)
+		{
+			mine |= (color[i] == -1) ? 1 : 0;
+			tent[i] = 0; // stamps of earlier steps must not look like this step's
+		}
+		if (mine)
+		{
+			atomicOr(&blockUncoloured, 1);
+		}
+		__syncthreads();
+		if (blockUncoloured)
+		{
+			atomicAdd(counts + CNT_UNCOLOURED, 1);
+		}
 	}
 	grid.sync();
-	int* in = colorA;
-	int* out = colorB;
-	for (int round = 0; round < 8192; ++round)
+	if (*((volatile int*)(counts + CNT_UNCOLOURED)) == 0)
 	{
+		return;
+	}
+
+	for (int round = 1; round < 100000; ++round)
+	{
+		// phase A: tentative colours
+		for (int i = tid; i < n; i += stride)
+		{
+			if (color[i] != -1)
+			{
+				continue;
+			}
+			int2 e = itemBodies[i];
+			unsigned long long forbidden = 0ull;
+#pragma unroll
+			for (int side = 0; side < 2; ++side)
+			{
+				int body = side == 0 ? e.x : e.y;
+				if (body < 0)
+				{
+					continue;
+				}
+				int begin = adjStart[body], end = adjStart[body + 1];
+				for (int k = begin; k < end; ++k)
+				{
+					int cj = color[adj[k]];
+					if (cj >= 0 && cj < S2B_MAX_COLORS)
+					{
+						forbidden |= 1ull << cj;
+					}
+				}
+			}
+			unsigned long long freeMask = ~forbidden;
+			int pick = freeMask == 0ull ? S2B_MAX_COLORS : (__ffsll((long long)freeMask) - 1);
+			if (pick >= maxColors)
+			{
+				pick = S2B_OVERFLOW_KEY;
+			}
+			tent[i] = (round << 8) | pick;
+		}
+		grid.sync();
+
+		// phase B: commit unless a higher-priority neighbour took the same colour in this round
 		int* counter = counts + CNT_REMAINING + (round % 3);
 		int localRemaining = 0;
 		for (int i = tid; i < n; i += stride)
 		{
-			int c = s2bColorRound(i, itemBodies, adjStart, adj, in, maxColors);
-			out[i] = c;
-			localRemaining += (c == -1) ? 1 : 0;
+			if (color[i] != -1)
+			{
+				continue;
+			}
+			int mine = tent[i];
+			int pick = mine & 0xFF;
+			bool commit = true;
+			if (pick != S2B_OVERFLOW_KEY)
+			{
+				int2 e = itemBodies[i];
+#pragma unroll
+				for (int side = 0; side < 2; ++side)
+				{
+					int body = side == 0 ? e.x : e.y;
+					if (body < 0)
+					{
+						continue;
+					}
+					int begin = adjStart[body], end = adjStart[body + 1];
+					for (int k = begin; k < end; ++k)
+					{
+						int j = adj[k];
+						if (j != i && tent[j] == mine && s2bHigherPriority((unsigned)j, (unsigned)i))
+						{
+							commit = false;
+						}
+					}
+				}
+			}
+			if (commit)
+			{
+				color[i] = pick;
+			}
+			else
+			{
+				localRemaining += 1;
+			}
 		}
 		if (localRemaining > 0)
 		{
@@ -338,22 +427,11 @@ __global__ void s2bColorKernel(int* counts, const int2* itemBodies, const int* a
 		if (tid == 0)
 		{
 			counts[CNT_REMAINING + ((round + 2) % 3)] = 0;
-			counts[CNT_ROUNDS] = round + 1;
+			counts[CNT_ROUNDS] = round;
 		}
-		int* tmp = in;
-		in = out;
-		out = tmp;
 		if (remaining == 0)
 		{
 			break;
-		}
-	}
-	// make colorA the final array
-	if (in != colorA)
-	{
-		for (int i = tid; i < n; i += stride)
-		{
-			colorA[i] = in[i];
 		}
 	}
 }
@@ -427,121 +505,94 @@ __global__ void s2bBuildSources(const int* counts, const int* cPerm, const int* 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// passes: ops applied to ranges of bodies / contact constraints / joint constraints
+// Programs: every solver variant is a short list of PASSES over bodies, joint constraints and contact constraints.
+// The list is built on the host from the variant's driver in the reference (citations in buildProgram) and executed
+// either by ONE persistent cooperative kernel (grid barrier after every dependent phase) or launch by launch.
 // ---------------------------------------------------------------------------------------------------------------
 
-enum PassOp
+enum PassKind
 {
-	// body ops
-	OP_INTEGRATE_VELOCITIES,
-	OP_INTEGRATE_POSITIONS,
-	OP_FINALIZE_POSITIONS,
-	// contact ops
-	OP_PREPARE_SOFT,
-	OP_PREPARE_PGS,
-	OP_WARM_START,
-	OP_SOLVE_TGS_SOFT_BIAS,
-	OP_SOLVE_TGS_SOFT_RELAX,
-	OP_STORE,
+	PASS_BODY = 0,	// every body slot, no ordering
+	PASS_FLAT = 1,	// every joint / contact constraint, no ordering between them (prepare, store)
+	PASS_GROUP = 2, // Gauss-Seidel: groups in order, a barrier after each, then the serial overflow group
 };
 
-template <int OP> __device__ __forceinline__ void s2bBodyOp(const SolveArgs& a, int i)
+enum BodyOp
 {
-	if (OP == OP_INTEGRATE_VELOCITIES)
-	{
-		s2bIntegrateVelocity(a, i, a.ctx.h);
-	}
-	else if (OP == OP_INTEGRATE_POSITIONS)
-	{
-		s2bIntegratePosition(a, i, a.ctx.h);
-	}
-	else if (OP == OP_FINALIZE_POSITIONS)
-	{
-		s2bFinalizePosition(a, i);
-	}
-}
+	BOP_NONE = 0,
+	BOP_INTEGRATE_VELOCITIES,
+	BOP_INTEGRATE_POSITIONS,
+	BOP_FINALIZE_POSITIONS,
+	BOP_JACOBI_RESET,
+	BOP_JACOBI_APPLY,
+	BOP_XPBD_INTEGRATE,
+	BOP_XPBD_PROJECT,
+	BOP_XPBD_FINALIZE,
+};
 
-template <int OP> __device__ __forceinline__ void s2bContactOp(const SolveArgs& a, int t)
+enum ContactOp
 {
-	if (OP == OP_PREPARE_SOFT)
-	{
-		s2bPrepareContact<PREPARE_SOFT>(a, t);
-	}
-	else if (OP == OP_PREPARE_PGS)
-	{
-		s2bPrepareContact<PREPARE_PGS>(a, t);
-	}
-	else if (OP == OP_WARM_START)
-	{
-		s2bWarmStartContact(a, t);
-	}
-	else if (OP == OP_SOLVE_TGS_SOFT_BIAS)
-	{
-		s2bSolveContactTgsSoft(a, t, a.ctx.inv_h, true);
-	}
-	else if (OP == OP_SOLVE_TGS_SOFT_RELAX)
-	{
-		s2bSolveContactTgsSoft(a, t, a.ctx.inv_h, false);
-	}
-	else if (OP == OP_STORE)
-	{
-		s2bStoreContactImpulses(a, t, 1.0f);
-	}
-}
+	COP_NONE = 0,
+	COP_PREPARE,		// s2PrepareContacts_PGS / _Soft / local TGS_NGS flavour: same arithmetic, optional columns differ
+	COP_PREPARE_COLD,	// XPBD: impulses always start at zero
+	COP_PREPARE_STICKY,
+	COP_WARM_START,
+	COP_WARM_START_FIXED,
+	COP_TGS_SOFT_BIAS,
+	COP_TGS_SOFT_RELAX,
+	COP_PGS_BAUMGARTE,
+	COP_PGS,
+	COP_PGS_SOFT_BIAS,
+	COP_PGS_SOFT_RELAX,
+	COP_JACOBI_BIAS,
+	COP_JACOBI_RELAX,
+	COP_SOFTSTEP_BIAS,
+	COP_SOFTSTEP_RELAX,
+	COP_TGS,
+	COP_NGS,
+	COP_STICKY_BIAS,
+	COP_STICKY_RELAX,
+	COP_XPBD_POSITIONS,
+	COP_XPBD_VELOCITIES,
+	COP_STORE,
+	COP_STORE_SCALED, // XPBD stores impulse * inv_h
+};
 
 enum JointOp
 {
-	JOP_NONE,
+	JOP_NONE = 0,
 	JOP_PREPARE_SOFT_WARM,	// s2PrepareJoint_Soft(..., warmStart = true)
-	JOP_PREPARE_SOFT_COLD,	// s2PrepareJoint_Soft(..., warmStart = false)
+	JOP_PREPARE_SOFT_FLAG,	// s2PrepareJoint_Soft(..., context->warmStart)
 	JOP_PREPARE_RIGID_FLAG, // s2PrepareJoint(..., context->warmStart)
+	JOP_PREPARE_RIGID_COLD, // s2PrepareJoint(..., false)
+	JOP_PREPARE_XPBD,
 	JOP_WARM_START,
-	JOP_SOLVE_SOFT_BIAS,
-	JOP_SOLVE_SOFT_RELAX,
-	JOP_SOLVE_BAUMGARTE_BIAS,
-	JOP_SOLVE_BAUMGARTE_RELAX,
+	JOP_SOFT_BIAS,
+	JOP_SOFT_RELAX,
+	JOP_BAUMGARTE_BIAS,
+	JOP_BAUMGARTE_RELAX,
+	JOP_RIGID,
+	JOP_POSITION,
+	JOP_XPBD,
 	JOP_STORE,
 };
 
-template <int JOP> __device__ __forceinline__ void s2bJointOp(const SolveArgs& a, int t, const int* jointSlots, const int* jPerm)
+struct PassDesc
 {
-	if (JOP == JOP_PREPARE_SOFT_WARM)
-	{
-		s2bPrepareJoint<JPREP_SOFT>(a, t, jointSlots[jPerm[t]], true);
-	}
-	else if (JOP == JOP_PREPARE_SOFT_COLD)
-	{
-		s2bPrepareJoint<JPREP_SOFT>(a, t, jointSlots[jPerm[t]], false);
-	}
-	else if (JOP == JOP_PREPARE_RIGID_FLAG)
-	{
-		s2bPrepareJoint<JPREP_RIGID>(a, t, jointSlots[jPerm[t]], a.ctx.warmStart != 0);
-	}
-	else if (JOP == JOP_WARM_START)
-	{
-		s2bWarmStartJoint(a, t);
-	}
-	else if (JOP == JOP_SOLVE_SOFT_BIAS)
-	{
-		s2bSolveJointSoft(a, t, a.ctx.h, a.ctx.inv_h, true);
-	}
-	else if (JOP == JOP_SOLVE_SOFT_RELAX)
-	{
-		s2bSolveJointSoft(a, t, a.ctx.h, a.ctx.inv_h, false);
-	}
-	else if (JOP == JOP_SOLVE_BAUMGARTE_BIAS)
-	{
-		s2bSolveJointBaumgarte(a, t, a.ctx.h, a.ctx.inv_h, true);
-	}
-	else if (JOP == JOP_SOLVE_BAUMGARTE_RELAX)
-	{
-		s2bSolveJointBaumgarte(a, t, a.ctx.h, a.ctx.inv_h, false);
-	}
-	else if (JOP == JOP_STORE)
-	{
-		s2bStoreJointImpulses(a, t);
-	}
-}
+	unsigned char kind, bodyOp, jointOp, contactOp;
+};
+
+#define S2B_MAX_SEGMENTS 6
+#define S2B_MAX_SEGMENT_PASSES 8
+
+// a program = segments executed in order, each a list of passes repeated `repeat` times
+struct Program
+{
+	int segmentCount;
+	int repeat[S2B_MAX_SEGMENTS];
+	int passCount[S2B_MAX_SEGMENTS];
+	PassDesc passes[S2B_MAX_SEGMENTS][S2B_MAX_SEGMENT_PASSES];
+};
 
 struct PassPtrs
 {
@@ -549,67 +600,230 @@ struct PassPtrs
 	const int* jPerm;
 };
 
-// ---- multi-launch kernels -------------------------------------------------------------------------------------
+__device__ __forceinline__ void s2bRunBodyOp(int op, const SolveArgs& a, int i)
+{
+	switch (op)
+	{
+		case BOP_INTEGRATE_VELOCITIES:
+			s2bIntegrateVelocity(a, i, a.ctx.h);
+			break;
+		case BOP_INTEGRATE_POSITIONS:
+			s2bIntegratePosition(a, i, a.ctx.h);
+			break;
+		case BOP_FINALIZE_POSITIONS:
+			s2bFinalizePosition(a, i);
+			break;
+		case BOP_JACOBI_RESET:
+			s2bJacobiReset(a, i);
+			break;
+		case BOP_JACOBI_APPLY:
+			s2bJacobiApply(a, i);
+			break;
+		case BOP_XPBD_INTEGRATE:
+			s2bXpbdIntegrate(a, i, a.ctx.h);
+			break;
+		case BOP_XPBD_PROJECT:
+			s2bXpbdProjectVelocity(a, i, a.xpbdInvH);
+			break;
+		case BOP_XPBD_FINALIZE:
+			s2bXpbdFinalize(a, i);
+			break;
+		default:
+			break;
+	}
+}
 
-template <int OP> __global__ void s2bBodyPassKernel(SolveArgs a)
+__device__ __forceinline__ void s2bRunContactOp(int op, const SolveArgs& a, int t)
+{
+	float inv_h = a.ctx.inv_h;
+	switch (op)
+	{
+		case COP_PREPARE:
+			s2bPrepareContact<PREPARE_SOFT>(a, t);
+			break;
+		case COP_PREPARE_COLD:
+			s2bPrepareContact<PREPARE_COLD>(a, t);
+			break;
+		case COP_PREPARE_STICKY:
+			s2bPrepareContactSticky(a, t);
+			break;
+		case COP_WARM_START:
+			s2bWarmStartContact(a, t);
+			break;
+		case COP_WARM_START_FIXED:
+			s2bWarmStartContactFixed(a, t);
+			break;
+		case COP_TGS_SOFT_BIAS:
+			s2bSolveContactTgsSoft(a, t, inv_h, true);
+			break;
+		case COP_TGS_SOFT_RELAX:
+			s2bSolveContactTgsSoft(a, t, inv_h, false);
+			break;
+		case COP_PGS_BAUMGARTE:
+			s2bSolveContactFixed<0>(a, t, inv_h, true);
+			break;
+		case COP_PGS:
+			s2bSolveContactPgs(a, t);
+			break;
+		case COP_PGS_SOFT_BIAS:
+			s2bSolveContactFixed<1>(a, t, inv_h, true);
+			break;
+		case COP_PGS_SOFT_RELAX:
+			s2bSolveContactFixed<1>(a, t, inv_h, false);
+			break;
+		case COP_JACOBI_BIAS:
+			s2bSolveContactFixed<2>(a, t, inv_h, true);
+			break;
+		case COP_JACOBI_RELAX:
+			s2bSolveContactFixed<2>(a, t, inv_h, false);
+			break;
+		case COP_SOFTSTEP_BIAS:
+			s2bSolveContactSubstep<0>(a, t, inv_h, true);
+			break;
+		case COP_SOFTSTEP_RELAX:
+			s2bSolveContactSubstep<0>(a, t, inv_h, false);
+			break;
+		case COP_TGS:
+			s2bSolveContactSubstep<1>(a, t, inv_h, true);
+			break;
+		case COP_NGS:
+			s2bSolveContactNgs(a, t);
+			break;
+		case COP_STICKY_BIAS:
+			s2bSolveContactSticky(a, t, inv_h, true);
+			break;
+		case COP_STICKY_RELAX:
+			s2bSolveContactSticky(a, t, inv_h, false);
+			break;
+		case COP_XPBD_POSITIONS:
+			s2bSolveContactXpbdPositions(a, t, a.ctx.h);
+			break;
+		case COP_XPBD_VELOCITIES:
+			s2bSolveContactXpbdVelocities(a, t, a.ctx.h);
+			break;
+		case COP_STORE:
+			s2bStoreContactImpulses(a, t, 1.0f);
+			break;
+		case COP_STORE_SCALED:
+			s2bStoreContactImpulses(a, t, a.xpbdInvH);
+			break;
+		default:
+			break;
+	}
+}
+
+__device__ __forceinline__ void s2bRunJointOp(int op, const SolveArgs& a, int t, const PassPtrs& p)
+{
+	switch (op)
+	{
+		case JOP_PREPARE_SOFT_WARM:
+			s2bPrepareJoint<JPREP_SOFT>(a, t, p.jointSlots[p.jPerm[t]], true);
+			break;
+		case JOP_PREPARE_SOFT_FLAG:
+			s2bPrepareJoint<JPREP_SOFT>(a, t, p.jointSlots[p.jPerm[t]], a.ctx.warmStart != 0);
+			break;
+		case JOP_PREPARE_RIGID_FLAG:
+			s2bPrepareJoint<JPREP_RIGID>(a, t, p.jointSlots[p.jPerm[t]], a.ctx.warmStart != 0);
+			break;
+		case JOP_PREPARE_RIGID_COLD:
+			s2bPrepareJoint<JPREP_RIGID>(a, t, p.jointSlots[p.jPerm[t]], false);
+			break;
+		case JOP_PREPARE_XPBD:
+			s2bPrepareJoint<JPREP_XPBD>(a, t, p.jointSlots[p.jPerm[t]], false);
+			break;
+		case JOP_WARM_START:
+			s2bWarmStartJoint(a, t);
+			break;
+		case JOP_SOFT_BIAS:
+			s2bSolveJointSoft(a, t, a.ctx.h, a.ctx.inv_h, true);
+			break;
+		case JOP_SOFT_RELAX:
+			s2bSolveJointSoft(a, t, a.ctx.h, a.ctx.inv_h, false);
+			break;
+		case JOP_BAUMGARTE_BIAS:
+			s2bSolveJointBaumgarte(a, t, a.ctx.h, a.ctx.inv_h, true);
+			break;
+		case JOP_BAUMGARTE_RELAX:
+			s2bSolveJointBaumgarte(a, t, a.ctx.h, a.ctx.inv_h, false);
+			break;
+		case JOP_RIGID:
+			s2bSolveJointRigid(a, t, a.ctx.h);
+			break;
+		case JOP_POSITION:
+			s2bSolveJointPosition(a, t);
+			break;
+		case JOP_XPBD:
+			s2bSolveJointXpbd(a, t);
+			break;
+		case JOP_STORE:
+			s2bStoreJointImpulses(a, t);
+			break;
+		default:
+			break;
+	}
+}
+
+// ---- launch-by-launch kernels (profiling / cross-check path) ----------------------------------------------------
+
+__global__ void __launch_bounds__(S2B_BLOCK) s2bBodyPassKernel(SolveArgs a, int bodyOp)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < a.bodies.capacity)
 	{
-		s2bBodyOp<OP>(a, i);
+		s2bRunBodyOp(bodyOp, a, i);
 	}
 }
 
-// one group (or the whole range when begin/end span everything): joints first, then contacts
-template <int JOP, int OP> __global__ void s2bRangePassKernel(SolveArgs a, PassPtrs p, int jBegin, int jEnd, int cBegin, int cEnd)
+// one group (or the whole range): joints first, then contacts
+__global__ void __launch_bounds__(S2B_BLOCK) s2bRangePassKernel(SolveArgs a, PassPtrs p, int jointOp, int contactOp, int jBegin, int jEnd,
+															   int cBegin, int cEnd)
 {
 	int t = blockIdx.x * blockDim.x + threadIdx.x;
-	int nj = jEnd - jBegin;
+	int nj = jointOp != JOP_NONE ? jEnd - jBegin : 0;
 	if (t < nj)
 	{
-		if (JOP != JOP_NONE)
-		{
-			s2bJointOp<JOP>(a, jBegin + t, p.jointSlots, p.jPerm);
-		}
+		s2bRunJointOp(jointOp, a, jBegin + t, p);
 	}
-	else if (t - nj < cEnd - cBegin)
+	else if (contactOp != COP_NONE && t - nj < cEnd - cBegin)
 	{
-		s2bContactOp<OP>(a, cBegin + (t - nj));
+		s2bRunContactOp(contactOp, a, cBegin + (t - nj));
 	}
 }
 
 // serial overflow group: one thread walks the items in order
-template <int JOP, int OP> __global__ void s2bSerialPassKernel(SolveArgs a, PassPtrs p, int jBegin, int jEnd, int cBegin, int cEnd)
+__global__ void s2bSerialPassKernel(SolveArgs a, PassPtrs p, int jointOp, int contactOp, int jBegin, int jEnd, int cBegin, int cEnd)
 {
 	if (blockIdx.x == 0 && threadIdx.x == 0)
 	{
-		if (JOP != JOP_NONE)
+		if (jointOp != JOP_NONE)
 		{
 			for (int t = jBegin; t < jEnd; ++t)
 			{
-				s2bJointOp<JOP>(a, t, p.jointSlots, p.jPerm);
+				s2bRunJointOp(jointOp, a, t, p);
 			}
 		}
-		for (int t = cBegin; t < cEnd; ++t)
+		if (contactOp != COP_NONE)
 		{
-			s2bContactOp<OP>(a, t);
+			for (int t = cBegin; t < cEnd; ++t)
+			{
+				s2bRunContactOp(contactOp, a, t);
+			}
 		}
 	}
 }
 
-// ---- persistent kernel helpers --------------------------------------------------------------------------------
+// ---- the persistent cooperative kernel ------------------------------------------------------------------------
 
-template <int OP> __device__ __forceinline__ void s2bGridBodyPass(const SolveArgs& a)
+__device__ __forceinline__ void s2bGridBodyPass(int bodyOp, const SolveArgs& a)
 {
 	int stride = gridDim.x * blockDim.x;
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.bodies.capacity; i += stride)
 	{
-		s2bBodyOp<OP>(a, i);
+		s2bRunBodyOp(bodyOp, a, i);
 	}
 }
 
-// whole-range pass (prepare / store): no ordering constraints between items
-template <int JOP, int OP> __device__ __forceinline__ void s2bGridFlatPass(const SolveArgs& a, const PassPtrs& p)
+__device__ __forceinline__ void s2bGridFlatPass(int jointOp, int contactOp, const SolveArgs& a, const PassPtrs& p)
 {
 	int nJ = a.counts[CNT_JOINTS], nC = a.counts[CNT_CONTACTS];
 	int stride = gridDim.x * blockDim.x;
@@ -617,98 +831,93 @@ template <int JOP, int OP> __device__ __forceinline__ void s2bGridFlatPass(const
 	{
 		if (t < nJ)
 		{
-			if (JOP != JOP_NONE)
+			if (jointOp != JOP_NONE)
 			{
-				s2bJointOp<JOP>(a, t, p.jointSlots, p.jPerm);
+				s2bRunJointOp(jointOp, a, t, p);
 			}
 		}
-		else
+		else if (contactOp != COP_NONE)
 		{
-			s2bContactOp<OP>(a, t - nJ);
+			s2bRunContactOp(contactOp, a, t - nJ);
 		}
 	}
 }
 
-// Gauss-Seidel pass: groups in order with a grid barrier after each, then the serial overflow group
-template <int JOP, int OP> __device__ __forceinline__ void s2bGridGroupPass(const SolveArgs& a, const PassPtrs& p, cg::grid_group& grid)
+__device__ __forceinline__ void s2bGridGroupPass(int jointOp, int contactOp, const SolveArgs& a, const PassPtrs& p, cg::grid_group& grid)
 {
 	int groups = a.counts[CNT_GROUPS];
 	int stride = gridDim.x * blockDim.x;
 	int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	for (int g = 0; g < groups; ++g)
 	{
-		int jBegin = a.jGroupOff[g], jEnd = a.jGroupOff[g + 1];
-		int cBegin = a.cGroupOff[g], cEnd = a.cGroupOff[g + 1];
-		int nj = jEnd - jBegin, n = nj + (cEnd - cBegin);
-		for (int t = tid; t < n; t += stride)
+		int jBegin = a.jGroupOff[g], cBegin = a.cGroupOff[g];
+		int nj = jointOp != JOP_NONE ? a.jGroupOff[g + 1] - jBegin : 0;
+		int nc = contactOp != COP_NONE ? a.cGroupOff[g + 1] - cBegin : 0;
+		if (nj + nc == 0)
+		{
+			continue; // uniform: every thread reads the same table
+		}
+		for (int t = tid; t < nj + nc; t += stride)
 		{
 			if (t < nj)
 			{
-				if (JOP != JOP_NONE)
-				{
-					s2bJointOp<JOP>(a, jBegin + t, p.jointSlots, p.jPerm);
-				}
+				s2bRunJointOp(jointOp, a, jBegin + t, p);
 			}
 			else
 			{
-				s2bContactOp<OP>(a, cBegin + (t - nj));
+				s2bRunContactOp(contactOp, a, cBegin + (t - nj));
 			}
 		}
 		grid.sync();
 	}
-	int ovC = a.counts[CNT_OVERFLOW_C], ovJ = a.counts[CNT_OVERFLOW_J];
+	int ovC = contactOp != COP_NONE ? a.counts[CNT_OVERFLOW_C] : 0;
+	int ovJ = jointOp != JOP_NONE ? a.counts[CNT_OVERFLOW_J] : 0;
 	if (ovC + ovJ > 0)
 	{
 		if (tid == 0)
 		{
 			int jBegin = a.jGroupOff[S2B_MAX_COLORS], cBegin = a.cGroupOff[S2B_MAX_COLORS];
-			if (JOP != JOP_NONE)
+			for (int t = 0; t < ovJ; ++t)
 			{
-				for (int t = 0; t < ovJ; ++t)
-				{
-					s2bJointOp<JOP>(a, jBegin + t, p.jointSlots, p.jPerm);
-				}
+				s2bRunJointOp(jointOp, a, jBegin + t, p);
 			}
 			for (int t = 0; t < ovC; ++t)
 			{
-				s2bContactOp<OP>(a, cBegin + t);
+				s2bRunContactOp(contactOp, a, cBegin + t);
 			}
 		}
 		grid.sync();
 	}
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// s2Solve_TGS_Soft (reference src/solve_tgs_soft.c:138-280) as one persistent cooperative kernel
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(S2B_BLOCK) s2bPersistentTgsSoft(SolveArgs a, PassPtrs p)
+// The whole solver stage of one step: the variant's program from prepare to store, one launch.
+__global__ void __launch_bounds__(S2B_BLOCK) s2bPersistentSolve(SolveArgs a, PassPtrs p, Program prog)
 {
 	cg::grid_group grid = cg::this_grid();
-
-	// prepare (joints always warm start here: reference solve_tgs_soft.c:204-205)
-	s2bGridFlatPass<JOP_PREPARE_SOFT_WARM, OP_PREPARE_SOFT>(a, p);
-	grid.sync();
-
-	int substeps = a.ctx.iterations;
-	for (int s = 0; s < substeps; ++s)
+	for (int s = 0; s < prog.segmentCount; ++s)
 	{
-		s2bGridBodyPass<OP_INTEGRATE_VELOCITIES>(a);
-		grid.sync();
-		if (a.ctx.warmStart)
+		for (int r = 0; r < prog.repeat[s]; ++r)
 		{
-			s2bGridGroupPass<JOP_WARM_START, OP_WARM_START>(a, p, grid);
-		}
-		s2bGridGroupPass<JOP_SOLVE_SOFT_BIAS, OP_SOLVE_TGS_SOFT_BIAS>(a, p, grid);
-		s2bGridBodyPass<OP_INTEGRATE_POSITIONS>(a);
-		grid.sync();
-		if (a.ctx.extraIterations > 0)
-		{
-			s2bGridGroupPass<JOP_SOLVE_SOFT_RELAX, OP_SOLVE_TGS_SOFT_RELAX>(a, p, grid);
+			for (int k = 0; k < prog.passCount[s]; ++k)
+			{
+				PassDesc pass = prog.passes[s][k];
+				if (pass.kind == PASS_BODY)
+				{
+					s2bGridBodyPass(pass.bodyOp, a);
+					grid.sync();
+				}
+				else if (pass.kind == PASS_FLAT)
+				{
+					s2bGridFlatPass(pass.jointOp, pass.contactOp, a, p);
+					grid.sync();
+				}
+				else
+				{
+					s2bGridGroupPass(pass.jointOp, pass.contactOp, a, p, grid);
+				}
+			}
 		}
 	}
-
-	s2bGridBodyPass<OP_FINALIZE_POSITIONS>(a);
-	s2bGridFlatPass<JOP_STORE, OP_STORE>(a, p);
 }
 
 __global__ void s2bMeterWork(const int* counts, int passes, unsigned long long* work)
@@ -735,69 +944,263 @@ static SoftCoef makeSoft(float h, float hertz, float zeta)
 
 struct HostPlan
 {
-	// multi-launch mode only
+	// launch-by-launch mode only
 	int groups = 0;
 	std::vector<int> cOff, jOff;
 };
 
-template <int OP> static void launchBodyPass(s2bWorld* w, const SolveArgs& a)
+static PassDesc bodyPass(int op)
 {
-	if (a.bodies.capacity > 0)
-	{
-		auto kernel = s2bBodyPassKernel<OP>;
-		S2B_LAUNCH(w, kernel, gridFor(a.bodies.capacity, S2B_BLOCK), S2B_BLOCK, 0, a);
-	}
+	PassDesc d = {PASS_BODY, (unsigned char)op, JOP_NONE, COP_NONE};
+	return d;
 }
 
-template <int JOP, int OP> static void launchFlatPass(s2bWorld* w, const SolveArgs& a, const PassPtrs& p, int nJ, int nC)
+static PassDesc flatPass(int jop, int cop)
 {
-	if (nJ + nC > 0)
-	{
-		auto kernel = s2bRangePassKernel<JOP, OP>;
-		S2B_LAUNCH(w, kernel, gridFor(nJ + nC, S2B_BLOCK), S2B_BLOCK, 0, a, p, 0, nJ, 0, nC);
-	}
+	PassDesc d = {PASS_FLAT, BOP_NONE, (unsigned char)jop, (unsigned char)cop};
+	return d;
 }
 
-template <int JOP, int OP> static void launchGroupPass(s2bWorld* w, const SolveArgs& a, const PassPtrs& p, const HostPlan& plan)
+static PassDesc groupPass(int jop, int cop)
 {
-	for (int g = 0; g < plan.groups; ++g)
-	{
-		int jb = plan.jOff[g], je = plan.jOff[g + 1], cb = plan.cOff[g], ce = plan.cOff[g + 1];
-		int n = (je - jb) + (ce - cb);
-		if (n > 0)
-		{
-			auto kernel = s2bRangePassKernel<JOP, OP>;
-			S2B_LAUNCH(w, kernel, gridFor(n, S2B_BLOCK), S2B_BLOCK, 0, a, p, jb, je, cb, ce);
-		}
-	}
-	int G = (int)plan.cOff.size() - 2; // index of the overflow group
-	int jb = plan.jOff[G], je = plan.jOff[G + 1], cb = plan.cOff[G], ce = plan.cOff[G + 1];
-	if ((je - jb) + (ce - cb) > 0)
-	{
-		auto kernel = s2bSerialPassKernel<JOP, OP>;
-		S2B_LAUNCH(w, kernel, 1, 32, 0, a, p, jb, je, cb, ce);
-	}
+	PassDesc d = {PASS_GROUP, BOP_NONE, (unsigned char)jop, (unsigned char)cop};
+	return d;
 }
 
-static void runTgsSoftMultiLaunch(s2bWorld* w, const SolveArgs& a, const PassPtrs& p, const HostPlan& plan, int nJ, int nC)
+struct ProgramBuilder
 {
-	launchFlatPass<JOP_PREPARE_SOFT_WARM, OP_PREPARE_SOFT>(w, a, p, nJ, nC);
-	for (int s = 0; s < a.ctx.iterations; ++s)
+	Program prog;
+	ProgramBuilder()
 	{
-		launchBodyPass<OP_INTEGRATE_VELOCITIES>(w, a);
-		if (a.ctx.warmStart)
+		memset(&prog, 0, sizeof(prog));
+	}
+	void segment(int repeat)
+	{
+		prog.repeat[prog.segmentCount] = repeat;
+		prog.passCount[prog.segmentCount] = 0;
+		prog.segmentCount += 1;
+	}
+	void add(PassDesc d)
+	{
+		int s = prog.segmentCount - 1;
+		prog.passes[s][prog.passCount[s]++] = d;
+	}
+};
+
+// The stage list of every variant, taken from the variant's driver in the reference. Also returns
+// the number of solve passes per step that count as constraint-iterations.
+static Program buildProgram(int solverType, const s2bStepContext& ctx, int* countedPasses)
+{
+	ProgramBuilder b;
+	int S = ctx.iterations, E = ctx.extraIterations;
+	bool warm = ctx.warmStart != 0;
+	*countedPasses = 0;
+	switch (solverType)
+	{
+		case 7: // s2Solve_TGS_Soft, reference src/solve_tgs_soft.c:138-280
+		case 5: // s2Solve_SoftStep, reference src/solve_soft_step.c:182-311 (fixed anchors for velocity / impulse)
 		{
-			launchGroupPass<JOP_WARM_START, OP_WARM_START>(w, a, p, plan);
+			bool softStep = solverType == 5;
+			b.segment(1);
+			b.add(flatPass(JOP_PREPARE_SOFT_WARM, COP_PREPARE));
+			b.segment(S);
+			b.add(bodyPass(BOP_INTEGRATE_VELOCITIES));
+			if (warm)
+			{
+				b.add(groupPass(JOP_WARM_START, softStep ? COP_WARM_START_FIXED : COP_WARM_START));
+			}
+			b.add(groupPass(JOP_SOFT_BIAS, softStep ? COP_SOFTSTEP_BIAS : COP_TGS_SOFT_BIAS));
+			b.add(bodyPass(BOP_INTEGRATE_POSITIONS));
+			if (E > 0)
+			{
+				b.add(groupPass(JOP_SOFT_RELAX, softStep ? COP_SOFTSTEP_RELAX : COP_TGS_SOFT_RELAX));
+			}
+			b.segment(1);
+			b.add(bodyPass(BOP_FINALIZE_POSITIONS));
+			b.add(flatPass(JOP_STORE, COP_STORE));
+			*countedPasses = S * (1 + (E > 0 ? 1 : 0));
+			break;
 		}
-		launchGroupPass<JOP_SOLVE_SOFT_BIAS, OP_SOLVE_TGS_SOFT_BIAS>(w, a, p, plan);
-		launchBodyPass<OP_INTEGRATE_POSITIONS>(w, a);
-		if (a.ctx.extraIterations > 0)
+		case 1: // s2Solve_PGS, reference src/solve_pgs.c:125-213
+		case 2: // s2Solve_PGS_NGS, reference src/solve_pgs_ngs.c:149-255
+		case 4: // s2Solve_PGS_Soft, reference src/solve_pgs_soft.c:127-242
+		case 0: // s2Solve_Jacobi, reference src/solve_jacobi.c:134-292
 		{
-			launchGroupPass<JOP_SOLVE_SOFT_RELAX, OP_SOLVE_TGS_SOFT_RELAX>(w, a, p, plan);
+			bool soft = solverType == 4 || solverType == 0;
+			bool jacobi = solverType == 0;
+			b.segment(1);
+			if (jacobi)
+			{
+				b.add(bodyPass(BOP_JACOBI_RESET));
+			}
+			b.add(bodyPass(BOP_INTEGRATE_VELOCITIES));
+			b.add(flatPass(soft ? JOP_PREPARE_SOFT_FLAG : JOP_PREPARE_RIGID_FLAG, COP_PREPARE));
+			if (warm)
+			{
+				// all contacts are warm started before any joint (reference e.g. src/solve_pgs.c:166-184)
+				b.add(groupPass(JOP_NONE, COP_WARM_START));
+				b.add(groupPass(JOP_WARM_START, COP_NONE));
+			}
+			b.segment(S);
+			if (solverType == 1)
+			{
+				b.add(groupPass(JOP_BAUMGARTE_BIAS, COP_PGS_BAUMGARTE));
+			}
+			else if (solverType == 2)
+			{
+				b.add(groupPass(JOP_RIGID, COP_PGS));
+			}
+			else if (solverType == 4)
+			{
+				b.add(groupPass(JOP_SOFT_BIAS, COP_PGS_SOFT_BIAS));
+			}
+			else
+			{
+				b.add(groupPass(JOP_SOFT_BIAS, COP_JACOBI_BIAS));
+				b.add(bodyPass(BOP_JACOBI_APPLY));
+			}
+			b.segment(1);
+			b.add(bodyPass(BOP_INTEGRATE_POSITIONS));
+			if (solverType == 1)
+			{
+				b.add(bodyPass(BOP_FINALIZE_POSITIONS));
+				b.add(flatPass(JOP_STORE, COP_STORE));
+				*countedPasses = S;
+			}
+			else if (solverType == 2)
+			{
+				b.add(flatPass(JOP_NONE, COP_STORE)); // impulses are stored before the position iterations
+				b.segment(E);
+				b.add(groupPass(JOP_POSITION, COP_NGS));
+				b.segment(1);
+				b.add(bodyPass(BOP_FINALIZE_POSITIONS));
+				b.add(flatPass(JOP_STORE, COP_NONE));
+				*countedPasses = S + E;
+			}
+			else
+			{
+				b.segment(E);
+				if (jacobi)
+				{
+					b.add(groupPass(JOP_SOFT_RELAX, COP_JACOBI_RELAX));
+					b.add(bodyPass(BOP_JACOBI_APPLY));
+				}
+				else
+				{
+					b.add(groupPass(JOP_SOFT_RELAX, COP_PGS_SOFT_RELAX));
+				}
+				b.segment(1);
+				b.add(bodyPass(BOP_FINALIZE_POSITIONS));
+				b.add(flatPass(JOP_STORE, COP_STORE));
+				*countedPasses = S + E;
+			}
+			break;
+		}
+		case 8: // s2Solve_TGS_NGS, reference src/solve_tgs_ngs.c:207-317
+		{
+			b.segment(1);
+			b.add(flatPass(JOP_PREPARE_RIGID_FLAG, COP_PREPARE));
+			b.segment(S);
+			b.add(bodyPass(BOP_INTEGRATE_VELOCITIES));
+			if (warm)
+			{
+				b.add(groupPass(JOP_WARM_START, COP_WARM_START));
+			}
+			b.add(groupPass(JOP_RIGID, COP_TGS));
+			b.add(bodyPass(BOP_INTEGRATE_POSITIONS));
+			b.add(groupPass(JOP_POSITION, COP_NGS));
+			b.segment(1);
+			b.add(bodyPass(BOP_FINALIZE_POSITIONS));
+			b.add(flatPass(JOP_STORE, COP_STORE));
+			*countedPasses = 2 * S;
+			break;
+		}
+		case 6: // s2Solve_TGS_Sticky, reference src/solve_tgs_sticky.c:313-417
+		{
+			b.segment(1);
+			b.add(flatPass(JOP_PREPARE_RIGID_COLD, COP_PREPARE_STICKY));
+			b.segment(S);
+			b.add(bodyPass(BOP_INTEGRATE_VELOCITIES));
+			b.add(groupPass(JOP_BAUMGARTE_BIAS, COP_STICKY_BIAS));
+			b.add(bodyPass(BOP_INTEGRATE_POSITIONS));
+			b.segment(1);
+			b.add(bodyPass(BOP_FINALIZE_POSITIONS));
+			b.segment(E);
+			b.add(groupPass(JOP_BAUMGARTE_RELAX, COP_STICKY_RELAX));
+			b.segment(1);
+			b.add(flatPass(JOP_STORE, COP_STORE));
+			*countedPasses = S + E;
+			break;
+		}
+		case 9: // s2Solve_XPBD, reference src/solve_xpbd.c:342-530
+		{
+			b.segment(1);
+			b.add(flatPass(JOP_PREPARE_XPBD, COP_PREPARE_COLD));
+			b.segment(S);
+			b.add(bodyPass(BOP_XPBD_INTEGRATE));
+			b.add(groupPass(JOP_XPBD, COP_XPBD_POSITIONS));
+			b.add(bodyPass(BOP_XPBD_PROJECT));
+			b.add(groupPass(JOP_NONE, COP_XPBD_VELOCITIES));
+			b.segment(1);
+			b.add(bodyPass(BOP_XPBD_FINALIZE));
+			b.add(flatPass(JOP_STORE, COP_STORE_SCALED));
+			*countedPasses = 2 * S;
+			break;
+		}
+		default:
+			break;
+	}
+	return b.prog;
+}
+
+static void runProgramLaunchByLaunch(s2bWorld* w, const SolveArgs& a, const PassPtrs& p, const Program& prog, const HostPlan& plan, int nJ,
+									 int nC)
+{
+	for (int s = 0; s < prog.segmentCount; ++s)
+	{
+		for (int r = 0; r < prog.repeat[s]; ++r)
+		{
+			for (int k = 0; k < prog.passCount[s]; ++k)
+			{
+				PassDesc pass = prog.passes[s][k];
+				if (pass.kind == PASS_BODY)
+				{
+					if (a.bodies.capacity > 0)
+					{
+						S2B_LAUNCH(w, s2bBodyPassKernel, gridFor(a.bodies.capacity, S2B_BLOCK), S2B_BLOCK, 0, a, (int)pass.bodyOp);
+					}
+				}
+				else if (pass.kind == PASS_FLAT)
+				{
+					if (nJ + nC > 0)
+					{
+						S2B_LAUNCH(w, s2bRangePassKernel, gridFor(nJ + nC, S2B_BLOCK), S2B_BLOCK, 0, a, p, (int)pass.jointOp,
+								   (int)pass.contactOp, 0, nJ, 0, nC);
+					}
+				}
+				else
+				{
+					for (int g = 0; g < plan.groups; ++g)
+					{
+						int jb = plan.jOff[g], je = plan.jOff[g + 1], cb = plan.cOff[g], ce = plan.cOff[g + 1];
+						int n = (pass.jointOp != JOP_NONE ? je - jb : 0) + (pass.contactOp != COP_NONE ? ce - cb : 0);
+						if (n > 0)
+						{
+							S2B_LAUNCH(w, s2bRangePassKernel, gridFor(n, S2B_BLOCK), S2B_BLOCK, 0, a, p, (int)pass.jointOp,
+									   (int)pass.contactOp, jb, je, cb, ce);
+						}
+					}
+					int G = (int)plan.cOff.size() - 2; // table index of the overflow group
+					int jb = plan.jOff[G], je = plan.jOff[G + 1], cb = plan.cOff[G], ce = plan.cOff[G + 1];
+					int n = (pass.jointOp != JOP_NONE ? je - jb : 0) + (pass.contactOp != COP_NONE ? ce - cb : 0);
+					if (n > 0)
+					{
+						S2B_LAUNCH(w, s2bSerialPassKernel, 1, 32, 0, a, p, (int)pass.jointOp, (int)pass.contactOp, jb, je, cb, ce);
+					}
+				}
+			}
 		}
 	}
-	launchBodyPass<OP_FINALIZE_POSITIONS>(w, a);
-	launchFlatPass<JOP_STORE, OP_STORE>(w, a, p, nJ, nC);
 }
 
 // wavefront levels on the host (validation schedule): level(i) = 1 + max level of earlier items sharing a movable body
@@ -942,11 +1345,18 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 	cudaStream_t st = w->stream;
 	s2bStepContext ctx = *ctxIn;
 
-	if (solverType != 7)
+	if (solverType == 3 || solverType < 0 || solverType > 9)
 	{
-		fprintf(stderr, "solver2d-b200: solver type %d is not implemented on the device yet\n", solverType);
+		// s2_solverPGS_NGS_Block (2x2 block LCP) is the one variant not on the device yet
+		fprintf(stderr, "solver2d-b200: solver type %d is not implemented on the device — there is no CPU fallback\n", solverType);
 		abort();
 	}
+	if (solverType == 9 && (ctx.iterations == 0 || ctx.dt == 0.0f))
+	{
+		return; // s2Solve_XPBD leaves early (reference src/solve_xpbd.c:345-353)
+	}
+	int countedPasses = 0;
+	Program program = buildProgram(solverType, ctx, &countedPasses);
 
 	int contactCount = w->contactCount;
 	int jointCap = w->jointCap;
@@ -1081,9 +1491,21 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 	a.solverType = solverType;
 	a.sticky = w->sticky ? 1 : 0;
 
-	// hertz clamps of the variant (reference src/solve_tgs_soft.c:185-186)
+	// hertz clamps of the variant: TGS_Soft (reference src/solve_tgs_soft.c:185-186), SoftStep (src/solve_soft_step.c:216-217),
+	// PGS_Soft / Jacobi (src/solve_pgs_soft.c:162-163, src/solve_jacobi.c:169-170); unused by the rigid variants
 	float contactHertz = S2_MIN(s2_contactHertz, 0.25f * ctx.inv_h);
 	float jointHertz = S2_MIN(s2_jointHertz, 0.125f * ctx.inv_h);
+	if (solverType == 5)
+	{
+		jointHertz = S2_MIN(s2_jointHertz, 0.25f * ctx.inv_h);
+	}
+	else if (solverType == 4 || solverType == 0)
+	{
+		contactHertz = S2_MIN(s2_contactHertz, 0.333f * ctx.inv_h);
+		jointHertz = S2_MIN(s2_jointHertz, 0.5f * ctx.inv_h);
+	}
+	// XPBD recomputes its inverse sub-step as 1 / h (reference src/solve_xpbd.c:399-400), not inv_dt * iterations
+	a.xpbdInvH = ctx.h != 0.0f ? 1.0f / ctx.h : 0.0f;
 	a.contactHertz = contactHertz;
 	a.jointHertz = jointHertz;
 	a.softDynamic = makeSoft(ctx.h, contactHertz, 10.0f);
@@ -1116,11 +1538,22 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 			S2B_LAUNCH(w, s2bFillAdjacency, gridFor(maxItems, 256), 256, 0, s->counts.p, s->itemBodies.p, s->adjStart.p,
 					   s->adjCursor.p, s->adj.p);
 
-			if (w->coopSupported)
+			if (w->coopSupported == 0)
 			{
-				int blocksPerSm = 0;
-				S2B_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, s2bColorKernel, 256, 0));
-				int grid = std::min(w->smCount * std::max(blocksPerSm, 1), std::max(1, gridFor(maxItems, 256)));
+				fprintf(stderr, "solver2d-b200: cooperative launch unsupported on this device\n");
+				abort();
+			}
+			{
+				// working colours start from the persisted ones; only constraints that appeared this step are uncoloured
+				S2B_LAUNCH(w, s2bSeedColors, gridFor(maxItems, 256), 256, 0, s->counts.p, s->jointSlots.p, s->activeSlots.p,
+						   w->jColor.p, w->contacts[w->cur].color.p, s->colorA.p, w->maxColors);
+				if (w->colorGrid == 0)
+				{
+					int blocksPerSm = 0;
+					S2B_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, s2bColorKernel, 256, 0));
+					w->colorGrid = w->smCount * std::min(std::max(blocksPerSm, 1), 2);
+				}
+				int grid = std::min(w->colorGrid, std::max(1, gridFor(maxItems, 256)));
 				int* countsPtr = s->counts.p;
 				const int2* ib = s->itemBodies.p;
 				const int* as = s->adjStart.p;
@@ -1131,11 +1564,8 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 				void* args[] = {&countsPtr, &ib, &as, &ad, &ca, &cb, &mc};
 				S2B_CHECK(cudaLaunchCooperativeKernel((void*)s2bColorKernel, dim3(grid), dim3(256), args, 0, st));
 				w->kernelLaunches += 1;
-			}
-			else
-			{
-				fprintf(stderr, "solver2d-b200: cooperative launch unsupported on this device\n");
-				abort();
+				S2B_LAUNCH(w, s2bStoreColors, gridFor(maxItems, 256), 256, 0, s->counts.p, s->jointSlots.p, s->activeSlots.p,
+						   w->jColor.p, w->contacts[w->cur].color.p, s->colorA.p);
 			}
 
 			// colour-major order: 8-bit stable radix sort of (colour, natural index), joints and contacts separately
@@ -1231,33 +1661,38 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 	{
 		// wavefront tables hold CNT_GROUPS levels and no overflow group; the overflow counts are zero so the kernel
 		// never indexes past them
-		int blocksPerSm = 0;
-		S2B_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, s2bPersistentTgsSoft, S2B_BLOCK, 0));
-		blocksPerSm = std::min(std::max(blocksPerSm, 1), 4);
+		if (w->solveGrid == 0)
+		{
+			int blocksPerSm = 0;
+			S2B_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, s2bPersistentSolve, S2B_BLOCK, 0));
+			const char* env = getenv("S2B_SOLVE_BLOCKS_PER_SM");
+			int want = env != nullptr ? atoi(env) : 2;
+			w->solveGrid = w->smCount * std::min(std::max(blocksPerSm, 1), std::max(want, 1));
+		}
 		int wanted = std::max(gridFor(std::max(maxItems, bodyCap), S2B_BLOCK), 1);
-		int grid = std::min(w->smCount * blocksPerSm, wanted);
-		void* args[] = {&a, &pp};
+		int grid = std::min(w->solveGrid, wanted);
+		void* args[] = {&a, &pp, &program};
 		if (w->solveKernelStart == nullptr)
 		{
 			S2B_CHECK(cudaEventCreate(&w->solveKernelStart));
 			S2B_CHECK(cudaEventCreate(&w->solveKernelEnd));
 		}
 		S2B_CHECK(cudaEventRecord(w->solveKernelStart, st));
-		S2B_CHECK(cudaLaunchCooperativeKernel((void*)s2bPersistentTgsSoft, dim3(grid), dim3(S2B_BLOCK), args, 0, st));
+		S2B_CHECK(cudaLaunchCooperativeKernel((void*)s2bPersistentSolve, dim3(grid), dim3(S2B_BLOCK), args, 0, st));
 		S2B_CHECK(cudaEventRecord(w->solveKernelEnd, st));
 		w->solveKernelTimed = true;
 		w->kernelLaunches += 1;
 	}
 	else
 	{
-		runTgsSoftMultiLaunch(w, a, pp, plan, hostNJ, hostNC);
+		runProgramLaunchByLaunch(w, a, pp, program, plan, hostNJ, hostNC);
+		w->solveKernelTimed = false;
 	}
 
 	// work meter: constraint-iterations of this step = (contact constraints + joints) x solve passes
 	{
 		w->dWork.reserve(4, st, true);
-		int passes = ctx.iterations * (1 + (ctx.extraIterations > 0 ? 1 : 0));
-		S2B_LAUNCH(w, s2bMeterWork, 1, 1, 0, s->counts.p, passes, w->dWork.p);
+		S2B_LAUNCH(w, s2bMeterWork, 1, 1, 0, s->counts.p, countedPasses, w->dWork.p);
 	}
 }
 

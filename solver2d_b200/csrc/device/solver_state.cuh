@@ -21,6 +21,7 @@ enum
 	CNT_OVERFLOW_J = 4, // joints in the overflow group
 	CNT_REMAINING = 5, // colouring work counters (three rotating slots: 5, 6, 7)
 	CNT_ROUNDS = 8,
+	CNT_UNCOLOURED = 9, // blocks that saw an uncoloured item at the start of the colouring kernel
 	CNT_SIZE = 16
 };
 
@@ -41,6 +42,7 @@ struct SolveArgs
 	SoftCoef softJoint;
 	float contactHertz;
 	float jointHertz;
+	float xpbdInvH;
 	int solverType;
 	int sticky;
 };

@@ -66,6 +66,7 @@ __global__ void s2bScatterJoints(const s2bJointRow* __restrict__ rows, int count
 	j.target[i] = make_float4(r->target[0], r->target[1], 0.0f, 0.0f);
 	j.imp[i] = make_float4(r->impulse[0], r->impulse[1], r->motorImpulse, 0.0f);
 	j.limp[i] = make_float4(r->lowerImpulse, r->upperImpulse, 0.0f, 0.0f);
+	j.color[i] = -1;
 }
 
 __device__ __forceinline__ int s2bPackCache(const s2bContactRow* r)
@@ -98,6 +99,7 @@ __global__ void s2bScatterContacts(const s2bContactRow* __restrict__ rows, int c
 	int ids = (r->points[0].id & 0xFFFF) | ((r->points[1].id & 0xFFFF) << 16);
 	c.info[t] = make_int4(flags, ids, s2bPackCache(r), __float_as_int(r->cacheMetric));
 	c.nf[t] = make_float4(r->normal[0], r->normal[1], r->friction, 0.0f);
+	c.color[t] = -1;
 	for (int p = 0; p < 2; ++p)
 	{
 		const s2bContactPoint* q = r->points + p;
@@ -356,6 +358,7 @@ extern "C" void s2b_world_destroy(s2bWorld* w)
 	w->jTarget.release();
 	w->jImp.release();
 	w->jLimp.release();
+	w->jColor.release();
 	w->jointPairKeys.release();
 	w->jointDestroyKeys.release();
 	w->dState.release();
@@ -453,6 +456,7 @@ static void reserveJoints(s2bWorld* w, int cap)
 	w->jTarget.reserve(cap, s);
 	w->jImp.reserve(cap, s);
 	w->jLimp.reserve(cap, s);
+	w->jColor.reserve(cap, s);
 	w->jointCap = (int)w->jHead.cap;
 }
 

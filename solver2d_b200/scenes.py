@@ -20,7 +20,7 @@ import math
 from dataclasses import dataclass, field
 
 from . import capi
-from .capi import (BodyId, Capsule, Circle, Segment, Vec2, default_body_def, default_revolute_def,
+from .capi import (BodyId, Capsule, Circle, Segment, Vec2, default_body_def, default_mouse_def, default_revolute_def,
                    default_shape_def)
 
 
@@ -203,6 +203,65 @@ def tumbler(lib, solver="TGS_Soft", grid=100, half_extent=30.0) -> Scene:
     for i in range(grid):
         for j in range(grid):
             bd.position = Vec2((j - 0.5 * (grid - 1)) * pitch, half_extent + (i - 0.5 * (grid - 1)) * pitch)
+            bid = lib.s2CreateBody(world, C.byref(bd))
+            lib.s2CreatePolygonShape(bid, C.byref(sd), C.byref(box))
+            sc.bodies.append(bid)
+    return sc
+
+
+def limited_chains(lib, solver="TGS_Soft", chains=3, links=6) -> Scene:
+    """Joint feature coverage: hanging capsule chains whose revolute joints have angle limits (every joint), a motor
+    (every other joint), collideConnected on one chain, and a mouse joint dragging the last link of the first chain
+    (s2DefaultMouseJointDef pattern of reference samples/sample.cpp). The chains swing into a pile of boxes on the
+    ground so that joints and contacts share bodies."""
+    world = lib.create_world(solver)
+    sc = Scene(lib, world, name=f"chains{chains}x{links}")
+    gid = _ground(lib, world, 30.0)
+    sc.bodies.append(gid)
+    sd = default_shape_def()
+    sd.density = 2.0
+    cap = Capsule(Vec2(-0.4, 0.0), Vec2(0.4, 0.0), 0.12)
+    for c in range(chains):
+        x0 = -6.0 + 6.0 * c
+        y0 = 6.0
+        prev = gid
+        for i in range(links):
+            bd = default_body_def()
+            bd.type = capi.DYNAMIC_BODY
+            bd.position = Vec2(x0 + 0.5 + 1.0 * i, y0)
+            bid = lib.s2CreateBody(world, C.byref(bd))
+            lib.s2CreateCapsuleShape(bid, C.byref(sd), C.byref(cap))
+            sc.bodies.append(bid)
+            jd = default_revolute_def()
+            pivot = Vec2(x0 + 1.0 * i, y0)
+            jd.bodyIdA = prev
+            jd.bodyIdB = bid
+            jd.localAnchorA = lib.s2Body_GetLocalPoint(prev, pivot)
+            jd.localAnchorB = lib.s2Body_GetLocalPoint(bid, pivot)
+            jd.enableLimit = True
+            jd.lowerAngle = -0.25 * math.pi if i > 0 else -0.6 * math.pi
+            jd.upperAngle = 0.15 * math.pi if i > 0 else 0.1 * math.pi
+            if i % 2 == 1:
+                jd.enableMotor = True
+                jd.motorSpeed = 0.5 if c % 2 == 0 else -0.5
+                jd.maxMotorTorque = 30.0
+            jd.collideConnected = c == 1
+            sc.joints.append(lib.s2CreateRevoluteJoint(world, C.byref(jd)))
+            prev = bid
+        if c == 0:
+            md = default_mouse_def()
+            md.bodyIdA = gid
+            md.bodyIdB = prev
+            md.target = Vec2(x0 + links + 1.0, y0 - 1.0)
+            md.hertz = 5.0
+            md.dampingRatio = 0.7
+            sc.joints.append(lib.s2CreateMouseJoint(world, C.byref(md)))
+    bd = default_body_def()
+    bd.type = capi.DYNAMIC_BODY
+    box = lib.s2MakeSquare(0.3)
+    for i in range(4):
+        for j in range(10):
+            bd.position = Vec2(-8.0 + 1.7 * j + 0.1 * i, 0.35 + 0.65 * i)
             bid = lib.s2CreateBody(world, C.byref(bd))
             lib.s2CreatePolygonShape(bid, C.byref(sd), C.byref(box))
             sc.bodies.append(bid)

@@ -43,6 +43,14 @@ def _pin(reference, recipe, solver, warm_steps, vel, pos, warm_start=True, **kw)
         live = oc["pointCount"] > j
         assert bit_equal(oc["points"]["normalImpulse"][:, j][live], cf2[slots, base + P["normalImpulse"]][live])
         assert bit_equal(oc["points"]["tangentImpulse"][:, j][live], cf2[slots, base + P["tangentImpulse"]][live])
+        if solver == "TGS_Sticky":
+            for name in ("frictionAnchorA", "frictionAnchorB", "frictionNormalA", "frictionNormalB"):
+                got = oc["points"][name][:, j][live]
+                want = np.stack([cf2[slots, base + P[name]], cf2[slots, base + P[name] + 1]], axis=1)[live]
+                assert bit_equal(got, want), name
+    if solver == "TGS_Sticky":
+        live = oc["pointCount"] > 0
+        assert np.array_equal(oc["frictionPersisted"][live], ci2[slots, refmod.CONTACT_I["frictionPersisted"]][live])
     sc.destroy()
     return len(contacts), int((joints["flags"] & 1).sum())
 
@@ -84,3 +92,37 @@ def test_oracle_order_changes_result(reference):
     b, _, _ = O.solve(7, bodies, contacts, joints, ctx, order=order)
     assert not bit_equal(a["linearVelocity"], b["linearVelocity"])
     sc.destroy()
+
+
+VARIANTS = ["Jacobi", "PGS", "PGS_NGS", "PGS_Soft", "SoftStep", "TGS_Sticky", "TGS_Soft", "TGS_NGS", "XPBD"]
+
+
+@pytest.mark.parametrize("solver", VARIANTS)
+def test_variant_pyramid_pinned(reference, solver):
+    # the reference's Jacobi variant blows a pyramid apart within five steps (its own behaviour): pin it early
+    warm = 2 if solver == "Jacobi" else 40
+    nc, _ = _pin(reference, scenes.pyramid, solver, warm, 4, 2, base_count=10)
+    assert nc > 50
+
+
+@pytest.mark.parametrize("solver", VARIANTS)
+def test_variant_cold_start_pinned(reference, solver):
+    _pin(reference, scenes.pyramid, solver, 2 if solver == "Jacobi" else 30, 3, 1, warm_start=False, base_count=8)
+
+
+@pytest.mark.parametrize("solver", VARIANTS)
+def test_variant_bridge_pinned(reference, solver):
+    _, nj = _pin(reference, scenes.bridge, solver, 12, 4, 2, count=30)
+    assert nj == 31
+
+
+@pytest.mark.parametrize("solver", VARIANTS)
+def test_variant_limits_motors_mouse_pinned(reference, solver):
+    nc, nj = _pin(reference, scenes.limited_chains, solver, 40, 4, 2)
+    assert nj == 19 and nc > 20
+
+
+@pytest.mark.parametrize("solver", VARIANTS)
+def test_variant_mixed_shapes_pinned(reference, solver):
+    nc, _ = _pin(reference, scenes.mixed_shapes, solver, 100, 4, 2)
+    assert nc > 20

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 DT = 1.0 / 60.0
 
 
-def _case(reference, dev, recipe, solver, warm, vel, pos, persistent, max_colors=None, **kw):
+def _case(reference, dev, recipe, solver, warm, vel, pos, persistent, max_colors=None, warm_start=True, **kw):
     R = reference
     O = port.load()
     sc = recipe(R, solver, **kw)
@@ -23,7 +23,7 @@ def _case(reference, dev, recipe, solver, warm, vel, pos, persistent, max_colors
     bodies = body_rows_from_ref(*R.bodies(sc.world))
     contacts, _ = contact_rows_from_ref(*R.contacts(sc.world))
     joints = joint_rows_from_ref(*R.joints(sc.world))
-    ctx = device.make_context(solver, DT, vel, pos, True)
+    ctx = device.make_context(solver, DT, vel, pos, warm_start)
 
     dw = dev.create_world(capi.SOLVER[solver])
     dw.upload_bodies(bodies, len(bodies))
@@ -36,6 +36,7 @@ def _case(reference, dev, recipe, solver, warm, vel, pos, persistent, max_colors
     dw.solve(ctx)
     got = dw.download_all_bodies(len(bodies))
     got_contacts = dw.download_contacts(len(contacts))
+    got_joints = dw.download_joints(len(joints))
     order, group_sizes = dw.solve_order(len(contacts) + len(joints))
     counters = dw.counters()
     dw.destroy()
@@ -68,6 +69,15 @@ def _case(reference, dev, recipe, solver, warm, vel, pos, persistent, max_colors
     live = contacts["pointCount"] > 0
     assert bit_equal(got_contacts["points"]["normalImpulse"][live], oc["points"]["normalImpulse"][live])
     assert bit_equal(got_contacts["points"]["tangentImpulse"][live], oc["points"]["tangentImpulse"][live])
+    if solver == "TGS_Sticky":
+        assert np.array_equal(got_contacts["frictionPersisted"][live], oc["frictionPersisted"][live])
+        for name in ("frictionAnchorA", "frictionAnchorB", "frictionNormalA", "frictionNormalB"):
+            for j in range(2):
+                has = contacts["pointCount"] > j
+                assert bit_equal(got_contacts["points"][name][:, j][has], oc["points"][name][:, j][has]), name
+    jlive = (joints["flags"] & 1) == 1
+    for name in ("impulse", "motorImpulse", "lowerImpulse", "upperImpulse"):
+        assert bit_equal(got_joints[name][jlive], oj[name][jlive]), name
     sc.destroy()
     return counters
 
@@ -88,3 +98,35 @@ def test_color_schedule_with_overflow_group(reference, dev):
 def test_color_schedule_joints_and_contacts(reference, dev):
     c = _case(reference, dev, scenes.joint_contact_stress, "TGS_Soft", 90, 4, 2, True, bridges=3, planks=24, grid=9)
     assert c.jointCount == 75 and c.constraintCount > 20
+
+
+VARIANTS = ["Jacobi", "PGS", "PGS_NGS", "PGS_Soft", "SoftStep", "TGS_Sticky", "TGS_Soft", "TGS_NGS", "XPBD"]
+
+
+@pytest.mark.parametrize("persistent", [True, False])
+@pytest.mark.parametrize("solver", VARIANTS)
+def test_variant_color_pyramid(reference, dev, solver, persistent):
+    warm = 2 if solver == "Jacobi" else 30  # the reference's Jacobi blows a pyramid apart within five steps
+    c = _case(reference, dev, scenes.pyramid, solver, warm, 4, 2, persistent, base_count=16)
+    assert c.constraintCount > 100 and c.overflowCount == 0
+
+
+@pytest.mark.parametrize("solver", VARIANTS)
+def test_variant_color_limits_motors_mouse(reference, dev, solver):
+    c = _case(reference, dev, scenes.limited_chains, solver, 40, 4, 2, True)
+    assert c.jointCount == 19 and c.constraintCount > 20
+
+
+@pytest.mark.parametrize("solver", VARIANTS)
+def test_variant_color_mixed_shapes_with_overflow(reference, dev, solver):
+    c = _case(reference, dev, scenes.mixed_shapes, solver, 100, 4, 2, True, max_colors=2)
+    assert c.constraintCount > 20 and c.overflowCount > 0
+
+
+@pytest.mark.parametrize("solver", VARIANTS)
+def test_variant_color_cold_start(reference, dev, solver):
+    R = reference
+    warm = 2 if solver == "Jacobi" else 20
+    c = _case(reference, dev, scenes.joint_contact_stress, solver, warm, 3, 1, False, warm_start=False, bridges=2, planks=16,
+              grid=6)
+    assert c.jointCount == 34

@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 DT = 1.0 / 60.0
 
 
-def _one_case(reference, dev, recipe, solver, warm_steps, vel_iters, pos_iters, schedule, persistent, **kw):
+def _one_case(reference, dev, recipe, solver, warm_steps, vel_iters, pos_iters, schedule, persistent, warm_start=True, **kw):
     R = reference
     sc = recipe(R, solver, **kw)
     for _ in range(warm_steps):
@@ -31,9 +31,9 @@ def _one_case(reference, dev, recipe, solver, warm_steps, vel_iters, pos_iters, 
     dw = load_device_world_from_ref(dev, R, sc.world, solver)
     dw.set_schedule(schedule)
     dw.set_persistent(persistent)
-    ctx = device.make_context(solver, DT, vel_iters, pos_iters, True)
+    ctx = device.make_context(solver, DT, vel_iters, pos_iters, warm_start)
 
-    R.step_solve(sc.world, DT, vel_iters, pos_iters, True)
+    R.step_solve(sc.world, DT, vel_iters, pos_iters, warm_start)
     bf, bi = R.bodies(sc.world)
     cf, ci = R.contacts(sc.world)
 
@@ -48,6 +48,10 @@ def _one_case(reference, dev, recipe, solver, warm_steps, vel_iters, pos_iters, 
     ref_imp = np.stack([cf[dw.ref_contact_slots, refmod.CONTACT_F["points"] + refmod.POINT_STRIDE * j + P["normalImpulse"]]
                         for j in range(2)], axis=1)
     dev_imp = contacts["points"]["normalImpulse"]
+    ref_timp = np.stack([cf[dw.ref_contact_slots, refmod.CONTACT_F["points"] + refmod.POINT_STRIDE * j + P["tangentImpulse"]]
+                         for j in range(2)], axis=1)
+    dev_timp = contacts["points"]["tangentImpulse"]
+    two = np.stack([contacts["pointCount"] > 0, contacts["pointCount"] > 1], axis=1) if len(contacts) else None
     diff["impulse"] = float(np.abs(ref_imp - dev_imp).max()) if len(contacts) else 0.0
     valid = bi[:, 0] == 1
     F = refmod.BODY_F
@@ -55,7 +59,12 @@ def _one_case(reference, dev, recipe, solver, warm_steps, vel_iters, pos_iters, 
              and bit_equal(rows["linearVelocity"][valid], bf[valid, F["v"]:F["v"] + 2])
              and bit_equal(rows["angularVelocity"][valid], bf[valid, F["w"]])
              and bit_equal(rows["rot"][valid], bf[valid, F["rot"]:F["rot"] + 2])
-             and bit_equal(ref_imp, dev_imp))
+             and bit_equal(ref_imp, dev_imp)
+             and (two is None or bit_equal(ref_timp[two], dev_timp[two])))
+    if solver == "TGS_Sticky" and len(contacts):
+        live = contacts["pointCount"] > 0
+        exact = exact and bool(np.array_equal(contacts["frictionPersisted"][live],
+                                              ci[dw.ref_contact_slots, refmod.CONTACT_I["frictionPersisted"]][live]))
     dw.destroy()
     sc.destroy()
     return diff, exact, counters
@@ -97,3 +106,31 @@ def test_tgs_soft_no_warm_start_and_no_relax(reference, dev):
     assert max(compare_bodies(rows, bf, bi).values()) == 0.0
     dw.destroy()
     sc.destroy()
+
+
+VARIANTS = ["Jacobi", "PGS", "PGS_NGS", "PGS_Soft", "SoftStep", "TGS_Sticky", "TGS_Soft", "TGS_NGS", "XPBD"]
+
+
+@pytest.mark.parametrize("persistent", [True, False])
+@pytest.mark.parametrize("solver", VARIANTS)
+def test_variant_wavefront_bit_exact_pyramid(reference, dev, solver, persistent):
+    warm = 2 if solver == "Jacobi" else 30  # the reference's Jacobi blows a pyramid apart within five steps
+    diff, exact, counters = _one_case(reference, dev, scenes.pyramid, solver, warm, 4, 2, device.SCHEDULE_WAVEFRONT,
+                                      persistent, base_count=12)
+    assert counters.constraintCount > 50
+    assert exact, f"{solver} not bit-exact: {diff}"
+
+
+@pytest.mark.parametrize("solver", VARIANTS)
+def test_variant_wavefront_bit_exact_joints(reference, dev, solver):
+    diff, exact, counters = _one_case(reference, dev, scenes.limited_chains, solver, 40, 4, 2, device.SCHEDULE_WAVEFRONT, True)
+    assert counters.jointCount == 19
+    assert exact, f"{solver} not bit-exact: {diff}"
+
+
+@pytest.mark.parametrize("solver", VARIANTS)
+def test_variant_wavefront_bit_exact_cold_mixed(reference, dev, solver):
+    diff, exact, counters = _one_case(reference, dev, scenes.mixed_shapes, solver, 100, 3, 1, device.SCHEDULE_WAVEFRONT, True,
+                                      warm_start=False)
+    assert counters.constraintCount > 20
+    assert exact, f"{solver} not bit-exact: {diff}"
