@@ -285,6 +285,9 @@ S2B_API float s2b_elapsed_ms(s2bWorld* world);
 S2B_API float s2b_time_color_kernel(s2bWorld* world, const s2bStepContext* context, int reps, int* constraints);
 
 S2B_API const char* s2b_version(void);
+// Evaluate the device's atan2 (include/solver2d/atan2_f32.h) on the GPU for `count` host-resident (y, x) pairs: a
+// probe for the parity tests, which compare it bit for bit with the host C library's atan2f.
+S2B_API void s2b_eval_atan2(const float* y, const float* x, float* out, int32_t count);
 // sizeof of {s2bBodyRow, s2bShapeRow, s2bJointRow, s2bContactRow, s2bStepContext, s2bCounters}: lets an FFI binding
 // verify its struct mirrors at load time.
 S2B_API void s2b_abi_sizes(int32_t out[6]);

@@ -9,9 +9,18 @@
 //   * s2NormalizeRot guards on mag > 0 and multiplies by 1.0f/mag instead of dividing (reference math.h:201-207).
 #pragma once
 
+#include "solver2d/atan2_f32.h"
 #include "solver2d/types.h"
 
 #include <math.h>
+
+// atan2f as the reference's C library computes it: libm on the host, the bit-identical restatement on the device
+// (see solver2d/atan2_f32.h for why CUDA's own atan2f will not do)
+#if defined(__CUDA_ARCH__)
+	#define S2_ATAN2F(Y, X) s2Atan2F32((Y), (X))
+#else
+	#define S2_ATAN2F(Y, X) atan2f((Y), (X))
+#endif
 
 #define S2_MIN(A, B) ((A) < (B) ? (A) : (B))
 #define S2_MAX(A, B) ((A) > (B) ? (A) : (B))
@@ -231,7 +240,7 @@ S2_INLINE float s2ComputeAngularVelocity(s2Rot q1, s2Rot q2, float inv_h)
 
 S2_INLINE float s2Rot_GetAngle(s2Rot q)
 {
-	return atan2f(q.s, q.c);
+	return S2_ATAN2F(q.s, q.c);
 }
 
 S2_INLINE s2Vec2 s2Rot_GetXAxis(s2Rot q)
@@ -269,7 +278,7 @@ S2_INLINE float s2RelativeAngle(s2Rot b, s2Rot a)
 {
 	float s = b.s * a.c - b.c * a.s;
 	float c = b.c * a.c + b.s * a.s;
-	return atan2f(s, c);
+	return S2_ATAN2F(s, c);
 }
 
 S2_INLINE s2Vec2 s2RotateVector(s2Rot q, s2Vec2 v)

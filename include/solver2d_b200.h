@@ -31,6 +31,10 @@ S2B_API int32_t s2World_GetBodyTransforms(s2WorldId worldId, float* out, int32_t
 S2B_API float s2World_TimedSteps(s2WorldId worldId, int32_t steps, float timeStep, int32_t velIters, int32_t posIters,
 								 bool warmStart, int32_t flushL2);
 
+// The float atan2 the device kernels use (include/solver2d/atan2_f32.h), evaluated on the host: lets a CPU-only test
+// pin it to the C library's atan2f.
+S2B_API float s2Atan2Device(float y, float x);
+
 #ifdef __cplusplus
 }
 #endif

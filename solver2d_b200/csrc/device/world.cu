@@ -878,3 +878,33 @@ extern "C" const char* s2b_version(void)
 {
 	return "solver2d-b200 0.1 (sm_100a)";
 }
+
+__global__ void s2bEvalAtan2Kernel(const float* y, const float* x, float* out, int n)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n)
+	{
+		out[i] = S2_ATAN2F(y[i], x[i]);
+	}
+}
+
+extern "C" void s2b_eval_atan2(const float* y, const float* x, float* out, int32_t count)
+{
+	if (count <= 0)
+	{
+		return;
+	}
+	float *dy = nullptr, *dx = nullptr, *dout = nullptr;
+	size_t bytes = sizeof(float) * (size_t)count;
+	S2B_CHECK(cudaMalloc(&dy, bytes));
+	S2B_CHECK(cudaMalloc(&dx, bytes));
+	S2B_CHECK(cudaMalloc(&dout, bytes));
+	S2B_CHECK(cudaMemcpy(dy, y, bytes, cudaMemcpyHostToDevice));
+	S2B_CHECK(cudaMemcpy(dx, x, bytes, cudaMemcpyHostToDevice));
+	s2bEvalAtan2Kernel<<<(count + 255) / 256, 256>>>(dy, dx, dout, count);
+	S2B_CHECK(cudaGetLastError());
+	S2B_CHECK(cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost));
+	cudaFree(dy);
+	cudaFree(dx);
+	cudaFree(dout);
+}

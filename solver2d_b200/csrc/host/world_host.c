@@ -799,3 +799,8 @@ int32_t s2World_GetBodyTransforms(s2WorldId worldId, float* out, int32_t capacit
 	}
 	return world->bodyPool.capacity;
 }
+
+float s2Atan2Device(float y, float x)
+{
+	return s2Atan2F32(y, x);
+}

@@ -158,3 +158,22 @@ def test_falling_boxes_pair_set_tracks_reference(reference, product, dev):
     assert dpos <= 1e-4, dpos
     sr.destroy()
     sp.destroy()
+
+
+def test_device_atan2_bit_equal_to_libm(dev):
+    """Joint-limit rows read the joint angle through atan2f: the device restatement (include/solver2d/atan2_f32.h) must
+    return the bits of the host C library the reference links against. 400k inputs on the GPU vs libm."""
+    import ctypes as C
+    import ctypes.util
+    from test_host_cpu import _atan2_inputs
+    y, x = _atan2_inputs(200_000, 5)
+    out = np.empty_like(y)
+    dev.lib.s2b_eval_atan2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    dev.lib.s2b_eval_atan2(y.ctypes.data, x.ctypes.data, out.ctypes.data, len(y))
+    libm = C.CDLL(ctypes.util.find_library("m"))
+    libm.atan2f.restype = C.c_float
+    libm.atan2f.argtypes = [C.c_float, C.c_float]
+    want = np.array([libm.atan2f(float(a), float(b)) for a, b in zip(y, x)], np.float32)
+    nan = np.isnan(want)
+    assert np.array_equal(np.isnan(out), nan)
+    assert np.array_equal(out[~nan].view(np.uint32), want[~nan].view(np.uint32))

@@ -156,3 +156,32 @@ def test_manifold_functions_match_reference_bitwise(reference, product):
             for cr, cp in zip(cacheR, cacheP):
                 assert cr.count == cp.count and bytes(cr.indexA) == bytes(cp.indexA) and bytes(cr.indexB) == bytes(cp.indexB)
     assert hits > 1500  # the sweep actually produced contacts
+
+
+def _atan2_inputs(n, seed):
+    rng = np.random.default_rng(seed)
+    # (sin, cos)-like pairs as s2RelativeAngle produces them, raw bit patterns, and the special values
+    a = rng.uniform(-np.pi, np.pi, n)
+    y = [np.sin(a).astype(np.float32), rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32).view(np.float32),
+         np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, 1e-40, -1e-40, 3e38, 0.4375, 0.6875, 1.1875, 2.4375] * 13, np.float32)]
+    x = [np.cos(a).astype(np.float32), rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32).view(np.float32),
+         np.repeat(np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, 1e-40, -1e-40, 3e38, 0.4375, 0.6875, 1.1875, 2.4375],
+                            np.float32), 13)]
+    return np.concatenate(y), np.concatenate(x)
+
+
+def test_device_atan2_restatement_equals_libm_on_host():
+    """include/solver2d/atan2_f32.h (what the kernels call) against the C library atan2f the reference is linked with."""
+    import ctypes.util
+    lib = C.CDLL(device.LIB_PATH)
+    lib.s2Atan2Device.restype = C.c_float
+    lib.s2Atan2Device.argtypes = [C.c_float, C.c_float]
+    libm = C.CDLL(ctypes.util.find_library("m"))
+    libm.atan2f.restype = C.c_float
+    libm.atan2f.argtypes = [C.c_float, C.c_float]
+    y, x = _atan2_inputs(150000, 11)
+    mine = np.array([lib.s2Atan2Device(float(a), float(b)) for a, b in zip(y, x)], np.float32)
+    want = np.array([libm.atan2f(float(a), float(b)) for a, b in zip(y, x)], np.float32)
+    nan = np.isnan(want)
+    assert np.array_equal(np.isnan(mine), nan)
+    assert np.array_equal(mine[~nan].view(np.uint32), want[~nan].view(np.uint32))

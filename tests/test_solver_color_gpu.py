@@ -62,10 +62,15 @@ def _case(reference, dev, recipe, solver, warm, vel, pos, persistent, max_colors
 
     ob, oc, oj = O.solve(capi.SOLVER[solver], bodies, contacts, joints, ctx, order=order)
     valid = (bodies["flags"] & 1) == 1
-    assert bit_equal(got["position"][valid], ob["position"][valid])
-    assert bit_equal(got["rot"][valid], ob["rot"][valid])
-    assert bit_equal(got["linearVelocity"][valid], ob["linearVelocity"][valid])
-    assert bit_equal(got["angularVelocity"][valid], ob["angularVelocity"][valid])
+    report = {}
+    for name in ("position", "rot", "linearVelocity", "angularVelocity"):
+        g = np.ascontiguousarray(got[name][valid]).reshape(int(valid.sum()), -1)
+        o = np.ascontiguousarray(ob[name][valid]).reshape(int(valid.sum()), -1)
+        bad = np.nonzero((g.view(np.uint32) != o.view(np.uint32)).any(axis=1))[0]
+        if len(bad):
+            report[name] = dict(count=len(bad), first=np.nonzero(valid)[0][bad[:8]].tolist(),
+                                maxabs=float(np.abs(g[bad] - o[bad]).max()))
+    assert not report, f"{solver}: device != permuted oracle: {report}"
     live = contacts["pointCount"] > 0
     assert bit_equal(got_contacts["points"]["normalImpulse"][live], oc["points"]["normalImpulse"][live])
     assert bit_equal(got_contacts["points"]["tangentImpulse"][live], oc["points"]["tangentImpulse"][live])
