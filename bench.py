@@ -258,11 +258,19 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    e2e_parts = [0.0, 0.0, 0.0]
     for s in range(e2e_steps):
         f = forces if (s & 1) == 0 else -forces
+        ta = time.perf_counter()
         L.s2World_ApplyForcesToCenters(sc.world, idx.ctypes.data, f.ctypes.data, len(idx))
+        tb = time.perf_counter()
         sc.step(DT, args.substeps, args.relax, True)
+        tc = time.perf_counter()
         L.s2World_GetBodyTransforms(sc.world, transforms.ctypes.data, counters.bodyCapacity)
+        td = time.perf_counter()
+        e2e_parts[0] += tb - ta
+        e2e_parts[1] += tc - tb
+        e2e_parts[2] += td - tc
         exchange()
     torch.cuda.synchronize()
     e2e_time = time.perf_counter() - t0
@@ -299,8 +307,10 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
             "step_ms_stats": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)), "max": float(np.max(step_ms)),
                               "pair_passes_total": int(counters.pairPassCount)},
             "e2e": {"value": e2e_value, "unit": "constraint-iters/s", "ms_per_step": 1e3 * e2e_time_max / e2e_steps,
-                    "h2d_bytes_per_step": int(len(idx) * 16), "d2h_bytes_per_step": int(counters.bodyCapacity * 48),
-                    "steps": e2e_steps, "clock": "host wall clock, synchronised on both sides"},
+                    "h2d_bytes_per_step": int(len(idx) * 12), "d2h_bytes_per_step": int(nb * 16),
+                    "steps": e2e_steps, "clock": "host wall clock, synchronised on both sides",
+                    "host_ms_per_step": {"apply_forces": 1e3 * e2e_parts[0] / e2e_steps, "step_call": 1e3 * e2e_parts[1] / e2e_steps,
+                                         "get_transforms_incl_wait": 1e3 * e2e_parts[2] / e2e_steps}},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "s2bPersistentTgsSoft (whole solver stage of one step)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,

@@ -31,6 +31,9 @@ typedef struct s2bWorld s2bWorld;
 
 // flags shared by all rows
 #define S2B_ROW_VALID 0x1
+// body rows only: the slot already holds this body on the device, so the row's force / torque are ADDED to what the device
+// accumulated since the last step (bulk forces) instead of replacing it
+#define S2B_BODY_ADD_FORCE 0x8
 
 // One rigid body; mirrors the solver-relevant fields of s2Body (reference src/body.h:16-76).
 typedef struct s2bBodyRow
@@ -188,6 +191,9 @@ S2B_API void s2b_set_max_colors(s2bWorld* world, int maxColors);
 // Use the single persistent cooperative kernel for the solver stage (1, default where supported) or one launch
 // per group and pass (0; used for per-kernel profiling and as a cross-check).
 S2B_API void s2b_set_persistent(s2bWorld* world, int enable);
+// Warm start of the sub-stepping variants as a per-body gather fused with s2IntegrateVelocities (1, default) or as
+// grouped constraint passes like every other pass (0; cross-check). Both give bit-identical results.
+S2B_API void s2b_set_warm_gather(s2bWorld* world, int enable);
 
 // ---- host -> device -------------------------------------------------------------------------------------------
 
@@ -205,7 +211,8 @@ S2B_API void s2b_upload_contacts(s2bWorld* world, const s2bContactRow* rows, int
 //                 (replaces s2DestroyContactsBetweenBodies, reference src/joint.c:120-152, 214-217).
 S2B_API void s2b_upload_joint_pairs(s2bWorld* world, const uint64_t* blockKeys, int blockCount, const uint64_t* destroyKeys,
 									int destroyCount);
-// Only force / torque of the listed bodies (the per-frame input of s2Body_ApplyForceToCenter).
+// Force / torque of the listed bodies (the per-frame input of s2Body_ApplyForceToCenter), ADDED to the device's
+// accumulators; s2b_finalize zeroes them at the end of every step (reference src/world.c:275-276).
 typedef struct s2bForceRow
 {
 	int32_t index;
@@ -213,6 +220,9 @@ typedef struct s2bForceRow
 	float torque;
 } s2bForceRow;
 S2B_API void s2b_upload_forces(s2bWorld* world, const s2bForceRow* rows, int count);
+// Bulk form of s2Body_ApplyForceToCenter (reference src/body.c:206-212): force[k] is ADDED to body bodyIndices[k]. The
+// host arrays are copied into page-locked staging before the call returns; the H2D copy and the add are asynchronous.
+S2B_API void s2b_add_forces(s2bWorld* world, const int32_t* bodyIndices, const float* forcesXY, int count);
 // Page-locked host memory for row staging (uploads from it are asynchronous DMA).
 S2B_API void* s2b_host_alloc(size_t bytes);
 S2B_API void s2b_host_free(void* p);
@@ -247,6 +257,9 @@ S2B_API void s2b_download_all_bodies(s2bWorld* world, s2bBodyRow* rows, int capa
 // force.xy, torque} gathered on the device and copied into a pinned buffer owned by the world. The pointer stays valid
 // until the next call. Synchronises.
 S2B_API const float* s2b_sync_body_state(s2bWorld* world, int capacity);
+// Transforms only: {origin.x, origin.y, rot.s, rot.c} of body slots [0, count) into `out` (4 floats per slot, pageable or
+// page-locked host memory). What a renderer reads every frame (reference src/world.c:369-412 reads them per shape).
+S2B_API void s2b_download_transforms(s2bWorld* world, float* out, int count);
 S2B_API void s2b_download_shape_boxes(s2bWorld* world, float* aabb4, float* fat4, int32_t* flags, int capacity);
 S2B_API void s2b_download_joints(s2bWorld* world, s2bJointRow* rows, int capacity);
 // returns the number of contacts written (<= maxCount), in device order (sorted by shape-pair key)

@@ -266,6 +266,7 @@ struct s2bWorld
 	int schedule = S2B_SCHEDULE_COLOR;
 	int maxColors = 24;
 	int persistent = 1;
+	int gatherWarm = 1; // per-body warm-start gather (warm_gather.cuh); s2b_set_warm_gather / S2B_WARM_GATHER=0 disable it
 	int smCount = 148;
 	int coopSupported = 0;
 	int colorGrid = 0;	// cooperative grid sizes, computed once
@@ -294,6 +295,15 @@ struct s2bWorld
 
 	// pinned read-back buffer of s2b_sync_body_state
 	float* hostState = nullptr;
+	// bulk paths (s2b_add_forces, s2b_download_transforms)
+	void* bulkHost[2] = {nullptr, nullptr};
+	size_t bulkBytes[2] = {0, 0};
+	cudaEvent_t bulkEvent[2] = {nullptr, nullptr};
+	int bulkNext = 0, bulkCurrent = 0;
+	DevArray<char> dBulk;
+	float* hostXf = nullptr;
+	size_t hostXfFloats = 0;
+	DevArray<float4> dXf;
 	size_t hostStateFloats = 0;
 	DevArray<float4> dState;
 

@@ -14,6 +14,7 @@
 //               cooperative kernel (grid barrier between groups) or as one launch per group (profiling / cross-check)
 //   store       accumulated impulses back to the persistent manifolds / joints
 #include "joint_kernels.cuh"
+#include "warm_gather.cuh"
 
 #include <cooperative_groups.h>
 #include <cub/cub.cuh>
@@ -528,6 +529,8 @@ enum BodyOp
 	BOP_XPBD_INTEGRATE,
 	BOP_XPBD_PROJECT,
 	BOP_XPBD_FINALIZE,
+	BOP_INTEGRATE_VELOCITIES_WARM,		 // s2IntegrateVelocities + warm start gathered per body (warm_gather.cuh)
+	BOP_INTEGRATE_VELOCITIES_WARM_FIXED, // same with the prepare-time anchors of SoftStep
 };
 
 enum ContactOp
@@ -624,6 +627,12 @@ __device__ __forceinline__ void s2bRunBodyOp(int op, const SolveArgs& a, int i)
 			break;
 		case BOP_XPBD_PROJECT:
 			s2bXpbdProjectVelocity(a, i, a.xpbdInvH);
+			break;
+		case BOP_INTEGRATE_VELOCITIES_WARM:
+			s2bIntegrateVelocityWarm<false>(a, i, a.ctx.h);
+			break;
+		case BOP_INTEGRATE_VELOCITIES_WARM_FIXED:
+			s2bIntegrateVelocityWarm<true>(a, i, a.ctx.h);
 			break;
 		case BOP_XPBD_FINALIZE:
 			s2bXpbdFinalize(a, i);
@@ -989,7 +998,7 @@ struct ProgramBuilder
 
 // The stage list of every variant, taken from the variant's driver in the reference. Also returns
 // the number of solve passes per step that count as constraint-iterations.
-static Program buildProgram(int solverType, const s2bStepContext& ctx, int* countedPasses)
+static Program buildProgram(int solverType, const s2bStepContext& ctx, bool gatherWarm, int* countedPasses)
 {
 	ProgramBuilder b;
 	int S = ctx.iterations, E = ctx.extraIterations;
@@ -1004,10 +1013,17 @@ static Program buildProgram(int solverType, const s2bStepContext& ctx, int* coun
 			b.segment(1);
 			b.add(flatPass(JOP_PREPARE_SOFT_WARM, COP_PREPARE));
 			b.segment(S);
-			b.add(bodyPass(BOP_INTEGRATE_VELOCITIES));
-			if (warm)
+			if (warm && gatherWarm)
 			{
-				b.add(groupPass(JOP_WARM_START, softStep ? COP_WARM_START_FIXED : COP_WARM_START));
+				b.add(bodyPass(softStep ? BOP_INTEGRATE_VELOCITIES_WARM_FIXED : BOP_INTEGRATE_VELOCITIES_WARM));
+			}
+			else
+			{
+				b.add(bodyPass(BOP_INTEGRATE_VELOCITIES));
+				if (warm)
+				{
+					b.add(groupPass(JOP_WARM_START, softStep ? COP_WARM_START_FIXED : COP_WARM_START));
+				}
 			}
 			b.add(groupPass(JOP_SOFT_BIAS, softStep ? COP_SOFTSTEP_BIAS : COP_TGS_SOFT_BIAS));
 			b.add(bodyPass(BOP_INTEGRATE_POSITIONS));
@@ -1101,10 +1117,17 @@ static Program buildProgram(int solverType, const s2bStepContext& ctx, int* coun
 			b.segment(1);
 			b.add(flatPass(JOP_PREPARE_RIGID_FLAG, COP_PREPARE));
 			b.segment(S);
-			b.add(bodyPass(BOP_INTEGRATE_VELOCITIES));
-			if (warm)
+			if (warm && gatherWarm)
 			{
-				b.add(groupPass(JOP_WARM_START, COP_WARM_START));
+				b.add(bodyPass(BOP_INTEGRATE_VELOCITIES_WARM));
+			}
+			else
+			{
+				b.add(bodyPass(BOP_INTEGRATE_VELOCITIES));
+				if (warm)
+				{
+					b.add(groupPass(JOP_WARM_START, COP_WARM_START));
+				}
 			}
 			b.add(groupPass(JOP_RIGID, COP_TGS));
 			b.add(bodyPass(BOP_INTEGRATE_POSITIONS));
@@ -1356,7 +1379,9 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 		return; // s2Solve_XPBD leaves early (reference src/solve_xpbd.c:345-353)
 	}
 	int countedPasses = 0;
-	Program program = buildProgram(solverType, ctx, &countedPasses);
+	// per-sub-step warm starting as a per-body gather (warm_gather.cuh); S2B_WARM_GATHER=0 keeps the grouped passes
+	bool gatherWarm = w->gatherWarm != 0 && ctx.warmStart != 0 && (solverType == 7 || solverType == 5 || solverType == 8);
+	Program program = buildProgram(solverType, ctx, gatherWarm, &countedPasses);
 
 	int contactCount = w->contactCount;
 	int jointCap = w->jointCap;
@@ -1386,6 +1411,12 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 	s->jGroupOff.reserve(S2B_MAX_COLORS + 2, st, false);
 	s->cPerm.reserve(nC, st, false);
 	s->jPerm.reserve(nJ, st, false);
+	if (gatherWarm)
+	{
+		s->itemVal.reserve(nI, st, false);
+		s->incWork.reserve(2 * nI, st, false);
+		s->incList.reserve(2 * nI, st, false);
+	}
 	s->idx.reserve(nC, st, false);
 	s->nf.reserve(nC, st, false);
 	s->src.reserve(nC, st, false);
@@ -1521,7 +1552,7 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 
 	if (maxItems > 0)
 	{
-		bool wantAdj = w->schedule == S2B_SCHEDULE_COLOR;
+		bool wantAdj = w->schedule == S2B_SCHEDULE_COLOR || gatherWarm;
 		if (wantAdj)
 		{
 			S2B_CHECK(cudaMemsetAsync(s->degree.p, 0, sizeof(int) * ((size_t)bodyCap + 1), st));
@@ -1530,13 +1561,18 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 		S2B_LAUNCH(w, s2bItemEndpoints, gridFor(maxItems, 256), 256, 0, s->counts.p, s->jointSlots.p, s->activeSlots.p,
 				   jointView(w), makeView(w->contacts[w->cur]), bodyView(w), s->itemBodies.p, wantAdj ? s->degree.p : nullptr);
 
-		if (w->schedule == S2B_SCHEDULE_COLOR)
+		if (wantAdj)
 		{
 			size_t tb = s->cubTemp.cap;
 			cub::DeviceScan::ExclusiveSum(s->cubTemp.p, tb, s->degree.p, s->adjStart.p, bodyCap + 1, st);
 			w->kernelLaunches += 2;
 			S2B_LAUNCH(w, s2bFillAdjacency, gridFor(maxItems, 256), 256, 0, s->counts.p, s->itemBodies.p, s->adjStart.p,
 					   s->adjCursor.p, s->adj.p);
+		}
+
+		if (w->schedule == S2B_SCHEDULE_COLOR)
+		{
+			size_t tb = s->cubTemp.cap;
 
 			if (w->coopSupported == 0)
 			{
@@ -1635,9 +1671,23 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 			S2B_LAUNCH(w, s2bBuildSources, gridFor(contactCount, 256), 256, 0, s->counts.p, s->cPerm.p, s->activeSlots.p,
 					   s->src.p);
 		}
+
+		if (gatherWarm)
+		{
+			// incidence lists of the movable bodies in solve order
+			int tableEntries = w->schedule == S2B_SCHEDULE_COLOR ? S2B_MAX_COLORS + 1 : std::max(plan.groups, 1);
+			S2B_LAUNCH(w, s2bItemOrderKernel, gridFor(maxItems, 256), 256, 0, s->counts.p, s->cPerm.p, s->jPerm.p, s->cGroupOff.p,
+					   s->jGroupOff.p, tableEntries, s->itemVal.p);
+			S2B_LAUNCH(w, s2bSortIncidenceKernel, gridFor(bodyCap, 128), 128, 0, bodyCap, s->adjStart.p, s->adj.p, s->itemBodies.p,
+					   s->itemVal.p, s->incWork.p, s->incList.p);
+		}
 	}
 	else
 	{
+		if (gatherWarm)
+		{
+			S2B_CHECK(cudaMemsetAsync(s->adjStart.p, 0, sizeof(int) * ((size_t)bodyCap + 2), st));
+		}
 		// no constraints at all: bodies still integrate
 		plan.groups = 0;
 		plan.cOff.assign(S2B_MAX_COLORS + 2, 0);
@@ -1655,6 +1705,8 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 	// (the group tables may have been re-allocated by the schedule step: take the pointers now)
 	a.cGroupOff = s->cGroupOff.p;
 	a.jGroupOff = s->jGroupOff.p;
+	a.incStart = gatherWarm ? s->adjStart.p : nullptr;
+	a.incList = gatherWarm ? s->incList.p : nullptr;
 	pp.jPerm = s->jPerm.p;
 	bool usePersistent = w->persistent != 0 && w->coopSupported != 0;
 	if (usePersistent)

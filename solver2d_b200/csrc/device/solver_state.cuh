@@ -35,6 +35,8 @@ struct SolveArgs
 	const int* counts;	  // CNT_*
 	const int* cGroupOff; // contact-constraint group offsets, CNT_GROUPS + 2 entries (last group = overflow)
 	const int* jGroupOff; // joint-constraint group offsets, same shape
+	const int* incStart;  // per body: range of its incidence list (warm_gather.cuh); null when the gather is not used
+	const int* incList;	  // incidence entries sorted by solve order
 	s2bStepContext ctx;
 	float2 gravity;
 	SoftCoef softDynamic; // contact, both bodies movable
@@ -67,6 +69,8 @@ struct SolverScratch
 	DevArray<int> cPerm;				// solve position -> natural contact-constraint index
 	DevArray<int> jPerm;
 	DevArray<char> cubTemp;
+	DevArray<unsigned long long> itemVal, incWork; // warm-start gather: per-item sort value, per-body sort scratch
+	DevArray<int> incList;
 	int maxGroups = 0;
 
 	// contact constraint columns

@@ -1,0 +1,266 @@
+// solver2d-b200 — warm starting as a per-body GATHER fused with s2IntegrateVelocities.
+//
+// The sub-stepping variants warm start every sub-step (reference src/solve_tgs_soft.c:217-233,
+// src/solve_soft_step.c:246-262, src/solve_tgs_ngs.c:270-286). Run constraint by constraint that costs one grid
+// barrier per colour. But a warm start only ADDS terms to v and w that do not depend on v and w themselves:
+//     contact:  P = ln * n + lt * t ;  w -/+= invI * cross(r, P) ;  v = v -/+ invM * P        (r from the rotation, which
+//     joint:    P = impulse        ;  w -/+= invI * (cross(r, P) + axial) ;  v = v -/+ invM * P   no warm start changes)
+// so each body can collect its own terms. Float addition is not associative, therefore the terms are added in exactly
+// the order the constraint-by-constraint pass would have produced them: the incidence list of every movable body is
+// sorted by position in the solve order (group-major; joints before contacts inside a group; serial order inside
+// the overflow group). The result is bit-identical to the grouped pass, with no barrier between colours and the
+// integrate-velocities body pass folded in.
+#pragma once
+
+#include "joint_kernels.cuh"
+
+// incidence entry: (t << 2) | (side << 1) | isContact — t = position in the contact / joint constraint stream
+#define S2B_INC_CONTACT 1
+#define S2B_INC_SIDE_B 2
+
+// FIXED = false: anchors rotated by the current rotation (s2WarmStartContacts, reference src/solve_common.c:276-326)
+// FIXED = true : prepare-time anchors (s2WarmStartContacts_Fixed, reference src/solve_soft_step.c:16-63)
+template <bool FIXED> __device__ __forceinline__ void s2bIntegrateVelocityWarm(const SolveArgs& a, int i, float h)
+{
+	unsigned f = a.bodies.flags[i];
+	if ((f & S2B_BODY_VALID) == 0)
+	{
+		return;
+	}
+	float4 vel = a.bodies.vel[i];
+	float4 prm = a.bodies.prm[i];
+	float invMass = vel.w, invI = prm.w;
+	s2Vec2 v = V2(vel.x, vel.y);
+	float w = vel.z;
+	bool dynamic = S2B_BODY_TYPE(f) == S2B_BODY_DYNAMIC;
+
+	// s2IntegrateVelocities (reference src/solve_common.c:10-45)
+	if (dynamic)
+	{
+		float4 frc = a.bodies.frc[i];
+		s2Vec2 gravity = V2(a.gravity.x, a.gravity.y);
+		v = s2Add(v, s2MulSV(h * invMass, s2MulAdd(V2(frc.x, frc.y), frc.w * prm.z, gravity)));
+		w = w + h * invI * frc.z;
+		v = s2MulSV(1.0f / (1.0f + h * prm.x), v);
+		w *= 1.0f / (1.0f + h * prm.y);
+	}
+
+	int begin = a.incStart[i], end = a.incStart[i + 1];
+	if (begin == end)
+	{
+		if (dynamic)
+		{
+			a.bodies.vel[i] = make_float4(v.x, v.y, w, invMass);
+		}
+		return;
+	}
+
+	float4 pose = a.bodies.pose[i];
+	s2Rot q = R2(pose.z, pose.w);
+	for (int k = begin; k < end; ++k)
+	{
+		int e = a.incList[k];
+		int t = e >> 2;
+		bool sideB = (e & S2B_INC_SIDE_B) != 0;
+		if (e & S2B_INC_CONTACT)
+		{
+			int2 idx = a.cc.idx[t];
+			float4 nf = a.cc.nf[t];
+			s2Vec2 normal = V2(nf.x, nf.y);
+			s2Vec2 tangent = s2RightPerp(normal);
+			int pointCount = (idx.y & S2B_CF_TWO_POINTS) ? 2 : 1;
+#pragma unroll
+			for (int j = 0; j < 2; ++j)
+			{
+				if (j < pointCount)
+				{
+					float4 la = FIXED ? a.cc.r0[j][t] : a.cc.anchor[j][t];
+					float2 l = a.cc.lambda[j][t];
+					s2Vec2 local = sideB ? V2(la.z, la.w) : V2(la.x, la.y);
+					s2Vec2 r = FIXED ? local : s2RotateVector(q, local);
+					s2Vec2 P = s2Add(s2MulSV(l.x, normal), s2MulSV(l.y, tangent));
+					if (sideB)
+					{
+						w += invI * s2Cross(r, P);
+						v = s2MulAdd(v, invMass, P);
+					}
+					else
+					{
+						w -= invI * s2Cross(r, P);
+						v = s2MulAdd(v, -invMass, P);
+					}
+				}
+			}
+		}
+		else
+		{
+			int4 head = a.jc.head[t];
+			float4 anchor = a.jc.anchor[t];
+			float4 imp = a.jc.imp[t];
+			s2Vec2 P = V2(imp.x, imp.y);
+			if (S2B_JOINT_TYPE(head.x) == S2B_JOINT_MOUSE)
+			{
+				// s2WarmStartMouse (reference src/mouse_joint.c:85-107): body B only
+				s2Vec2 rB = s2RotateVector(q, V2(anchor.z, anchor.w));
+				v = s2MulAdd(v, invMass, P);
+				w += invI * (s2Cross(rB, P) + imp.z);
+			}
+			else
+			{
+				// s2WarmStartRevolute (reference src/revolute_joint.c:107-150)
+				float4 limp = a.jc.limp[t];
+				float axialImpulse = imp.z + limp.x - limp.y;
+				if (sideB)
+				{
+					s2Vec2 rB = s2RotateVector(q, V2(anchor.z, anchor.w));
+					v = s2MulAdd(v, invMass, P);
+					w += invI * (s2Cross(rB, P) + axialImpulse);
+				}
+				else
+				{
+					s2Vec2 rA = s2RotateVector(q, V2(anchor.x, anchor.y));
+					v = s2MulSub(v, invMass, P);
+					w -= invI * (s2Cross(rA, P) + axialImpulse);
+				}
+			}
+		}
+	}
+	a.bodies.vel[i] = make_float4(v.x, v.y, w, invMass);
+}
+
+// ---- building the sorted incidence lists (once per step, after the solve order is known) --------------------------
+
+// value of an item in the per-body sort: high word = (group << 1 | isContact), low word = the incidence entry without its
+// side bit, whose top bits are the stream position t. Sorting the 64-bit values orders by (group, joints first, t).
+__global__ void s2bItemOrderKernel(const int* counts, const int* cPerm, const int* jPerm, const int* cGroupOff, const int* jGroupOff,
+								   int tableEntries, unsigned long long* itemVal)
+{
+	int nJ = counts[CNT_JOINTS], nC = counts[CNT_CONTACTS];
+	int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= nJ + nC)
+	{
+		return;
+	}
+	bool isContact = p >= nJ;
+	int t = isContact ? p - nJ : p;
+	const int* off = isContact ? cGroupOff : jGroupOff;
+	// largest g in [0, tableEntries) with off[g] <= t
+	int lo = 0, hi = tableEntries - 1;
+	while (lo < hi)
+	{
+		int mid = (lo + hi + 1) >> 1;
+		if (off[mid] <= t)
+		{
+			lo = mid;
+		}
+		else
+		{
+			hi = mid - 1;
+		}
+	}
+	int natural = isContact ? cPerm[t] : jPerm[t];
+	int item = isContact ? nJ + natural : natural;
+	unsigned long long key = ((unsigned long long)(unsigned)((lo << 1) | (isContact ? 1 : 0))) << 32;
+	unsigned entry = ((unsigned)t << 2) | (isContact ? S2B_INC_CONTACT : 0);
+	itemVal[item] = key | entry;
+}
+
+__global__ void s2bSortIncidenceKernel(int bodyCapacity, const int* adjStart, const int* adj, const int2* itemBodies,
+									   const unsigned long long* itemVal, unsigned long long* work, int* incList)
+{
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= bodyCapacity)
+	{
+		return;
+	}
+	int begin = adjStart[b], end = adjStart[b + 1];
+	int n = end - begin;
+	if (n == 0)
+	{
+		return;
+	}
+	unsigned long long* v = work + begin;
+	for (int k = 0; k < n; ++k)
+	{
+		int item = adj[begin + k];
+		unsigned long long val = itemVal[item];
+		if (itemBodies[item].x != b)
+		{
+			val |= S2B_INC_SIDE_B;
+		}
+		v[k] = val;
+	}
+	if (n <= 24)
+	{
+		for (int k = 1; k < n; ++k)
+		{
+			unsigned long long x = v[k];
+			int m = k - 1;
+			while (m >= 0 && v[m] > x)
+			{
+				v[m + 1] = v[m];
+				m -= 1;
+			}
+			v[m + 1] = x;
+		}
+	}
+	else
+	{
+		// heap sort: bodies touching hundreds of constraints (a container wall) stay O(n log n)
+		for (int start = n / 2 - 1; start >= 0; --start)
+		{
+			int root = start;
+			for (;;)
+			{
+				int child = 2 * root + 1;
+				if (child >= n)
+				{
+					break;
+				}
+				if (child + 1 < n && v[child] < v[child + 1])
+				{
+					child += 1;
+				}
+				if (v[root] >= v[child])
+				{
+					break;
+				}
+				unsigned long long tmp = v[root];
+				v[root] = v[child];
+				v[child] = tmp;
+				root = child;
+			}
+		}
+		for (int last = n - 1; last > 0; --last)
+		{
+			unsigned long long tmp = v[0];
+			v[0] = v[last];
+			v[last] = tmp;
+			int root = 0;
+			for (;;)
+			{
+				int child = 2 * root + 1;
+				if (child >= last)
+				{
+					break;
+				}
+				if (child + 1 < last && v[child] < v[child + 1])
+				{
+					child += 1;
+				}
+				if (v[root] >= v[child])
+				{
+					break;
+				}
+				unsigned long long t2 = v[root];
+				v[root] = v[child];
+				v[child] = t2;
+				root = child;
+			}
+		}
+	}
+	for (int k = 0; k < n; ++k)
+	{
+		incList[begin + k] = (int)(unsigned)(v[k] & 0xFFFFFFFFull);
+	}
+}

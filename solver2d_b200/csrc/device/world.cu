@@ -23,7 +23,15 @@ __global__ void s2bScatterBodies(const s2bBodyRow* __restrict__ rows, int count,
 	b.pose[i] = make_float4(0.0f, 0.0f, r.rot[0], r.rot[1]);
 	b.pos[i] = make_float4(r.position[0], r.position[1], r.invI, r.I);
 	b.org[i] = make_float4(r.origin[0], r.origin[1], r.localCenter[0], r.localCenter[1]);
-	b.frc[i] = make_float4(r.force[0], r.force[1], r.torque, r.mass);
+	if (r.flags & S2B_BODY_ADD_FORCE)
+	{
+		float4 f = b.frc[i];
+		b.frc[i] = make_float4(f.x + r.force[0], f.y + r.force[1], f.z + r.torque, r.mass);
+	}
+	else
+	{
+		b.frc[i] = make_float4(r.force[0], r.force[1], r.torque, r.mass);
+	}
 	b.prm[i] = make_float4(r.linearDamping, r.angularDamping, r.gravityScale, r.invI);
 	b.flags[i] = (uint8_t)(r.flags & 0x7);
 }
@@ -307,6 +315,13 @@ extern "C" s2bWorld* s2b_world_create(int cudaDevice, int solverType)
 	S2B_CHECK(cudaGetDeviceProperties(&prop, cudaDevice));
 	w->smCount = prop.multiProcessorCount;
 	w->coopSupported = prop.cooperativeLaunch;
+	{
+		const char* env = getenv("S2B_WARM_GATHER");
+		if (env != nullptr)
+		{
+			w->gatherWarm = atoi(env) != 0 ? 1 : 0;
+		}
+	}
 	w->solverType = solverType;
 	w->sticky = (solverType == 6); // s2_solverTGS_Sticky
 	S2B_CHECK(cudaMallocHost((void**)&w->hostMail, MAIL_COUNT * sizeof(int)));
@@ -404,6 +419,11 @@ extern "C" void s2b_set_max_colors(s2bWorld* w, int maxColors)
 extern "C" void s2b_set_persistent(s2bWorld* w, int enable)
 {
 	w->persistent = enable;
+}
+
+extern "C" void s2b_set_warm_gather(s2bWorld* w, int enable)
+{
+	w->gatherWarm = enable;
 }
 
 static void reserveBodies(s2bWorld* w, int cap)
@@ -551,7 +571,32 @@ __global__ void s2bScatterForces(const s2bForceRow* __restrict__ rows, int count
 	}
 	s2bForceRow r = rows[t];
 	float4 f = b.frc[r.index];
-	b.frc[r.index] = make_float4(r.force[0], r.force[1], r.torque, f.w);
+	b.frc[r.index] = make_float4(f.x + r.force[0], f.y + r.force[1], f.z + r.torque, f.w);
+}
+
+__global__ void s2bAddForcesKernel(const int* __restrict__ indices, const float2* __restrict__ forces, int count, BodyView b)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= count)
+	{
+		return;
+	}
+	int i = indices[t];
+	float2 add = forces[t];
+	float4 f = b.frc[i];
+	b.frc[i] = make_float4(f.x + add.x, f.y + add.y, f.z, f.w);
+}
+
+__global__ void s2bGatherTransforms(BodyView b, int count, float4* out)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count)
+	{
+		return;
+	}
+	float4 org = b.org[i];
+	float4 pose = b.pose[i];
+	out[i] = make_float4(org.x, org.y, pose.z, pose.w);
 }
 
 extern "C" void s2b_upload_forces(s2bWorld* w, const s2bForceRow* rows, int count)
@@ -565,6 +610,81 @@ extern "C" void s2b_upload_forces(s2bWorld* w, const s2bForceRow* rows, int coun
 	S2B_LAUNCH(w, s2bScatterForces, gridFor(count, 128), 128, 0, d, count, bodyView(w));
 	S2B_CHECK(cudaFreeAsync(d, w->stream));
 	S2B_CHECK(cudaStreamSynchronize(w->stream));
+}
+
+// page-locked staging for the bulk paths: two buffers used alternately, each guarded by an event so that the host never
+// overwrites a buffer whose H2D copy is still in flight and never has to synchronise the stream
+static void* bulkStaging(s2bWorld* w, size_t bytes)
+{
+	int k = w->bulkNext;
+	w->bulkNext ^= 1;
+	if (w->bulkEvent[k] == nullptr)
+	{
+		S2B_CHECK(cudaEventCreateWithFlags(&w->bulkEvent[k], cudaEventDisableTiming));
+	}
+	else
+	{
+		S2B_CHECK(cudaEventSynchronize(w->bulkEvent[k]));
+	}
+	if (bytes > w->bulkBytes[k])
+	{
+		if (w->bulkHost[k] != nullptr)
+		{
+			cudaFreeHost(w->bulkHost[k]);
+		}
+		w->bulkBytes[k] = bytes + bytes / 2;
+		S2B_CHECK(cudaMallocHost(&w->bulkHost[k], w->bulkBytes[k]));
+	}
+	w->bulkCurrent = k;
+	return w->bulkHost[k];
+}
+
+extern "C" void s2b_add_forces(s2bWorld* w, const int32_t* bodyIndices, const float* forcesXY, int count)
+{
+	if (count <= 0)
+	{
+		return;
+	}
+	S2B_CHECK(cudaSetDevice(w->device));
+	size_t idxBytes = sizeof(int32_t) * (size_t)count;
+	size_t idxPadded = (idxBytes + 15) & ~(size_t)15;
+	size_t bytes = idxPadded + sizeof(float) * 2 * (size_t)count;
+	char* host = (char*)bulkStaging(w, bytes);
+	memcpy(host, bodyIndices, idxBytes);
+	memcpy(host + idxPadded, forcesXY, sizeof(float) * 2 * (size_t)count);
+	w->dBulk.reserve(bytes, w->stream, false, false);
+	S2B_CHECK(cudaMemcpyAsync(w->dBulk.p, host, bytes, cudaMemcpyHostToDevice, w->stream));
+	S2B_CHECK(cudaEventRecord(w->bulkEvent[w->bulkCurrent], w->stream));
+	S2B_LAUNCH(w, s2bAddForcesKernel, gridFor(count, 256), 256, 0, (const int*)w->dBulk.p, (const float2*)(w->dBulk.p + idxPadded), count,
+			   bodyView(w));
+}
+
+extern "C" void s2b_download_transforms(s2bWorld* w, float* out, int count)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	if (count > w->bodyCap)
+	{
+		count = w->bodyCap;
+	}
+	if (count <= 0)
+	{
+		return;
+	}
+	size_t floats = 4 * (size_t)count;
+	if (floats > w->hostXfFloats)
+	{
+		if (w->hostXf != nullptr)
+		{
+			cudaFreeHost(w->hostXf);
+		}
+		w->hostXfFloats = floats + floats / 2;
+		S2B_CHECK(cudaMallocHost((void**)&w->hostXf, sizeof(float) * w->hostXfFloats));
+	}
+	w->dXf.reserve((size_t)count, w->stream, false, false);
+	S2B_LAUNCH(w, s2bGatherTransforms, gridFor(count, 256), 256, 0, bodyView(w), count, w->dXf.p);
+	S2B_CHECK(cudaMemcpyAsync(w->hostXf, w->dXf.p, sizeof(float) * floats, cudaMemcpyDeviceToHost, w->stream));
+	S2B_CHECK(cudaStreamSynchronize(w->stream));
+	memcpy(out, w->hostXf, sizeof(float) * floats);
 }
 
 extern "C" void* s2b_host_alloc(size_t bytes)

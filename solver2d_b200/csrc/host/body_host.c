@@ -20,6 +20,11 @@ s2BodyId s2CreateBody(s2WorldId worldId, const s2BodyDef* def)
 	s2World* world = s2GetWorldFromId(worldId);
 	s2Body* b = (s2Body*)s2AllocObject(&world->bodyPool);
 	world->bodies = (s2Body*)world->bodyPool.memory;
+	if (b->object.index + 1 > world->bodyHighWater)
+	{
+		world->bodyHighWater = b->object.index + 1;
+	}
+	b->onDevice = false;
 
 	b->type = def->type;
 	b->origin = def->position;
@@ -73,6 +78,7 @@ void s2DestroyBody(s2BodyId bodyId)
 		s2MarkShapeDirty(world, shape);
 	}
 	s2FreeObject(&world->bodyPool, &body->object);
+	body->onDevice = false;
 	s2MarkBodyDirty(world, body);
 }
 

@@ -117,6 +117,7 @@ typedef struct s2Body
 	// dirty bookkeeping
 	bool rowDirty;	 // whole row must be re-uploaded
 	bool forceDirty; // only force / torque changed
+	bool onDevice;	 // the device already holds a row for this body: uploads add its pending force instead of setting it
 } s2Body;
 
 typedef struct s2Shape
@@ -205,6 +206,7 @@ typedef struct s2World
 	bool stateFresh;	 // host body / joint state mirrors the device
 	bool boxesFresh;	 // host shape AABBs mirror the device
 	uint64_t stepId;
+	int32_t bodyHighWater; // one past the largest body slot ever used
 	s2Vec2 gravity;
 
 	// row staging (pinned host memory owned by the device library)

@@ -150,7 +150,7 @@ static void* s2Staging(s2World* world, size_t bytes)
 static void s2FillBodyRow(s2bBodyRow* r, const s2Body* b)
 {
 	r->index = b->object.index;
-	r->flags = s2IsFree(&b->object) ? 0 : (S2B_ROW_VALID | ((int32_t)b->type << 1));
+	r->flags = s2IsFree(&b->object) ? 0 : (S2B_ROW_VALID | ((int32_t)b->type << 1) | (b->onDevice ? S2B_BODY_ADD_FORCE : 0));
 	r->origin[0] = b->origin.x;
 	r->origin[1] = b->origin.y;
 	r->position[0] = b->position.x;
@@ -283,7 +283,8 @@ void s2FlushToDevice(s2World* world)
 			s2FillBodyRow(rows + i, b);
 			b->rowDirty = false;
 			b->forceDirty = false;
-			// the step consumes applied forces (reference src/world.c:275-276)
+			b->onDevice = s2IsFree(&b->object) == false;
+			// the pending force now lives on the device, which zeroes it at the end of the step (reference src/world.c:275-276)
 			b->force = s2Vec2_zero;
 			b->torque = 0.0f;
 		}
@@ -413,11 +414,7 @@ void s2SyncStateToHost(s2World* world)
 		b->rot.c = r[5];
 		b->linearVelocity = s2MakeVec2(r[6], r[7]);
 		b->angularVelocity = r[8];
-		if (b->forceDirty == false)
-		{
-			b->force = s2MakeVec2(r[9], r[10]);
-			b->torque = r[11];
-		}
+		// force / torque are not mirrored: on the host they only hold what has not been uploaded yet
 	}
 
 	int jcap = world->jointPool.capacity;
@@ -755,14 +752,14 @@ void s2World_Flush(s2WorldId worldId)
 
 void s2World_ApplyForcesToCenters(s2WorldId worldId, const int32_t* bodyIndices, const float* forcesXY, int32_t count)
 {
+	// bulk s2Body_ApplyForceToCenter: the forces go straight to the device accumulators. Rows that are still dirty on the
+	// host are uploaded first so that a body created since the last step exists before it receives its force.
 	s2World* world = s2GetWorldFromId(worldId);
-	for (int32_t i = 0; i < count; ++i)
+	if (world->dirtyBodies.count > 0)
 	{
-		s2Body* body = world->bodies + bodyIndices[i];
-		body->force.x += forcesXY[2 * i];
-		body->force.y += forcesXY[2 * i + 1];
-		s2MarkBodyForceDirty(world, body);
+		s2FlushToDevice(world);
 	}
+	s2b_add_forces(world->device, bodyIndices, forcesXY, count);
 }
 
 float s2World_TimedSteps(s2WorldId worldId, int32_t steps, float timeStep, int32_t velIters, int32_t posIters, bool warmStart,
@@ -786,17 +783,15 @@ float s2World_TimedSteps(s2WorldId worldId, int32_t steps, float timeStep, int32
 
 int32_t s2World_GetBodyTransforms(s2WorldId worldId, float* out, int32_t capacity)
 {
+	// transforms straight from the device columns: one gather + one D2H of 16 B per used slot; the host body structs are not
+	// refreshed (their lazy read-back stays pending for whoever asks for velocities etc.)
 	s2World* world = s2GetWorldFromId(worldId);
-	s2SyncStateToHost(world);
-	int32_t cap = world->bodyPool.capacity < capacity ? world->bodyPool.capacity : capacity;
-	for (int32_t i = 0; i < cap; ++i)
+	if (world->dirtyBodies.count > 0)
 	{
-		const s2Body* b = world->bodies + i;
-		out[4 * i + 0] = b->origin.x;
-		out[4 * i + 1] = b->origin.y;
-		out[4 * i + 2] = b->rot.s;
-		out[4 * i + 3] = b->rot.c;
+		s2FlushToDevice(world); // a transform set through the API since the last step wins
 	}
+	int32_t n = world->bodyHighWater < capacity ? world->bodyHighWater : capacity;
+	s2b_download_transforms(world->device, out, n);
 	return world->bodyPool.capacity;
 }
 

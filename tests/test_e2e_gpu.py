@@ -177,3 +177,56 @@ def test_device_atan2_bit_equal_to_libm(dev):
     nan = np.isnan(want)
     assert np.array_equal(np.isnan(out), nan)
     assert np.array_equal(out[~nan].view(np.uint32), want[~nan].view(np.uint32))
+
+
+def test_bulk_force_and_transform_paths_equal_per_body_api(reference, product, dev):
+    """s2World_ApplyForcesToCenters / s2World_GetBodyTransforms (device-side add + 16 B/body read-back) against the
+    per-body calls they stand for, and against the reference driven by the same per-body forces (order-preserving
+    schedule, so the comparison with the reference is bit-exact too)."""
+    import ctypes as C
+    R, P = reference, product
+    L = P.lib
+    L.s2World_ApplyForcesToCenters.argtypes = [capi.WorldId, C.c_void_p, C.c_void_p, C.c_int32]
+    L.s2World_GetBodyTransforms.restype = C.c_int32
+    L.s2World_GetBodyTransforms.argtypes = [capi.WorldId, C.c_void_p, C.c_int32]
+    sr = scenes.pyramid(R, "TGS_Soft", base_count=9)
+    sa = scenes.pyramid(P, "TGS_Soft", base_count=9)   # per-body API
+    sb = scenes.pyramid(P, "TGS_Soft", base_count=9)   # bulk API
+    dws = [device.DeviceWorld.attach(dev, s.world) for s in (sa, sb)]
+    for dw in dws:
+        dw.set_schedule(device.SCHEDULE_WAVEFRONT)
+    pushed = list(range(1, len(sa.bodies), 3))
+    idx = np.array([sb.bodies[k].index for k in pushed], dtype=np.int32)
+    for step in range(40):
+        f = np.zeros((len(pushed), 2), dtype=np.float32)
+        f[:, 0] = 3.0 * np.sin(0.3 * step + np.arange(len(pushed)))
+        f[:, 1] = 1.5
+        R.step_collide(sr.world)
+        keys, *_ = _ref_pair_table(R, sr.world)
+        for dw in dws:
+            dw.set_contact_order(keys)
+        for k, (fx, fy) in zip(pushed, f):
+            R.s2Body_ApplyForceToCenter(sr.bodies[k], capi.Vec2(float(fx), float(fy)))
+            P.s2Body_ApplyForceToCenter(sa.bodies[k], capi.Vec2(float(fx), float(fy)))
+        L.s2World_ApplyForcesToCenters(sb.world, idx.ctypes.data, f.ctypes.data, len(idx))
+        if step % 7 == 3:
+            # a per-body force and a state edit AFTER the bulk call must not drop the bulk force of those bodies
+            for lib, sc in ((R, sr), (P, sa), (P, sb)):
+                lib.s2Body_ApplyForceToCenter(sc.bodies[pushed[0]], capi.Vec2(0.5, 0.25))
+                lib.s2Body_SetLinearVelocity(sc.bodies[pushed[1]], capi.Vec2(0.1, -0.2))
+        R.step_solve(sr.world, DT, 4, 2, True)
+        R.step_finalize(sr.world)
+        sa.step(DT, 4, 2, True)
+        sb.step(DT, 4, 2, True)
+    cap = dws[1].counters().bodyCapacity
+    xf = np.zeros((cap, 4), dtype=np.float32)
+    assert len(sb.bodies) <= L.s2World_GetBodyTransforms(sb.world, xf.ctypes.data, cap) <= cap
+    pa = _positions(P, sa)
+    pr = _positions(R, sr)
+    pb = np.array([xf[b.index, :2] for b in sb.bodies], dtype=np.float64)
+    assert np.array_equal(pa, pb), "bulk and per-body paths differ"
+    assert np.array_equal(pa, pr), f"public API with forces differs from the reference: {np.abs(pa - pr).max()}"
+    ang_b = np.arctan2(xf[[b.index for b in sb.bodies], 2].astype(np.float64), xf[[b.index for b in sb.bodies], 3].astype(np.float64))
+    assert np.abs(ang_b - _angles(R, sr)).max() < 1e-6
+    for s in (sr, sa, sb):
+        s.destroy()

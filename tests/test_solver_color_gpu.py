@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 DT = 1.0 / 60.0
 
 
-def _case(reference, dev, recipe, solver, warm, vel, pos, persistent, max_colors=None, warm_start=True, **kw):
+def _case(reference, dev, recipe, solver, warm, vel, pos, persistent, max_colors=None, warm_start=True, warm_gather=True, **kw):
     R = reference
     O = port.load()
     sc = recipe(R, solver, **kw)
@@ -31,6 +31,7 @@ def _case(reference, dev, recipe, solver, warm, vel, pos, persistent, max_colors
     dw.upload_contacts(contacts)
     dw.set_schedule(device.SCHEDULE_COLOR)
     dw.set_persistent(persistent)
+    dw.set_warm_gather(warm_gather)
     if max_colors is not None:
         dw.set_max_colors(max_colors)
     dw.solve(ctx)
@@ -135,3 +136,13 @@ def test_variant_color_cold_start(reference, dev, solver):
     c = _case(reference, dev, scenes.joint_contact_stress, solver, warm, 3, 1, False, warm_start=False, bridges=2, planks=16,
               grid=6)
     assert c.jointCount == 34
+
+
+@pytest.mark.parametrize("solver", ["TGS_Soft", "SoftStep", "TGS_NGS"])
+def test_grouped_warm_start_path_still_matches(reference, dev, solver):
+    """The per-sub-step warm start runs as a per-body gather by default; the grouped constraint passes it replaces
+    must give the same bits (both are compared with the permuted oracle)."""
+    c = _case(reference, dev, scenes.limited_chains, solver, 40, 4, 2, True, warm_gather=False)
+    assert c.jointCount == 19
+    c = _case(reference, dev, scenes.pyramid, solver, 30, 4, 2, True, warm_gather=False, max_colors=3, base_count=14)
+    assert c.overflowCount > 0
