@@ -194,6 +194,10 @@ S2B_API void s2b_set_persistent(s2bWorld* world, int enable);
 // Warm start of the sub-stepping variants as a per-body gather fused with s2IntegrateVelocities (1, default) or as
 // grouped constraint passes like every other pass (0; cross-check). Both give bit-identical results.
 S2B_API void s2b_set_warm_gather(s2bWorld* world, int enable);
+// Gauss-Seidel passes of the persistent kernel synchronised by one grid barrier per colour (0, default) or by per-body
+// tickets (1: a constraint waits only for the previous constraint on each of its bodies; no barrier inside a sweep).
+// Same bits either way; the ticketed form measured SLOWER on B200 (75 k pollers saturate L2), kept as an experiment.
+S2B_API void s2b_set_dataflow(s2bWorld* world, int enable);
 
 // ---- host -> device -------------------------------------------------------------------------------------------
 

@@ -266,6 +266,8 @@ struct s2bWorld
 	int schedule = S2B_SCHEDULE_COLOR;
 	int maxColors = 24;
 	int persistent = 1;
+	int dataflow = 0;	// ticketed Gauss-Seidel passes in the persistent kernel (experimental, slower on B200: DESIGN.md §3.1);
+						// s2b_set_dataflow / S2B_DATAFLOW=1 enable it
 	int gatherWarm = 1; // per-body warm-start gather (warm_gather.cuh); s2b_set_warm_gather / S2B_WARM_GATHER=0 disable it
 	int smCount = 148;
 	int coopSupported = 0;

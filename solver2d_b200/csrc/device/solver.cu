@@ -899,10 +899,138 @@ __device__ __forceinline__ void s2bGridGroupPass(int jointOp, int contactOp, con
 	}
 }
 
+// ---- ticketed ("dataflow") Gauss-Seidel pass ------------------------------------------------------------------
+// A grid barrier after every colour costs ~1.2 us plus the tail of the slowest block, ten times per pass; on a 100 k-body
+// scene that is most of the solver's time. What a constraint really has to wait for is only the previous constraint that
+// touched each of its two bodies. Every movable body therefore carries a TICKET = number of incident constraints executed
+// on it so far in this launch; the k-th item of a body's (solve-ordered) incidence list of d items runs in pass m when the
+// ticket reads m * d + k, and sets it to m * d + k + 1 when done (release / acquire at GPU scope). The passes keep the
+// stream order (group-major), so the outcome is bit-identical to the barrier version — the colouring now only decides how
+// much runs concurrently — and the whole Gauss-Seidel sweep needs no grid barrier at all.
+// Progress: every thread walks its items in stream order, an item only waits for items earlier in that order, and all
+// blocks of a cooperative launch are resident, so the earliest unfinished item can always run. The work sits INSIDE the
+// polling loop so that a lane that is ready never waits at a reconvergence point for a lane that is still polling.
+
+#define S2B_FLOW_SPIN_LIMIT (1 << 22)
+
+__device__ __forceinline__ int s2bLoadAcquire(const int* p)
+{
+	int v;
+	asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
+__device__ __forceinline__ void s2bStoreRelaxed(int* p, int v)
+{
+	asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <bool JOINT>
+__device__ __forceinline__ void s2bFlowItem(int op, const SolveArgs& a, const PassPtrs& p, int t, int passIndex)
+{
+	int ia, ib;
+	int2 fa, fb;
+	if (JOINT)
+	{
+		int4 head = a.jc.head[t];
+		ia = head.y;
+		ib = head.z;
+		fa = a.jFlowA[t];
+		fb = a.jFlowB[t];
+	}
+	else
+	{
+		int2 idx = a.cc.idx[t];
+		ia = idx.x;
+		ib = idx.y & S2B_CF_INDEX_MASK;
+		fa = a.cFlowA[t];
+		fb = a.cFlowB[t];
+	}
+	int needA = passIndex * fa.y + fa.x, needB = passIndex * fb.y + fb.x;
+	bool done = false;
+	int spins = 0;
+	while (done == false)
+	{
+		bool ready = true;
+		if (fa.x >= 0)
+		{
+			ready = s2bLoadAcquire(a.bodyTicket + ia) == needA;
+		}
+		if (ready && fb.x >= 0)
+		{
+			ready = s2bLoadAcquire(a.bodyTicket + ib) == needB;
+		}
+		if (ready)
+		{
+			if (JOINT)
+			{
+				s2bRunJointOp(op, a, t, p);
+			}
+			else
+			{
+				s2bRunContactOp(op, a, t);
+			}
+			__threadfence();
+			if (fa.x >= 0)
+			{
+				s2bStoreRelaxed(a.bodyTicket + ia, needA + 1);
+			}
+			if (fb.x >= 0)
+			{
+				s2bStoreRelaxed(a.bodyTicket + ib, needB + 1);
+			}
+			done = true;
+		}
+		else if (a.flowSleepNs > 0)
+		{
+			__nanosleep(a.flowSleepNs);
+		}
+		if (done == false && (++spins > S2B_FLOW_SPIN_LIMIT || ((spins & 1023) == 0 && *(volatile int*)a.flowError != 0)))
+		{
+			// never expected; bail out of the whole launch quickly instead of hanging the device
+			a.flowError[0] = 1;
+			done = true;
+		}
+	}
+}
+
+// joints and contacts of every group in stream order, no barrier; a pass with an op of only one kind still walks the other
+// kind (op NONE) to keep the tickets of its bodies moving
+__device__ __forceinline__ void s2bGridFlowPass(int jointOp, int contactOp, const SolveArgs& a, const PassPtrs& p, int passIndex)
+{
+	int groups = a.counts[CNT_GROUPS];
+	int stride = gridDim.x * blockDim.x;
+	int tid = blockIdx.x * blockDim.x + threadIdx.x;
+	int ovC = a.counts[CNT_OVERFLOW_C], ovJ = a.counts[CNT_OVERFLOW_J];
+	for (int g = 0; g <= groups; ++g)
+	{
+		bool overflow = g == groups;
+		if (overflow && ovC + ovJ == 0)
+		{
+			break;
+		}
+		int table = overflow ? S2B_MAX_COLORS : g;
+		int jBegin = a.jGroupOff[table], cBegin = a.cGroupOff[table];
+		int nj = overflow ? ovJ : a.jGroupOff[g + 1] - jBegin;
+		int nc = overflow ? ovC : a.cGroupOff[g + 1] - cBegin;
+		for (int t = tid; t < nj; t += stride)
+		{
+			s2bFlowItem<true>(jointOp, a, p, jBegin + t, passIndex);
+		}
+		for (int t = tid; t < nc; t += stride)
+		{
+			s2bFlowItem<false>(contactOp, a, p, cBegin + t, passIndex);
+		}
+	}
+}
+
 // The whole solver stage of one step: the variant's program from prepare to store, one launch.
 __global__ void __launch_bounds__(S2B_BLOCK) s2bPersistentSolve(SolveArgs a, PassPtrs p, Program prog)
 {
 	cg::grid_group grid = cg::this_grid();
+	bool flow = a.bodyTicket != nullptr;
+	bool pendingFlow = false; // a ticketed pass has run since the last grid barrier
+	int flowPasses = 0;
 	for (int s = 0; s < prog.segmentCount; ++s)
 	{
 		for (int r = 0; r < prog.repeat[s]; ++r)
@@ -910,20 +1038,34 @@ __global__ void __launch_bounds__(S2B_BLOCK) s2bPersistentSolve(SolveArgs a, Pas
 			for (int k = 0; k < prog.passCount[s]; ++k)
 			{
 				PassDesc pass = prog.passes[s][k];
+				if (pass.kind == PASS_GROUP)
+				{
+					if (flow)
+					{
+						s2bGridFlowPass(pass.jointOp, pass.contactOp, a, p, flowPasses);
+						flowPasses += 1;
+						pendingFlow = true;
+					}
+					else
+					{
+						s2bGridGroupPass(pass.jointOp, pass.contactOp, a, p, grid);
+					}
+					continue;
+				}
+				if (pendingFlow)
+				{
+					grid.sync(); // body and flat passes read what the ticketed passes wrote
+					pendingFlow = false;
+				}
 				if (pass.kind == PASS_BODY)
 				{
 					s2bGridBodyPass(pass.bodyOp, a);
-					grid.sync();
-				}
-				else if (pass.kind == PASS_FLAT)
-				{
-					s2bGridFlatPass(pass.jointOp, pass.contactOp, a, p);
-					grid.sync();
 				}
 				else
 				{
-					s2bGridGroupPass(pass.jointOp, pass.contactOp, a, p, grid);
+					s2bGridFlatPass(pass.jointOp, pass.contactOp, a, p);
 				}
+				grid.sync();
 			}
 		}
 	}
@@ -1382,6 +1524,9 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 	// per-sub-step warm starting as a per-body gather (warm_gather.cuh); S2B_WARM_GATHER=0 keeps the grouped passes
 	bool gatherWarm = w->gatherWarm != 0 && ctx.warmStart != 0 && (solverType == 7 || solverType == 5 || solverType == 8);
 	Program program = buildProgram(solverType, ctx, gatherWarm, &countedPasses);
+	// ticketed Gauss-Seidel passes instead of a grid barrier per colour (persistent kernel only); S2B_DATAFLOW=0 disables
+	bool dataflow = w->dataflow != 0 && w->persistent != 0 && w->coopSupported != 0;
+	bool needInc = gatherWarm || dataflow;
 
 	int contactCount = w->contactCount;
 	int jointCap = w->jointCap;
@@ -1411,11 +1556,16 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 	s->jGroupOff.reserve(S2B_MAX_COLORS + 2, st, false);
 	s->cPerm.reserve(nC, st, false);
 	s->jPerm.reserve(nJ, st, false);
-	if (gatherWarm)
+	if (needInc)
 	{
 		s->itemVal.reserve(nI, st, false);
 		s->incWork.reserve(2 * nI, st, false);
 		s->incList.reserve(2 * nI, st, false);
+	}
+	if (dataflow)
+	{
+		s->flow.reserve(2 * nC + 2 * nJ, st, false);
+		s->bodyTicket.reserve((size_t)bodyCap + 2, st, false);
 	}
 	s->idx.reserve(nC, st, false);
 	s->nf.reserve(nC, st, false);
@@ -1552,7 +1702,7 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 
 	if (maxItems > 0)
 	{
-		bool wantAdj = w->schedule == S2B_SCHEDULE_COLOR || gatherWarm;
+		bool wantAdj = w->schedule == S2B_SCHEDULE_COLOR || needInc;
 		if (wantAdj)
 		{
 			S2B_CHECK(cudaMemsetAsync(s->degree.p, 0, sizeof(int) * ((size_t)bodyCap + 1), st));
@@ -1672,19 +1822,28 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 					   s->src.p);
 		}
 
-		if (gatherWarm)
+		if (needInc)
 		{
-			// incidence lists of the movable bodies in solve order
+			// incidence lists of the movable bodies in solve order (+ the ticket ordinals of every constraint)
 			int tableEntries = w->schedule == S2B_SCHEDULE_COLOR ? S2B_MAX_COLORS + 1 : std::max(plan.groups, 1);
 			S2B_LAUNCH(w, s2bItemOrderKernel, gridFor(maxItems, 256), 256, 0, s->counts.p, s->cPerm.p, s->jPerm.p, s->cGroupOff.p,
 					   s->jGroupOff.p, tableEntries, s->itemVal.p);
+			int2 *cfa = nullptr, *cfb = nullptr, *jfa = nullptr, *jfb = nullptr;
+			if (dataflow)
+			{
+				S2B_CHECK(cudaMemsetAsync(s->flow.p, 0xFF, sizeof(int2) * (2 * nC + 2 * nJ), st));
+				cfa = s->flow.p;
+				cfb = s->flow.p + nC;
+				jfa = s->flow.p + 2 * nC;
+				jfb = s->flow.p + 2 * nC + nJ;
+			}
 			S2B_LAUNCH(w, s2bSortIncidenceKernel, gridFor(bodyCap, 128), 128, 0, bodyCap, s->adjStart.p, s->adj.p, s->itemBodies.p,
-					   s->itemVal.p, s->incWork.p, s->incList.p);
+					   s->itemVal.p, s->incWork.p, s->incList.p, cfa, cfb, jfa, jfb);
 		}
 	}
 	else
 	{
-		if (gatherWarm)
+		if (needInc)
 		{
 			S2B_CHECK(cudaMemsetAsync(s->adjStart.p, 0, sizeof(int) * ((size_t)bodyCap + 2), st));
 		}
@@ -1707,6 +1866,17 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 	a.jGroupOff = s->jGroupOff.p;
 	a.incStart = gatherWarm ? s->adjStart.p : nullptr;
 	a.incList = gatherWarm ? s->incList.p : nullptr;
+	if (dataflow)
+	{
+		S2B_CHECK(cudaMemsetAsync(s->bodyTicket.p, 0, sizeof(int) * ((size_t)bodyCap + 2), st));
+		a.bodyTicket = s->bodyTicket.p;
+		a.flowError = s->bodyTicket.p + bodyCap + 1;
+		s->flowErrorOffset = bodyCap + 1;
+		a.cFlowA = s->flow.p;
+		a.cFlowB = s->flow.p + nC;
+		a.jFlowA = s->flow.p + 2 * nC;
+		a.jFlowB = s->flow.p + 2 * nC + nJ;
+	}
 	pp.jPerm = s->jPerm.p;
 	bool usePersistent = w->persistent != 0 && w->coopSupported != 0;
 	if (usePersistent)
@@ -1721,7 +1891,17 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 			int want = env != nullptr ? atoi(env) : 2;
 			w->solveGrid = w->smCount * std::min(std::max(blocksPerSm, 1), std::max(want, 1));
 		}
-		int wanted = std::max(gridFor(std::max(maxItems, bodyCap), S2B_BLOCK), 1);
+		int threads = S2B_BLOCK;
+		{
+			const char* env = getenv("S2B_SOLVE_THREADS");
+			if (env != nullptr && atoi(env) >= 32 && atoi(env) <= S2B_BLOCK)
+			{
+				threads = atoi(env) & ~31;
+			}
+			env = getenv("S2B_FLOW_SLEEP_NS");
+			a.flowSleepNs = env != nullptr ? atoi(env) : 0;
+		}
+		int wanted = std::max(gridFor(std::max(maxItems, bodyCap), threads), 1);
 		int grid = std::min(w->solveGrid, wanted);
 		void* args[] = {&a, &pp, &program};
 		if (w->solveKernelStart == nullptr)
@@ -1730,7 +1910,7 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 			S2B_CHECK(cudaEventCreate(&w->solveKernelEnd));
 		}
 		S2B_CHECK(cudaEventRecord(w->solveKernelStart, st));
-		S2B_CHECK(cudaLaunchCooperativeKernel((void*)s2bPersistentSolve, dim3(grid), dim3(S2B_BLOCK), args, 0, st));
+		S2B_CHECK(cudaLaunchCooperativeKernel((void*)s2bPersistentSolve, dim3(grid), dim3(threads), args, 0, st));
 		S2B_CHECK(cudaEventRecord(w->solveKernelEnd, st));
 		w->solveKernelTimed = true;
 		w->kernelLaunches += 1;
@@ -1862,6 +2042,16 @@ extern "C" void s2b_get_counters(s2bWorld* w, s2bCounters* out)
 		out->jointCount = counts[CNT_JOINTS];
 		out->groupCount = counts[CNT_GROUPS];
 		out->overflowCount = counts[CNT_OVERFLOW_C] + counts[CNT_OVERFLOW_J];
+		if (w->scratch->bodyTicket.p != nullptr && w->scratch->flowErrorOffset > 0)
+		{
+			int flag = 0;
+			S2B_CHECK(cudaMemcpy(&flag, w->scratch->bodyTicket.p + w->scratch->flowErrorOffset, sizeof(int), cudaMemcpyDeviceToHost));
+			if (flag != 0)
+			{
+				fprintf(stderr, "solver2d-b200: a ticketed solver pass ran into its spin limit (internal error)\n");
+				abort();
+			}
+		}
 	}
 	out->treeHeight = w->treeHeight;
 	out->movedCount = w->hostMail[MAIL_MOVED];

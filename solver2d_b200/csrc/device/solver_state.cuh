@@ -37,6 +37,12 @@ struct SolveArgs
 	const int* jGroupOff; // joint-constraint group offsets, same shape
 	const int* incStart;  // per body: range of its incidence list (warm_gather.cuh); null when the gather is not used
 	const int* incList;	  // incidence entries sorted by solve order
+	// ticketed ("dataflow") Gauss-Seidel passes: null when the passes synchronise with grid barriers instead
+	int* bodyTicket;			   // per body: incident-item executions completed in this launch
+	const int2 *cFlowA, *cFlowB;   // per contact constraint and side: {ordinal in the body's incidence list, its degree} or -1
+	const int2 *jFlowA, *jFlowB;   // same per joint constraint
+	int flowSleepNs;			   // back-off between polls (0 = none)
+	int* flowError;				   // set when a wait ran into its spin limit (a bug, never expected)
 	s2bStepContext ctx;
 	float2 gravity;
 	SoftCoef softDynamic; // contact, both bodies movable
@@ -71,6 +77,9 @@ struct SolverScratch
 	DevArray<char> cubTemp;
 	DevArray<unsigned long long> itemVal, incWork; // warm-start gather: per-item sort value, per-body sort scratch
 	DevArray<int> incList;
+	DevArray<int2> flow;	  // cFlowA | cFlowB | jFlowA | jFlowB
+	DevArray<int> bodyTicket; // + 1 int error flag at the end
+	int flowErrorOffset = 0;
 	int maxGroups = 0;
 
 	// contact constraint columns

@@ -165,8 +165,11 @@ __global__ void s2bItemOrderKernel(const int* counts, const int* cPerm, const in
 	itemVal[item] = key | entry;
 }
 
+// Besides the sorted list this also hands every constraint its ORDINAL in the lists of its two bodies (k-th of d incident
+// items): what the ticketed Gauss-Seidel passes (solver.cu, "dataflow") wait on instead of a grid barrier.
 __global__ void s2bSortIncidenceKernel(int bodyCapacity, const int* adjStart, const int* adj, const int2* itemBodies,
-									   const unsigned long long* itemVal, unsigned long long* work, int* incList)
+									   const unsigned long long* itemVal, unsigned long long* work, int* incList, int2* cFlowA,
+									   int2* cFlowB, int2* jFlowA, int2* jFlowB)
 {
 	int b = blockIdx.x * blockDim.x + threadIdx.x;
 	if (b >= bodyCapacity)
@@ -261,6 +264,20 @@ __global__ void s2bSortIncidenceKernel(int bodyCapacity, const int* adjStart, co
 	}
 	for (int k = 0; k < n; ++k)
 	{
-		incList[begin + k] = (int)(unsigned)(v[k] & 0xFFFFFFFFull);
+		int e = (int)(unsigned)(v[k] & 0xFFFFFFFFull);
+		incList[begin + k] = e;
+		if (cFlowA != nullptr)
+		{
+			int t = e >> 2;
+			int2 ticket = make_int2(k, n);
+			if (e & S2B_INC_CONTACT)
+			{
+				((e & S2B_INC_SIDE_B) ? cFlowB : cFlowA)[t] = ticket;
+			}
+			else
+			{
+				((e & S2B_INC_SIDE_B) ? jFlowB : jFlowA)[t] = ticket;
+			}
+		}
 	}
 }

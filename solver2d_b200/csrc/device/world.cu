@@ -321,6 +321,11 @@ extern "C" s2bWorld* s2b_world_create(int cudaDevice, int solverType)
 		{
 			w->gatherWarm = atoi(env) != 0 ? 1 : 0;
 		}
+		env = getenv("S2B_DATAFLOW");
+		if (env != nullptr)
+		{
+			w->dataflow = atoi(env) != 0 ? 1 : 0;
+		}
 	}
 	w->solverType = solverType;
 	w->sticky = (solverType == 6); // s2_solverTGS_Sticky
@@ -424,6 +429,11 @@ extern "C" void s2b_set_persistent(s2bWorld* w, int enable)
 extern "C" void s2b_set_warm_gather(s2bWorld* w, int enable)
 {
 	w->gatherWarm = enable;
+}
+
+extern "C" void s2b_set_dataflow(s2bWorld* w, int enable)
+{
+	w->dataflow = enable;
 }
 
 static void reserveBodies(s2bWorld* w, int cap)

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 DT = 1.0 / 60.0
 
 
-def _case(reference, dev, recipe, solver, warm, vel, pos, persistent, max_colors=None, warm_start=True, warm_gather=True, **kw):
+def _case(reference, dev, recipe, solver, warm, vel, pos, persistent, max_colors=None, warm_start=True, warm_gather=True, dataflow=False, **kw):
     R = reference
     O = port.load()
     sc = recipe(R, solver, **kw)
@@ -32,6 +32,7 @@ def _case(reference, dev, recipe, solver, warm, vel, pos, persistent, max_colors
     dw.set_schedule(device.SCHEDULE_COLOR)
     dw.set_persistent(persistent)
     dw.set_warm_gather(warm_gather)
+    dw.set_dataflow(dataflow)
     if max_colors is not None:
         dw.set_max_colors(max_colors)
     dw.solve(ctx)
@@ -145,4 +146,15 @@ def test_grouped_warm_start_path_still_matches(reference, dev, solver):
     c = _case(reference, dev, scenes.limited_chains, solver, 40, 4, 2, True, warm_gather=False)
     assert c.jointCount == 19
     c = _case(reference, dev, scenes.pyramid, solver, 30, 4, 2, True, warm_gather=False, max_colors=3, base_count=14)
+    assert c.overflowCount > 0
+
+
+@pytest.mark.parametrize("solver", VARIANTS)
+def test_ticketed_passes_match(reference, dev, solver):
+    """Experimental schedule: Gauss-Seidel passes synchronised by per-body tickets instead of one grid barrier per
+    colour. Must give the same bits as the default (both are compared with the permuted oracle)."""
+    c = _case(reference, dev, scenes.limited_chains, solver, 40, 4, 2, True, dataflow=True)
+    assert c.jointCount == 19
+    warm = 2 if solver == "Jacobi" else 30
+    c = _case(reference, dev, scenes.pyramid, solver, warm, 4, 2, True, dataflow=True, max_colors=3, base_count=14)
     assert c.overflowCount > 0
