@@ -301,6 +301,10 @@ S2B_API float s2b_elapsed_ms(s2bWorld* world);
 // launches the largest colour's solve kernel `reps` times, returns mean ms; *constraints receives its size.
 S2B_API float s2b_time_color_kernel(s2bWorld* world, const s2bStepContext* context, int reps, int* constraints);
 
+// Diagnostic: have the persistent solver kernel stamp %globaltimer after every grid barrier of the NEXT solves (capacity
+// stamps per solve; 0 = off). s2b_get_solve_trace returns entries (code << 48 | nanoseconds), code = (pass kind << 8 | op).
+S2B_API void s2b_set_solve_trace(s2bWorld* world, int capacity);
+S2B_API int s2b_get_solve_trace(s2bWorld* world, uint64_t* out, int maxEntries);
 S2B_API const char* s2b_version(void);
 // Evaluate the device's atan2 (include/solver2d/atan2_f32.h) on the GPU for `count` host-resident (y, x) pairs: a
 // probe for the parity tests, which compare it bit for bit with the host C library's atan2f.

@@ -277,19 +277,44 @@ __device__ __forceinline__ void s2bWarmStartContact(const SolveArgs& a, int t)
 // Algorithmic traffic per 2-point constraint: stream idx 8 + nf 16 + 2 x (anchor 16 + pm 16 + lambda 8 r + 8 w)
 // = 120 B, bodies 2 x (vel 16 + pose 16 r, vel 16 w) = 96 B.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void s2bSolveContactTgsSoft(const SolveArgs& a, int t, float inv_h, bool useBias)
+// the constraint-stream part of a contact constraint: everything a solve pass reads that no other thread writes, so it
+// may be loaded BEFORE the grid barrier that precedes the pass (the body columns may not)
+struct ContactStream
+{
+	int2 idx;
+	float4 nf;
+	float4 la0, la1, pm0, pm1;
+	float2 l0, l1;
+};
+
+__device__ __forceinline__ ContactStream s2bLoadContactStream(const SolveArgs& a, int t)
 {
 	const ConstraintView& cc = a.cc;
-	int2 idx = cc.idx[t];
+	ContactStream cs;
+	cs.idx = cc.idx[t];
+	cs.nf = cc.nf[t];
+	cs.la0 = cc.anchor[0][t];
+	cs.pm0 = cc.pm[0][t];
+	cs.l0 = cc.lambda[0][t];
+	cs.la1 = cc.anchor[1][t];
+	cs.pm1 = cc.pm[1][t];
+	cs.l1 = cc.lambda[1][t];
+	return cs;
+}
+
+__device__ __forceinline__ void s2bSolveContactTgsSoftStream(const SolveArgs& a, int t, const ContactStream& cs, float inv_h, bool useBias)
+{
+	const ConstraintView& cc = a.cc;
+	int2 idx = cs.idx;
 	int ia = idx.x, ib = idx.y & S2B_CF_INDEX_MASK;
 	int pointCount = (idx.y & S2B_CF_TWO_POINTS) ? 2 : 1;
 	const SoftCoef soft = ((unsigned)idx.y & S2B_CF_STATIC_SOFT) ? a.softStatic : a.softDynamic;
 
-	float4 nf = cc.nf[t];
-	float4 la0 = cc.anchor[0][t], pm0 = cc.pm[0][t];
-	float2 l0 = cc.lambda[0][t];
-	float4 la1 = cc.anchor[1][t], pm1 = cc.pm[1][t];
-	float2 l1 = cc.lambda[1][t];
+	float4 nf = cs.nf;
+	float4 la0 = cs.la0, pm0 = cs.pm0;
+	float2 l0 = cs.l0;
+	float4 la1 = cs.la1, pm1 = cs.pm1;
+	float2 l1 = cs.l1;
 
 	float4 velA = a.bodies.vel[ia], velB = a.bodies.vel[ib];
 	float4 poseA = a.bodies.pose[ia], poseB = a.bodies.pose[ib];
@@ -389,6 +414,12 @@ __device__ __forceinline__ void s2bSolveContactTgsSoft(const SolveArgs& a, int t
 	}
 	BodyPair bp = {ia, ib, velA, velB, (mA != 0.0f) || (iA != 0.0f), (mB != 0.0f) || (iB != 0.0f)};
 	s2bStoreVelocities(a, bp, vA, wA, vB, wB);
+}
+
+__device__ __forceinline__ void s2bSolveContactTgsSoft(const SolveArgs& a, int t, float inv_h, bool useBias)
+{
+	ContactStream cs = s2bLoadContactStream(a, t);
+	s2bSolveContactTgsSoftStream(a, t, cs, inv_h, useBias);
 }
 
 // ===============================================================================================================

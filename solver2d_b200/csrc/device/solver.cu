@@ -852,11 +852,29 @@ __device__ __forceinline__ void s2bGridFlatPass(int jointOp, int contactOp, cons
 	}
 }
 
+// diagnostic time stamps (s2b_set_solve_trace): code = what just finished (pass kind << 8 | op), stamped by one thread
+__device__ __forceinline__ void s2bTrace(const SolveArgs& a, int code)
+{
+	if (a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
+	{
+		unsigned long long now;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+		unsigned long long n = a.trace[0];
+		if ((int)n + 1 < a.traceCap)
+		{
+			a.trace[1 + n] = ((unsigned long long)code << 48) | (now & 0xFFFFFFFFFFFFull);
+			a.trace[0] = n + 1;
+		}
+	}
+}
+
 __device__ __forceinline__ void s2bGridGroupPass(int jointOp, int contactOp, const SolveArgs& a, const PassPtrs& p, cg::grid_group& grid)
 {
 	int groups = a.counts[CNT_GROUPS];
 	int stride = gridDim.x * blockDim.x;
 	int tid = blockIdx.x * blockDim.x + threadIdx.x;
+	// (Loading the next group's constraint stream between barrier_arrive and barrier_wait was tried: no gain — the pass
+	// time is the barrier plus the dependent body loads, not the stream loads — and it cost registers. See DESIGN.md.)
 	for (int g = 0; g < groups; ++g)
 	{
 		int jBegin = a.jGroupOff[g], cBegin = a.cGroupOff[g];
@@ -878,6 +896,7 @@ __device__ __forceinline__ void s2bGridGroupPass(int jointOp, int contactOp, con
 			}
 		}
 		grid.sync();
+		s2bTrace(a, (PASS_GROUP << 8) | contactOp);
 	}
 	int ovC = contactOp != COP_NONE ? a.counts[CNT_OVERFLOW_C] : 0;
 	int ovJ = jointOp != JOP_NONE ? a.counts[CNT_OVERFLOW_J] : 0;
@@ -1028,6 +1047,7 @@ __device__ __forceinline__ void s2bGridFlowPass(int jointOp, int contactOp, cons
 __global__ void __launch_bounds__(S2B_BLOCK) s2bPersistentSolve(SolveArgs a, PassPtrs p, Program prog)
 {
 	cg::grid_group grid = cg::this_grid();
+	s2bTrace(a, 0xFFFF);
 	bool flow = a.bodyTicket != nullptr;
 	bool pendingFlow = false; // a ticketed pass has run since the last grid barrier
 	int flowPasses = 0;
@@ -1066,6 +1086,7 @@ __global__ void __launch_bounds__(S2B_BLOCK) s2bPersistentSolve(SolveArgs a, Pas
 					s2bGridFlatPass(pass.jointOp, pass.contactOp, a, p);
 				}
 				grid.sync();
+				s2bTrace(a, (pass.kind << 8) | (pass.kind == PASS_BODY ? pass.bodyOp : pass.contactOp));
 			}
 		}
 	}
@@ -1901,6 +1922,13 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 			env = getenv("S2B_FLOW_SLEEP_NS");
 			a.flowSleepNs = env != nullptr ? atoi(env) : 0;
 		}
+		if (s->traceCap > 0)
+		{
+			s->trace.reserve((size_t)s->traceCap, st, false);
+			S2B_CHECK(cudaMemsetAsync(s->trace.p, 0, sizeof(unsigned long long), st));
+			a.trace = s->trace.p;
+			a.traceCap = s->traceCap;
+		}
 		int wanted = std::max(gridFor(std::max(maxItems, bodyCap), threads), 1);
 		int grid = std::min(w->solveGrid, wanted);
 		void* args[] = {&a, &pp, &program};
@@ -2057,6 +2085,30 @@ extern "C" void s2b_get_counters(s2bWorld* w, s2bCounters* out)
 	out->movedCount = w->hostMail[MAIL_MOVED];
 	out->pairPassCount = w->pairPassCount;
 	out->kernelLaunches = w->kernelLaunches;
+}
+
+extern "C" void s2b_set_solve_trace(s2bWorld* w, int capacity)
+{
+	s2bGetSolverScratch(w)->traceCap = capacity > 0 ? capacity + 1 : 0;
+}
+
+extern "C" int s2b_get_solve_trace(s2bWorld* w, uint64_t* out, int maxEntries)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	S2B_CHECK(cudaStreamSynchronize(w->stream));
+	SolverScratch* s = s2bGetSolverScratch(w);
+	if (s->trace.p == nullptr || s->traceCap == 0)
+	{
+		return 0;
+	}
+	unsigned long long n = 0;
+	S2B_CHECK(cudaMemcpy(&n, s->trace.p, sizeof(n), cudaMemcpyDeviceToHost));
+	int count = (int)std::min<unsigned long long>(n, (unsigned long long)maxEntries);
+	if (count > 0)
+	{
+		S2B_CHECK(cudaMemcpy(out, s->trace.p + 1, sizeof(uint64_t) * (size_t)count, cudaMemcpyDeviceToHost));
+	}
+	return count;
 }
 
 extern "C" float s2b_time_color_kernel(s2bWorld* w, const s2bStepContext* context, int reps, int* constraints)

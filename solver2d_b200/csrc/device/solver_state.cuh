@@ -41,6 +41,8 @@ struct SolveArgs
 	int* bodyTicket;			   // per body: incident-item executions completed in this launch
 	const int2 *cFlowA, *cFlowB;   // per contact constraint and side: {ordinal in the body's incidence list, its degree} or -1
 	const int2 *jFlowA, *jFlowB;   // same per joint constraint
+	unsigned long long* trace; // diagnostic: block 0 stamps %globaltimer after every grid barrier (null = off)
+	int traceCap;
 	int flowSleepNs;			   // back-off between polls (0 = none)
 	int* flowError;				   // set when a wait ran into its spin limit (a bug, never expected)
 	s2bStepContext ctx;
@@ -80,6 +82,8 @@ struct SolverScratch
 	DevArray<int2> flow;	  // cFlowA | cFlowB | jFlowA | jFlowB
 	DevArray<int> bodyTicket; // + 1 int error flag at the end
 	int flowErrorOffset = 0;
+	DevArray<unsigned long long> trace; // [0] = number of stamps, then (code << 48 | ns) entries
+	int traceCap = 0;
 	int maxGroups = 0;
 
 	// contact constraint columns

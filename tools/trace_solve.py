@@ -1,0 +1,35 @@
+"""GPU box: where does the persistent solver kernel spend its time? Stamps after every grid barrier (s2b_set_solve_trace)."""
+import ctypes as C
+import sys
+import numpy as np
+from solver2d_b200 import capi, device, scenes
+
+base = int(sys.argv[1]) if len(sys.argv) > 1 else 447
+P = capi.Solver2D(device.LIB_PATH)
+dev = device.Device()
+sc = scenes.pyramid(P, "TGS_Soft", base_count=base)
+dw = device.DeviceWorld.attach(dev, sc.world)
+L = dev.lib
+L.s2b_set_solve_trace.argtypes = [C.c_void_p, C.c_int]
+L.s2b_get_solve_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+L.s2b_get_solve_trace.restype = C.c_int
+for _ in range(12):
+    sc.step(1 / 60, 4, 2, True)
+L.s2b_set_solve_trace(dw.h, 512)
+for _ in range(3):
+    dw.flush_l2()
+    sc.step(1 / 60, 4, 2, True)
+out = np.zeros(512, dtype=np.uint64)
+n = L.s2b_get_solve_trace(dw.h, out.ctypes.data, 512)
+ns = (out[:n] & np.uint64((1 << 48) - 1)).astype(np.int64)
+code = (out[:n] >> np.uint64(48)).astype(np.int64)
+dt = np.diff(ns)
+names = {0: "body", 1: "flat", 2: "group"}
+agg = {}
+for c, d in zip(code[1:], dt):
+    key = (names.get(int(c) >> 8, "?"), int(c) & 0xFF)
+    agg.setdefault(key, []).append(int(d))
+print("stamps", n, "total us", (ns[-1] - ns[0]) / 1e3)
+for key, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+    print(f"{key[0]:6s} op {key[1]:3d}: n={len(v):3d} total {sum(v)/1e3:8.1f} us  mean {np.mean(v)/1e3:6.2f} us  min {min(v)/1e3:6.2f}  max {max(v)/1e3:6.2f}")
+print("sequence (us):", [round(d / 1e3, 2) for d in dt[:40]])
