@@ -150,6 +150,20 @@ def run_reference(args, rank: int, world_size: int):
     print(json.dumps(line), flush=True)
 
 
+def aggregate_over_ranks(dist, device, total_ms, e2e_time, work, e2e_work):
+    """Whole-job numbers of an N-rank run: the time of the job is the MAX over ranks, its work the SUM (weak scaling:
+    every rank steps its own replica). dist = torch.distributed or None for a single process."""
+    import torch
+    t_vals = torch.tensor([total_ms, e2e_time], dtype=torch.float64, device=device)
+    w_vals = torch.tensor([float(work), float(e2e_work)], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t_vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w_vals, op=dist.ReduceOp.SUM)
+    total_ms_max, e2e_time_max = t_vals.tolist()
+    work_all, e2e_work_all = w_vals.tolist()
+    return total_ms_max, e2e_time_max, work_all, e2e_work_all
+
+
 def run_ours(args, rank: int, world_size: int, local_rank: int):
     os.environ["S2B_DEVICE"] = str(local_rank)  # worlds of this process live on its own GPU
     import torch
@@ -190,12 +204,19 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
         gather_in = torch.empty((nb + 8) * 8, dtype=torch.float32, device="cuda")
         gather_out = torch.empty(world_size * (nb + 8) * 8, dtype=torch.float32, device="cuda")
 
+    ext_stream = None
+    if dist is not None:
+        L.s2b_get_stream.restype = C.c_void_p
+        L.s2b_get_stream.argtypes = [C.c_void_p]
+        # the collective is enqueued on the world's own stream, right behind the step: no host synchronisation
+        ext_stream = torch.cuda.ExternalStream(int(L.s2b_get_stream(dw.h)), device=torch.device("cuda", local_rank))
+
     def exchange():
         if dist is None:
             return
         L.s2b_pack_body_state(dw.h, 0, nb, C.c_void_p(gather_in.data_ptr()))
-        dw.sync()
-        dist.all_gather_into_tensor(gather_out, gather_in)
+        with torch.cuda.stream(ext_stream):
+            dist.all_gather_into_tensor(gather_out, gather_in)
 
     # ---- warm-up (includes the first-step all-pairs broad phase) ----
     for _ in range(args.warmup):
@@ -222,17 +243,21 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
             total_ms += step_ms[-1]
             solve_kernel_ms.append(float(L.s2b_last_solve_kernel_ms(dw.h)))
     else:
+        ex_events = []
         for _ in range(args.steps):
             step_ms.append(float(L.s2World_TimedSteps(sc.world, 1, DT, args.substeps, args.relax, True, 1 if args.flush_l2 else 0)))
             total_ms += step_ms[-1]
             solve_kernel_ms.append(float(L.s2b_last_solve_kernel_ms(dw.h)))
             t0 = torch.cuda.Event(enable_timing=True)
             t1 = torch.cuda.Event(enable_timing=True)
-            t0.record()
+            with torch.cuda.stream(ext_stream):
+                t0.record()
             exchange()
-            t1.record()
-            t1.synchronize()
-            total_ms += t0.elapsed_time(t1)
+            with torch.cuda.stream(ext_stream):
+                t1.record()
+            ex_events.append((t0, t1))
+        torch.cuda.synchronize()
+        total_ms += sum(a.elapsed_time(b) for a, b in ex_events)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -276,14 +301,7 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
     e2e_time = time.perf_counter() - t0
     e2e_work, _ = get_work(reset=True)
 
-    # ---- aggregate over ranks: whole-job work / max time ----
-    t_vals = torch.tensor([total_ms, e2e_time], dtype=torch.float64, device="cuda")
-    w_vals = torch.tensor([float(work), float(e2e_work)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t_vals, op=dist.ReduceOp.MAX)
-        dist.all_reduce(w_vals, op=dist.ReduceOp.SUM)
-    total_ms_max, e2e_time_max = t_vals.tolist()
-    work_all, e2e_work_all = w_vals.tolist()
+    total_ms_max, e2e_time_max, work_all, e2e_work_all = aggregate_over_ranks(dist, "cuda", total_ms, e2e_time, work, e2e_work)
 
     if rank == 0:
         value = work_all / (total_ms_max * 1e-3)

@@ -253,6 +253,10 @@ S2B_API void s2b_step(s2bWorld* world, int solverType, const s2bStepContext* con
 // ---- device -> host (synchronising) ---------------------------------------------------------------------------
 
 S2B_API void s2b_sync(s2bWorld* world);
+// The CUDA stream (cudaStream_t, returned as an opaque pointer) every operation of this world is enqueued on: lets a
+// caller order its own work — e.g. an NCCL collective over s2b_pack_body_state's output — after the step without a host
+// synchronisation.
+S2B_API void* s2b_get_stream(s2bWorld* world);
 // rows[i].index selects the slot to read for i < count (flags are filled in).
 S2B_API void s2b_download_bodies(s2bWorld* world, s2bBodyRow* rows, int count);
 // every slot 0..capacity-1 in order

@@ -763,6 +763,11 @@ extern "C" void s2b_set_contact_order(s2bWorld* w, const uint64_t* pairKeys, int
 	w->orderHint.assign(pairKeys, pairKeys + (count > 0 ? count : 0));
 }
 
+extern "C" void* s2b_get_stream(s2bWorld* w)
+{
+	return (void*)w->stream;
+}
+
 extern "C" void s2b_sync(s2bWorld* w)
 {
 	S2B_CHECK(cudaSetDevice(w->device));
