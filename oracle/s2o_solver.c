@@ -48,6 +48,9 @@ typedef struct s2oConstraint
 {
 	int row, indexA, indexB, pointCount;
 	int unpersist; // TGS_Sticky: friction hit its limit in some pass
+	// PGS_NGS_Block
+	s2Mat22 K, normalMass;
+	float velocityBias[2];
 	s2Vec2 normal;
 	float friction;
 	s2oPoint points[2];

@@ -850,6 +850,319 @@ __device__ __forceinline__ void s2bSolveContactNgs(const SolveArgs& a, int t)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// PGS_NGS_Block (reference src/solve_pgs_ngs_block.c): Box2D-2.4 style block solver — the two normal rows of a 2-point
+// manifold are solved together as a 2x2 LCP by total enumeration. Optional stream columns used here:
+//   r0[j]      prepare-time anchors rA.xy rB.xy (the velocity rows never move their anchors)
+//   fanchor[0] K      = {k11, k12, k12, k22}   (cx.x cx.y cy.x cy.y)
+//   fanchor[1] K^-1   (s2GetInverse22)
+//   tsep[j].x  velocityBias of point j = -max(0, separation * inv_dt)
+// ---------------------------------------------------------------------------------------------------------------
+
+// s2CreateContactSolver, the per-constraint part (reference src/solve_pgs_ngs_block.c:135-262): the PGS prepare plus the
+// speculative velocity bias and the 2x2 block; a manifold whose two rows are nearly dependent (condition number guard
+// 1000) is solved, warm started AND stored as a 1-point manifold from here on.
+__device__ __forceinline__ void s2bPrepareContactBlock(const SolveArgs& a, int t)
+{
+	s2bPrepareContact<PREPARE_PGS>(a, t);
+	const ConstraintView& cc = a.cc;
+	int2 idx = cc.idx[t];
+	int slot = cc.src[t];
+	float4 nf = cc.nf[t];
+	s2Vec2 normal = V2(nf.x, nf.y);
+	float mA = a.bodies.vel[idx.x].w, mB = a.bodies.vel[idx.y & S2B_CF_INDEX_MASK].w;
+	float iA = nf.w, iB = cc.pm[0][t].w;
+	int pointCount = (idx.y & S2B_CF_TWO_POINTS) ? 2 : 1;
+#pragma unroll
+	for (int j = 0; j < 2; ++j)
+	{
+		float separation = j < pointCount ? a.contacts.impulse[j][slot].x : 0.0f;
+		cc.tsep[j][t] = make_float2(-S2_MAX(0.0f, separation * a.ctx.inv_dt), 0.0f);
+	}
+	s2Mat22 K = s2Mat22_zero, invK = s2Mat22_zero;
+	if (pointCount == 2)
+	{
+		float4 r1 = cc.r0[0][t], r2 = cc.r0[1][t];
+		float rn1A = s2Cross(V2(r1.x, r1.y), normal);
+		float rn1B = s2Cross(V2(r1.z, r1.w), normal);
+		float rn2A = s2Cross(V2(r2.x, r2.y), normal);
+		float rn2B = s2Cross(V2(r2.z, r2.w), normal);
+		float k11 = mA + mB + iA * rn1A * rn1A + iB * rn1B * rn1B;
+		float k22 = mA + mB + iA * rn2A * rn2A + iB * rn2B * rn2B;
+		float k12 = mA + mB + iA * rn1A * rn2A + iB * rn1B * rn2B;
+		const float k_maxConditionNumber = 1000.0f;
+		if (k11 * k11 < k_maxConditionNumber * (k11 * k22 - k12 * k12))
+		{
+			K.cx = V2(k11, k12);
+			K.cy = V2(k12, k22);
+			invK = s2GetInverse22(K);
+		}
+		else
+		{
+			cc.idx[t] = make_int2(idx.x, (int)((unsigned)idx.y & ~(unsigned)S2B_CF_TWO_POINTS));
+		}
+	}
+	cc.fanchor[0][t] = make_float4(K.cx.x, K.cx.y, K.cy.x, K.cy.y);
+	cc.fanchor[1][t] = make_float4(invK.cx.x, invK.cx.y, invK.cy.x, invK.cy.y);
+}
+
+// s2BlockSolveVelocity, one constraint (reference src/solve_pgs_ngs_block.c:329-658)
+__device__ __forceinline__ void s2bSolveContactBlockVelocity(const SolveArgs& a, int t)
+{
+	ContactLoad c = s2bLoadContact(a, t);
+	s2Vec2 vA = V2(c.velA.x, c.velA.y), vB = V2(c.velB.x, c.velB.y);
+	float wA = c.velA.z, wB = c.velB.z;
+	s2Vec2 normal = V2(c.nf.x, c.nf.y);
+	s2Vec2 tangent = s2CrossVS(normal, 1.0f);
+	float friction = c.nf.z;
+	float mA = c.mA, mB = c.mB, iA = c.iA, iB = c.iB;
+	float2 lam[2] = {a.cc.lambda[0][t], a.cc.lambda[1][t]};
+	float4 r0[2] = {a.cc.r0[0][t], a.cc.r0[1][t]};
+	float4 pm[2] = {a.cc.pm[0][t], a.cc.pm[1][t]};
+	float bias[2] = {a.cc.tsep[0][t].x, a.cc.tsep[1][t].x};
+
+	// friction rows first
+#pragma unroll
+	for (int j = 0; j < 2; ++j)
+	{
+		if (j < c.pointCount)
+		{
+			s2Vec2 rA = V2(r0[j].x, r0[j].y), rB = V2(r0[j].z, r0[j].w);
+			s2Vec2 vrB = s2Add(vB, s2CrossSV(wB, rB));
+			s2Vec2 vrA = s2Add(vA, s2CrossSV(wA, rA));
+			s2Vec2 dv = s2Sub(vrB, vrA);
+			float vt = s2Dot(dv, tangent);
+			float lambda = pm[j].z * (-vt);
+			float maxFriction = friction * lam[j].x;
+			float newImpulse = S2_CLAMP(lam[j].y + lambda, -maxFriction, maxFriction);
+			lambda = newImpulse - lam[j].y;
+			lam[j].y = newImpulse;
+			s2Vec2 P = s2MulSV(lambda, tangent);
+			vA = s2MulSub(vA, mA, P);
+			wA -= iA * s2Cross(rA, P);
+			vB = s2MulAdd(vB, mB, P);
+			wB += iB * s2Cross(rB, P);
+		}
+	}
+
+	if (c.pointCount == 1)
+	{
+		s2Vec2 rA = V2(r0[0].x, r0[0].y), rB = V2(r0[0].z, r0[0].w);
+		s2Vec2 vrB = s2Add(vB, s2CrossSV(wB, rB));
+		s2Vec2 vrA = s2Add(vA, s2CrossSV(wA, rA));
+		s2Vec2 dv = s2Sub(vrB, vrA);
+		float vn = s2Dot(dv, normal);
+		float lambda = -pm[0].y * (vn - bias[0]);
+		float newImpulse = S2_MAX(lam[0].x + lambda, 0.0f);
+		lambda = newImpulse - lam[0].x;
+		lam[0].x = newImpulse;
+		s2Vec2 P = s2MulSV(lambda, normal);
+		vA = s2MulSub(vA, mA, P);
+		wA -= iA * s2Cross(rA, P);
+		vB = s2MulAdd(vB, mB, P);
+		wB += iB * s2Cross(rB, P);
+	}
+	else
+	{
+		// 2x2 LCP:  vn = K x + b',  vn >= 0, x >= 0, vn_i x_i = 0, with b' = b - K a (a = accumulated impulses)
+		float4 kk = a.cc.fanchor[0][t], ik = a.cc.fanchor[1][t];
+		s2Mat22 K, normalMass;
+		K.cx = V2(kk.x, kk.y);
+		K.cy = V2(kk.z, kk.w);
+		normalMass.cx = V2(ik.x, ik.y);
+		normalMass.cy = V2(ik.z, ik.w);
+		s2Vec2 rA1 = V2(r0[0].x, r0[0].y), rB1 = V2(r0[0].z, r0[0].w);
+		s2Vec2 rA2 = V2(r0[1].x, r0[1].y), rB2 = V2(r0[1].z, r0[1].w);
+		s2Vec2 acc = V2(lam[0].x, lam[1].x);
+		s2Vec2 vrA = s2Add(vA, s2CrossSV(wA, rA1));
+		s2Vec2 vrB = s2Add(vB, s2CrossSV(wB, rB1));
+		s2Vec2 dv1 = s2Sub(vrB, vrA);
+		vrA = s2Add(vA, s2CrossSV(wA, rA2));
+		vrB = s2Add(vB, s2CrossSV(wB, rB2));
+		s2Vec2 dv2 = s2Sub(vrB, vrA);
+		float vn1 = s2Dot(dv1, normal);
+		float vn2 = s2Dot(dv2, normal);
+		s2Vec2 b = V2(vn1 - bias[0], vn2 - bias[1]);
+		b = s2Sub(b, s2MulMV(K, acc));
+
+		bool solved = false;
+		s2Vec2 x = s2Neg(s2MulMV(normalMass, b));
+		if (x.x >= 0.0f && x.y >= 0.0f)
+		{
+			solved = true; // case 1: both rows active
+		}
+		if (solved == false)
+		{
+			x.x = -pm[0].y * b.x;
+			x.y = 0.0f;
+			vn2 = K.cx.y * x.x + b.y;
+			if (x.x >= 0.0f && vn2 >= 0.0f)
+			{
+				solved = true; // case 2: row 1 active, row 2 separating
+			}
+		}
+		if (solved == false)
+		{
+			x.x = 0.0f;
+			x.y = -pm[1].y * b.y;
+			vn1 = K.cy.x * x.y + b.x;
+			if (x.y >= 0.0f && vn1 >= 0.0f)
+			{
+				solved = true; // case 3: row 2 active
+			}
+		}
+		if (solved == false)
+		{
+			x.x = 0.0f;
+			x.y = 0.0f;
+			if (b.x >= 0.0f && b.y >= 0.0f)
+			{
+				solved = true; // case 4: both separating
+			}
+		}
+		if (solved)
+		{
+			s2Vec2 d = s2Sub(x, acc);
+			s2Vec2 P1 = s2MulSV(d.x, normal);
+			s2Vec2 P2 = s2MulSV(d.y, normal);
+			vA = s2MulSub(vA, mA, s2Add(P1, P2));
+			wA -= iA * (s2Cross(rA1, P1) + s2Cross(rA2, P2));
+			vB = s2MulAdd(vB, mB, s2Add(P1, P2));
+			wB += iB * (s2Cross(rB1, P1) + s2Cross(rB2, P2));
+			lam[0].x = x.x;
+			lam[1].x = x.y;
+		}
+		// no case holds (numerically inconsistent): the impulses stay as they are (reference :653-654)
+	}
+
+	a.cc.lambda[0][t] = lam[0];
+	if (c.pointCount == 2)
+	{
+		a.cc.lambda[1][t] = lam[1];
+	}
+	s2bStoreContactVelocities(a, c, vA, wA, vB, wB);
+}
+
+// s2BlockSolvePosition, one constraint (reference src/solve_pgs_ngs_block.c:679-890): non-linear Gauss-Seidel on the
+// positions with the block re-linearised at the current pose (condition number guard 10000, else point by point)
+__device__ __forceinline__ void s2bSolveContactBlockPosition(const SolveArgs& a, int t)
+{
+	ContactLoad c = s2bLoadContact(a, t);
+	float4 poseA = a.bodies.pose[c.ia], poseB = a.bodies.pose[c.ib];
+	s2Vec2 dcA = V2(poseA.x, poseA.y), dcB = V2(poseB.x, poseB.y);
+	s2Rot qA = R2(poseA.z, poseA.w), qB = R2(poseB.z, poseB.w);
+	s2Vec2 normal = V2(c.nf.x, c.nf.y);
+	float mA = c.mA, mB = c.mB, iA = c.iA, iB = c.iB;
+	float slop = s2_linearSlop;
+	float4 la[2] = {a.cc.anchor[0][t], a.cc.anchor[1][t]};
+	float adj[2] = {a.cc.pm[0][t].x, a.cc.pm[1][t].x};
+
+	bool pointwise = c.pointCount != 2;
+	if (c.pointCount == 2)
+	{
+		s2Vec2 rA1 = s2RotateVector(qA, V2(la[0].x, la[0].y));
+		s2Vec2 rB1 = s2RotateVector(qB, V2(la[0].z, la[0].w));
+		s2Vec2 rA2 = s2RotateVector(qA, V2(la[1].x, la[1].y));
+		s2Vec2 rB2 = s2RotateVector(qB, V2(la[1].z, la[1].w));
+		s2Vec2 dc = s2Sub(dcB, dcA);
+		s2Vec2 d1 = s2Add(dc, s2Sub(rB1, rA1));
+		float separation1 = s2Dot(d1, normal) + adj[0];
+		s2Vec2 d2 = s2Add(dc, s2Sub(rB2, rA2));
+		float separation2 = s2Dot(d2, normal) + adj[1];
+		float C1 = S2_CLAMP(s2_baumgarte * (separation1 + slop), -s2_maxLinearCorrection, 0.0f);
+		float C2 = S2_CLAMP(s2_baumgarte * (separation2 + slop), -s2_maxLinearCorrection, 0.0f);
+		s2Vec2 b = V2(C1, C2);
+		float rn1A = s2Cross(rA1, normal);
+		float rn1B = s2Cross(rB1, normal);
+		float rn2A = s2Cross(rA2, normal);
+		float rn2B = s2Cross(rB2, normal);
+		float k11 = mA + mB + iA * rn1A * rn1A + iB * rn1B * rn1B;
+		float k22 = mA + mB + iA * rn2A * rn2A + iB * rn2B * rn2B;
+		float k12 = mA + mB + iA * rn1A * rn2A + iB * rn1B * rn2B;
+		const float k_maxConditionNumber = 10000.0f;
+		if (k11 * k11 < k_maxConditionNumber * (k11 * k22 - k12 * k12))
+		{
+			s2Mat22 K;
+			K.cx = V2(k11, k12);
+			K.cy = V2(k12, k22);
+			s2Mat22 invK = s2GetInverse22(K);
+			bool solved = false;
+			s2Vec2 x = s2Neg(s2MulMV(invK, b));
+			if (x.x >= 0.0f && x.y >= 0.0f)
+			{
+				solved = true;
+			}
+			if (solved == false)
+			{
+				x.x = -b.x / k11;
+				x.y = 0.0f;
+				float vn2 = K.cx.y * x.x + b.y;
+				if (x.x >= 0.0f && vn2 >= 0.0f)
+				{
+					solved = true;
+				}
+			}
+			if (solved == false)
+			{
+				x.x = 0.0f;
+				x.y = -b.y / k22;
+				float vn1 = K.cy.x * x.y + b.x;
+				if (x.y >= 0.0f && vn1 >= 0.0f)
+				{
+					solved = true;
+				}
+			}
+			// the fourth case (both rows satisfied) moves nothing
+			if (solved)
+			{
+				s2Vec2 P1 = s2MulSV(x.x, normal);
+				s2Vec2 P2 = s2MulSV(x.y, normal);
+				dcA = s2MulSub(dcA, mA, s2Add(P1, P2));
+				qA = s2IntegrateRot(qA, -iA * (s2Cross(rA1, P1) + s2Cross(rA2, P2)));
+				dcB = s2MulAdd(dcB, mB, s2Add(P1, P2));
+				qB = s2IntegrateRot(qB, iB * (s2Cross(rB1, P1) + s2Cross(rB2, P2)));
+			}
+		}
+		else
+		{
+			pointwise = true; // manifold_degenerate
+		}
+	}
+	if (pointwise)
+	{
+#pragma unroll
+		for (int j = 0; j < 2; ++j)
+		{
+			if (j < c.pointCount)
+			{
+				s2Vec2 rA = s2RotateVector(qA, V2(la[j].x, la[j].y));
+				s2Vec2 rB = s2RotateVector(qB, V2(la[j].z, la[j].w));
+				s2Vec2 d = s2Add(s2Sub(dcB, dcA), s2Sub(rB, rA));
+				float separation = s2Dot(d, normal) + adj[j];
+				float C = S2_CLAMP(s2_baumgarte * (separation + slop), -s2_maxLinearCorrection, 0.0f);
+				float rnA = s2Cross(rA, normal);
+				float rnB = s2Cross(rB, normal);
+				float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+				float impulse = K > 0.0f ? -C / K : 0.0f;
+				s2Vec2 P = s2MulSV(impulse, normal);
+				dcA = s2MulSub(dcA, mA, P);
+				qA = s2IntegrateRot(qA, -iA * s2Cross(rA, P));
+				dcB = s2MulAdd(dcB, mB, P);
+				qB = s2IntegrateRot(qB, iB * s2Cross(rB, P));
+			}
+		}
+	}
+
+	if ((mA != 0.0f) || (iA != 0.0f))
+	{
+		a.bodies.pose[c.ia] = make_float4(dcA.x, dcA.y, qA.s, qA.c);
+	}
+	if ((mB != 0.0f) || (iB != 0.0f))
+	{
+		a.bodies.pose[c.ib] = make_float4(dcB.x, dcB.y, qB.s, qB.c);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // TGS_Sticky (reference src/solve_tgs_sticky.c)
 // ---------------------------------------------------------------------------------------------------------------
 

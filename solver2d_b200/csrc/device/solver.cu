@@ -112,10 +112,13 @@ static VariantColumns columnsFor(int solverType)
 		case 0: // Jacobi
 		case 1: // PGS
 		case 2: // PGS_NGS
-		case 3: // PGS_NGS_Block
 		case 4: // PGS_Soft
 			c.r0 = true;
 			c.sep = true;
+			break;
+		case 3: // PGS_NGS_Block: fixed anchors + the block columns (K, K^-1, velocity bias) in the sticky scratch columns
+			c.r0 = true;
+			c.sticky = true;
 			break;
 		case 5: // SoftStep
 			c.r0 = true;
@@ -539,6 +542,7 @@ enum ContactOp
 	COP_PREPARE,		// s2PrepareContacts_PGS / _Soft / local TGS_NGS flavour: same arithmetic, optional columns differ
 	COP_PREPARE_COLD,	// XPBD: impulses always start at zero
 	COP_PREPARE_STICKY,
+	COP_PREPARE_BLOCK,
 	COP_WARM_START,
 	COP_WARM_START_FIXED,
 	COP_TGS_SOFT_BIAS,
@@ -557,6 +561,8 @@ enum ContactOp
 	COP_STICKY_RELAX,
 	COP_XPBD_POSITIONS,
 	COP_XPBD_VELOCITIES,
+	COP_BLOCK_VELOCITY,
+	COP_BLOCK_POSITION,
 	COP_STORE,
 	COP_STORE_SCALED, // XPBD stores impulse * inv_h
 };
@@ -655,6 +661,15 @@ __device__ __forceinline__ void s2bRunContactOp(int op, const SolveArgs& a, int 
 			break;
 		case COP_PREPARE_STICKY:
 			s2bPrepareContactSticky(a, t);
+			break;
+		case COP_PREPARE_BLOCK:
+			s2bPrepareContactBlock(a, t);
+			break;
+		case COP_BLOCK_VELOCITY:
+			s2bSolveContactBlockVelocity(a, t);
+			break;
+		case COP_BLOCK_POSITION:
+			s2bSolveContactBlockPosition(a, t);
 			break;
 		case COP_WARM_START:
 			s2bWarmStartContact(a, t);
@@ -1275,6 +1290,33 @@ static Program buildProgram(int solverType, const s2bStepContext& ctx, bool gath
 			}
 			break;
 		}
+		case 3: // s2Solve_PGS_NGS_Block, reference src/solve_pgs_ngs_block.c:892-963
+		{
+			b.segment(1);
+			b.add(bodyPass(BOP_INTEGRATE_VELOCITIES));
+			b.add(flatPass(JOP_PREPARE_RIGID_FLAG, COP_PREPARE_BLOCK));
+			// s2CreateContactSolver applies the (possibly zero) stored impulses unconditionally (:264-299), before any joint
+			b.add(groupPass(JOP_NONE, COP_WARM_START_FIXED));
+			if (warm)
+			{
+				b.add(groupPass(JOP_WARM_START, COP_NONE));
+			}
+			b.segment(S);
+			b.add(groupPass(JOP_RIGID, COP_BLOCK_VELOCITY));
+			b.segment(1);
+			b.add(flatPass(JOP_NONE, COP_STORE)); // before the position iterations (:934)
+			b.add(bodyPass(BOP_INTEGRATE_POSITIONS));
+			b.segment(E);
+			// the position iterations visit the contacts BEFORE the joints (:938-952): two sweeps keep that order in
+			// every schedule
+			b.add(groupPass(JOP_NONE, COP_BLOCK_POSITION));
+			b.add(groupPass(JOP_POSITION, COP_NONE));
+			b.segment(1);
+			b.add(bodyPass(BOP_FINALIZE_POSITIONS));
+			b.add(flatPass(JOP_STORE, COP_NONE));
+			*countedPasses = S + E;
+			break;
+		}
 		case 8: // s2Solve_TGS_NGS, reference src/solve_tgs_ngs.c:207-317
 		{
 			b.segment(1);
@@ -1531,9 +1573,8 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 	cudaStream_t st = w->stream;
 	s2bStepContext ctx = *ctxIn;
 
-	if (solverType == 3 || solverType < 0 || solverType > 9)
+	if (solverType < 0 || solverType > 9)
 	{
-		// s2_solverPGS_NGS_Block (2x2 block LCP) is the one variant not on the device yet
 		fprintf(stderr, "solver2d-b200: solver type %d is not implemented on the device — there is no CPU fallback\n", solverType);
 		abort();
 	}

@@ -94,7 +94,7 @@ def test_oracle_order_changes_result(reference):
     sc.destroy()
 
 
-VARIANTS = ["Jacobi", "PGS", "PGS_NGS", "PGS_Soft", "SoftStep", "TGS_Sticky", "TGS_Soft", "TGS_NGS", "XPBD"]
+VARIANTS = ["Jacobi", "PGS", "PGS_NGS", "PGS_NGS_Block", "PGS_Soft", "SoftStep", "TGS_Sticky", "TGS_Soft", "TGS_NGS", "XPBD"]
 
 
 @pytest.mark.parametrize("solver", VARIANTS)

@@ -107,7 +107,7 @@ def test_color_schedule_joints_and_contacts(reference, dev):
     assert c.jointCount == 75 and c.constraintCount > 20
 
 
-VARIANTS = ["Jacobi", "PGS", "PGS_NGS", "PGS_Soft", "SoftStep", "TGS_Sticky", "TGS_Soft", "TGS_NGS", "XPBD"]
+VARIANTS = ["Jacobi", "PGS", "PGS_NGS", "PGS_NGS_Block", "PGS_Soft", "SoftStep", "TGS_Sticky", "TGS_Soft", "TGS_NGS", "XPBD"]
 
 
 @pytest.mark.parametrize("persistent", [True, False])

@@ -108,7 +108,7 @@ def test_tgs_soft_no_warm_start_and_no_relax(reference, dev):
     sc.destroy()
 
 
-VARIANTS = ["Jacobi", "PGS", "PGS_NGS", "PGS_Soft", "SoftStep", "TGS_Sticky", "TGS_Soft", "TGS_NGS", "XPBD"]
+VARIANTS = ["Jacobi", "PGS", "PGS_NGS", "PGS_NGS_Block", "PGS_Soft", "SoftStep", "TGS_Sticky", "TGS_Soft", "TGS_NGS", "XPBD"]
 
 
 @pytest.mark.parametrize("persistent", [True, False])
