@@ -173,7 +173,8 @@ typedef struct s2bCounters
 	int32_t treeHeight;		 // depth of the last BVH
 	int32_t movedCount;		 // proxies whose fat AABB changed in the last finalize
 	int32_t pairPassCount;	 // number of broad-phase passes run so far
-	int32_t kernelLaunches;	 // CUDA kernels launched by this world since creation
+	int32_t kernelLaunches;	 // CUDA kernels launched by this world since creation (graph replays count their kernels)
+	int32_t graphReplays;	 // solver stages executed as a CUDA graph replay
 	int64_t scratchBytes;	 // device bytes of per-step scratch currently reserved
 } s2bCounters;
 
@@ -194,6 +195,9 @@ S2B_API void s2b_set_persistent(s2bWorld* world, int enable);
 // Warm start of the sub-stepping variants as a per-body gather fused with s2IntegrateVelocities (1, default) or as
 // grouped constraint passes like every other pass (0; cross-check). Both give bit-identical results.
 S2B_API void s2b_set_warm_gather(s2bWorld* world, int enable);
+// Replay the solver stage (set-up kernels + persistent kernel, ~30 launches) as ONE CUDA graph launch while its inputs'
+// shapes and addresses are unchanged (1, default) or always launch kernel by kernel (0).
+S2B_API void s2b_set_graph(s2bWorld* world, int enable);
 // Gauss-Seidel passes of the persistent kernel synchronised by one grid barrier per colour (0, default) or by per-body
 // tickets (1: a constraint waits only for the previous constraint on each of its bodies; no barrier inside a sweep).
 // Same bits either way; the ticketed form measured SLOWER on B200 (75 k pollers saturate L2), kept as an experiment.

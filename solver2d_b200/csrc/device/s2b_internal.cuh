@@ -41,6 +41,14 @@
 #define S2B_CI_PERSISTED1 0x10
 
 // A growable device array. grow() keeps the old contents (device-to-device copy on the world's stream).
+// bumped whenever any device array is re-allocated: a captured CUDA graph bakes device pointers in, so the solver's graph
+// cache keys on this epoch
+inline unsigned long long& s2bAllocEpoch()
+{
+	static unsigned long long epoch = 0;
+	return epoch;
+}
+
 template <typename T> struct DevArray
 {
 	T* p = nullptr;
@@ -74,6 +82,7 @@ template <typename T> struct DevArray
 		}
 		p = q;
 		cap = newCap;
+		s2bAllocEpoch() += 1;
 	}
 
 	void release()
@@ -266,6 +275,8 @@ struct s2bWorld
 	int schedule = S2B_SCHEDULE_COLOR;
 	int maxColors = 24;
 	int persistent = 1;
+	int useGraph = 1;		// replay the solver stage as a CUDA graph when nothing changed; s2b_set_graph / S2B_GRAPH=0 disable
+	bool capturing = false; // a stream capture of the solver stage is in progress
 	int dataflow = 0;	// ticketed Gauss-Seidel passes in the persistent kernel (experimental, slower on B200: DESIGN.md §3.1);
 						// s2b_set_dataflow / S2B_DATAFLOW=1 enable it
 	int gatherWarm = 1; // per-body warm-start gather (warm_gather.cuh); s2b_set_warm_gather / S2B_WARM_GATHER=0 disable it

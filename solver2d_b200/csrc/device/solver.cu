@@ -1582,6 +1582,50 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 	{
 		return; // s2Solve_XPBD leaves early (reference src/solve_xpbd.c:345-353)
 	}
+	// ---- CUDA graph of the stage ----
+	// A steady scene runs the SAME ~30 launches with the SAME arguments every step (counts live in device memory). The
+	// second consecutive step with an unchanged signature is captured into a graph; after that the stage is one
+	// cudaGraphLaunch until the signature changes (a contact table rebuilt by the pair pass, a re-allocation, other step
+	// parameters). S2B_GRAPH=0 disables it.
+	bool graphable = w->schedule == S2B_SCHEDULE_COLOR && w->persistent != 0 && w->coopSupported != 0 && s->graphDisabled == false &&
+					 s->traceCap == 0 && w->contactCount + w->jointCap > 0 && w->useGraph != 0;
+	std::vector<unsigned char> sig;
+	if (graphable)
+	{
+		auto put = [&sig](const void* ptr, size_t n) {
+			const unsigned char* b = (const unsigned char*)ptr;
+			sig.insert(sig.end(), b, b + n);
+		};
+		unsigned long long epoch = s2bAllocEpoch();
+		int ints[] = {solverType, w->contactCount, w->jointCap, w->bodyCap, w->cur, w->maxColors, w->gatherWarm, w->dataflow, w->sticky ? 1 : 0};
+		put(&ctx, sizeof(ctx));
+		put(ints, sizeof(ints));
+		put(&epoch, sizeof(epoch));
+		put(&w->gravity, sizeof(w->gravity));
+		if (s->graphExec != nullptr && sig == s->graphSig)
+		{
+			S2B_CHECK(cudaGraphLaunch(s->graphExec, st));
+			w->kernelLaunches += s->graphLaunches;
+			w->solveKernelTimed = true;
+			s->hostCountsValid = false;
+			s->graphReplays += 1;
+			return;
+		}
+	}
+	bool capturing = graphable && sig == s->graphCandidate;
+	int launchesBefore = w->kernelLaunches;
+	if (capturing)
+	{
+		if (s->graphExec != nullptr)
+		{
+			cudaGraphExecDestroy(s->graphExec);
+			s->graphExec = nullptr;
+		}
+		S2B_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+	}
+	s->graphCandidate = sig;
+	w->capturing = capturing;
+
 	int countedPasses = 0;
 	// per-sub-step warm starting as a per-body gather (warm_gather.cuh); S2B_WARM_GATHER=0 keeps the grouped passes
 	bool gatherWarm = w->gatherWarm != 0 && ctx.warmStart != 0 && (solverType == 7 || solverType == 5 || solverType == 8);
@@ -1978,9 +2022,11 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 			S2B_CHECK(cudaEventCreate(&w->solveKernelStart));
 			S2B_CHECK(cudaEventCreate(&w->solveKernelEnd));
 		}
-		S2B_CHECK(cudaEventRecord(w->solveKernelStart, st));
+		// (inside a capture the time stamps become external event-record nodes so that they are taken on every replay)
+		unsigned evFlags = capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
+		S2B_CHECK(cudaEventRecordWithFlags(w->solveKernelStart, st, evFlags));
 		S2B_CHECK(cudaLaunchCooperativeKernel((void*)s2bPersistentSolve, dim3(grid), dim3(threads), args, 0, st));
-		S2B_CHECK(cudaEventRecord(w->solveKernelEnd, st));
+		S2B_CHECK(cudaEventRecordWithFlags(w->solveKernelEnd, st, evFlags));
 		w->solveKernelTimed = true;
 		w->kernelLaunches += 1;
 	}
@@ -1994,6 +2040,35 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 	{
 		w->dWork.reserve(4, st, true);
 		S2B_LAUNCH(w, s2bMeterWork, 1, 1, 0, s->counts.p, countedPasses, w->dWork.p);
+	}
+
+	if (capturing)
+	{
+		w->capturing = false;
+		cudaGraph_t graph = nullptr;
+		cudaError_t err = cudaStreamEndCapture(st, &graph);
+		if (err == cudaSuccess && graph != nullptr)
+		{
+			err = cudaGraphInstantiate(&s->graphExec, graph, 0);
+			cudaGraphDestroy(graph);
+		}
+		if (err != cudaSuccess || s->graphExec == nullptr)
+		{
+			// capture not possible on this driver: nothing ran, so run this step eagerly and stop trying
+			(void)cudaGetLastError();
+			fprintf(stderr, "solver2d-b200: CUDA graph capture of the solver stage failed (%s); continuing without graphs\n",
+					cudaGetErrorString(err));
+			s->graphExec = nullptr;
+			s->graphDisabled = true;
+			s->graphCandidate.clear();
+			w->kernelLaunches = launchesBefore;
+			s2bSolve(w, solverType, ctxIn);
+			return;
+		}
+		s->graphSig = sig;
+		s->graphLaunches = w->kernelLaunches - launchesBefore;
+		s->graphCaptures += 1;
+		S2B_CHECK(cudaGraphLaunch(s->graphExec, st));
 	}
 }
 
@@ -2126,6 +2201,7 @@ extern "C" void s2b_get_counters(s2bWorld* w, s2bCounters* out)
 	out->movedCount = w->hostMail[MAIL_MOVED];
 	out->pairPassCount = w->pairPassCount;
 	out->kernelLaunches = w->kernelLaunches;
+	out->graphReplays = w->scratch != nullptr ? w->scratch->graphReplays : 0;
 }
 
 extern "C" void s2b_set_solve_trace(s2bWorld* w, int capacity)

@@ -98,6 +98,14 @@ struct SolverScratch
 	DevArray<int4> jhead;
 	DevArray<float4> janchor, jmass, jd0ax, jlim, jmotor, jcoef, jpivot, jimp, jlimp;
 
+	// CUDA graph of the whole solver stage (set-up kernels + persistent kernel), replayed while nothing it depends on
+	// changes: see s2bSolve
+	cudaGraphExec_t graphExec = nullptr;
+	std::vector<unsigned char> graphSig, graphCandidate;
+	int graphLaunches = 0;
+	bool graphDisabled = false;
+	int graphReplays = 0, graphCaptures = 0;
+
 	// host mirrors (valid when the last solve synchronised: multi-launch and wavefront modes)
 	int hostContacts = 0, hostJoints = 0, hostGroups = 0, hostOverflowC = 0, hostOverflowJ = 0;
 	bool hostCountsValid = false;

@@ -321,6 +321,11 @@ extern "C" s2bWorld* s2b_world_create(int cudaDevice, int solverType)
 		{
 			w->gatherWarm = atoi(env) != 0 ? 1 : 0;
 		}
+		env = getenv("S2B_GRAPH");
+		if (env != nullptr)
+		{
+			w->useGraph = atoi(env) != 0 ? 1 : 0;
+		}
 		env = getenv("S2B_DATAFLOW");
 		if (env != nullptr)
 		{
@@ -429,6 +434,11 @@ extern "C" void s2b_set_persistent(s2bWorld* w, int enable)
 extern "C" void s2b_set_warm_gather(s2bWorld* w, int enable)
 {
 	w->gatherWarm = enable;
+}
+
+extern "C" void s2b_set_graph(s2bWorld* w, int enable)
+{
+	w->useGraph = enable;
 }
 
 extern "C" void s2b_set_dataflow(s2bWorld* w, int enable)

@@ -230,3 +230,24 @@ def test_bulk_force_and_transform_paths_equal_per_body_api(reference, product, d
     assert np.abs(ang_b - _angles(R, sr)).max() < 1e-6
     for s in (sr, sa, sb):
         s.destroy()
+
+
+@pytest.mark.parametrize("solver", ["TGS_Soft", "PGS_NGS_Block", "XPBD"])
+def test_graph_replay_gives_the_same_bits(product, dev, solver):
+    """The solver stage is replayed as a CUDA graph while its inputs' shapes and addresses stand still. Same scene with
+    and without it: identical bits; and the replay really happens."""
+    P = product
+    sa = scenes.joint_contact_stress(P, solver, bridges=2, planks=16, grid=6)
+    sb = scenes.joint_contact_stress(P, solver, bridges=2, planks=16, grid=6)
+    da = device.DeviceWorld.attach(dev, sa.world)
+    db = device.DeviceWorld.attach(dev, sb.world)
+    da.set_graph(True)
+    db.set_graph(False)
+    for _ in range(60):
+        sa.step(DT, 4, 2, True)
+        sb.step(DT, 4, 2, True)
+    assert np.array_equal(_positions(P, sa), _positions(P, sb))
+    assert np.array_equal(_angles(P, sa), _angles(P, sb))
+    assert da.counters().graphReplays > 10 and db.counters().graphReplays == 0
+    sa.destroy()
+    sb.destroy()
