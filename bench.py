@@ -219,17 +219,23 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
             dist.all_gather_into_tensor(gather_out, gather_in)
 
     # ---- warm-up (includes the first-step all-pairs broad phase) ----
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup - 3, 0)):
         sc.step(DT, args.substeps, args.relax, True)
         exchange()
     dw.sync()
-    get_work(reset=True)
-    launches0 = dw.counters().kernelLaunches
 
     # ---- value: device-resident, CUDA events per step, L2 flushed between steps ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.25)  # let nvidia-smi attach before the timed region (its first query stalls launches for milliseconds)
+    # the last warm-up steps go through the timed entry point so that its one-off costs (L2-flush buffer) are paid here
+    for _ in range(min(3, args.warmup)):
+        L.s2World_TimedSteps(sc.world, 1, DT, args.substeps, args.relax, True, 1 if args.flush_l2 else 0)
+        exchange()
+    dw.sync()
+    get_work(reset=True)
+    launches0 = dw.counters().kernelLaunches
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -322,7 +328,8 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
                                                                         f", x{world_size} + NCCL all-gather of body state"),
                        "schedule": "graph colouring, persistent cooperative solver kernel"},
             "stage_ms_last_step": {"pairs": stage_ms[0], "contacts": stage_ms[1], "solve": stage_ms[2], "finalize": stage_ms[3]},
-            "step_ms_stats": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)), "max": float(np.max(step_ms)),
+            "step_ms_stats": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)), "max": float(np.max(step_ms)), "argmax": int(np.argmax(step_ms)),
+                              "over_2x_median": [round(float(x), 3) for x in step_ms if x > 2 * np.median(step_ms)],
                               "pair_passes_total": int(counters.pairPassCount)},
             "e2e": {"value": e2e_value, "unit": "constraint-iters/s", "ms_per_step": 1e3 * e2e_time_max / e2e_steps,
                     "h2d_bytes_per_step": int(len(idx) * 12), "d2h_bytes_per_step": int(nb * 16),

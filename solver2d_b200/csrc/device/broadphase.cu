@@ -42,7 +42,18 @@ struct BroadScratch
 	DevArray<int> mergeSrcIn, mergeSrcOut;
 	DevArray<char> cubTemp;
 	int newPairCap = 0;
+	// the hierarchy of the last pass: while no shape was created, destroyed or re-uploaded its TOPOLOGY is reused and only
+	// the boxes are refitted (boxes drift a little per step; a periodic rebuild keeps the tree tight)
+	bool treeValid = false;
+	int treeShapeCap = 0;
+	int treeReuses = 0;
+	// open-addressing hash set of the shape-pair keys of the current contact table ("does this pair already exist?")
+	DevArray<unsigned long long> pairHash;
+	unsigned long long hashMask = 0;
+	unsigned long long hashVersion = ~0ull; // contact table version the set was built from
 };
+
+#define S2B_TREE_REUSE_LIMIT 16
 
 static BroadScratch* getBroad(s2bWorld* w)
 {
@@ -175,6 +186,55 @@ __device__ __forceinline__ bool s2bJointOverride(const unsigned long long* keys,
 		}
 	}
 	return l < count && keys[l] == key;
+}
+
+// pair-key hash set (replaces an 18-step binary search per candidate pair by one or two probes)
+__device__ __forceinline__ unsigned long long s2bMix64(unsigned long long x)
+{
+	x ^= x >> 33;
+	x *= 0xff51afd7ed558ccdull;
+	x ^= x >> 33;
+	x *= 0xc4ceb9fe1a85ec53ull;
+	x ^= x >> 33;
+	return x;
+}
+
+__global__ void s2bBuildPairHash(const unsigned long long* keys, int count, unsigned long long* table, unsigned long long mask)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count)
+	{
+		return;
+	}
+	unsigned long long key = keys[i];
+	unsigned long long slot = s2bMix64(key) & mask;
+	for (;;)
+	{
+		unsigned long long prev = atomicCAS(table + slot, ~0ull, key);
+		if (prev == ~0ull || prev == key)
+		{
+			return;
+		}
+		slot = (slot + 1) & mask;
+	}
+}
+
+__device__ __forceinline__ bool s2bPairInHash(const unsigned long long* table, unsigned long long mask, unsigned long long key)
+{
+	unsigned long long slot = s2bMix64(key) & mask;
+	for (;;)
+	{
+		unsigned long long v = table[slot];
+		if (v == key)
+		{
+			return true;
+		}
+		if (v == ~0ull)
+		{
+			return false;
+		}
+		slot = (slot + 1) & mask;
+	}
 }
 
 __device__ __forceinline__ bool s2bKeyExists(const unsigned long long* keys, int count, unsigned long long key)
@@ -400,7 +460,7 @@ __global__ void s2bFlagMovedLeaves(ShapeView s, const int* leafShape, const int*
 
 __global__ void __launch_bounds__(128) s2bFindPairs(ShapeView s, BodyView b, const int* leafShape, const int* sortedLeaf, int* counters,
 								 const int* movedLeaves, const int2* children, const float4* nodeBox,
-								 const unsigned long long* oldKeys, int oldCount, const unsigned long long* jointKeys,
+								 const unsigned long long* pairHash, unsigned long long hashMask, const unsigned long long* jointKeys,
 								 int jointKeyCount, unsigned long long* newKey, int2* newShapes, int newCap)
 {
 	int n = counters[BC_LEAVES];
@@ -462,7 +522,11 @@ __global__ void __launch_bounds__(128) s2bFindPairs(ShapeView s, BodyView b, con
 			unsigned long long lo = (unsigned long long)(other < shapeQ ? other : shapeQ);
 			unsigned long long hi = (unsigned long long)(other < shapeQ ? shapeQ : other);
 			unsigned long long pairKey = (lo << 32) | hi;
-			if (s2bKeyExists(oldKeys, oldCount, pairKey))
+			if (bodyO == bodyQ)
+			{
+				continue;
+			}
+			if (s2bPairInHash(pairHash, hashMask, pairKey))
 			{
 				continue;
 			}
@@ -476,10 +540,6 @@ __global__ void __launch_bounds__(128) s2bFindPairs(ShapeView s, BodyView b, con
 			{
 				shapeA = shapeQ;
 				shapeB = other;
-			}
-			if (bodyO == bodyQ)
-			{
-				continue;
 			}
 			int4 filterO = s.filter[other];
 			if (s2bShouldShapesCollide(shapeA == shapeQ ? filterQ : filterO, shapeA == shapeQ ? filterO : filterQ) == false)
@@ -722,41 +782,74 @@ void s2bBroadphaseUpdatePairs(s2bWorld* w)
 		tempBytes = std::max(tempBytes, need);
 		B->cubTemp.reserve(tempBytes + 256, st, false, false);
 
-		S2B_CHECK(cudaMemsetAsync(B->counters.p, 0, sizeof(int) * BC_SIZE, st));
+		bool reuseTree = B->treeValid && w->pairsDirty == false && B->treeShapeCap == shapeCap && B->treeReuses < S2B_TREE_REUSE_LIMIT;
+		if (reuseTree)
+		{
+			// keep BC_LEAVES (and the stale height); clear the per-pass counters
+			S2B_CHECK(cudaMemsetAsync(B->counters.p + BC_NEW_PAIRS, 0, sizeof(int) * (BC_SIZE - BC_NEW_PAIRS), st));
+			B->treeReuses += 1;
+		}
+		else
+		{
+			S2B_CHECK(cudaMemsetAsync(B->counters.p, 0, sizeof(int) * BC_SIZE, st));
 
-		// ---- leaves ----
-		S2B_LAUNCH(w, s2bFlagValidShapes, gridFor(shapeCap, 256), 256, 0, sv, B->validFlag.p);
-		size_t tb = B->cubTemp.cap;
-		cub::DeviceSelect::Flagged(B->cubTemp.p, tb, thrust::counting_iterator<int>(0), B->validFlag.p, B->leafShape.p,
-								   B->counters.p + BC_LEAVES, shapeCap, st);
-		w->kernelLaunches += 2;
+			// ---- leaves ----
+			S2B_LAUNCH(w, s2bFlagValidShapes, gridFor(shapeCap, 256), 256, 0, sv, B->validFlag.p);
+			size_t tb = B->cubTemp.cap;
+			cub::DeviceSelect::Flagged(B->cubTemp.p, tb, thrust::counting_iterator<int>(0), B->validFlag.p, B->leafShape.p,
+									   B->counters.p + BC_LEAVES, shapeCap, st);
+			w->kernelLaunches += 2;
 
-		// ---- Morton order ----
-		int initBounds[4] = {0x7F7FFFFF, 0x7F7FFFFF, (int)0x80800000, (int)0x80800000};
-		// ordered encoding: +FLT_MAX -> 0x7F7FFFFF, -FLT_MAX -> 0xFF7FFFFF ^ 0x7FFFFFFF = 0x80800000
-		S2B_CHECK(cudaMemcpyAsync(B->boundsBits.p, initBounds, sizeof(initBounds), cudaMemcpyHostToDevice, st));
-		S2B_LAUNCH(w, s2bSceneBounds, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->counters.p, B->boundsBits.p);
-		S2B_LAUNCH(w, s2bMortonCodes, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->counters.p, B->boundsBits.p,
-				   B->mortonIn.p, B->leafIn.p, shapeCap);
-		tb = B->cubTemp.cap;
-		cub::DeviceRadixSort::SortPairs(B->cubTemp.p, tb, B->mortonIn.p, B->mortonOut.p, B->leafIn.p, B->leafOut.p, shapeCap, 0, 32, st);
-		w->kernelLaunches += 5;
+			// ---- Morton order ----
+			int initBounds[4] = {0x7F7FFFFF, 0x7F7FFFFF, (int)0x80800000, (int)0x80800000};
+			// ordered encoding: +FLT_MAX -> 0x7F7FFFFF, -FLT_MAX -> 0xFF7FFFFF ^ 0x7FFFFFFF = 0x80800000
+			S2B_CHECK(cudaMemcpyAsync(B->boundsBits.p, initBounds, sizeof(initBounds), cudaMemcpyHostToDevice, st));
+			S2B_LAUNCH(w, s2bSceneBounds, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->counters.p, B->boundsBits.p);
+			S2B_LAUNCH(w, s2bMortonCodes, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->counters.p, B->boundsBits.p,
+					   B->mortonIn.p, B->leafIn.p, shapeCap);
+			tb = B->cubTemp.cap;
+			cub::DeviceRadixSort::SortPairs(B->cubTemp.p, tb, B->mortonIn.p, B->mortonOut.p, B->leafIn.p, B->leafOut.p, shapeCap, 0, 32, st);
+			w->kernelLaunches += 5;
 
-		// ---- hierarchy + refit ----
+			// ---- hierarchy ----
+			S2B_LAUNCH(w, s2bBuildRadixTree, gridFor(shapeCap, 256), 256, 0, B->mortonOut.p, B->counters.p, B->children.p, B->parent.p);
+			B->treeValid = true;
+			B->treeShapeCap = shapeCap;
+			B->treeReuses = 0;
+		}
+
+		// ---- refit ----
 		S2B_CHECK(cudaMemsetAsync(B->visit.p, 0, sizeof(int) * nS, st));
-		S2B_LAUNCH(w, s2bBuildRadixTree, gridFor(shapeCap, 256), 256, 0, B->mortonOut.p, B->counters.p, B->children.p, B->parent.p);
 		S2B_LAUNCH(w, s2bRefit, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->leafOut.p, B->counters.p, B->children.p,
 				   B->parent.p, B->nodeBox.p, B->visit.p, B->nodeHeight.p, B->counters.p);
+
+		// ---- pair-key hash set of the current contact table (rebuilt only when the table changed) ----
+		if (B->hashVersion != w->contactTableVersion || B->pairHash.p == nullptr)
+		{
+			unsigned long long size = 1024;
+			while (size < 2ull * (unsigned long long)std::max(oldCount, 1))
+			{
+				size <<= 1;
+			}
+			B->pairHash.reserve((size_t)size, st, false, false);
+			B->hashMask = size - 1;
+			S2B_CHECK(cudaMemsetAsync(B->pairHash.p, 0xFF, sizeof(unsigned long long) * (size_t)size, st));
+			if (oldCount > 0)
+			{
+				S2B_LAUNCH(w, s2bBuildPairHash, gridFor(oldCount, 256), 256, 0, cur.key.p, oldCount, B->pairHash.p, B->hashMask);
+			}
+			B->hashVersion = w->contactTableVersion;
+		}
 
 		// ---- queries from moved proxies ----
 		S2B_LAUNCH(w, s2bFlagMovedLeaves, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->leafOut.p, B->counters.p,
 				   B->movedFlag.p);
-		tb = B->cubTemp.cap;
+		size_t tb = B->cubTemp.cap;
 		cub::DeviceSelect::Flagged(B->cubTemp.p, tb, thrust::counting_iterator<int>(0), B->movedFlag.p, B->movedLeaves.p,
 								   B->counters.p + BC_MOVED, shapeCap, st);
 		w->kernelLaunches += 2;
 		S2B_LAUNCH(w, s2bFindPairs, gridFor(shapeCap, 128), 128, 0, sv, bv, B->leafShape.p, B->leafOut.p, B->counters.p,
-				   B->movedLeaves.p, B->children.p, B->nodeBox.p, cur.key.p, oldCount, w->jointPairKeys.p, w->jointPairCount,
+				   B->movedLeaves.p, B->children.p, B->nodeBox.p, B->pairHash.p, B->hashMask, w->jointPairKeys.p, w->jointPairCount,
 				   B->newKey.p, B->newShapes.p, newCap);
 
 		// ---- survivors ----
@@ -810,6 +903,7 @@ void s2bBroadphaseUpdatePairs(s2bWorld* w)
 		}
 		w->cur ^= 1;
 		w->contactCount = total;
+		w->contactTableVersion += 1;
 		break;
 	}
 

@@ -276,7 +276,8 @@ struct s2bWorld
 	int maxColors = 24;
 	int persistent = 1;
 	int useGraph = 1;		// replay the solver stage as a CUDA graph when nothing changed; s2b_set_graph / S2B_GRAPH=0 disable
-	bool capturing = false; // a stream capture of the solver stage is in progress
+	bool capturing = false;
+	unsigned long long contactTableVersion = 0; // bumped whenever the contact table is replaced (pair pass commit, upload) // a stream capture of the solver stage is in progress
 	int dataflow = 0;	// ticketed Gauss-Seidel passes in the persistent kernel (experimental, slower on B200: DESIGN.md §3.1);
 						// s2b_set_dataflow / S2B_DATAFLOW=1 enable it
 	int gatherWarm = 1; // per-body warm-start gather (warm_gather.cuh); s2b_set_warm_gather / S2B_WARM_GATHER=0 disable it

@@ -550,6 +550,7 @@ extern "C" void s2b_upload_contacts(s2bWorld* w, const s2bContactRow* rows, int 
 	ContactColumns& c = w->contacts[w->cur];
 	c.reserve((size_t)(count > 0 ? count : 1), w->stream, w->sticky, false);
 	w->contactCount = count;
+	w->contactTableVersion += 1;
 	if (count <= 0)
 	{
 		return;
