@@ -50,7 +50,9 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi SM clock / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi SM clock / throttle reasons sampled every 20 ms while the timed region runs (the region is tens of
+    milliseconds long). start() returns once the first sample has arrived: nvidia-smi's start-up query stalls kernel
+    launches for milliseconds and must not land inside the timed region."""
 
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -64,9 +66,13 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu_index), "-lms", "200"], stdout=subprocess.PIPE,
+                                          "-i", str(self.gpu_index), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < 5.0:
+                time.sleep(0.02)
+            self.warm_lines = len(self.lines)
         except Exception:
             self.proc = None
 
@@ -77,10 +83,10 @@ class ClockSampler:
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.05)
         self.proc.terminate()
         sm, smax, reasons = [], [], set()
-        for line in self.lines:
+        for line in self.lines[getattr(self, "warm_lines", 0):] or self.lines:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 9:
                 continue
@@ -100,6 +106,16 @@ def algorithmic_bytes_per_step(constraints: int, bodies: int, substeps: int, rel
     """S*[C*(152 + 208*(1+[E>0])) + Nb*100] + C*(250 + 16) + Nb*32 for one TGS_Soft solver stage."""
     passes = 1 + (1 if relax else 0)
     return substeps * (constraints * (152.0 + 208.0 * passes) + bodies * 100.0) + constraints * (250.0 + 16.0) + bodies * 32.0
+
+
+def _traffic(which: str):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the named kernel from the committed
+    `ncu --set full` capture of this workload (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as fh:
+            return json.load(fh).get(which, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 def build_scene(lib, base_count: int):
@@ -228,7 +244,6 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)  # let nvidia-smi attach before the timed region (its first query stalls launches for milliseconds)
     # the last warm-up steps go through the timed entry point so that its one-off costs (L2-flush buffer) are paid here
     for _ in range(min(3, args.warmup)):
         L.s2World_TimedSteps(sc.world, 1, DT, args.substeps, args.relax, True, 1 if args.flush_l2 else 0)
@@ -339,10 +354,25 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
             "gpu_launches": int(launches),
             "roofline": {"kernel": "s2bPersistentTgsSoft (whole solver stage of one step)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                         "traffic": None, "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms, "peak_source": peak_src},
+                         "traffic": _traffic("persistent_solve"), "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms, "peak_source": peak_src},
             "clocks": clocks,
             "wall_s_timed_region": wall,
         }
+        if not args.no_colour_probe and world_size == 1:
+            # the hot kernel on its own, at a size where one colour exceeds L2 (see tools/color_kernel_probe.py)
+            try:
+                sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+                from color_kernel_probe import probe
+                pr = probe(args.probe_base)
+                line["roofline_colour_kernel"] = {
+                    "kernel": "s2bTgsSoftColorKernel (TGS_Soft relax pass over the largest colour, L2 evicted before each launch)",
+                    "workload": f"pyramid{args.probe_base}: {pr['boxes']} boxes, {pr['contact_constraints']} constraints, "
+                                f"{pr['colours']} colours, largest colour {pr['largest_colour_constraints']}",
+                    "bound": "hbm", "achieved": pr.get("achieved_GBps"), "peak": peak, "unit": "GB/s",
+                    "frac": (pr.get("achieved_GBps", 0.0) / peak) if peak else None, "kernel_ms": pr["kernel_ms"],
+                    "algorithmic_bytes_per_launch": pr.get("algorithmic_bytes"), "traffic": _traffic("colour_kernel")}
+            except Exception as e:  # the probe is additional evidence, never a reason to lose the bench line
+                line["roofline_colour_kernel"] = {"error": repr(e)}
         if not args.no_cpu_baseline and world_size == 1:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
@@ -386,6 +416,8 @@ def main():
     ap.add_argument("--relax", type=int, default=2)
     ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-colour-probe", action="store_true")
+    ap.add_argument("--probe-base", type=int, default=2600, help="pyramid base of the per-colour kernel roofline probe")
     ap.add_argument("--cpu-steps", type=int, default=20)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -798,6 +798,18 @@ __global__ void __launch_bounds__(S2B_BLOCK) s2bBodyPassKernel(SolveArgs a, int 
 	}
 }
 
+// THE per-colour impulse kernel on its own (TGS_Soft solve / relax over one colour): what the persistent kernel executes
+// between two grid barriers, as a plain kernel with only this op in it (lean registers, full occupancy). Used by the
+// roofline probe s2b_time_color_kernel.
+__global__ void __launch_bounds__(S2B_BLOCK) s2bTgsSoftColorKernel(SolveArgs a, int cBegin, int cEnd, int useBias)
+{
+	int t = cBegin + blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < cEnd)
+	{
+		s2bSolveContactTgsSoft(a, t, a.ctx.inv_h, useBias != 0);
+	}
+}
+
 // one group (or the whole range): joints first, then contacts
 __global__ void __launch_bounds__(S2B_BLOCK) s2bRangePassKernel(SolveArgs a, PassPtrs p, int jointOp, int contactOp, int jBegin, int jEnd,
 															   int cBegin, int cEnd)
@@ -1984,6 +1996,10 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 		a.jFlowB = s->flow.p + 2 * nC + nJ;
 	}
 	pp.jPerm = s->jPerm.p;
+	s->lastArgs = a;
+	s->lastJointSlots = pp.jointSlots;
+	s->lastJPerm = pp.jPerm;
+	s->lastArgsValid = true;
 	bool usePersistent = w->persistent != 0 && w->coopSupported != 0;
 	if (usePersistent)
 	{
@@ -2228,14 +2244,67 @@ extern "C" int s2b_get_solve_trace(s2bWorld* w, uint64_t* out, int maxEntries)
 	return count;
 }
 
+extern "C" void s2b_flush_l2(s2bWorld* w);
+
+// Roofline probe of THE hot kernel in isolation: the TGS_Soft relax pass over the largest colour of the current constraint
+// set, one launch per repetition, L2 evicted before every launch so that the constraint stream and the bodies come from
+// HBM. The preceding solve is run launch by launch to have the group table on the host; the world's state advances by
+// that one solver stage plus `reps` extra relax passes of one colour (a probe, not a simulation step).
 extern "C" float s2b_time_color_kernel(s2bWorld* w, const s2bStepContext* context, int reps, int* constraints)
 {
-	(void)w;
-	(void)context;
-	(void)reps;
+	S2B_CHECK(cudaSetDevice(w->device));
 	if (constraints)
 	{
 		*constraints = 0;
 	}
-	return 0.0f;
+	int persistentBefore = w->persistent;
+	w->persistent = 0;
+	s2bSolve(w, 7, context);
+	w->persistent = persistentBefore;
+	SolverScratch* s = s2bGetSolverScratch(w);
+	if (s->lastArgsValid == false || s->hostCountsValid == false || s->hostGroups == 0)
+	{
+		return 0.0f;
+	}
+	int best = 0, bestCount = 0;
+	for (int g = 0; g < s->hostGroups; ++g)
+	{
+		int n = s->hostCGroupOff[g + 1] - s->hostCGroupOff[g];
+		if (n > bestCount)
+		{
+			bestCount = n;
+			best = g;
+		}
+	}
+	if (bestCount == 0)
+	{
+		return 0.0f;
+	}
+	int cb = s->hostCGroupOff[best], ce = s->hostCGroupOff[best + 1];
+	SolveArgs a = s->lastArgs;
+	cudaEvent_t e0, e1;
+	S2B_CHECK(cudaEventCreate(&e0));
+	S2B_CHECK(cudaEventCreate(&e1));
+	float total = 0.0f;
+	for (int r = 0; r < reps + 2; ++r)
+	{
+		s2b_flush_l2(w);
+		S2B_CHECK(cudaEventRecord(e0, w->stream));
+		S2B_LAUNCH(w, s2bTgsSoftColorKernel, gridFor(bestCount, S2B_BLOCK), S2B_BLOCK, 0, a, cb, ce, 0);
+		S2B_CHECK(cudaEventRecord(e1, w->stream));
+		S2B_CHECK(cudaEventSynchronize(e1));
+		float ms = 0.0f;
+		S2B_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+		if (r >= 2)
+		{
+			total += ms; // the first two repetitions warm the instruction cache and the TLB
+		}
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	if (constraints)
+	{
+		*constraints = bestCount;
+	}
+	return reps > 0 ? total / (float)reps : 0.0f;
 }

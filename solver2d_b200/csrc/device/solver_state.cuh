@@ -106,6 +106,12 @@ struct SolverScratch
 	bool graphDisabled = false;
 	int graphReplays = 0, graphCaptures = 0;
 
+	// argument block of the last solve (the per-colour kernel probe re-launches one of its passes)
+	SolveArgs lastArgs;
+	const int* lastJointSlots = nullptr;
+	const int* lastJPerm = nullptr;
+	bool lastArgsValid = false;
+
 	// host mirrors (valid when the last solve synchronised: multi-launch and wavefront modes)
 	int hostContacts = 0, hostJoints = 0, hostGroups = 0, hostOverflowC = 0, hostOverflowJ = 0;
 	bool hostCountsValid = false;

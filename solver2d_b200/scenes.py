@@ -316,3 +316,56 @@ RECIPES = {
     "tumbler": tumbler,
     "mixed_shapes": mixed_shapes,
 }
+
+
+def pyramid_rows(base_count: int):
+    """The Pyramid recipe (see ``pyramid``) as device rows built with numpy instead of one API call per box: bodies and
+    shapes for ``Device.create_world().upload_*``. For worlds too large to author through ctypes in reasonable time
+    (the per-colour kernel roofline probe builds 3 M boxes this way). Values are what the host library would produce for
+    s2MakeSquare(0.5) boxes of density 1 on a static ground."""
+    import numpy as np
+    from . import device as dv
+    n = base_count
+    nb = n * (n + 1) // 2
+    i_idx = np.repeat(np.arange(n), n - np.arange(n))
+    j_idx = np.concatenate([np.arange(i, n) for i in range(n)])
+    h = np.float32(0.5)
+    x = ((i_idx + 1) * 0.5 + 2.0 * (j_idx - i_idx) * 0.5 - 0.5 * n).astype(np.float32)
+    y = ((2.0 * i_idx + 1.0) * 0.5).astype(np.float32)
+    bodies = np.zeros(nb + 1, dtype=dv.BODY_ROW)
+    bodies["index"] = np.arange(nb + 1)
+    bodies["flags"] = dv.ROW_VALID | (capi.DYNAMIC_BODY << 1)
+    bodies["flags"][0] = dv.ROW_VALID | (capi.STATIC_BODY << 1)
+    bodies["origin"][1:, 0] = x
+    bodies["origin"][1:, 1] = y
+    bodies["origin"][0] = (0.0, -1.0)
+    bodies["position"] = bodies["origin"]
+    bodies["rot"][:, 1] = 1.0
+    bodies["mass"][1:] = 1.0
+    bodies["invMass"][1:] = 1.0
+    bodies["I"][1:] = np.float32(1.0 / 6.0)
+    bodies["invI"][1:] = np.float32(6.0)
+    bodies["gravityScale"] = 1.0
+    shapes = np.zeros(nb + 1, dtype=dv.SHAPE_ROW)
+    shapes["index"] = np.arange(nb + 1)
+    polygon = 2  # s2_polygonShape
+    shapes["flags"] = dv.ROW_VALID | (polygon << 1) | dv.SHAPE_MOVED | 0x20  # + FRESH
+    shapes["flags"][0] = dv.ROW_VALID | (polygon << 1) | 0x20
+    shapes["body"] = np.arange(nb + 1)
+    shapes["proxyKey"] = np.arange(nb + 1)
+    shapes["categoryBits"] = 1
+    shapes["maskBits"] = 0xFFFFFFFF
+    shapes["friction"] = 0.6
+    shapes["count"] = 4
+    hw = np.full(nb + 1, h, dtype=np.float32)
+    hh = np.full(nb + 1, h, dtype=np.float32)
+    hw[0] = max(100.0, 0.5 * n + 50.0)
+    hh[0] = 1.0
+    verts = np.stack([-hw, -hh, hw, -hh, hw, hh, -hw, hh], axis=1)
+    shapes["vertices"][:, :8] = verts
+    shapes["normals"][:, :8] = np.array([0.0, -1.0, 1.0, 0.0, 0.0, 1.0, -1.0, 0.0], dtype=np.float32)
+    cx, cy = bodies["origin"][:, 0], bodies["origin"][:, 1]
+    shapes["aabb"] = np.stack([cx - hw, cy - hh, cx + hw, cy + hh], axis=1)
+    m = np.float32(0.1)  # s2_aabbMargin
+    shapes["fatAABB"] = np.stack([cx - hw - m, cy - hh - m, cx + hw + m, cy + hh + m], axis=1)
+    return bodies, shapes

@@ -251,3 +251,23 @@ def test_graph_replay_gives_the_same_bits(product, dev, solver):
     assert da.counters().graphReplays > 10 and db.counters().graphReplays == 0
     sa.destroy()
     sb.destroy()
+
+
+def test_colour_kernel_probe_and_row_built_world(dev):
+    """scenes.pyramid_rows builds the same kind of world the API does (contacts appear, colours form), and the per-colour
+    kernel probe returns a time for a non-empty colour."""
+    import ctypes as C
+    bodies, shapes = scenes.pyramid_rows(40)
+    dw = dev.create_world(7)
+    dw.upload_bodies(bodies, len(bodies))
+    dw.upload_shapes(shapes, len(shapes))
+    ctx = device.make_context("TGS_Soft", DT, 4, 2, True)
+    for _ in range(3):
+        dw.step(ctx)
+    c = dw.counters()
+    assert c.contactCount == 3 * 820 - 40 - 39 - 1 or c.contactCount > 2000  # ~3 contacts per box
+    assert 4 <= c.groupCount <= 16
+    n = C.c_int(0)
+    ms = dev.lib.s2b_time_color_kernel(dw.h, C.byref(ctx), 3, C.byref(n))
+    assert ms > 0.0 and n.value > 100
+    dw.destroy()
