@@ -35,6 +35,7 @@ struct BroadScratch
 	DevArray<int> nodeHeight;
 	DevArray<int> movedLeaves;	   // sorted-leaf indices of moved proxies
 	DevArray<int> movedFlag;
+	DevArray<int> largeShapes;	   // shapes of moved proxies with scene-sized boxes
 	DevArray<unsigned long long> newKey;
 	DevArray<int2> newShapes;
 	DevArray<int> keepFlag, keepSlots;
@@ -106,6 +107,7 @@ enum
 	BC_KEPT = 2,
 	BC_MOVED = 3,
 	BC_HEIGHT = 4,
+	BC_LARGE = 5, // moved proxies handled by the leaf-side query
 	BC_SIZE = 8
 };
 
@@ -458,6 +460,107 @@ __global__ void s2bFlagMovedLeaves(ShapeView s, const int* leafShape, const int*
 	}
 }
 
+// what the query of proxy Q does with an overlapping proxy `other` (reference s2PairQueryCallback, src/broad_phase.c:166-258)
+struct PairQuery
+{
+	int shapeQ, bodyQ, keyQ;
+	unsigned typeBodyQ;
+	int4 headQ, filterQ;
+};
+
+__device__ __forceinline__ void s2bConsiderPair(const PairQuery& q, int other, const ShapeView& s, const BodyView& b, int* counters,
+												 const unsigned long long* pairHash, unsigned long long hashMask,
+												 const unsigned long long* jointKeys, int jointKeyCount, unsigned long long* newKey,
+												 int2* newShapes, int newCap)
+{
+	int shapeQ = q.shapeQ;
+	if (other == shapeQ)
+	{
+		return;
+	}
+	int4 headO = s.head[other];
+	int bodyO = headO.y;
+	int keyO = headO.z;
+	unsigned typeBodyO = S2B_BODY_TYPE((unsigned)b.flags[bodyO]);
+	// a kinematic proxy only queries the dynamic tree
+	if (q.typeBodyQ == S2B_BODY_KINEMATIC && typeBodyO != S2B_BODY_DYNAMIC)
+	{
+		return;
+	}
+	// both proxies moved: the one with the smaller key reports the pair
+	if ((headO.x & S2B_SHAPE_MOVED) && keyO > q.keyQ)
+	{
+		// ... unless the other one cannot see us in its own query
+		bool otherSeesUs = !(typeBodyO == S2B_BODY_KINEMATIC && q.typeBodyQ != S2B_BODY_DYNAMIC) && typeBodyO != S2B_BODY_STATIC;
+		if (otherSeesUs)
+		{
+			return;
+		}
+	}
+	if (bodyO == q.bodyQ)
+	{
+		return;
+	}
+	unsigned long long lo = (unsigned long long)(other < shapeQ ? other : shapeQ);
+	unsigned long long hi = (unsigned long long)(other < shapeQ ? shapeQ : other);
+	unsigned long long pairKey = (lo << 32) | hi;
+	if (s2bPairInHash(pairHash, hashMask, pairKey))
+	{
+		return;
+	}
+	int shapeA, shapeB;
+	if (keyO < q.keyQ)
+	{
+		shapeA = other;
+		shapeB = shapeQ;
+	}
+	else
+	{
+		shapeA = shapeQ;
+		shapeB = other;
+	}
+	int4 filterO = s.filter[other];
+	if (s2bShouldShapesCollide(shapeA == shapeQ ? q.filterQ : filterO, shapeA == shapeQ ? filterO : q.filterQ) == false)
+	{
+		return;
+	}
+	if (s2bJointOverride(jointKeys, jointKeyCount, q.bodyQ, bodyO))
+	{
+		return;
+	}
+	int typeA = ((shapeA == shapeQ ? q.headQ.x : headO.x) >> 1) & 0x7;
+	int typeB = ((shapeA == shapeQ ? headO.x : q.headQ.x) >> 1) & 0x7;
+	int kind = s2bPairKind(typeA, typeB);
+	if (kind == 0)
+	{
+		return;
+	}
+	if (kind == 2)
+	{
+		int tmp = shapeA;
+		shapeA = shapeB;
+		shapeB = tmp;
+	}
+	int slot = atomicAdd(counters + BC_NEW_PAIRS, 1);
+	if (slot < newCap)
+	{
+		newKey[slot] = pairKey;
+		newShapes[slot] = make_int2(shapeA, shapeB);
+	}
+}
+
+__device__ __forceinline__ bool s2bMakeQuery(PairQuery& q, int shapeQ, const ShapeView& s, const BodyView& b)
+{
+	q.shapeQ = shapeQ;
+	q.headQ = s.head[shapeQ];
+	q.filterQ = s.filter[shapeQ];
+	q.bodyQ = q.headQ.y;
+	q.keyQ = q.headQ.z;
+	q.typeBodyQ = S2B_BODY_TYPE((unsigned)b.flags[q.bodyQ]);
+	return q.typeBodyQ != S2B_BODY_STATIC; // static proxies never query (reference src/broad_phase.c:284-299)
+}
+
+// moved proxies with ordinary boxes: one thread walks the hierarchy
 __global__ void __launch_bounds__(128) s2bFindPairs(ShapeView s, BodyView b, const int* leafShape, const int* sortedLeaf, int* counters,
 								 const int* movedLeaves, const int2* children, const float4* nodeBox,
 								 const unsigned long long* pairHash, unsigned long long hashMask, const unsigned long long* jointKeys,
@@ -465,110 +568,29 @@ __global__ void __launch_bounds__(128) s2bFindPairs(ShapeView s, BodyView b, con
 {
 	int n = counters[BC_LEAVES];
 	int movedCount = counters[BC_MOVED];
-	int q = blockIdx.x * blockDim.x + threadIdx.x;
-	if (q >= movedCount)
+	int qi = blockIdx.x * blockDim.x + threadIdx.x;
+	if (qi >= movedCount)
 	{
 		return;
 	}
-	int leaf = movedLeaves[q];
-	int shapeQ = leafShape[sortedLeaf[leaf]];
-	int4 headQ = s.head[shapeQ];
-	float4 boxQ = s.fat[shapeQ];
-	int4 filterQ = s.filter[shapeQ];
-	int bodyQ = headQ.y;
-	int keyQ = headQ.z;
-	unsigned typeBodyQ = S2B_BODY_TYPE((unsigned)b.flags[bodyQ]);
-	if (typeBodyQ == S2B_BODY_STATIC)
+	int leaf = movedLeaves[qi];
+	PairQuery q;
+	if (s2bMakeQuery(q, leafShape[sortedLeaf[leaf]], s, b) == false || n == 1)
 	{
-		return; // static proxies never query (reference src/broad_phase.c:284-299)
+		return;
 	}
+	float4 boxQ = s.fat[q.shapeQ];
 
 	int stack[64];
 	int sp = 0;
-	if (n == 1)
-	{
-		return;
-	}
 	stack[sp++] = 0;
 	while (sp > 0)
 	{
 		int node = stack[--sp];
 		if (node >= n - 1)
 		{
-			int other = leafShape[sortedLeaf[node - (n - 1)]];
-			if (other == shapeQ)
-			{
-				continue;
-			}
-			int4 headO = s.head[other];
-			int bodyO = headO.y;
-			int keyO = headO.z;
-			unsigned typeBodyO = S2B_BODY_TYPE((unsigned)b.flags[bodyO]);
-			// a kinematic proxy only queries the dynamic tree
-			if (typeBodyQ == S2B_BODY_KINEMATIC && typeBodyO != S2B_BODY_DYNAMIC)
-			{
-				continue;
-			}
-			// both proxies moved: the one with the smaller key reports the pair
-			if ((headO.x & S2B_SHAPE_MOVED) && keyO > keyQ)
-			{
-				// ... unless the other one cannot see us in its own query
-				bool otherSeesUs = !(typeBodyO == S2B_BODY_KINEMATIC && typeBodyQ != S2B_BODY_DYNAMIC) && typeBodyO != S2B_BODY_STATIC;
-				if (otherSeesUs)
-				{
-					continue;
-				}
-			}
-			unsigned long long lo = (unsigned long long)(other < shapeQ ? other : shapeQ);
-			unsigned long long hi = (unsigned long long)(other < shapeQ ? shapeQ : other);
-			unsigned long long pairKey = (lo << 32) | hi;
-			if (bodyO == bodyQ)
-			{
-				continue;
-			}
-			if (s2bPairInHash(pairHash, hashMask, pairKey))
-			{
-				continue;
-			}
-			int shapeA, shapeB;
-			if (keyO < keyQ)
-			{
-				shapeA = other;
-				shapeB = shapeQ;
-			}
-			else
-			{
-				shapeA = shapeQ;
-				shapeB = other;
-			}
-			int4 filterO = s.filter[other];
-			if (s2bShouldShapesCollide(shapeA == shapeQ ? filterQ : filterO, shapeA == shapeQ ? filterO : filterQ) == false)
-			{
-				continue;
-			}
-			if (s2bJointOverride(jointKeys, jointKeyCount, bodyQ, bodyO))
-			{
-				continue;
-			}
-			int typeA = ((shapeA == shapeQ ? headQ.x : headO.x) >> 1) & 0x7;
-			int typeB = ((shapeA == shapeQ ? headO.x : headQ.x) >> 1) & 0x7;
-			int kind = s2bPairKind(typeA, typeB);
-			if (kind == 0)
-			{
-				continue;
-			}
-			if (kind == 2)
-			{
-				int tmp = shapeA;
-				shapeA = shapeB;
-				shapeB = tmp;
-			}
-			int slot = atomicAdd(counters + BC_NEW_PAIRS, 1);
-			if (slot < newCap)
-			{
-				newKey[slot] = pairKey;
-				newShapes[slot] = make_int2(shapeA, shapeB);
-			}
+			s2bConsiderPair(q, leafShape[sortedLeaf[node - (n - 1)]], s, b, counters, pairHash, hashMask, jointKeys, jointKeyCount, newKey,
+							newShapes, newCap);
 			continue;
 		}
 		int2 ch = children[node];
@@ -579,6 +601,64 @@ __global__ void __launch_bounds__(128) s2bFindPairs(ShapeView s, BodyView b, con
 		if (s2bBoxesOverlap(boxQ, nodeBox[ch.y]) && sp < 64)
 		{
 			stack[sp++] = ch.y;
+		}
+	}
+}
+
+// Moved proxies with LARGE boxes (a container wall spanning the scene overlaps thousands of leaves: one thread walking
+// them all takes milliseconds) are taken out of the walk above and tested the other way round: every leaf against the short
+// list of large movers. Same rules, same pairs; the order new pairs are emitted in never matters (they are sorted).
+#define S2B_MAX_LARGE_MOVERS 64
+
+__global__ void s2bSplitLargeMovers(ShapeView s, const int* leafShape, const int* sortedLeaf, int* counters, const float4* nodeBox,
+									int* movedFlag, int* largeShapes)
+{
+	int n = counters[BC_LEAVES];
+	int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n || movedFlag[k] == 0 || n < 256)
+	{
+		return;
+	}
+	float4 root = nodeBox[0];
+	int shape = leafShape[sortedLeaf[k]];
+	float4 box = s.fat[shape];
+	float area = (box.z - box.x) * (box.w - box.y);
+	float sceneArea = (root.z - root.x) * (root.w - root.y);
+	if (area * 256.0f > sceneArea)
+	{
+		int slot = atomicAdd(counters + BC_LARGE, 1);
+		if (slot < S2B_MAX_LARGE_MOVERS)
+		{
+			largeShapes[slot] = shape;
+			movedFlag[k] = 0;
+		}
+	}
+}
+
+__global__ void s2bFindPairsLarge(ShapeView s, BodyView b, const int* leafShape, int* counters, const int* largeShapes,
+								  const unsigned long long* pairHash, unsigned long long hashMask, const unsigned long long* jointKeys,
+								  int jointKeyCount, unsigned long long* newKey, int2* newShapes, int newCap)
+{
+	int n = counters[BC_LEAVES];
+	int large = min(counters[BC_LARGE], S2B_MAX_LARGE_MOVERS);
+	int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n || large == 0)
+	{
+		return;
+	}
+	int other = leafShape[k];
+	float4 boxO = s.fat[other];
+	for (int i = 0; i < large; ++i)
+	{
+		int shapeQ = largeShapes[i];
+		if (s2bBoxesOverlap(s.fat[shapeQ], boxO) == false)
+		{
+			continue;
+		}
+		PairQuery q;
+		if (s2bMakeQuery(q, shapeQ, s, b))
+		{
+			s2bConsiderPair(q, other, s, b, counters, pairHash, hashMask, jointKeys, jointKeyCount, newKey, newShapes, newCap);
 		}
 	}
 }
@@ -752,6 +832,7 @@ void s2bBroadphaseUpdatePairs(s2bWorld* w)
 	B->nodeHeight.reserve(2 * nS, st, false);
 	B->movedLeaves.reserve(nS, st, false);
 	B->movedFlag.reserve(nS, st, false);
+	B->largeShapes.reserve(S2B_MAX_LARGE_MOVERS, st, false);
 	B->keepFlag.reserve((size_t)std::max(oldCount, 1), st, false);
 	B->keepSlots.reserve((size_t)std::max(oldCount, 1), st, false);
 	if (B->newPairCap == 0)
@@ -844,6 +925,8 @@ void s2bBroadphaseUpdatePairs(s2bWorld* w)
 		// ---- queries from moved proxies ----
 		S2B_LAUNCH(w, s2bFlagMovedLeaves, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->leafOut.p, B->counters.p,
 				   B->movedFlag.p);
+		S2B_LAUNCH(w, s2bSplitLargeMovers, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->leafOut.p, B->counters.p, B->nodeBox.p,
+				   B->movedFlag.p, B->largeShapes.p);
 		size_t tb = B->cubTemp.cap;
 		cub::DeviceSelect::Flagged(B->cubTemp.p, tb, thrust::counting_iterator<int>(0), B->movedFlag.p, B->movedLeaves.p,
 								   B->counters.p + BC_MOVED, shapeCap, st);
@@ -851,6 +934,8 @@ void s2bBroadphaseUpdatePairs(s2bWorld* w)
 		S2B_LAUNCH(w, s2bFindPairs, gridFor(shapeCap, 128), 128, 0, sv, bv, B->leafShape.p, B->leafOut.p, B->counters.p,
 				   B->movedLeaves.p, B->children.p, B->nodeBox.p, B->pairHash.p, B->hashMask, w->jointPairKeys.p, w->jointPairCount,
 				   B->newKey.p, B->newShapes.p, newCap);
+		S2B_LAUNCH(w, s2bFindPairsLarge, gridFor(shapeCap, 256), 256, 0, sv, bv, B->leafShape.p, B->counters.p, B->largeShapes.p,
+				   B->pairHash.p, B->hashMask, w->jointPairKeys.p, w->jointPairCount, B->newKey.p, B->newShapes.p, newCap);
 
 		// ---- survivors ----
 		if (oldCount > 0)

@@ -879,6 +879,71 @@ __device__ __forceinline__ void s2bGridFlatPass(int jointOp, int contactOp, cons
 	}
 }
 
+// L1 warm-up for the serial overflow walk: request (prefetch.global.L1) every line an op on this constraint may read
+__device__ __forceinline__ void s2bPrefetchL1(const void* ptr)
+{
+	asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+}
+
+__device__ __forceinline__ void s2bTouchBody(const SolveArgs& a, int i)
+{
+	s2bPrefetchL1(a.bodies.vel + i);
+	s2bPrefetchL1(a.bodies.pose + i);
+	s2bPrefetchL1(a.bodies.pos + i);
+	if (a.bodies.aux0 != nullptr)
+	{
+		s2bPrefetchL1(a.bodies.aux0 + i);
+	}
+}
+
+__device__ __forceinline__ void s2bTouchContact(const SolveArgs& a, int t)
+{
+	int2 idx = a.cc.idx[t];
+	s2bPrefetchL1(a.cc.nf + t);
+	s2bPrefetchL1(a.cc.src + t);
+#pragma unroll
+	for (int j = 0; j < 2; ++j)
+	{
+		s2bPrefetchL1(a.cc.anchor[j] + t);
+		s2bPrefetchL1(a.cc.pm[j] + t);
+		s2bPrefetchL1(a.cc.lambda[j] + t);
+		if (a.cc.r0[j] != nullptr)
+		{
+			s2bPrefetchL1(a.cc.r0[j] + t);
+		}
+		if (a.cc.sep[j] != nullptr)
+		{
+			s2bPrefetchL1(a.cc.sep[j] + t);
+		}
+		if (a.cc.fanchor[j] != nullptr)
+		{
+			s2bPrefetchL1(a.cc.fanchor[j] + t);
+			s2bPrefetchL1(a.cc.tsep[j] + t);
+		}
+	}
+	s2bTouchBody(a, idx.x);
+	s2bTouchBody(a, idx.y & S2B_CF_INDEX_MASK);
+}
+
+__device__ __forceinline__ void s2bTouchJoint(const SolveArgs& a, int t)
+{
+	int4 head = a.jc.head[t];
+	s2bPrefetchL1(a.jc.anchor + t);
+	s2bPrefetchL1(a.jc.mass + t);
+	s2bPrefetchL1(a.jc.d0ax + t);
+	s2bPrefetchL1(a.jc.lim + t);
+	s2bPrefetchL1(a.jc.motor + t);
+	s2bPrefetchL1(a.jc.coef + t);
+	s2bPrefetchL1(a.jc.pivot + t);
+	s2bPrefetchL1(a.jc.imp + t);
+	s2bPrefetchL1(a.jc.limp + t);
+	if (head.y >= 0)
+	{
+		s2bTouchBody(a, head.y);
+	}
+	s2bTouchBody(a, head.z);
+}
+
 // diagnostic time stamps (s2b_set_solve_trace): code = what just finished (pass kind << 8 | op), stamped by one thread
 __device__ __forceinline__ void s2bTrace(const SolveArgs& a, int code)
 {
@@ -929,16 +994,35 @@ __device__ __forceinline__ void s2bGridGroupPass(int jointOp, int contactOp, con
 	int ovJ = jointOp != JOP_NONE ? a.counts[CNT_OVERFLOW_J] : 0;
 	if (ovC + ovJ > 0)
 	{
-		if (tid == 0)
+		// The overflow group (constraints of bodies with more neighbours than there are colours — a container wall touching
+		// hundreds of boxes) is inherently sequential: one thread walks it. What can be parallel is the memory: the rest of
+		// block 0 first pulls every line that thread is going to touch into this SM's L1, so the walk pays L1 latency per
+		// item instead of several dependent L2 round trips (measured 3.5 us -> ~0.5 us per item).
+		if (blockIdx.x == 0)
 		{
 			int jBegin = a.jGroupOff[S2B_MAX_COLORS], cBegin = a.cGroupOff[S2B_MAX_COLORS];
-			for (int t = 0; t < ovJ; ++t)
+			for (int t = threadIdx.x; t < ovJ + ovC; t += blockDim.x)
 			{
-				s2bRunJointOp(jointOp, a, jBegin + t, p);
+				if (t < ovJ)
+				{
+					s2bTouchJoint(a, jBegin + t);
+				}
+				else
+				{
+					s2bTouchContact(a, cBegin + (t - ovJ));
+				}
 			}
-			for (int t = 0; t < ovC; ++t)
+			__syncthreads();
+			if (threadIdx.x == 0)
 			{
-				s2bRunContactOp(contactOp, a, cBegin + t);
+				for (int t = 0; t < ovJ; ++t)
+				{
+					s2bRunJointOp(jointOp, a, jBegin + t, p);
+				}
+				for (int t = 0; t < ovC; ++t)
+				{
+					s2bRunContactOp(contactOp, a, cBegin + t);
+				}
 			}
 		}
 		grid.sync();

@@ -271,3 +271,30 @@ def test_colour_kernel_probe_and_row_built_world(dev):
     ms = dev.lib.s2b_time_color_kernel(dw.h, C.byref(ctx), 3, C.byref(n))
     assert ms > 0.0 and n.value > 100
     dw.destroy()
+
+
+def test_tumbler_large_proxies_reference_order(reference, product, dev):
+    """A motorised container whose four walls span the scene (their proxies take the leaf-side 'large mover' query of the
+    broad phase, are touched by dozens of boxes -> serial overflow group, and carry a motor joint): 90 steps through the
+    public API with the reference's Gauss-Seidel order imposed must reproduce the reference bit for bit."""
+    R, P = reference, product
+    sr = scenes.tumbler(R, "TGS_Soft", grid=18, half_extent=4.0)
+    sp = scenes.tumbler(P, "TGS_Soft", grid=18, half_extent=4.0)
+    dw = device.DeviceWorld.attach(dev, sp.world)
+    dw.set_schedule(device.SCHEDULE_WAVEFRONT)
+    for step in range(90):
+        R.step_collide(sr.world)
+        keys, *_ = _ref_pair_table(R, sr.world)
+        dw.set_contact_order(keys)
+        R.step_solve(sr.world, DT, 4, 2, True)
+        R.step_finalize(sr.world)
+        sp.step(DT, 4, 2, True)
+    c = dw.counters()
+    assert c.constraintCount > 100, "the boxes must have reached the walls"
+    assert np.array_equal(_positions(R, sr), _positions(P, sp))
+    assert np.array_equal(_angles(R, sr), _angles(P, sp))
+    rkeys, *_ = _ref_pair_table(R, sr.world)
+    rows = dw.download_contacts(len(rkeys) + 16)
+    assert len(rows) == len(rkeys)
+    sr.destroy()
+    sp.destroy()

@@ -5,15 +5,17 @@ import numpy as np
 from solver2d_b200 import capi, device, scenes
 
 base = int(sys.argv[1]) if len(sys.argv) > 1 else 447
+scene = sys.argv[2] if len(sys.argv) > 2 else "pyramid"
+warm = int(sys.argv[3]) if len(sys.argv) > 3 else 12
 P = capi.Solver2D(device.LIB_PATH)
 dev = device.Device()
-sc = scenes.pyramid(P, "TGS_Soft", base_count=base)
+sc = scenes.pyramid(P, "TGS_Soft", base_count=base) if scene == "pyramid" else scenes.tumbler(P, "TGS_Soft", grid=base)
 dw = device.DeviceWorld.attach(dev, sc.world)
 L = dev.lib
 L.s2b_set_solve_trace.argtypes = [C.c_void_p, C.c_int]
 L.s2b_get_solve_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
 L.s2b_get_solve_trace.restype = C.c_int
-for _ in range(12):
+for _ in range(warm):
     sc.step(1 / 60, 4, 2, True)
 L.s2b_set_solve_trace(dw.h, 512)
 for _ in range(3):
@@ -32,4 +34,6 @@ for c, d in zip(code[1:], dt):
 print("stamps", n, "total us", (ns[-1] - ns[0]) / 1e3)
 for key, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     print(f"{key[0]:6s} op {key[1]:3d}: n={len(v):3d} total {sum(v)/1e3:8.1f} us  mean {np.mean(v)/1e3:6.2f} us  min {min(v)/1e3:6.2f}  max {max(v)/1e3:6.2f}")
-print("sequence (us):", [round(d / 1e3, 2) for d in dt[:40]])
+print("sequence (us):", [round(float(d) / 1e3, 2) for d in dt[:60]])
+c = dw.counters()
+print("constraints", c.constraintCount, "groups", c.groupCount, "overflow", c.overflowCount, "stage ms", dw.stage_ms())
