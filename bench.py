@@ -242,7 +242,7 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
 
     # ---- value: device-resident, CUDA events per step, L2 flushed between steps ----
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and os.environ.get("BENCH_NO_SAMPLER") is None:
         sampler.start()
     # the last warm-up steps go through the timed entry point so that its one-off costs (L2-flush buffer) are paid here
     for _ in range(min(3, args.warmup)):

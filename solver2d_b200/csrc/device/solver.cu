@@ -26,7 +26,6 @@ namespace cg = cooperative_groups;
 
 #define S2B_MAX_COLORS 64
 #define S2B_OVERFLOW_KEY 255
-#define S2B_BLOCK 256
 
 // ---------------------------------------------------------------------------------------------------------------
 // scratch management
@@ -1191,6 +1190,17 @@ __global__ void __launch_bounds__(S2B_BLOCK) s2bPersistentSolve(SolveArgs a, Pas
 				if (pass.kind == PASS_BODY)
 				{
 					s2bGridBodyPass(pass.bodyOp, a);
+					if (a.heavyBodies != nullptr)
+					{
+						if (pass.bodyOp == BOP_INTEGRATE_VELOCITIES_WARM)
+						{
+							s2bGatherHeavyBodies<false>(a, a.ctx.h);
+						}
+						else if (pass.bodyOp == BOP_INTEGRATE_VELOCITIES_WARM_FIXED)
+						{
+							s2bGatherHeavyBodies<true>(a, a.ctx.h);
+						}
+					}
 				}
 				else
 				{
@@ -1763,6 +1773,7 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 		s->itemVal.reserve(nI, st, false);
 		s->incWork.reserve(2 * nI, st, false);
 		s->incList.reserve(2 * nI, st, false);
+		s->heavyBodies.reserve(S2B_MAX_HEAVY_BODIES + 1, st, false);
 	}
 	if (dataflow)
 	{
@@ -2039,8 +2050,14 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 				jfa = s->flow.p + 2 * nC;
 				jfb = s->flow.p + 2 * nC + nJ;
 			}
+			int* heavy = nullptr;
+			if (gatherWarm && w->persistent != 0 && w->coopSupported != 0)
+			{
+				S2B_CHECK(cudaMemsetAsync(s->heavyBodies.p, 0, sizeof(int), st));
+				heavy = s->heavyBodies.p;
+			}
 			S2B_LAUNCH(w, s2bSortIncidenceKernel, gridFor(bodyCap, 128), 128, 0, bodyCap, s->adjStart.p, s->adj.p, s->itemBodies.p,
-					   s->itemVal.p, s->incWork.p, s->incList.p, cfa, cfb, jfa, jfb);
+					   s->itemVal.p, s->incWork.p, s->incList.p, cfa, cfb, jfa, jfb, heavy);
 		}
 	}
 	else
@@ -2068,6 +2085,7 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 	a.jGroupOff = s->jGroupOff.p;
 	a.incStart = gatherWarm ? s->adjStart.p : nullptr;
 	a.incList = gatherWarm ? s->incList.p : nullptr;
+	a.heavyBodies = (gatherWarm && maxItems > 0 && w->persistent != 0 && w->coopSupported != 0) ? s->heavyBodies.p : nullptr;
 	if (dataflow)
 	{
 		S2B_CHECK(cudaMemsetAsync(s->bodyTicket.p, 0, sizeof(int) * ((size_t)bodyCap + 2), st));

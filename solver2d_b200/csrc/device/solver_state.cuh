@@ -4,6 +4,9 @@
 
 #include "s2b_internal.cuh"
 
+// threads per block of the solver kernels
+#define S2B_BLOCK 256
+
 // soft-constraint coefficients (reference src/solve_common.c:264-271)
 struct SoftCoef
 {
@@ -37,6 +40,7 @@ struct SolveArgs
 	const int* jGroupOff; // joint-constraint group offsets, same shape
 	const int* incStart;  // per body: range of its incidence list (warm_gather.cuh); null when the gather is not used
 	const int* incList;	  // incidence entries sorted by solve order
+	const int* heavyBodies; // [0] count, then body indices with more than S2B_HEAVY_DEGREE incident items (null = none split off)
 	// ticketed ("dataflow") Gauss-Seidel passes: null when the passes synchronise with grid barriers instead
 	int* bodyTicket;			   // per body: incident-item executions completed in this launch
 	const int2 *cFlowA, *cFlowB;   // per contact constraint and side: {ordinal in the body's incidence list, its degree} or -1
@@ -79,6 +83,7 @@ struct SolverScratch
 	DevArray<char> cubTemp;
 	DevArray<unsigned long long> itemVal, incWork; // warm-start gather: per-item sort value, per-body sort scratch
 	DevArray<int> incList;
+	DevArray<int> heavyBodies;
 	DevArray<int2> flow;	  // cFlowA | cFlowB | jFlowA | jFlowB
 	DevArray<int> bodyTicket; // + 1 int error flag at the end
 	int flowErrorOffset = 0;

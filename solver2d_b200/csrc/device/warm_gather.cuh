@@ -17,6 +17,9 @@
 // incidence entry: (t << 2) | (side << 1) | isContact — t = position in the contact / joint constraint stream
 #define S2B_INC_CONTACT 1
 #define S2B_INC_SIDE_B 2
+// bodies with more incident constraints than this are gathered by a whole block instead of one thread
+#define S2B_HEAVY_DEGREE 48
+#define S2B_MAX_HEAVY_BODIES 1024
 
 // FIXED = false: anchors rotated by the current rotation (s2WarmStartContacts, reference src/solve_common.c:276-326)
 // FIXED = true : prepare-time anchors (s2WarmStartContacts_Fixed, reference src/solve_soft_step.c:16-63)
@@ -53,6 +56,10 @@ template <bool FIXED> __device__ __forceinline__ void s2bIntegrateVelocityWarm(c
 			a.bodies.vel[i] = make_float4(v.x, v.y, w, invMass);
 		}
 		return;
+	}
+	if (a.heavyBodies != nullptr && end - begin > S2B_HEAVY_DEGREE)
+	{
+		return; // a hub body (container wall ...): gathered by a whole block, s2bGatherHeavyBodies
 	}
 
 	float4 pose = a.bodies.pose[i];
@@ -128,6 +135,169 @@ template <bool FIXED> __device__ __forceinline__ void s2bIntegrateVelocityWarm(c
 	a.bodies.vel[i] = make_float4(v.x, v.y, w, invMass);
 }
 
+// ---- hub bodies -----------------------------------------------------------------------------------------------------
+// A container touching hundreds of boxes has hundreds of incident constraints; one thread walking them is ~0.6 us per entry.
+// The terms tw = -/+ invI * (cross(r, P) [+ axial]) and tv = (-/+ invM) * P do not involve v or w, so a whole block forms them
+// in parallel (shared memory) and ONE thread then adds them to v, w in list order: the same float operations in the same
+// order as the serial walk, hence the same bits.
+struct GatherTerms
+{
+	int np;
+	float tw0, tw1;
+	s2Vec2 tv0, tv1;
+};
+
+template <bool FIXED>
+__device__ __forceinline__ GatherTerms s2bGatherTermsOf(const SolveArgs& a, int e, s2Rot q, float invMass, float invI)
+{
+	GatherTerms g;
+	g.np = 0;
+	g.tw0 = g.tw1 = 0.0f;
+	g.tv0 = g.tv1 = V2(0.0f, 0.0f);
+	int t = e >> 2;
+	bool sideB = (e & S2B_INC_SIDE_B) != 0;
+	if (e & S2B_INC_CONTACT)
+	{
+		int2 idx = a.cc.idx[t];
+		float4 nf = a.cc.nf[t];
+		s2Vec2 normal = V2(nf.x, nf.y);
+		s2Vec2 tangent = s2RightPerp(normal);
+		g.np = (idx.y & S2B_CF_TWO_POINTS) ? 2 : 1;
+#pragma unroll
+		for (int j = 0; j < 2; ++j)
+		{
+			if (j < g.np)
+			{
+				float4 la = FIXED ? a.cc.r0[j][t] : a.cc.anchor[j][t];
+				float2 l = a.cc.lambda[j][t];
+				s2Vec2 local = sideB ? V2(la.z, la.w) : V2(la.x, la.y);
+				s2Vec2 r = FIXED ? local : s2RotateVector(q, local);
+				s2Vec2 P = s2Add(s2MulSV(l.x, normal), s2MulSV(l.y, tangent));
+				float c = invI * s2Cross(r, P);
+				float tw = sideB ? c : -c;
+				s2Vec2 tv = s2MulSV(sideB ? invMass : -invMass, P);
+				if (j == 0)
+				{
+					g.tw0 = tw;
+					g.tv0 = tv;
+				}
+				else
+				{
+					g.tw1 = tw;
+					g.tv1 = tv;
+				}
+			}
+		}
+	}
+	else
+	{
+		int4 head = a.jc.head[t];
+		float4 anchor = a.jc.anchor[t];
+		float4 imp = a.jc.imp[t];
+		s2Vec2 P = V2(imp.x, imp.y);
+		g.np = 1;
+		if (S2B_JOINT_TYPE(head.x) == S2B_JOINT_MOUSE)
+		{
+			s2Vec2 rB = s2RotateVector(q, V2(anchor.z, anchor.w));
+			g.tv0 = s2MulSV(invMass, P);
+			g.tw0 = invI * (s2Cross(rB, P) + imp.z);
+		}
+		else
+		{
+			float4 limp = a.jc.limp[t];
+			float axialImpulse = imp.z + limp.x - limp.y;
+			if (sideB)
+			{
+				s2Vec2 rB = s2RotateVector(q, V2(anchor.z, anchor.w));
+				g.tv0 = s2MulSV(invMass, P);
+				g.tw0 = invI * (s2Cross(rB, P) + axialImpulse);
+			}
+			else
+			{
+				s2Vec2 rA = s2RotateVector(q, V2(anchor.x, anchor.y));
+				s2Vec2 mp = s2MulSV(invMass, P);
+				g.tv0 = V2(-mp.x, -mp.y);
+				g.tw0 = -(invI * (s2Cross(rA, P) + axialImpulse));
+			}
+		}
+	}
+	return g;
+}
+
+// called by every block of the persistent kernel after the per-thread gather; block b takes hub bodies b, b + gridDim, ...
+template <bool FIXED> __device__ __forceinline__ void s2bGatherHeavyBodies(const SolveArgs& a, float h)
+{
+	__shared__ float sTw0[S2B_BLOCK], sTw1[S2B_BLOCK], sX0[S2B_BLOCK], sY0[S2B_BLOCK], sX1[S2B_BLOCK], sY1[S2B_BLOCK];
+	__shared__ int sNp[S2B_BLOCK];
+	int heavy = min(a.heavyBodies[0], S2B_MAX_HEAVY_BODIES);
+	for (int hb = blockIdx.x; hb < heavy; hb += gridDim.x)
+	{
+		int i = a.heavyBodies[1 + hb];
+		unsigned f = a.bodies.flags[i];
+		float4 vel = a.bodies.vel[i];
+		float4 prm = a.bodies.prm[i];
+		float invMass = vel.w, invI = prm.w;
+		s2Vec2 v = V2(vel.x, vel.y);
+		float w = vel.z;
+		if (S2B_BODY_TYPE(f) == S2B_BODY_DYNAMIC)
+		{
+			// s2IntegrateVelocities (reference src/solve_common.c:10-45), computed redundantly by every thread
+			float4 frc = a.bodies.frc[i];
+			s2Vec2 gravity = V2(a.gravity.x, a.gravity.y);
+			v = s2Add(v, s2MulSV(h * invMass, s2MulAdd(V2(frc.x, frc.y), frc.w * prm.z, gravity)));
+			w = w + h * invI * frc.z;
+			v = s2MulSV(1.0f / (1.0f + h * prm.x), v);
+			w *= 1.0f / (1.0f + h * prm.y);
+		}
+		float4 pose = a.bodies.pose[i];
+		s2Rot q = R2(pose.z, pose.w);
+		int begin = a.incStart[i], end = a.incStart[i + 1];
+		for (int k0 = begin; k0 < end; k0 += blockDim.x)
+		{
+			int k = k0 + threadIdx.x;
+			GatherTerms g;
+			g.np = 0;
+			g.tw0 = g.tw1 = 0.0f;
+			g.tv0 = g.tv1 = V2(0.0f, 0.0f);
+			if (k < end)
+			{
+				g = s2bGatherTermsOf<FIXED>(a, a.incList[k], q, invMass, invI);
+			}
+			sNp[threadIdx.x] = g.np;
+			sTw0[threadIdx.x] = g.tw0;
+			sTw1[threadIdx.x] = g.tw1;
+			sX0[threadIdx.x] = g.tv0.x;
+			sY0[threadIdx.x] = g.tv0.y;
+			sX1[threadIdx.x] = g.tv1.x;
+			sY1[threadIdx.x] = g.tv1.y;
+			__syncthreads();
+			if (threadIdx.x == 0)
+			{
+				int count = min((int)blockDim.x, end - k0);
+				for (int u = 0; u < count; ++u)
+				{
+					int np = sNp[u];
+					if (np >= 1)
+					{
+						w = w + sTw0[u];
+						v = V2(v.x + sX0[u], v.y + sY0[u]);
+					}
+					if (np == 2)
+					{
+						w = w + sTw1[u];
+						v = V2(v.x + sX1[u], v.y + sY1[u]);
+					}
+				}
+			}
+			__syncthreads();
+		}
+		if (threadIdx.x == 0)
+		{
+			a.bodies.vel[i] = make_float4(v.x, v.y, w, invMass);
+		}
+	}
+}
+
 // ---- building the sorted incidence lists (once per step, after the solve order is known) --------------------------
 
 // value of an item in the per-body sort: high word = (group << 1 | isContact), low word = the incidence entry without its
@@ -169,7 +339,7 @@ __global__ void s2bItemOrderKernel(const int* counts, const int* cPerm, const in
 // items): what the ticketed Gauss-Seidel passes (solver.cu, "dataflow") wait on instead of a grid barrier.
 __global__ void s2bSortIncidenceKernel(int bodyCapacity, const int* adjStart, const int* adj, const int2* itemBodies,
 									   const unsigned long long* itemVal, unsigned long long* work, int* incList, int2* cFlowA,
-									   int2* cFlowB, int2* jFlowA, int2* jFlowB)
+									   int2* cFlowB, int2* jFlowA, int2* jFlowB, int* heavyBodies)
 {
 	int b = blockIdx.x * blockDim.x + threadIdx.x;
 	if (b >= bodyCapacity)
@@ -181,6 +351,14 @@ __global__ void s2bSortIncidenceKernel(int bodyCapacity, const int* adjStart, co
 	if (n == 0)
 	{
 		return;
+	}
+	if (heavyBodies != nullptr && n > S2B_HEAVY_DEGREE)
+	{
+		int slot = atomicAdd(heavyBodies, 1);
+		if (slot < S2B_MAX_HEAVY_BODIES)
+		{
+			heavyBodies[1 + slot] = b;
+		}
 	}
 	unsigned long long* v = work + begin;
 	for (int k = 0; k < n; ++k)
