@@ -118,8 +118,13 @@ def _traffic(which: str):
         return None
 
 
-def build_scene(lib, base_count: int):
+def build_scene(lib, base_count: int, workload: str = "pyramid", rank: int = 0, world_size: int = 1, field_count: int = 256):
+    """pyramid: the headline workload (one replica per rank). field: SURVEY §8d config 5 — `field_count` independent
+    pyramid worlds of `base_count` rows batched into one s2World per rank; world k lives on rank k mod world_size."""
     from solver2d_b200 import scenes
+    if workload == "field":
+        mine = len(range(rank, field_count, world_size))
+        return scenes.pyramid_field(lib, "TGS_Soft", count=mine, base_count=base_count, first=0)
     return scenes.pyramid(lib, "TGS_Soft", base_count=base_count)
 
 
@@ -131,7 +136,7 @@ def run_reference(args, rank: int, world_size: int):
     if not ref.available():
         ref.build_ref()
     R = ref.load()
-    sc = build_scene(R, args.base)
+    sc = build_scene(R, args.base, args.workload, 0, 1, args.field_count)
     nb = len(sc.bodies)
     idx = np.array([b.index for b in sc.bodies[1:]], dtype=np.int32)
     forces = np.zeros((len(idx), 2), dtype=np.float32)
@@ -156,7 +161,8 @@ def run_reference(args, rank: int, world_size: int):
         "impl": "reference", "metric": "constraint_iters_per_sec", "value": value, "unit": "constraint-iters/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"pyramid{args.base}_tgs_soft_s{args.substeps}_e{args.relax}", "boxes": nb - 1,
+        "config": {"workload": (f"field{args.field_count}x_pyramid{args.base}" if args.workload == "field" else f"pyramid{args.base}")
+                   + f"_tgs_soft_s{args.substeps}_e{args.relax}", "boxes": nb - 1,
                    "dt": DT, "note": "reference CPU path, 1 thread (the reference is single-threaded)"},
         "cpu_baseline": {"value": value, "unit": "constraint-iters/s", "cores": 1, "kind": "reference",
                          "sample": f"{args.steps} steps after {args.warmup} warm-up; first step {first:.3f} s"},
@@ -205,7 +211,7 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
     L.s2b_last_solve_kernel_ms.restype = C.c_float
     L.s2b_last_solve_kernel_ms.argtypes = [C.c_void_p]
 
-    sc = build_scene(P, args.base)
+    sc = build_scene(P, args.base, args.workload, rank, world_size, args.field_count)
     dw = device.DeviceWorld.attach(dev, sc.world)
     nb = len(sc.bodies)
 
@@ -335,8 +341,10 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
         line = {
             "metric": "constraint_iters_per_sec", "value": value, "unit": "constraint-iters/s", "n_gpus": world_size,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"pyramid{args.base}_tgs_soft_s{args.substeps}_e{args.relax}", "boxes": nb - 1,
+            "higher_is_better": True, "scaling": "strong" if args.workload == "field" else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": (f"field{args.field_count}x_pyramid{args.base}" if args.workload == "field" else f"pyramid{args.base}")
+                       + f"_tgs_soft_s{args.substeps}_e{args.relax}", "boxes": nb - 1,
                        "contact_constraints": constraints, "colours": counters.groupCount, "dt": DT,
                        "l2": "flushed between timed steps" if args.flush_l2 else "not flushed (working set < L2)",
                        "parallelism": "single island: replicas only" + ("" if world_size == 1 else
@@ -388,7 +396,7 @@ def cpu_baseline(args) -> dict:
     if not ref.available() and not ref.build_ref():
         return {"value": None, "unit": "constraint-iters/s", "cores": 1, "kind": "reference", "sample": "oracle/_ref missing"}
     R = ref.load()
-    sc = build_scene(R, args.base)
+    sc = build_scene(R, args.base, args.workload, 0, 1, args.field_count)
     t0 = time.perf_counter()
     sc.step(DT, args.substeps, args.relax, True)
     first = time.perf_counter() - t0
@@ -412,6 +420,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--base", type=int, default=447, help="pyramid base count (447 -> 100 128 boxes)")
+    ap.add_argument("--workload", choices=["pyramid", "field"], default="pyramid",
+                    help="pyramid = headline (replica per rank); field = config 5: --field-count worlds of --base rows, sharded over ranks")
+    ap.add_argument("--field-count", type=int, default=256)
     ap.add_argument("--substeps", type=int, default=4)
     ap.add_argument("--relax", type=int, default=2)
     ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false")

@@ -369,3 +369,37 @@ def pyramid_rows(base_count: int):
     m = np.float32(0.1)  # s2_aabbMargin
     shapes["fatAABB"] = np.stack([cx - hw - m, cy - hh - m, cx + hw + m, cy + hh + m], axis=1)
     return bodies, shapes
+
+
+def pyramid_field(lib: capi.Solver2D, solver="TGS_Soft", count=256, base_count=45, first=0, pitch=None) -> Scene:
+    """SURVEY §8d config 5, batched: ``count`` independent Pyramid worlds (each with its own static ground) laid side by
+    side in ONE s2World, ``pitch`` metres apart, so that a single set of launches steps them all — independent worlds are
+    disconnected islands of one constraint graph, which is what makes small worlds big enough for the GPU. ``first`` offsets
+    the world indices (rank r of an N-rank run builds worlds r, r + N, ... by passing the right slice)."""
+    world = lib.create_world(solver)
+    sc = Scene(lib, world, name=f"field{count}x{base_count}")
+    h = 0.5
+    if pitch is None:
+        pitch = float(base_count + 6)
+    box = lib.s2MakeSquare(h)
+    sd = default_shape_def()
+    sd.density = 1.0
+    for k in range(count):
+        x0 = (first + k) * pitch
+        bd = default_body_def()
+        bd.position = Vec2(x0, -1.0)
+        gid = lib.s2CreateBody(world, C.byref(bd))
+        ground = lib.s2MakeBox(0.5 * base_count + 2.0, 1.0)
+        lib.s2CreatePolygonShape(gid, C.byref(sd), C.byref(ground))
+        sc.bodies.append(gid)
+        bd = default_body_def()
+        bd.type = capi.DYNAMIC_BODY
+        for i in range(base_count):
+            y = (2.0 * i + 1.0) * h
+            for j in range(i, base_count):
+                x = (i + 1.0) * h + 2.0 * (j - i) * h - h * base_count
+                bd.position = Vec2(x0 + x, y)
+                bid = lib.s2CreateBody(world, C.byref(bd))
+                lib.s2CreatePolygonShape(bid, C.byref(sd), C.byref(box))
+                sc.bodies.append(bid)
+    return sc

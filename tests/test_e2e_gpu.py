@@ -298,3 +298,27 @@ def test_tumbler_large_proxies_reference_order(reference, product, dev):
     assert len(rows) == len(rkeys)
     sr.destroy()
     sp.destroy()
+
+
+def test_batched_worlds_field_reference_order(reference, product, dev):
+    """Config 5 in small: several independent pyramid worlds batched into one s2World (disconnected islands). Through the
+    public API with the reference's order imposed: bit-identical to the reference stepping the same field; and the worlds
+    really are independent (no pair ever forms between two of them)."""
+    R, P = reference, product
+    sr = scenes.pyramid_field(R, "TGS_Soft", count=4, base_count=6)
+    sp = scenes.pyramid_field(P, "TGS_Soft", count=4, base_count=6)
+    dw = device.DeviceWorld.attach(dev, sp.world)
+    dw.set_schedule(device.SCHEDULE_WAVEFRONT)
+    for step in range(60):
+        R.step_collide(sr.world)
+        keys, *_ = _ref_pair_table(R, sr.world)
+        dw.set_contact_order(keys)
+        R.step_solve(sr.world, DT, 4, 2, True)
+        R.step_finalize(sr.world)
+        sp.step(DT, 4, 2, True)
+    assert np.array_equal(_positions(R, sr), _positions(P, sp))
+    rows = dw.download_contacts(4096)
+    per_world = 1 + 6 * 7 // 2
+    assert np.array_equal(rows["bodyA"] // per_world, rows["bodyB"] // per_world), "a contact spans two worlds"
+    sr.destroy()
+    sp.destroy()
