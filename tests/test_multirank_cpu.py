@@ -26,7 +26,8 @@ nb = 7
 mine = torch.full(((nb + 8) * 8,), float(rank + 1), dtype=torch.float32)
 allb = torch.empty(dist.get_world_size() * (nb + 8) * 8, dtype=torch.float32)
 dist.all_gather_into_tensor(allb, mine)
-print(json.dumps({"rank": rank, "agg": out, "blocks": [float(allb[i * (nb + 8) * 8]) for i in range(dist.get_world_size())]}), flush=True)
+with open(os.path.join(os.environ["S2B_OUT"], f"rank{rank}.json"), "w") as fh:  # one file per rank: stdout of two ranks interleaves
+    json.dump({"rank": rank, "agg": out, "blocks": [float(allb[i * (nb + 8) * 8]) for i in range(dist.get_world_size())]}, fh)
 dist.barrier()
 dist.destroy_process_group()
 """
@@ -46,9 +47,9 @@ def _torchrun(args, extra_env=None, timeout=300):
 def test_rank_aggregation_and_exchange_layout(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    r = _torchrun([str(script)])
+    r = _torchrun([str(script)], extra_env={"S2B_OUT": str(tmp_path)})
     assert r.returncode == 0, r.stderr[-2000:]
-    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    lines = [json.load(open(tmp_path / f"rank{k}.json")) for k in range(2)]
     assert sorted(l["rank"] for l in lines) == [0, 1]
     for l in lines:
         total_ms_max, e2e_max, work_all, e2e_work_all = l["agg"]
