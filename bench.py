@@ -210,6 +210,7 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
     L.s2b_get_work.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.s2b_last_solve_kernel_ms.restype = C.c_float
     L.s2b_last_solve_kernel_ms.argtypes = [C.c_void_p]
+    L.s2b_flush_l2.argtypes = [C.c_void_p]
 
     sc = build_scene(P, args.base, args.workload, rank, world_size, args.field_count)
     dw = device.DeviceWorld.attach(dev, sc.world)
@@ -233,12 +234,26 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
         # the collective is enqueued on the world's own stream, right behind the step: no host synchronisation
         ext_stream = torch.cuda.ExternalStream(int(L.s2b_get_stream(dw.h)), device=torch.device("cuda", local_rank))
 
+    side_stream = torch.cuda.Stream(device=torch.device("cuda", local_rank)) if dist is not None else None
+    ex_state = {"done": None}
+
     def exchange():
+        """Pack this rank's body state on the world's stream, then all-gather it on a side stream: the collective runs
+        while the next step is already executing (nothing in a step depends on the other replicas' bodies). The next pack
+        waits for the previous all-gather to have consumed the buffer."""
         if dist is None:
             return
+        if ex_state["done"] is not None:
+            ext_stream.wait_event(ex_state["done"])
         L.s2b_pack_body_state(dw.h, 0, nb, C.c_void_p(gather_in.data_ptr()))
-        with torch.cuda.stream(ext_stream):
+        packed = torch.cuda.Event()
+        packed.record(ext_stream)
+        side_stream.wait_event(packed)
+        with torch.cuda.stream(side_stream):
             dist.all_gather_into_tensor(gather_out, gather_in)
+            done = torch.cuda.Event()
+            done.record(side_stream)
+        ex_state["done"] = done
 
     # ---- warm-up (includes the first-step all-pairs broad phase) ----
     for _ in range(max(args.warmup - 3, 0)):
@@ -256,7 +271,8 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
         exchange()
     dw.sync()
     get_work(reset=True)
-    launches0 = dw.counters().kernelLaunches
+    c0 = dw.counters()
+    launches0, captures0 = c0.kernelLaunches, c0.graphCaptures
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -270,21 +286,26 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
             total_ms += step_ms[-1]
             solve_kernel_ms.append(float(L.s2b_last_solve_kernel_ms(dw.h)))
     else:
-        ex_events = []
+        # per step: [L2 flush] e0 | step | pack | e1 ; the all-gather overlaps the next step on the side stream, only its
+        # tail after the last step is exposed and is added at the end
+        pairs = []
         for _ in range(args.steps):
-            step_ms.append(float(L.s2World_TimedSteps(sc.world, 1, DT, args.substeps, args.relax, True, 1 if args.flush_l2 else 0)))
-            total_ms += step_ms[-1]
-            solve_kernel_ms.append(float(L.s2b_last_solve_kernel_ms(dw.h)))
-            t0 = torch.cuda.Event(enable_timing=True)
-            t1 = torch.cuda.Event(enable_timing=True)
-            with torch.cuda.stream(ext_stream):
-                t0.record()
+            if args.flush_l2:
+                L.s2b_flush_l2(dw.h)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(ext_stream)
+            sc.step(DT, args.substeps, args.relax, True)
             exchange()
-            with torch.cuda.stream(ext_stream):
-                t1.record()
-            ex_events.append((t0, t1))
+            e1.record(ext_stream)
+            pairs.append((e0, e1))
+        tail = torch.cuda.Event(enable_timing=True)
+        ext_stream.wait_event(ex_state["done"])
+        tail.record(ext_stream)
         torch.cuda.synchronize()
-        total_ms += sum(a.elapsed_time(b) for a, b in ex_events)
+        step_ms = [a.elapsed_time(b) for a, b in pairs]
+        total_ms = sum(step_ms) + pairs[-1][1].elapsed_time(tail)
+        solve_kernel_ms.append(float(L.s2b_last_solve_kernel_ms(dw.h)))
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -353,7 +374,9 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
             "stage_ms_last_step": {"pairs": stage_ms[0], "contacts": stage_ms[1], "solve": stage_ms[2], "finalize": stage_ms[3]},
             "step_ms_stats": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)), "max": float(np.max(step_ms)), "argmax": int(np.argmax(step_ms)),
                               "over_2x_median": [round(float(x), 3) for x in step_ms if x > 2 * np.median(step_ms)],
-                              "pair_passes_total": int(counters.pairPassCount)},
+                              "pair_passes_total": int(counters.pairPassCount),
+                              "graph_captures_in_timed_region": int(counters.graphCaptures - captures0),
+                              "graph_replays_total": int(counters.graphReplays)},
             "e2e": {"value": e2e_value, "unit": "constraint-iters/s", "ms_per_step": 1e3 * e2e_time_max / e2e_steps,
                     "h2d_bytes_per_step": int(len(idx) * 12), "d2h_bytes_per_step": int(nb * 16),
                     "steps": e2e_steps, "clock": "host wall clock, synchronised on both sides",

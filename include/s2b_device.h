@@ -175,6 +175,7 @@ typedef struct s2bCounters
 	int32_t pairPassCount;	 // number of broad-phase passes run so far
 	int32_t kernelLaunches;	 // CUDA kernels launched by this world since creation (graph replays count their kernels)
 	int32_t graphReplays;	 // solver stages executed as a CUDA graph replay
+	int32_t graphCaptures;	 // times the solver stage was (re)captured into a graph
 	int64_t scratchBytes;	 // device bytes of per-step scratch currently reserved
 } s2bCounters;
 

@@ -2320,6 +2320,7 @@ extern "C" void s2b_get_counters(s2bWorld* w, s2bCounters* out)
 	out->pairPassCount = w->pairPassCount;
 	out->kernelLaunches = w->kernelLaunches;
 	out->graphReplays = w->scratch != nullptr ? w->scratch->graphReplays : 0;
+	out->graphCaptures = w->scratch != nullptr ? w->scratch->graphCaptures : 0;
 }
 
 extern "C" void s2b_set_solve_trace(s2bWorld* w, int capacity)

@@ -57,7 +57,7 @@ class Counters(C.Structure):
                 ("contactCount", C.c_int32), ("constraintCount", C.c_int32), ("jointCount", C.c_int32),
                 ("groupCount", C.c_int32), ("overflowCount", C.c_int32), ("treeHeight", C.c_int32),
                 ("movedCount", C.c_int32), ("pairPassCount", C.c_int32), ("kernelLaunches", C.c_int32),
-                ("graphReplays", C.c_int32), ("scratchBytes", C.c_int64)]
+                ("graphReplays", C.c_int32), ("graphCaptures", C.c_int32), ("scratchBytes", C.c_int64)]
 
 
 SCHEDULE_COLOR, SCHEDULE_WAVEFRONT = 0, 1
