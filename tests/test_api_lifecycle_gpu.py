@@ -230,3 +230,48 @@ def test_scripted_session_matches_reference(reference, dev, solver):
         assert sorted(dr) == sorted(dp), "s2World_Draw output differs"
     R.s2DestroyWorld(sr.world)
     P.s2DestroyWorld(sp.world)
+
+
+def test_edge_cases_match_reference(reference, dev):
+    """Empty world, a paused step (dt = 0: reference src/world.c:176-183 still runs the solver with inv_dt = 0), growth of
+    every pool after the world has been stepped (device columns re-allocated, solver graph re-captured), and a step with
+    zero relax iterations — all against the reference, reference order imposed."""
+    from test_e2e_gpu import _ref_pair_table
+    R = reference
+    P = capi.Solver2D(device.LIB_PATH)
+    # 1. an empty world steps (and reads back) without complaint
+    we = P.create_world("TGS_Soft")
+    P.step(we, DT, 4, 2, True)
+    assert P.s2World_GetStatistics(we).bodyCount == 0
+    P.s2DestroyWorld(we)
+
+    sr, sp = Session(R, "TGS_Soft"), Session(P, "TGS_Soft")
+    for s in (sr, sp):
+        s.body("ground", capi.STATIC_BODY, (0.0, -1.0), ("box", 40.0, 1.0))
+        for i in range(8):
+            s.body(f"a{i}", capi.DYNAMIC_BODY, (-3.0 + 0.9 * i, 0.6 + 0.05 * i), ("box", 0.4, 0.4))
+    dw = device.DeviceWorld.attach(dev, sp.world)
+    dw.set_schedule(device.SCHEDULE_WAVEFRONT)
+
+    def run(steps, dt, vel, pos):
+        for _ in range(steps):
+            R.step_collide(sr.world)
+            keys, *_ = _ref_pair_table(R, sr.world)
+            dw.set_contact_order(keys)
+            R.step_solve(sr.world, dt, vel, pos, True)
+            R.step_finalize(sr.world)
+            P.step(sp.world, dt, vel, pos, True)
+        a, b = sr.state(), sp.state()
+        assert np.array_equal(a, b), f"max {np.abs(a - b).max()}"
+
+    run(20, DT, 4, 2)
+    run(3, 0.0, 4, 2)      # paused
+    run(10, DT, 4, 0)      # no relax iterations
+    # 2. pools grow well past their initial capacity after stepping
+    for s in (sr, sp):
+        for k in range(300):
+            s.body(f"g{k}", capi.DYNAMIC_BODY, (-15.0 + 0.11 * k, 3.0 + 1.1 * (k % 7)), ("circle", 0.3) if k % 2 else ("box", 0.3, 0.3))
+    run(40, DT, 4, 2)
+    assert P.s2World_GetStatistics(sp.world).bodyCount == R.s2World_GetStatistics(sr.world).bodyCount == 309
+    R.s2DestroyWorld(sr.world)
+    P.s2DestroyWorld(sp.world)
