@@ -791,6 +791,9 @@ __global__ void s2bClearMovedFlags(ShapeView s, int* movedCounter)
 
 void s2bBroadphaseUpdatePairs(s2bWorld* w)
 {
+	// scratch of this pass is not referenced by the solver's graph; a REPLACED contact table is, and shows up in the graph
+	// signature through w->cur / w->contactCount / w->contactTableVersion
+	S2bEpochFreeze freeze;
 	cudaStream_t st = w->stream;
 	BroadScratch* B = getBroad(w);
 	w->dMovedFlag.reserve(4, st, true);

@@ -49,6 +49,20 @@ inline unsigned long long& s2bAllocEpoch()
 	return epoch;
 }
 
+// Scope guard for code whose (re)allocations no captured graph refers to (broad-phase scratch, transfer staging, the L2
+// flush buffer): the epoch is put back on exit so that those allocations do not force a re-capture of the solver graph.
+struct S2bEpochFreeze
+{
+	unsigned long long saved;
+	S2bEpochFreeze() : saved(s2bAllocEpoch())
+	{
+	}
+	~S2bEpochFreeze()
+	{
+		s2bAllocEpoch() = saved;
+	}
+};
+
 template <typename T> struct DevArray
 {
 	T* p = nullptr;

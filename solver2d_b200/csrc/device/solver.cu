@@ -1707,6 +1707,7 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 		put(&ctx, sizeof(ctx));
 		put(ints, sizeof(ints));
 		put(&epoch, sizeof(epoch));
+		put(&w->contactTableVersion, sizeof(w->contactTableVersion));
 		put(&w->gravity, sizeof(w->gravity));
 		if (s->graphExec != nullptr && sig == s->graphSig)
 		{
@@ -1716,6 +1717,20 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 			s->hostCountsValid = false;
 			s->graphReplays += 1;
 			return;
+		}
+	}
+	if (graphable && s->graphExec != nullptr && getenv("S2B_GRAPH_DEBUG") != nullptr)
+	{
+		// which part of the signature moved? layout: ctx | 9 ints | epoch | gravity
+		size_t n = std::min(sig.size(), s->graphSig.size());
+		for (size_t k = 0; k < n; ++k)
+		{
+			if (sig[k] != s->graphSig[k])
+			{
+				fprintf(stderr, "solver2d-b200: graph signature changed at byte %zu (ctx %zu B, ints from %zu, epoch at %zu)\n", k, sizeof(ctx),
+						sizeof(ctx), sizeof(ctx) + 9 * sizeof(int));
+				break;
+			}
 		}
 	}
 	bool capturing = graphable && sig == s->graphCandidate;

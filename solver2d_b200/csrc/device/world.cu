@@ -662,6 +662,8 @@ static void* bulkStaging(s2bWorld* w, size_t bytes)
 
 extern "C" void s2b_add_forces(s2bWorld* w, const int32_t* bodyIndices, const float* forcesXY, int count)
 {
+	S2bEpochFreeze freeze; // transfer / flush buffers are not part of any captured graph
+
 	if (count <= 0)
 	{
 		return;
@@ -682,6 +684,8 @@ extern "C" void s2b_add_forces(s2bWorld* w, const int32_t* bodyIndices, const fl
 
 extern "C" void s2b_download_transforms(s2bWorld* w, float* out, int count)
 {
+	S2bEpochFreeze freeze; // transfer / flush buffers are not part of any captured graph
+
 	S2B_CHECK(cudaSetDevice(w->device));
 	if (count > w->bodyCap)
 	{
@@ -738,6 +742,8 @@ __global__ void s2bGatherBodyState(BodyView b, int count, float4* out)
 
 extern "C" const float* s2b_sync_body_state(s2bWorld* w, int capacity)
 {
+	S2bEpochFreeze freeze; // transfer / flush buffers are not part of any captured graph
+
 	S2B_CHECK(cudaSetDevice(w->device));
 	if (capacity > w->bodyCap)
 	{
@@ -899,6 +905,8 @@ extern "C" void s2b_pack_body_state(s2bWorld* w, int first, int count, void* dev
 
 extern "C" void s2b_flush_l2(s2bWorld* w)
 {
+	S2bEpochFreeze freeze; // transfer / flush buffers are not part of any captured graph
+
 	S2B_CHECK(cudaSetDevice(w->device));
 	const size_t bytes = (size_t)256 << 20; // 2x the 126 MB L2
 	w->l2Flush.reserve(bytes, w->stream, false, false);
