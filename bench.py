@@ -320,7 +320,12 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
     idx = np.array([b.index for b in sc.bodies[1:]], dtype=np.int32)
     forces = np.zeros((len(idx), 2), dtype=np.float32)
     forces[:, 0] = 0.01
-    transforms = np.zeros((counters.bodyCapacity, 4), dtype=np.float32)
+    # the caller's buffers are page-locked host memory (the library's own allocator for that, s2b_host_alloc)
+    L.s2b_host_alloc.restype = C.c_void_p
+    L.s2b_host_alloc.argtypes = [C.c_size_t]
+    xf_bytes = counters.bodyCapacity * 16
+    xf_ptr = L.s2b_host_alloc(xf_bytes)
+    transforms = np.frombuffer((C.c_char * xf_bytes).from_address(xf_ptr), dtype=np.float32).reshape(counters.bodyCapacity, 4)
     e2e_steps = max(args.steps // 2, 3)
     for _ in range(2):
         L.s2World_ApplyForcesToCenters(sc.world, idx.ctypes.data, forces.ctypes.data, len(idx))

@@ -707,9 +707,18 @@ extern "C" void s2b_download_transforms(s2bWorld* w, float* out, int count)
 	}
 	w->dXf.reserve((size_t)count, w->stream, false, false);
 	S2B_LAUNCH(w, s2bGatherTransforms, gridFor(count, 256), 256, 0, bodyView(w), count, w->dXf.p);
-	S2B_CHECK(cudaMemcpyAsync(w->hostXf, w->dXf.p, sizeof(float) * floats, cudaMemcpyDeviceToHost, w->stream));
+	// a page-locked destination (s2b_host_alloc / cudaHostRegister) takes the DMA directly; pageable memory goes through the
+	// world's own pinned buffer and one host copy
+	cudaPointerAttributes attr;
+	bool pinned = cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+	(void)cudaGetLastError();
+	float* dst = pinned ? out : w->hostXf;
+	S2B_CHECK(cudaMemcpyAsync(dst, w->dXf.p, sizeof(float) * floats, cudaMemcpyDeviceToHost, w->stream));
 	S2B_CHECK(cudaStreamSynchronize(w->stream));
-	memcpy(out, w->hostXf, sizeof(float) * floats);
+	if (pinned == false)
+	{
+		memcpy(out, w->hostXf, sizeof(float) * floats);
+	}
 }
 
 extern "C" void* s2b_host_alloc(size_t bytes)
