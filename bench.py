@@ -281,10 +281,17 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
     step_ms = []
     total_ms = 0.0
     if dist is None:
+        host_ms = []
         for _ in range(args.steps):
+            th = time.perf_counter()
             step_ms.append(float(L.s2World_TimedSteps(sc.world, 1, DT, args.substeps, args.relax, True, 1 if args.flush_l2 else 0)))
+            host_ms.append(1e3 * (time.perf_counter() - th))
             total_ms += step_ms[-1]
             solve_kernel_ms.append(float(L.s2b_last_solve_kernel_ms(dw.h)))
+        if os.environ.get("BENCH_DEBUG"):
+            st = dw.stage_ms()
+            print("debug first steps: device ms", [round(x, 3) for x in step_ms[:4]], "host ms of the call", [round(x, 3) for x in host_ms[:4]],
+                  file=sys.stderr)
     else:
         # per step: [L2 flush] e0 | step | pack | e1 ; the all-gather overlaps the next step on the side stream, only its
         # tail after the last step is exposed and is added at the end
