@@ -31,6 +31,7 @@ struct BroadScratch
 	DevArray<int2> children;	   // internal nodes
 	DevArray<int> parent;		   // all nodes (internal [0,n-1), leaves [n-1, 2n-1))
 	DevArray<float4> nodeBox;	   // all nodes
+	DevArray<float4> pairBox;	   // per internal node: the boxes of its two children, adjacent
 	DevArray<int> visit;		   // refit arrival counters (internal nodes)
 	DevArray<int> nodeHeight;
 	DevArray<int> movedLeaves;	   // sorted-leaf indices of moved proxies
@@ -405,7 +406,7 @@ __global__ void s2bBuildRadixTree(const unsigned* codes, const int* counters, in
 }
 
 __global__ void s2bRefit(ShapeView s, const int* leafShape, const int* sortedLeaf, const int* counters, const int2* children,
-						 const int* parent, float4* nodeBox, int* visit, int* nodeHeight, int* countersOut)
+						 const int* parent, float4* nodeBox, float4* pairBox, int* visit, int* nodeHeight, int* countersOut)
 {
 	int n = counters[BC_LEAVES];
 	int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -436,6 +437,9 @@ __global__ void s2bRefit(ShapeView s, const int* leafShape, const int* sortedLea
 		float4 a = __ldcg(nodeBox + ch.x), b = __ldcg(nodeBox + ch.y);
 		box = make_float4(fminf(a.x, b.x), fminf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 		nodeBox[p] = box;
+		// the two child boxes side by side with their parent: a query reads both with one 32-byte access
+		pairBox[2 * p] = a;
+		pairBox[2 * p + 1] = b;
 		int h = 1 + max(__ldcg(nodeHeight + ch.x), __ldcg(nodeHeight + ch.y));
 		nodeHeight[p] = h;
 		if (p == 0)
@@ -562,7 +566,7 @@ __device__ __forceinline__ bool s2bMakeQuery(PairQuery& q, int shapeQ, const Sha
 
 // moved proxies with ordinary boxes: one thread walks the hierarchy
 __global__ void __launch_bounds__(128) s2bFindPairs(ShapeView s, BodyView b, const int* leafShape, const int* sortedLeaf, int* counters,
-								 const int* movedLeaves, const int2* children, const float4* nodeBox,
+								 const int* movedLeaves, const int2* children, const float4* pairBox,
 								 const unsigned long long* pairHash, unsigned long long hashMask, const unsigned long long* jointKeys,
 								 int jointKeyCount, unsigned long long* newKey, int2* newShapes, int newCap)
 {
@@ -581,26 +585,49 @@ __global__ void __launch_bounds__(128) s2bFindPairs(ShapeView s, BodyView b, con
 	}
 	float4 boxQ = s.fat[q.shapeQ];
 
+	// descend into one overlapping child directly and stack the other: half the stack traffic of push-both / pop
 	int stack[64];
 	int sp = 0;
-	stack[sp++] = 0;
-	while (sp > 0)
+	int node = 0;
+	for (;;)
 	{
-		int node = stack[--sp];
 		if (node >= n - 1)
 		{
 			s2bConsiderPair(q, leafShape[sortedLeaf[node - (n - 1)]], s, b, counters, pairHash, hashMask, jointKeys, jointKeyCount, newKey,
 							newShapes, newCap);
+			if (sp == 0)
+			{
+				break;
+			}
+			node = stack[--sp];
 			continue;
 		}
 		int2 ch = children[node];
-		if (s2bBoxesOverlap(boxQ, nodeBox[ch.x]) && sp < 64)
+		bool o0 = s2bBoxesOverlap(boxQ, pairBox[2 * node]);
+		bool o1 = s2bBoxesOverlap(boxQ, pairBox[2 * node + 1]);
+		if (o0 && o1)
 		{
-			stack[sp++] = ch.x;
+			if (sp < 64)
+			{
+				stack[sp++] = ch.y;
+			}
+			node = ch.x;
 		}
-		if (s2bBoxesOverlap(boxQ, nodeBox[ch.y]) && sp < 64)
+		else if (o0)
 		{
-			stack[sp++] = ch.y;
+			node = ch.x;
+		}
+		else if (o1)
+		{
+			node = ch.y;
+		}
+		else
+		{
+			if (sp == 0)
+			{
+				break;
+			}
+			node = stack[--sp];
 		}
 	}
 }
@@ -831,6 +858,7 @@ void s2bBroadphaseUpdatePairs(s2bWorld* w)
 	B->children.reserve(nS, st, false);
 	B->parent.reserve(2 * nS, st, false);
 	B->nodeBox.reserve(2 * nS, st, false);
+	B->pairBox.reserve(2 * nS, st, false);
 	B->visit.reserve(nS, st, false);
 	B->nodeHeight.reserve(2 * nS, st, false);
 	B->movedLeaves.reserve(nS, st, false);
@@ -905,7 +933,7 @@ void s2bBroadphaseUpdatePairs(s2bWorld* w)
 		// ---- refit ----
 		S2B_CHECK(cudaMemsetAsync(B->visit.p, 0, sizeof(int) * nS, st));
 		S2B_LAUNCH(w, s2bRefit, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->leafOut.p, B->counters.p, B->children.p,
-				   B->parent.p, B->nodeBox.p, B->visit.p, B->nodeHeight.p, B->counters.p);
+				   B->parent.p, B->nodeBox.p, B->pairBox.p, B->visit.p, B->nodeHeight.p, B->counters.p);
 
 		// ---- pair-key hash set of the current contact table (rebuilt only when the table changed) ----
 		if (B->hashVersion != w->contactTableVersion || B->pairHash.p == nullptr)
@@ -935,7 +963,7 @@ void s2bBroadphaseUpdatePairs(s2bWorld* w)
 								   B->counters.p + BC_MOVED, shapeCap, st);
 		w->kernelLaunches += 2;
 		S2B_LAUNCH(w, s2bFindPairs, gridFor(shapeCap, 128), 128, 0, sv, bv, B->leafShape.p, B->leafOut.p, B->counters.p,
-				   B->movedLeaves.p, B->children.p, B->nodeBox.p, B->pairHash.p, B->hashMask, w->jointPairKeys.p, w->jointPairCount,
+				   B->movedLeaves.p, B->children.p, B->pairBox.p, B->pairHash.p, B->hashMask, w->jointPairKeys.p, w->jointPairCount,
 				   B->newKey.p, B->newShapes.p, newCap);
 		S2B_LAUNCH(w, s2bFindPairsLarge, gridFor(shapeCap, 256), 256, 0, sv, bv, B->leafShape.p, B->counters.p, B->largeShapes.p,
 				   B->pairHash.p, B->hashMask, w->jointPairKeys.p, w->jointPairCount, B->newKey.p, B->newShapes.p, newCap);

@@ -360,6 +360,62 @@ __global__ void s2bSortIncidenceKernel(int bodyCapacity, const int* adjStart, co
 			heavyBodies[1 + slot] = b;
 		}
 	}
+	if (n <= 8)
+	{
+		// the common case (a box touches ~6 others): sort in registers, touch global memory once per entry
+		unsigned long long r[8];
+#pragma unroll
+		for (int k = 0; k < 8; ++k)
+		{
+			r[k] = ~0ull;
+			if (k < n)
+			{
+				int item = adj[begin + k];
+				unsigned long long val = itemVal[item];
+				if (itemBodies[item].x != b)
+				{
+					val |= S2B_INC_SIDE_B;
+				}
+				r[k] = val;
+			}
+		}
+		// odd-even transposition network on 8 keys (padding keys are the largest value and stay at the end)
+#pragma unroll
+		for (int pass = 0; pass < 8; ++pass)
+		{
+#pragma unroll
+			for (int k = pass & 1; k + 1 < 8; k += 2)
+			{
+				unsigned long long lo = r[k] < r[k + 1] ? r[k] : r[k + 1];
+				unsigned long long hi = r[k] < r[k + 1] ? r[k + 1] : r[k];
+				r[k] = lo;
+				r[k + 1] = hi;
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < 8; ++k)
+		{
+			if (k < n)
+			{
+				int e = (int)(unsigned)(r[k] & 0xFFFFFFFFull);
+				incList[begin + k] = e;
+				if (cFlowA != nullptr)
+				{
+					int t = e >> 2;
+					int2 ticket = make_int2(k, n);
+					if (e & S2B_INC_CONTACT)
+					{
+						((e & S2B_INC_SIDE_B) ? cFlowB : cFlowA)[t] = ticket;
+					}
+					else
+					{
+						((e & S2B_INC_SIDE_B) ? jFlowB : jFlowA)[t] = ticket;
+					}
+				}
+			}
+		}
+		return;
+	}
 	unsigned long long* v = work + begin;
 	for (int k = 0; k < n; ++k)
 	{
