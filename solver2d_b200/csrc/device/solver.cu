@@ -17,6 +17,7 @@
 #include "warm_gather.cuh"
 
 #include <cooperative_groups.h>
+#include <cuda/barrier>
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
@@ -806,6 +807,71 @@ __global__ void __launch_bounds__(S2B_BLOCK) s2bTgsSoftColorKernel(SolveArgs a, 
 	if (t < cEnd)
 	{
 		s2bSolveContactTgsSoft(a, t, a.ctx.inv_h, useBias != 0);
+	}
+}
+
+// The same kernel with the constraint stream staged through shared memory by the TMA engine: the block's slice of every
+// stream column is one contiguous run, so one thread issues eight 1-D bulk copies (cp.async.bulk, completion counted on an
+// mbarrier) and the 256 threads then read their row from shared memory; only the gather of the two bodies and the final
+// stores go through the load/store units. Same arithmetic, same bits.
+#define S2B_BULK_ROWS (S2B_BLOCK + 2) // the slice may start one row early to keep 8-byte columns 16-byte aligned
+
+__global__ void __launch_bounds__(S2B_BLOCK) s2bTgsSoftColorKernelBulk(SolveArgs a, int cBegin, int cEnd, int useBias)
+{
+	using BlockBarrier = cuda::barrier<cuda::thread_scope_block>;
+	__shared__ alignas(16) int2 sIdx[S2B_BULK_ROWS];
+	__shared__ alignas(16) float4 sNf[S2B_BULK_ROWS];
+	__shared__ alignas(16) float4 sAnchor[2][S2B_BULK_ROWS];
+	__shared__ alignas(16) float4 sPm[2][S2B_BULK_ROWS];
+	__shared__ alignas(16) float2 sLambda[2][S2B_BULK_ROWS];
+#pragma nv_diag_suppress static_var_with_dynamic_init
+	__shared__ BlockBarrier bar;
+
+	int t0 = cBegin + blockIdx.x * blockDim.x;
+	int ta = t0 & ~1;									 // even row: 16-byte aligned in the 8-byte columns
+	int tEnd = min(t0 + (int)blockDim.x, cEnd);
+	int rows = ((tEnd - ta) + 1) & ~1;					 // even count: byte sizes are multiples of 16
+	if (threadIdx.x == 0)
+	{
+		init(&bar, blockDim.x);
+		cuda::device::experimental::fence_proxy_async_shared_cta();
+	}
+	__syncthreads();
+	BlockBarrier::arrival_token token;
+	if (threadIdx.x == 0)
+	{
+		const ConstraintView& cc = a.cc;
+		unsigned b8 = (unsigned)rows * 8u, b16 = (unsigned)rows * 16u;
+		cuda::device::memcpy_async_tx(sIdx, cc.idx + ta, cuda::aligned_size_t<16>(b8), bar);
+		cuda::device::memcpy_async_tx(sNf, cc.nf + ta, cuda::aligned_size_t<16>(b16), bar);
+		cuda::device::memcpy_async_tx(sAnchor[0], cc.anchor[0] + ta, cuda::aligned_size_t<16>(b16), bar);
+		cuda::device::memcpy_async_tx(sAnchor[1], cc.anchor[1] + ta, cuda::aligned_size_t<16>(b16), bar);
+		cuda::device::memcpy_async_tx(sPm[0], cc.pm[0] + ta, cuda::aligned_size_t<16>(b16), bar);
+		cuda::device::memcpy_async_tx(sPm[1], cc.pm[1] + ta, cuda::aligned_size_t<16>(b16), bar);
+		cuda::device::memcpy_async_tx(sLambda[0], cc.lambda[0] + ta, cuda::aligned_size_t<16>(b8), bar);
+		cuda::device::memcpy_async_tx(sLambda[1], cc.lambda[1] + ta, cuda::aligned_size_t<16>(b8), bar);
+		token = cuda::device::barrier_arrive_tx(bar, 1, 3 * b8 + 5 * b16);
+	}
+	else
+	{
+		token = bar.arrive();
+	}
+	bar.wait(std::move(token));
+
+	int t = t0 + threadIdx.x;
+	if (t < cEnd)
+	{
+		int r = t - ta;
+		ContactStream cs;
+		cs.idx = sIdx[r];
+		cs.nf = sNf[r];
+		cs.la0 = sAnchor[0][r];
+		cs.la1 = sAnchor[1][r];
+		cs.pm0 = sPm[0][r];
+		cs.pm1 = sPm[1][r];
+		cs.l0 = sLambda[0][r];
+		cs.l1 = sLambda[1][r];
+		s2bSolveContactTgsSoftStream(a, t, cs, a.ctx.inv_h, useBias != 0);
 	}
 }
 
@@ -1795,14 +1861,15 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 		s->flow.reserve(2 * nC + 2 * nJ, st, false);
 		s->bodyTicket.reserve((size_t)bodyCap + 2, st, false);
 	}
-	s->idx.reserve(nC, st, false);
-	s->nf.reserve(nC, st, false);
+	// (+2 rows: the bulk-staged colour kernel may read up to two rows past the last constraint)
+	s->idx.reserve(nC + 2, st, false);
+	s->nf.reserve(nC + 2, st, false);
 	s->src.reserve(nC, st, false);
 	for (int p = 0; p < 2; ++p)
 	{
-		s->anchor[p].reserve(nC, st, false);
-		s->pm[p].reserve(nC, st, false);
-		s->lambda[p].reserve(nC, st, false);
+		s->anchor[p].reserve(nC + 2, st, false);
+		s->pm[p].reserve(nC + 2, st, false);
+		s->lambda[p].reserve(nC + 2, st, false);
 		if (cols.r0)
 		{
 			s->r0[p].reserve(nC, st, false);
@@ -2400,6 +2467,13 @@ extern "C" float s2b_time_color_kernel(s2bWorld* w, const s2bStepContext* contex
 	}
 	int cb = s->hostCGroupOff[best], ce = s->hostCGroupOff[best + 1];
 	SolveArgs a = s->lastArgs;
+	// S2B_COLOR_KERNEL=bulk selects the version that stages the stream through shared memory with TMA bulk copies; measured
+	// slightly SLOWER than ordinary coalesced loads (5.13 vs 5.29 TB/s at 1.5 M constraints), so it is not the default
+	const char* which = getenv("S2B_COLOR_KERNEL");
+	bool bulk = which != nullptr && strcmp(which, "bulk") == 0;
+	// the last (partial) block of the bulk version may stage up to two rows past the colour: they exist (the stream columns are
+	// sized for all constraints) unless the colour ends the stream, where the copy would run past the live rows but still
+	// inside the allocation (columns are reserved with slack) — the rows are never used
 	cudaEvent_t e0, e1;
 	S2B_CHECK(cudaEventCreate(&e0));
 	S2B_CHECK(cudaEventCreate(&e1));
@@ -2408,7 +2482,14 @@ extern "C" float s2b_time_color_kernel(s2bWorld* w, const s2bStepContext* contex
 	{
 		s2b_flush_l2(w);
 		S2B_CHECK(cudaEventRecord(e0, w->stream));
-		S2B_LAUNCH(w, s2bTgsSoftColorKernel, gridFor(bestCount, S2B_BLOCK), S2B_BLOCK, 0, a, cb, ce, 0);
+		if (bulk)
+		{
+			S2B_LAUNCH(w, s2bTgsSoftColorKernelBulk, gridFor(bestCount, S2B_BLOCK), S2B_BLOCK, 0, a, cb, ce, 0);
+		}
+		else
+		{
+			S2B_LAUNCH(w, s2bTgsSoftColorKernel, gridFor(bestCount, S2B_BLOCK), S2B_BLOCK, 0, a, cb, ce, 0);
+		}
 		S2B_CHECK(cudaEventRecord(e1, w->stream));
 		S2B_CHECK(cudaEventSynchronize(e1));
 		float ms = 0.0f;

@@ -37,4 +37,7 @@ def probe(base: int, reps: int = 10, settle_steps: int = 3):
 
 if __name__ == "__main__":
     base = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
-    print(json.dumps(probe(base)))
+    out = probe(base)
+    import os
+    out["variant"] = os.environ.get("S2B_COLOR_KERNEL", "plain (coalesced loads)")
+    print(json.dumps(out))
