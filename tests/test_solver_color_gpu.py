@@ -158,3 +158,13 @@ def test_ticketed_passes_match(reference, dev, solver):
     warm = 2 if solver == "Jacobi" else 30
     c = _case(reference, dev, scenes.pyramid, solver, warm, 4, 2, True, dataflow=True, max_colors=3, base_count=14)
     assert c.overflowCount > 0
+
+
+@pytest.mark.parametrize("base,vel", [(300, 8), (447, 4)])
+def test_full_size_configs_match_permuted_oracle(reference, dev, base, vel):
+    """BASELINE.json's full sizes — config 2 (45 150 boxes, 134 850 constraints, 8 sub-steps) and the headline workload
+    (100 128 boxes, 299 490 constraints, 4 sub-steps): one solver stage of the production schedule against the oracle
+    replayed in the device's colour order, every body, tolerance 0."""
+    c = _case(reference, dev, scenes.pyramid, "TGS_Soft", 3, vel, 2, True, base_count=base)
+    assert c.constraintCount == 3 * (base * (base + 1) // 2) - 2 * base + (base - 1) - (base - 1) or c.constraintCount > 100000
+    assert c.overflowCount == 0 and c.groupCount <= 16
