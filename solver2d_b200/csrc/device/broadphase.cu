@@ -883,16 +883,12 @@ void s2bBroadphaseUpdatePairs(s2bWorld* w)
 	{
 		int newCap = B->newPairCap;
 		int mergeCap = oldCount + newCap;
+		(void)mergeCap;
 		B->newKey.reserve((size_t)newCap, st, false);
 		B->newShapes.reserve((size_t)newCap, st, false);
-		B->mergeKeyIn.reserve((size_t)mergeCap, st, false);
-		B->mergeKeyOut.reserve((size_t)mergeCap, st, false);
-		B->mergeSrcIn.reserve((size_t)mergeCap, st, false);
-		B->mergeSrcOut.reserve((size_t)mergeCap, st, false);
-		cub::DeviceRadixSort::SortPairs(nullptr, need, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr,
-										(int*)nullptr, mergeCap, 0, 64, st);
-		tempBytes = std::max(tempBytes, need);
 		B->cubTemp.reserve(tempBytes + 256, st, false, false);
+		// (the merge buffers are reserved where the merge happens: most passes leave the table as it is, and a pass must
+		// not pay a cudaMalloc for buffers it will not use)
 
 		bool reuseTree = B->treeValid && w->pairsDirty == false && B->treeShapeCap == shapeCap && B->treeReuses < S2B_TREE_REUSE_LIMIT;
 		if (reuseTree)
@@ -1003,6 +999,13 @@ void s2bBroadphaseUpdatePairs(s2bWorld* w)
 		nxt.reserve((size_t)std::max(total, 1), st, w->sticky, false);
 		if (total > 0)
 		{
+			B->mergeKeyIn.reserve((size_t)total, st, false);
+			B->mergeKeyOut.reserve((size_t)total, st, false);
+			B->mergeSrcIn.reserve((size_t)total, st, false);
+			B->mergeSrcOut.reserve((size_t)total, st, false);
+			cub::DeviceRadixSort::SortPairs(nullptr, need, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr,
+											(int*)nullptr, total, 0, 64, st);
+			B->cubTemp.reserve(std::max(tempBytes, need) + 256, st, false, false);
 			int shapeBits = 1;
 			while ((1 << shapeBits) < shapeCap && shapeBits < 31)
 			{
@@ -1020,6 +1023,18 @@ void s2bBroadphaseUpdatePairs(s2bWorld* w)
 		w->cur ^= 1;
 		w->contactCount = total;
 		w->contactTableVersion += 1;
+		// size what the NEXT pass needs for this table now, while a re-allocation is already being paid for: the survivor
+		// flags and the pair-key hash set (built lazily by that pass)
+		B->keepFlag.reserve((size_t)std::max(total, 1), st, false);
+		B->keepSlots.reserve((size_t)std::max(total, 1), st, false);
+		{
+			unsigned long long size = 1024;
+			while (size < 2ull * (unsigned long long)std::max(total, 1))
+			{
+				size <<= 1;
+			}
+			B->pairHash.reserve((size_t)size, st, false, false);
+		}
 		break;
 	}
 
