@@ -259,8 +259,21 @@ __device__ __forceinline__ unsigned s2bPriority(unsigned i)
 	return h;
 }
 
-__device__ __forceinline__ bool s2bHigherPriority(unsigned j, unsigned i)
+// Who wins when two neighbouring items pick the same tentative colour. During the first S2B_INDEX_PRIORITY_ROUNDS rounds
+// the item with the SMALLER natural index wins: items are in shape-pair key order, which follows the geometry of scenes
+// that were built in order (stacks, pyramids, grids), and greedy colouring in that order is near-optimal there — the
+// 100 k-box pyramid gets 7 colours instead of the 10 a random order gives (6 is the lower bound: every box touches 6
+// others). The price is more rounds (a row of the pyramid is a chain in index order: ~1.5 rounds per box of a row), paid
+// once because colours persist. Chains longer than the limit (a 100 k-link rope) fall back to hashed priorities, whose
+// round count is logarithmic.
+#define S2B_INDEX_PRIORITY_ROUNDS 4096
+
+__device__ __forceinline__ bool s2bHigherPriority(unsigned j, unsigned i, bool byIndex)
 {
+	if (byIndex)
+	{
+		return j < i;
+	}
 	unsigned pj = s2bPriority(j), pi = s2bPriority(i);
 	return pj > pi || (pj == pi && j > i);
 }
@@ -406,7 +419,7 @@ __global__ void __launch_bounds__(256) s2bColorKernel(int* counts, const int2* i
 					for (int k = begin; k < end; ++k)
 					{
 						int j = adj[k];
-						if (j != i && tent[j] == mine && s2bHigherPriority((unsigned)j, (unsigned)i))
+						if (j != i && tent[j] == mine && s2bHigherPriority((unsigned)j, (unsigned)i, round <= S2B_INDEX_PRIORITY_ROUNDS))
 						{
 							commit = false;
 						}
