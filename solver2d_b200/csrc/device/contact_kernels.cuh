@@ -277,8 +277,9 @@ __device__ __forceinline__ void s2bWarmStartContact(const SolveArgs& a, int t)
 // Algorithmic traffic per 2-point constraint: stream idx 8 + nf 16 + 2 x (anchor 16 + pm 16 + lambda 8 r + 8 w)
 // = 120 B, bodies 2 x (vel 16 + pose 16 r, vel 16 w) = 96 B.
 // ---------------------------------------------------------------------------------------------------------------
-// the constraint-stream part of a contact constraint: everything a solve pass reads that no other thread writes, so it
-// may be loaded BEFORE the grid barrier that precedes the pass (the body columns may not)
+// the constraint-stream part of a contact constraint: everything a solve pass reads that no other thread writes. Kept
+// apart from the body loads so that a caller can stage it differently (the TMA bulk-copy variant of the colour kernel
+// reads it from shared memory)
 struct ContactStream
 {
 	int2 idx;

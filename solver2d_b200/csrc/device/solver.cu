@@ -2484,9 +2484,7 @@ extern "C" float s2b_time_color_kernel(s2bWorld* w, const s2bStepContext* contex
 	// slightly SLOWER than ordinary coalesced loads (5.13 vs 5.29 TB/s at 1.5 M constraints), so it is not the default
 	const char* which = getenv("S2B_COLOR_KERNEL");
 	bool bulk = which != nullptr && strcmp(which, "bulk") == 0;
-	// the last (partial) block of the bulk version may stage up to two rows past the colour: they exist (the stream columns are
-	// sized for all constraints) unless the colour ends the stream, where the copy would run past the live rows but still
-	// inside the allocation (columns are reserved with slack) — the rows are never used
+	// (the bulk version may stage up to two rows past the colour; the stream columns are reserved with two spare rows for that)
 	cudaEvent_t e0, e1;
 	S2B_CHECK(cudaEventCreate(&e0));
 	S2B_CHECK(cudaEventCreate(&e1));
