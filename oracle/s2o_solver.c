@@ -12,8 +12,8 @@
 // It shares the row structs of include/s2b_device.h (types only) and the float inlines of include/solver2d/math.h; it is
 // compiled with the reference's flags (gcc -std=gnu17 -O2, no FMA contraction).
 //
-// Restated: the nine variants north_star names — s2Solve_PGS, _PGS_NGS, _PGS_Soft, _TGS_Soft, _TGS_NGS, _TGS_Sticky,
-// _SoftStep, _XPBD, _Jacobi — with revolute and mouse joints (s2Solve_PGS_NGS_Block is not restated: SURVEY §8f-2).
+// Restated: all ten variants s2World_Step dispatches (reference src/world.c:206-256) — s2Solve_PGS, _PGS_NGS,
+// _PGS_NGS_Block, _PGS_Soft, _TGS_Soft, _TGS_NGS, _TGS_Sticky, _SoftStep, _XPBD, _Jacobi — with revolute and mouse joints.
 
 #include "s2b_device.h"
 #include "solver2d/constants.h"
