@@ -847,32 +847,22 @@ S2C_FN void s2cPolygonSAT(s2Manifold* manifold, const s2Polygon* polyA, const s2
 
 // s2CollidePolygons (reference src/manifold.c:509-650): GJK closest features, SAT when (nearly) overlapping,
 // vertex-vertex or edge clipping otherwise. Capsules and segments arrive here as 2-gons.
-S2C_FN void s2cCollidePolygons(s2Manifold* manifold, const s2Polygon* polyA, s2Transform xfA, const s2Polygon* polyB,
-							   s2Transform xfB, s2DistanceCache* cache)
+// This is the part after polyB has been moved into polyA's frame: `localB` = polyB under xf = xfA^-1 * xfB. The device
+// kernel builds localB itself, straight from the shape columns into shared memory (narrowphase.cu).
+S2C_FN void s2cCollidePolygonsLocal(s2Manifold* manifold, const s2Polygon* polyA, s2Transform xfA, const s2Polygon* localB,
+									s2Transform xf, s2DistanceCache* cache)
 {
 	s2cClearManifold(manifold);
-	float radius = polyA->radius + polyB->radius;
-
-	s2Transform xf = s2InvMulTransforms(xfA, xfB);
-
-	// polyB in polyA's frame
-	s2Polygon localPolyB;
-	localPolyB.count = polyB->count;
-	localPolyB.radius = polyB->radius;
-	for (int i = 0; i < localPolyB.count; ++i)
-	{
-		localPolyB.vertices[i] = s2TransformPoint(xf, polyB->vertices[i]);
-		localPolyB.normals[i] = s2RotateVector(xf.q, polyB->normals[i]);
-	}
+	float radius = polyA->radius + localB->radius;
 
 	s2Transform identity;
 	identity.p = s2cVec(0.0f, 0.0f);
 	identity.q.s = 0.0f;
 	identity.q.c = 1.0f;
 	int countA = S2_MIN(polyA->count, s2_maxPolygonVertices);
-	int countB = S2_MIN(localPolyB.count, s2_maxPolygonVertices);
+	int countB = S2_MIN(localB->count, s2_maxPolygonVertices);
 	s2DistanceOutput output =
-		s2cShapeDistance(cache, polyA->vertices, countA, 0.0f, identity, localPolyB.vertices, countB, 0.0f, identity, false);
+		s2cShapeDistance(cache, polyA->vertices, countA, 0.0f, identity, localB->vertices, countB, 0.0f, identity, false);
 
 	if (output.distance > radius + s2_speculativeDistance)
 	{
@@ -881,7 +871,7 @@ S2C_FN void s2cCollidePolygons(s2Manifold* manifold, const s2Polygon* polyA, s2T
 
 	if (output.distance < 0.1f * s2_linearSlop)
 	{
-		s2cPolygonSAT(manifold, polyA, &localPolyB);
+		s2cPolygonSAT(manifold, polyA, localB);
 		if (manifold->pointCount > 0)
 		{
 			manifold->normal = s2RotateVector(xfA.q, manifold->normal);
@@ -900,7 +890,7 @@ S2C_FN void s2cCollidePolygons(s2Manifold* manifold, const s2Polygon* polyA, s2T
 		s2Vec2 pB = output.pointB;
 		float distance = output.distance;
 		s2Vec2 normal = s2cNormalize(s2Sub(pB, pA));
-		s2Vec2 contactPointA = s2MulAdd(pB, 0.5f * (polyA->radius - localPolyB.radius - distance), normal);
+		s2Vec2 contactPointA = s2MulAdd(pB, 0.5f * (polyA->radius - localB->radius - distance), normal);
 
 		manifold->normal = s2RotateVector(xfA.q, normal);
 		manifold->points[0].localAnchorA = contactPointA;
@@ -923,12 +913,12 @@ S2C_FN void s2cCollidePolygons(s2Manifold* manifold, const s2Polygon* polyA, s2T
 	{
 		// one vertex of A against an edge of B
 		s2Vec2 axis = s2Sub(output.pointA, output.pointB);
-		float dot1 = s2Dot(axis, localPolyB.normals[b1]);
-		float dot2 = s2Dot(axis, localPolyB.normals[b2]);
+		float dot1 = s2Dot(axis, localB->normals[b1]);
+		float dot2 = s2Dot(axis, localB->normals[b2]);
 		edgeB = dot1 > dot2 ? b1 : b2;
 		flip = true;
 
-		axis = localPolyB.normals[edgeB];
+		axis = localB->normals[edgeB];
 		int edgeA1 = a1;
 		int edgeA2 = edgeA1 == 0 ? polyA->count - 1 : edgeA1 - 1;
 		dot1 = s2Dot(axis, polyA->normals[edgeA1]);
@@ -945,13 +935,13 @@ S2C_FN void s2cCollidePolygons(s2Manifold* manifold, const s2Polygon* polyA, s2T
 
 		axis = polyA->normals[edgeA];
 		int edgeB1 = b1;
-		int edgeB2 = edgeB1 == 0 ? localPolyB.count - 1 : edgeB1 - 1;
-		dot1 = s2Dot(axis, localPolyB.normals[edgeB1]);
-		dot2 = s2Dot(axis, localPolyB.normals[edgeB2]);
+		int edgeB2 = edgeB1 == 0 ? localB->count - 1 : edgeB1 - 1;
+		dot1 = s2Dot(axis, localB->normals[edgeB1]);
+		dot2 = s2Dot(axis, localB->normals[edgeB2]);
 		edgeB = dot1 < dot2 ? edgeB1 : edgeB2;
 	}
 
-	s2cClipPolygons(manifold, polyA, &localPolyB, edgeA, edgeB, flip);
+	s2cClipPolygons(manifold, polyA, localB, edgeA, edgeB, flip);
 	if (manifold->pointCount > 0)
 	{
 		manifold->normal = s2RotateVector(xfA.q, manifold->normal);
@@ -960,4 +950,25 @@ S2C_FN void s2cCollidePolygons(s2Manifold* manifold, const s2Polygon* polyA, s2T
 			manifold->points[i].localAnchorB = s2InvTransformPoint(xf, manifold->points[i].localAnchorA);
 		}
 	}
+}
+
+// polyB in polyA's frame (reference src/manifold.c:515-527)
+S2C_FN void s2cMakeLocalPolygon(s2Polygon* localB, const s2Polygon* polyB, s2Transform xf)
+{
+	localB->count = polyB->count;
+	localB->radius = polyB->radius;
+	for (int i = 0; i < localB->count; ++i)
+	{
+		localB->vertices[i] = s2TransformPoint(xf, polyB->vertices[i]);
+		localB->normals[i] = s2RotateVector(xf.q, polyB->normals[i]);
+	}
+}
+
+S2C_FN void s2cCollidePolygons(s2Manifold* manifold, const s2Polygon* polyA, s2Transform xfA, const s2Polygon* polyB,
+							   s2Transform xfB, s2DistanceCache* cache)
+{
+	s2Transform xf = s2InvMulTransforms(xfA, xfB);
+	s2Polygon localPolyB;
+	s2cMakeLocalPolygon(&localPolyB, polyB, xf);
+	s2cCollidePolygonsLocal(manifold, polyA, xfA, &localPolyB, xf, cache);
 }
