@@ -16,8 +16,10 @@
 
 #if defined(__CUDACC__)
 	#define S2C_FN static inline __host__ __device__
+	#define S2C_UNROLL _Pragma("unroll")
 #else
 	#define S2C_FN static inline
+	#define S2C_UNROLL
 #endif
 
 // ---- small helpers ----------------------------------------------------------------------------------------------
@@ -108,6 +110,16 @@ typedef struct s2cSimplex
 	s2cSimplexVertex v[3];
 	int count;
 } s2cSimplex;
+
+#define S2C_SET_SIMPLEX_VERTEX(dst, src) \
+	do \
+	{ \
+		(dst).indexA = (src).indexA; \
+		(dst).indexB = (src).indexB; \
+		(dst).wA = (src).wA; \
+		(dst).wB = (src).wB; \
+		(dst).w = (src).w; \
+	} while (0)
 
 // s2FindSupport (reference src/distance.c:117-132)
 S2C_FN int s2cFindSupport(const s2Vec2* vertices, int count, s2Vec2 direction)
@@ -275,17 +287,23 @@ S2C_FN s2DistanceOutput s2cShapeDistance(s2DistanceCache* cache, const s2Vec2* v
 	output.iterations = 0;
 
 	// simplex from the cache (reference s2MakeSimplexFromCache, distance.c:174-218)
+	// Every access to simplex.v[] and the cache index arrays below uses a literal index (loops over the at most three
+	// vertices are unrolled with a guard): on the device the simplex then lives in registers instead of the local stack.
 	s2cSimplex simplex;
 	simplex.count = cache->count;
-	for (int i = 0; i < simplex.count; ++i)
+	S2C_UNROLL
+	for (int i = 0; i < 3; ++i)
 	{
-		s2cSimplexVertex* v = simplex.v + i;
-		v->indexA = cache->indexA[i];
-		v->indexB = cache->indexB[i];
-		v->wA = s2TransformPoint(xfA, vertsA[v->indexA]);
-		v->wB = s2TransformPoint(xfB, vertsB[v->indexB]);
-		v->w = s2Sub(v->wB, v->wA);
-		v->a = -1.0f;
+		if (i < simplex.count)
+		{
+			s2cSimplexVertex* v = simplex.v + i;
+			v->indexA = cache->indexA[i];
+			v->indexB = cache->indexB[i];
+			v->wA = s2TransformPoint(xfA, vertsA[v->indexA]);
+			v->wB = s2TransformPoint(xfB, vertsB[v->indexB]);
+			v->w = s2Sub(v->wB, v->wA);
+			v->a = -1.0f;
+		}
 	}
 	if (simplex.count == 0)
 	{
@@ -305,10 +323,14 @@ S2C_FN s2DistanceOutput s2cShapeDistance(s2DistanceCache* cache, const s2Vec2* v
 	while (iter < maxIters)
 	{
 		int saveCount = simplex.count;
-		for (int i = 0; i < saveCount; ++i)
+		S2C_UNROLL
+		for (int i = 0; i < 3; ++i)
 		{
-			saveA[i] = simplex.v[i].indexA;
-			saveB[i] = simplex.v[i].indexB;
+			if (i < saveCount)
+			{
+				saveA[i] = simplex.v[i].indexA;
+				saveB[i] = simplex.v[i].indexB;
+			}
 		}
 
 		if (simplex.count == 2)
@@ -352,7 +374,9 @@ S2C_FN s2DistanceOutput s2cShapeDistance(s2DistanceCache* cache, const s2Vec2* v
 			break;
 		}
 
-		s2cSimplexVertex* vertex = simplex.v + simplex.count;
+		// the new vertex; it joins the simplex at v[count] (count is 1 or 2 here) unless it repeats a support point
+		s2cSimplexVertex fresh;
+		s2cSimplexVertex* vertex = &fresh;
 		vertex->indexA = s2cFindSupport(vertsA, countA, s2InvRotateVector(xfA.q, s2Neg(d)));
 		vertex->wA = s2TransformPoint(xfA, vertsA[vertex->indexA]);
 		vertex->indexB = s2cFindSupport(vertsB, countB, s2InvRotateVector(xfB.q, d));
@@ -363,12 +387,12 @@ S2C_FN s2DistanceOutput s2cShapeDistance(s2DistanceCache* cache, const s2Vec2* v
 
 		// a repeated support point terminates the iteration
 		bool duplicate = false;
-		for (int i = 0; i < saveCount; ++i)
+		S2C_UNROLL
+		for (int i = 0; i < 3; ++i)
 		{
-			if (vertex->indexA == saveA[i] && vertex->indexB == saveB[i])
+			if (i < saveCount && vertex->indexA == saveA[i] && vertex->indexB == saveB[i])
 			{
 				duplicate = true;
-				break;
 			}
 		}
 		if (duplicate)
@@ -376,6 +400,15 @@ S2C_FN s2DistanceOutput s2cShapeDistance(s2DistanceCache* cache, const s2Vec2* v
 			break;
 		}
 
+		// (the weight `a` of the slot is left as it is, like the reference: the next s2cSolveSimplex* sets it)
+		if (simplex.count == 1)
+		{
+			S2C_SET_SIMPLEX_VERTEX(simplex.v[1], fresh);
+		}
+		else
+		{
+			S2C_SET_SIMPLEX_VERTEX(simplex.v[2], fresh);
+		}
 		++simplex.count;
 	}
 
@@ -413,10 +446,14 @@ S2C_FN s2DistanceOutput s2cShapeDistance(s2DistanceCache* cache, const s2Vec2* v
 		cache->metric = s2Cross(s2Sub(simplex.v[1].w, simplex.v[0].w), s2Sub(simplex.v[2].w, simplex.v[0].w));
 	}
 	cache->count = (uint16_t)simplex.count;
-	for (int i = 0; i < simplex.count; ++i)
+	S2C_UNROLL
+	for (int i = 0; i < 3; ++i)
 	{
-		cache->indexA[i] = (uint8_t)simplex.v[i].indexA;
-		cache->indexB[i] = (uint8_t)simplex.v[i].indexB;
+		if (i < simplex.count)
+		{
+			cache->indexA[i] = (uint8_t)simplex.v[i].indexA;
+			cache->indexB[i] = (uint8_t)simplex.v[i].indexB;
+		}
 	}
 
 	if (useRadii)
