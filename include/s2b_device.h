@@ -177,6 +177,10 @@ typedef struct s2bCounters
 	int32_t graphReplays;	 // solver stages executed as a CUDA graph replay
 	int32_t graphCaptures;	 // times the solver stage was (re)captured into a graph
 	int64_t scratchBytes;	 // device bytes of per-step scratch currently reserved
+	int32_t regionCount;	 // region-local schedule: regions (= blocks of the persistent kernel) of the last solve, 0 = off
+	int32_t cutCount;		 // constraints that straddle two regions (solved in device-wide steps)
+	int32_t cutGroupCount;	 // colours of the cut set = device-wide steps per Gauss-Seidel sweep
+	int32_t reserved0;
 } s2bCounters;
 
 // ---- lifecycle ------------------------------------------------------------------------------------------------
@@ -199,6 +203,10 @@ S2B_API void s2b_set_warm_gather(s2bWorld* world, int enable);
 // Replay the solver stage (set-up kernels + persistent kernel, ~30 launches) as ONE CUDA graph launch while its inputs'
 // shapes and addresses are unchanged (1, default) or always launch kernel by kernel (0).
 S2B_API void s2b_set_graph(s2bWorld* world, int enable);
+// Region-local schedule of the persistent kernel (1, default): bodies are partitioned into one region per thread block,
+// constraints interior to a region run between block barriers, only the cut set needs grid barriers.
+// 0 = one device-wide step per colour (cross-check; same bits against the oracle replayed in the reported order).
+S2B_API void s2b_set_regions(s2bWorld* world, int enable);
 // Gauss-Seidel passes of the persistent kernel synchronised by one grid barrier per colour (0, default) or by per-body
 // tickets (1: a constraint waits only for the previous constraint on each of its bodies; no barrier inside a sweep).
 // Same bits either way; the ticketed form measured SLOWER on B200 (75 k pollers saturate L2), kept as an experiment.

@@ -52,7 +52,7 @@ __device__ __forceinline__ void s2bLoadLocalPolygon(s2Polygon* poly, const Shape
 	poly->radius = radius;
 }
 
-__global__ void __launch_bounds__(S2B_NP_BLOCK) s2bUpdateContactsKernel(ContactView c, int contactCount, ShapeView s, BodyView b, int sticky)
+__global__ void __launch_bounds__(S2B_NP_BLOCK) s2bUpdateContactsKernel(ContactView c, int contactCount, ShapeView s, BodyView b, int sticky, int* schedDirty)
 {
 	__shared__ float polyStore[S2B_NP_BLOCK * S2B_NP_THREAD_WORDS];
 	s2Polygon* polyA = reinterpret_cast<s2Polygon*>(polyStore + threadIdx.x * S2B_NP_THREAD_WORDS);
@@ -202,6 +202,10 @@ __global__ void __launch_bounds__(S2B_NP_BLOCK) s2bUpdateContactsKernel(ContactV
 	{
 		c.color[i] = -1; // not a constraint this step: its colour is free again
 	}
+	if ((pointCount > 0) != (oldCount > 0))
+	{
+		*schedDirty = 1; // the set of live constraints changed: the solve schedule has to be rebuilt (solver.cu, s2bScheduleGate)
+	}
 	for (int p = 0; p < 2; ++p)
 	{
 		c.anchor[p][i] = make_float4(m.points[p].localAnchorA.x, m.points[p].localAnchorA.y, m.points[p].localAnchorB.x,
@@ -217,5 +221,5 @@ void s2bNarrowphaseUpdate(s2bWorld* w)
 		return;
 	}
 	S2B_LAUNCH(w, s2bUpdateContactsKernel, gridFor(w->contactCount, S2B_NP_BLOCK), S2B_NP_BLOCK, 0, makeView(w->contacts[w->cur]), w->contactCount,
-			   shapeView(w), bodyView(w), w->sticky ? 1 : 0);
+			   shapeView(w), bodyView(w), w->sticky ? 1 : 0, w->schedDirty.p);
 }

@@ -292,6 +292,7 @@ struct s2bWorld
 	int useGraph = 1;		// replay the solver stage as a CUDA graph when nothing changed; s2b_set_graph / S2B_GRAPH=0 disable
 	bool capturing = false;
 	unsigned long long contactTableVersion = 0; // bumped whenever the contact table is replaced (pair pass commit, upload) // a stream capture of the solver stage is in progress
+	int useRegions = 1; // region-local schedule of the persistent kernel (persistent.cuh); s2b_set_regions / S2B_REGIONS=0 disable it
 	int dataflow = 0;	// ticketed Gauss-Seidel passes in the persistent kernel (experimental, slower on B200: DESIGN.md §3.1);
 						// s2b_set_dataflow / S2B_DATAFLOW=1 enable it
 	int gatherWarm = 1; // per-body warm-start gather (warm_gather.cuh); s2b_set_warm_gather / S2B_WARM_GATHER=0 disable it
@@ -299,6 +300,10 @@ struct s2bWorld
 	int coopSupported = 0;
 	int colorGrid = 0;	// cooperative grid sizes, computed once
 	int solveGrid = 0;
+	int solveGridSolver = -1; // variant the grid was sized for (each variant is its own kernel)
+	DevArray<int> schedDirty; // [0] != 0: the set of live constraints changed since the solve schedule was built (device flag)
+	DevArray<unsigned> solveBarrier; // arrival counter of the persistent kernel's grid barrier (persistent.cuh)
+	unsigned long long scheduleEpoch = 0; // bumped by every host-side change the solve schedule depends on (uploads, settings)
 
 	// bodies
 	int bodyCap = 0;

@@ -13,8 +13,7 @@
 //   iterate     the variant's schedule of body passes and per-group constraint passes, either as ONE persistent
 //               cooperative kernel (grid barrier between groups) or as one launch per group (profiling / cross-check)
 //   store       accumulated impulses back to the persistent manifolds / joints
-#include "joint_kernels.cuh"
-#include "warm_gather.cuh"
+#include "persistent.cuh"
 
 #include <cooperative_groups.h>
 #include <cuda/barrier>
@@ -24,9 +23,6 @@
 #include <algorithm>
 
 namespace cg = cooperative_groups;
-
-#define S2B_MAX_COLORS 64
-#define S2B_OVERFLOW_KEY 255
 
 // ---------------------------------------------------------------------------------------------------------------
 // scratch management
@@ -48,6 +44,11 @@ void s2bFreeSolverScratch(s2bWorld* w)
 	{
 		return;
 	}
+	if (s->graphExec != nullptr)
+	{
+		cudaGraphExecDestroy(s->graphExec);
+		s->graphExec = nullptr;
+	}
 	s->counts.release();
 	s->activeFlag.release();
 	s->activeSlots.release();
@@ -60,8 +61,18 @@ void s2bFreeSolverScratch(s2bWorld* w)
 	s->adj.release();
 	s->colorA.release();
 	s->colorB.release();
+	s->colorC.release();
+	s->itemRegion.release();
 	s->sortKeyIn.release();
 	s->sortKeyOut.release();
+	s->bodyKeyIn.release();
+	s->bodyKeyOut.release();
+	s->bodyValIn.release();
+	s->regBodies.release();
+	s->bodyRegion.release();
+	s->regBodyStart.release();
+	s->cRegOff.release();
+	s->jRegOff.release();
 	s->sortValIn.release();
 	s->sortValOut.release();
 	s->cGroupOff.release();
@@ -69,6 +80,13 @@ void s2bFreeSolverScratch(s2bWorld* w)
 	s->cPerm.release();
 	s->jPerm.release();
 	s->cubTemp.release();
+	s->itemVal.release();
+	s->incWork.release();
+	s->incList.release();
+	s->heavyBodies.release();
+	s->flow.release();
+	s->bodyTicket.release();
+	s->trace.release();
 	s->idx.release();
 	s->nf.release();
 	for (int p = 0; p < 2; ++p)
@@ -314,13 +332,59 @@ __global__ void s2bStoreColors(const int* counts, const int* jointSlots, const i
 
 // Cooperative kernel: speculative rounds until nothing is left uncoloured.
 // `tent` holds (round << 8 | colour) so a value written in an earlier round can never be mistaken for this round's.
+// validate != 0: persisted colours are first CHECKED against the current conflict graph — a body that became movable since
+// its constraints were coloured (a shape with density added to a massless body) makes constraints that share it conflict;
+// of two neighbours with the same colour the one with the larger index is uncoloured and picks again. Decided on the
+// colours as they were (two phases), so the outcome does not depend on thread timing.
 __global__ void __launch_bounds__(256) s2bColorKernel(int* counts, const int2* itemBodies, const int* adjStart, const int* adj, int* color,
-													  int* tent, int maxColors)
+													  int* tent, int maxColors, int indexRounds, int validate)
 {
 	cg::grid_group grid = cg::this_grid();
 	int n = counts[CNT_JOINTS] + counts[CNT_CONTACTS];
 	int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	int stride = gridDim.x * blockDim.x;
+
+	if (validate)
+	{
+		for (int i = tid; i < n; i += stride)
+		{
+			int ci = color[i];
+			int keep = 1;
+			if (ci >= 0 && ci < S2B_MAX_COLORS)
+			{
+				int2 e = itemBodies[i];
+#pragma unroll
+				for (int side = 0; side < 2; ++side)
+				{
+					int body = side == 0 ? e.x : e.y;
+					if (body < 0)
+					{
+						continue;
+					}
+					int begin = adjStart[body], end = adjStart[body + 1];
+					for (int k = begin; k < end; ++k)
+					{
+						int j = adj[k];
+						if (j < i && color[j] == ci)
+						{
+							keep = 0;
+						}
+					}
+				}
+			}
+			tent[i] = keep;
+		}
+		grid.sync();
+		for (int i = tid; i < n; i += stride)
+		{
+			if (tent[i] == 0)
+			{
+				color[i] = -1;
+			}
+		}
+		__threadfence();
+		grid.sync();
+	}
 
 	// nothing to colour (the common case on a settled scene): leave without a single grid barrier.
 	// Every thread evaluates the same predicate on data written by earlier kernels, so the exit is uniform.
@@ -419,7 +483,7 @@ __global__ void __launch_bounds__(256) s2bColorKernel(int* counts, const int2* i
 					for (int k = begin; k < end; ++k)
 					{
 						int j = adj[k];
-						if (j != i && tent[j] == mine && s2bHigherPriority((unsigned)j, (unsigned)i, round <= S2B_INDEX_PRIORITY_ROUNDS))
+						if (j != i && tent[j] == mine && s2bHigherPriority((unsigned)j, (unsigned)i, round <= indexRounds))
 						{
 							commit = false;
 						}
@@ -453,9 +517,214 @@ __global__ void __launch_bounds__(256) s2bColorKernel(int* counts, const int2* i
 	}
 }
 
-// sort keys: colour per item, split into the joint and the contact key arrays (values = natural index)
-__global__ void s2bMakeSortKeys(const int* counts, const int* color, unsigned char* jKeys, int* jVals, unsigned char* cKeys,
-								int* cVals)
+// ---------------------------------------------------------------------------------------------------------------
+// Regions (persistent.cuh): the bodies are cut into `regions` spatially compact sets of equal size — consecutive runs
+// of the Hilbert order of their centres of mass — one per block of the persistent kernel. Hub bodies (more incident
+// constraints than S2B_HEAVY_DEGREE: a container wall, the ground under a whole pile is static and does not count)
+// stay outside: every constraint that touches one is in the cut set and their body passes run grid-wide.
+// ---------------------------------------------------------------------------------------------------------------
+
+// order-preserving map float -> unsigned (larger float = larger key); NaN sorts high, harmless here
+__device__ __forceinline__ unsigned s2bOrderedKey(float f)
+{
+	unsigned u = __float_as_uint(f);
+	return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ float s2bFromOrderedKey(unsigned k)
+{
+	unsigned u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+	return __uint_as_float(u);
+}
+
+// bounding box of the centres of all valid bodies (4 x atomicMax on keys: max x, max -x, max y, max -y)
+__global__ void s2bBodyBoundsKernel(BodyView bodies, int* counts)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned kx = 0, knx = 0, ky = 0, kny = 0;
+	if (i < bodies.capacity && (bodies.flags[i] & S2B_BODY_VALID))
+	{
+		float4 pos = bodies.pos[i];
+		kx = s2bOrderedKey(pos.x);
+		knx = s2bOrderedKey(-pos.x);
+		ky = s2bOrderedKey(pos.y);
+		kny = s2bOrderedKey(-pos.y);
+	}
+	// warp-level maxima first: one atomic per warp and bound
+	for (int d = 16; d > 0; d >>= 1)
+	{
+		kx = max(kx, __shfl_xor_sync(0xFFFFFFFFu, kx, d));
+		knx = max(knx, __shfl_xor_sync(0xFFFFFFFFu, knx, d));
+		ky = max(ky, __shfl_xor_sync(0xFFFFFFFFu, ky, d));
+		kny = max(kny, __shfl_xor_sync(0xFFFFFFFFu, kny, d));
+	}
+	if ((threadIdx.x & 31) == 0 && (kx | knx | ky | kny) != 0)
+	{
+		unsigned* b = (unsigned*)(counts + CNT_BOUNDS);
+		atomicMax(b + 0, kx);
+		atomicMax(b + 1, knx);
+		atomicMax(b + 2, ky);
+		atomicMax(b + 3, kny);
+	}
+}
+
+// position along the Hilbert curve of order 16 through the cell (x, y), x, y < 65536
+__device__ __forceinline__ unsigned s2bHilbert16(unsigned x, unsigned y)
+{
+	unsigned d = 0;
+	for (unsigned s = 32768u; s > 0; s >>= 1)
+	{
+		unsigned rx = (x & s) ? 1u : 0u, ry = (y & s) ? 1u : 0u;
+		d += s * s * ((3u * rx) ^ ry);
+		if (ry == 0)
+		{
+			if (rx == 1)
+			{
+				x = 65535u - x;
+				y = 65535u - y;
+			}
+			unsigned t = x;
+			x = y;
+			y = t;
+		}
+	}
+	return d;
+}
+
+// sort key of every body slot: its Hilbert position, or 0xFFFFFFFF for slots that belong to no region (free slots, hub
+// bodies). Hub bodies are appended to the hub list (order irrelevant: each is processed on its own).
+__global__ void s2bBodyKeysKernel(BodyView bodies, int* counts, const int* degree, unsigned* keys, int* vals, int* hubs)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= bodies.capacity)
+	{
+		return;
+	}
+	vals[i] = i;
+	unsigned key = 0xFFFFFFFFu;
+	if (bodies.flags[i] & S2B_BODY_VALID)
+	{
+		if (degree[i] > S2B_HEAVY_DEGREE)
+		{
+			hubs[1 + atomicAdd(hubs, 1)] = i;
+		}
+		else
+		{
+			const unsigned* b = (const unsigned*)(counts + CNT_BOUNDS);
+			float maxX = s2bFromOrderedKey(b[0]), minX = -s2bFromOrderedKey(b[1]);
+			float maxY = s2bFromOrderedKey(b[2]), minY = -s2bFromOrderedKey(b[3]);
+			float extent = fmaxf(maxX - minX, maxY - minY);
+			float scale = extent > 0.0f ? 65535.0f / extent : 0.0f;
+			float4 pos = bodies.pos[i];
+			float fx = (pos.x - minX) * scale, fy = (pos.y - minY) * scale;
+			unsigned qx = fx >= 0.0f ? (fx < 65535.0f ? (unsigned)fx : 65535u) : 0u;
+			unsigned qy = fy >= 0.0f ? (fy < 65535.0f ? (unsigned)fy : 65535u) : 0u;
+			key = min(s2bHilbert16(qx, qy), 0xFFFFFFFEu);
+			atomicAdd(counts + CNT_OWNED, 1);
+		}
+	}
+	keys[i] = key;
+}
+
+// region of every body from its rank in the sorted order: equal chunks of the owned bodies
+__global__ void s2bAssignRegionsKernel(const int* counts, int bodyCapacity, int regions, const int* sortedBodies, int* bodyRegion,
+									   int* regBodyStart)
+{
+	int k = blockIdx.x * blockDim.x + threadIdx.x;
+	int owned = counts[CNT_OWNED];
+	int chunk = max((owned + regions - 1) / regions, 1);
+	if (k < bodyCapacity)
+	{
+		bodyRegion[sortedBodies[k]] = k < owned ? k / chunk : -1;
+	}
+	if (k <= regions)
+	{
+		long long start = (long long)k * chunk;
+		regBodyStart[k] = start < owned ? (int)start : owned;
+	}
+}
+
+// interior / cut classification of every item and the seed of the cut colouring.
+// useRegions == 0: every item is in the "cut" set and keeps its primary colour there (one device-wide group per colour).
+__global__ void s2bClassifyItemsKernel(int* counts, const int2* itemBodies, const int* bodyRegion, const int* color, int useRegions,
+									   int* itemRegion, int* cutColor)
+{
+	int n = counts[CNT_JOINTS] + counts[CNT_CONTACTS];
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	int colorsHere = 0, primaryHere = 0, cutHere = 0;
+	if (i < n)
+	{
+		int c = color[i];
+		int region = -1;
+		if (useRegions)
+		{
+			int2 e = itemBodies[i];
+			if (e.x < 0 && e.y < 0)
+			{
+				region = 0; // touches no movable body: conflicts with nothing
+			}
+			else
+			{
+				int ra = e.x >= 0 ? bodyRegion[e.x] : -2, rb = e.y >= 0 ? bodyRegion[e.y] : -2;
+				if (ra == -2)
+				{
+					region = rb;
+				}
+				else if (rb == -2 || rb == ra)
+				{
+					region = ra;
+				}
+			}
+		}
+		bool overflow = c < 0 || c >= S2B_MAX_COLORS;
+		if (overflow)
+		{
+			region = -1;
+		}
+		itemRegion[i] = region;
+		// 254 = takes no part in the cut colouring (interior, or already in the serial overflow group)
+		cutColor[i] = region >= 0 ? 254 : (overflow ? S2B_OVERFLOW_KEY : (useRegions ? -1 : c));
+		if (overflow == false)
+		{
+			colorsHere = c + 1;
+			primaryHere = region >= 0 ? c + 1 : 0;
+			cutHere = region < 0 ? 1 : 0;
+		}
+	}
+	for (int d = 16; d > 0; d >>= 1)
+	{
+		colorsHere = max(colorsHere, __shfl_xor_sync(0xFFFFFFFFu, colorsHere, d));
+		primaryHere = max(primaryHere, __shfl_xor_sync(0xFFFFFFFFu, primaryHere, d));
+		cutHere += __shfl_xor_sync(0xFFFFFFFFu, cutHere, d);
+	}
+	if ((threadIdx.x & 31) == 0)
+	{
+		if (colorsHere > 0)
+		{
+			atomicMax(counts + CNT_COLORS, colorsHere);
+		}
+		if (primaryHere > 0)
+		{
+			atomicMax(counts + CNT_PRIMARY, primaryHere);
+		}
+		if (cutHere > 0)
+		{
+			atomicAdd(counts + CNT_CUT, cutHere);
+		}
+	}
+}
+
+// Solve-order keys, 16 bits, joints and contacts in separate arrays (values = natural index):
+//   region * 64 + colour      interior constraints, region-major (region < 511)
+//   0x8000 + cut colour       the cut set (or, without regions, every constraint by its colour)
+//   0xFFFE                    serial overflow group
+//   0xFFFF                    unused tail of the arrays (memset), sorts behind everything
+#define S2B_KEY_CUT 0x8000
+#define S2B_KEY_OVERFLOW 0xFFFE
+#define S2B_KEY_DEAD 0xFFFF
+
+__global__ void s2bMakeSortKeys(const int* counts, const int* color, const int* itemRegion, const int* cutColor, unsigned short* jKeys,
+								int* jVals, unsigned short* cKeys, int* cVals)
 {
 	int nJ = counts[CNT_JOINTS], nC = counts[CNT_CONTACTS];
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -463,40 +732,75 @@ __global__ void s2bMakeSortKeys(const int* counts, const int* color, unsigned ch
 	{
 		return;
 	}
-	unsigned char key = (unsigned char)color[i];
+	int region = itemRegion[i];
+	int key;
+	if (region >= 0)
+	{
+		key = region * S2B_MAX_COLORS + color[i];
+	}
+	else
+	{
+		int cc = cutColor[i];
+		key = (cc >= 0 && cc < S2B_MAX_COLORS) ? S2B_KEY_CUT + cc : S2B_KEY_OVERFLOW;
+	}
 	if (i < nJ)
 	{
-		jKeys[i] = key;
+		jKeys[i] = (unsigned short)key;
 		jVals[i] = i;
 	}
 	else
 	{
-		cKeys[i - nJ] = key;
+		cKeys[i - nJ] = (unsigned short)key;
 		cVals[i - nJ] = i - nJ;
 	}
 }
 
-// group offsets from sorted colour keys: off[c] = first position with key >= c for c in [0, 64]; off[65] = n.
-// Group 64 is the serial overflow group.
-__global__ void s2bGroupOffsets(const int* counts, int which, const unsigned char* sortedKeys, int* off)
+__device__ __forceinline__ int s2bLowerBoundKey(const unsigned short* keys, int n, int key)
 {
-	int n = counts[which];
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i > n)
+	int lo = 0, hi = n;
+	while (lo < hi)
 	{
+		int mid = (lo + hi) >> 1;
+		if ((int)keys[mid] < key)
+		{
+			lo = mid + 1;
+		}
+		else
+		{
+			hi = mid;
+		}
+	}
+	return lo;
+}
+
+// Offset tables from the sorted keys (binary searches; entries beyond the live count hold S2B_KEY_DEAD):
+//   regOff[r * 65 + c]  = first row of (region r, colour c), c = 64: end of region r
+//   groupOff[g]         = first row of device-wide group g < 64; [64] = overflow group; [65] = live count
+__global__ void s2bBuildTablesKernel(int regions, const unsigned short* jSorted, int jN, const unsigned short* cSorted, int cN, int* jRegOff,
+									 int* cRegOff, int* jGroupOff, int* cGroupOff)
+{
+	int e = blockIdx.x * blockDim.x + threadIdx.x;
+	int regEntries = regions * S2B_REG_STRIDE;
+	if (e < regEntries)
+	{
+		int r = e / S2B_REG_STRIDE, c = e % S2B_REG_STRIDE;
+		int key = r * S2B_MAX_COLORS + c; // c == 64: first key of the next region
+		jRegOff[e] = s2bLowerBoundKey(jSorted, jN, key);
+		cRegOff[e] = s2bLowerBoundKey(cSorted, cN, key);
 		return;
 	}
-	int prev = i == 0 ? -1 : (sortedKeys[i - 1] == S2B_OVERFLOW_KEY ? S2B_MAX_COLORS : sortedKeys[i - 1]);
-	int cur = i == n ? S2B_MAX_COLORS + 1 : (sortedKeys[i] == S2B_OVERFLOW_KEY ? S2B_MAX_COLORS : sortedKeys[i]);
-	for (int c = prev + 1; c <= cur; ++c)
+	int g = e - regEntries;
+	if (g <= S2B_MAX_COLORS + 1)
 	{
-		off[c] = i;
+		int key = g < S2B_MAX_COLORS ? S2B_KEY_CUT + g : (g == S2B_MAX_COLORS ? S2B_KEY_OVERFLOW : S2B_KEY_DEAD);
+		jGroupOff[g] = s2bLowerBoundKey(jSorted, jN, key);
+		cGroupOff[g] = s2bLowerBoundKey(cSorted, cN, key);
 	}
 }
 
 __global__ void s2bFinishGroups(int* counts, const int* cOff, const int* jOff)
 {
-	// number of colour groups actually used (largest non-empty colour + 1)
+	// number of device-wide groups actually used (largest non-empty one + 1)
 	int groups = 0;
 	for (int c = 0; c < S2B_MAX_COLORS; ++c)
 	{
@@ -521,282 +825,238 @@ __global__ void s2bBuildSources(const int* counts, const int* cPerm, const int* 
 	}
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Programs: every solver variant is a short list of PASSES over bodies, joint constraints and contact constraints.
-// The list is built on the host from the variant's driver in the reference (citations in buildProgram) and executed
-// either by ONE persistent cooperative kernel (grid barrier after every dependent phase) or launch by launch.
-// ---------------------------------------------------------------------------------------------------------------
+// ---- building the sorted incidence lists (once per step, after the solve order is known) --------------------------
 
-enum PassKind
+// value of an item in the per-body sort: high word = (group << 1 | isContact), low word = the incidence entry without its
+// side bit, whose top bits are the stream position t. Sorting the 64-bit values orders by (group, joints first, t).
+__global__ void s2bItemOrderKernel(const int* counts, const int* cPerm, const int* jPerm, const int* cGroupOff, const int* jGroupOff,
+								   int tableEntries, unsigned long long* itemVal)
 {
-	PASS_BODY = 0,	// every body slot, no ordering
-	PASS_FLAT = 1,	// every joint / contact constraint, no ordering between them (prepare, store)
-	PASS_GROUP = 2, // Gauss-Seidel: groups in order, a barrier after each, then the serial overflow group
-};
-
-enum BodyOp
-{
-	BOP_NONE = 0,
-	BOP_INTEGRATE_VELOCITIES,
-	BOP_INTEGRATE_POSITIONS,
-	BOP_FINALIZE_POSITIONS,
-	BOP_JACOBI_RESET,
-	BOP_JACOBI_APPLY,
-	BOP_XPBD_INTEGRATE,
-	BOP_XPBD_PROJECT,
-	BOP_XPBD_FINALIZE,
-	BOP_INTEGRATE_VELOCITIES_WARM,		 // s2IntegrateVelocities + warm start gathered per body (warm_gather.cuh)
-	BOP_INTEGRATE_VELOCITIES_WARM_FIXED, // same with the prepare-time anchors of SoftStep
-};
-
-enum ContactOp
-{
-	COP_NONE = 0,
-	COP_PREPARE,		// s2PrepareContacts_PGS / _Soft / local TGS_NGS flavour: same arithmetic, optional columns differ
-	COP_PREPARE_COLD,	// XPBD: impulses always start at zero
-	COP_PREPARE_STICKY,
-	COP_PREPARE_BLOCK,
-	COP_WARM_START,
-	COP_WARM_START_FIXED,
-	COP_TGS_SOFT_BIAS,
-	COP_TGS_SOFT_RELAX,
-	COP_PGS_BAUMGARTE,
-	COP_PGS,
-	COP_PGS_SOFT_BIAS,
-	COP_PGS_SOFT_RELAX,
-	COP_JACOBI_BIAS,
-	COP_JACOBI_RELAX,
-	COP_SOFTSTEP_BIAS,
-	COP_SOFTSTEP_RELAX,
-	COP_TGS,
-	COP_NGS,
-	COP_STICKY_BIAS,
-	COP_STICKY_RELAX,
-	COP_XPBD_POSITIONS,
-	COP_XPBD_VELOCITIES,
-	COP_BLOCK_VELOCITY,
-	COP_BLOCK_POSITION,
-	COP_STORE,
-	COP_STORE_SCALED, // XPBD stores impulse * inv_h
-};
-
-enum JointOp
-{
-	JOP_NONE = 0,
-	JOP_PREPARE_SOFT_WARM,	// s2PrepareJoint_Soft(..., warmStart = true)
-	JOP_PREPARE_SOFT_FLAG,	// s2PrepareJoint_Soft(..., context->warmStart)
-	JOP_PREPARE_RIGID_FLAG, // s2PrepareJoint(..., context->warmStart)
-	JOP_PREPARE_RIGID_COLD, // s2PrepareJoint(..., false)
-	JOP_PREPARE_XPBD,
-	JOP_WARM_START,
-	JOP_SOFT_BIAS,
-	JOP_SOFT_RELAX,
-	JOP_BAUMGARTE_BIAS,
-	JOP_BAUMGARTE_RELAX,
-	JOP_RIGID,
-	JOP_POSITION,
-	JOP_XPBD,
-	JOP_STORE,
-};
-
-struct PassDesc
-{
-	unsigned char kind, bodyOp, jointOp, contactOp;
-};
-
-#define S2B_MAX_SEGMENTS 6
-#define S2B_MAX_SEGMENT_PASSES 8
-
-// a program = segments executed in order, each a list of passes repeated `repeat` times
-struct Program
-{
-	int segmentCount;
-	int repeat[S2B_MAX_SEGMENTS];
-	int passCount[S2B_MAX_SEGMENTS];
-	PassDesc passes[S2B_MAX_SEGMENTS][S2B_MAX_SEGMENT_PASSES];
-};
-
-struct PassPtrs
-{
-	const int* jointSlots;
-	const int* jPerm;
-};
-
-__device__ __forceinline__ void s2bRunBodyOp(int op, const SolveArgs& a, int i)
-{
-	switch (op)
+	int nJ = counts[CNT_JOINTS], nC = counts[CNT_CONTACTS];
+	int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= nJ + nC)
 	{
-		case BOP_INTEGRATE_VELOCITIES:
-			s2bIntegrateVelocity(a, i, a.ctx.h);
-			break;
-		case BOP_INTEGRATE_POSITIONS:
-			s2bIntegratePosition(a, i, a.ctx.h);
-			break;
-		case BOP_FINALIZE_POSITIONS:
-			s2bFinalizePosition(a, i);
-			break;
-		case BOP_JACOBI_RESET:
-			s2bJacobiReset(a, i);
-			break;
-		case BOP_JACOBI_APPLY:
-			s2bJacobiApply(a, i);
-			break;
-		case BOP_XPBD_INTEGRATE:
-			s2bXpbdIntegrate(a, i, a.ctx.h);
-			break;
-		case BOP_XPBD_PROJECT:
-			s2bXpbdProjectVelocity(a, i, a.xpbdInvH);
-			break;
-		case BOP_INTEGRATE_VELOCITIES_WARM:
-			s2bIntegrateVelocityWarm<false>(a, i, a.ctx.h);
-			break;
-		case BOP_INTEGRATE_VELOCITIES_WARM_FIXED:
-			s2bIntegrateVelocityWarm<true>(a, i, a.ctx.h);
-			break;
-		case BOP_XPBD_FINALIZE:
-			s2bXpbdFinalize(a, i);
-			break;
-		default:
-			break;
+		return;
 	}
+	bool isContact = p >= nJ;
+	int t = isContact ? p - nJ : p;
+	const int* off = isContact ? cGroupOff : jGroupOff;
+	// largest g in [0, tableEntries) with off[g] <= t
+	int lo = 0, hi = tableEntries - 1;
+	while (lo < hi)
+	{
+		int mid = (lo + hi + 1) >> 1;
+		if (off[mid] <= t)
+		{
+			lo = mid;
+		}
+		else
+		{
+			hi = mid - 1;
+		}
+	}
+	int natural = isContact ? cPerm[t] : jPerm[t];
+	int item = isContact ? nJ + natural : natural;
+	unsigned long long key = ((unsigned long long)(unsigned)((lo << 1) | (isContact ? 1 : 0))) << 32;
+	unsigned entry = ((unsigned)t << 2) | (isContact ? S2B_INC_CONTACT : 0);
+	itemVal[item] = key | entry;
 }
 
-__device__ __forceinline__ void s2bRunContactOp(int op, const SolveArgs& a, int t)
+// The same from the 16-bit solve-order keys of the colour schedule (solver.cu, s2bMakeSortKeys): the key of an item IS its
+// group in serial order (region x colour, then cut colours, then the overflow group).
+__global__ void s2bItemOrderFromKeysKernel(const int* counts, const int* cPerm, const int* jPerm, const unsigned short* jKeys,
+										   const unsigned short* cKeys, unsigned long long* itemVal)
 {
-	float inv_h = a.ctx.inv_h;
-	switch (op)
+	int nJ = counts[CNT_JOINTS], nC = counts[CNT_CONTACTS];
+	int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= nJ + nC)
 	{
-		case COP_PREPARE:
-			s2bPrepareContact<PREPARE_SOFT>(a, t);
-			break;
-		case COP_PREPARE_COLD:
-			s2bPrepareContact<PREPARE_COLD>(a, t);
-			break;
-		case COP_PREPARE_STICKY:
-			s2bPrepareContactSticky(a, t);
-			break;
-		case COP_PREPARE_BLOCK:
-			s2bPrepareContactBlock(a, t);
-			break;
-		case COP_BLOCK_VELOCITY:
-			s2bSolveContactBlockVelocity(a, t);
-			break;
-		case COP_BLOCK_POSITION:
-			s2bSolveContactBlockPosition(a, t);
-			break;
-		case COP_WARM_START:
-			s2bWarmStartContact(a, t);
-			break;
-		case COP_WARM_START_FIXED:
-			s2bWarmStartContactFixed(a, t);
-			break;
-		case COP_TGS_SOFT_BIAS:
-			s2bSolveContactTgsSoft(a, t, inv_h, true);
-			break;
-		case COP_TGS_SOFT_RELAX:
-			s2bSolveContactTgsSoft(a, t, inv_h, false);
-			break;
-		case COP_PGS_BAUMGARTE:
-			s2bSolveContactFixed<0>(a, t, inv_h, true);
-			break;
-		case COP_PGS:
-			s2bSolveContactPgs(a, t);
-			break;
-		case COP_PGS_SOFT_BIAS:
-			s2bSolveContactFixed<1>(a, t, inv_h, true);
-			break;
-		case COP_PGS_SOFT_RELAX:
-			s2bSolveContactFixed<1>(a, t, inv_h, false);
-			break;
-		case COP_JACOBI_BIAS:
-			s2bSolveContactFixed<2>(a, t, inv_h, true);
-			break;
-		case COP_JACOBI_RELAX:
-			s2bSolveContactFixed<2>(a, t, inv_h, false);
-			break;
-		case COP_SOFTSTEP_BIAS:
-			s2bSolveContactSubstep<0>(a, t, inv_h, true);
-			break;
-		case COP_SOFTSTEP_RELAX:
-			s2bSolveContactSubstep<0>(a, t, inv_h, false);
-			break;
-		case COP_TGS:
-			s2bSolveContactSubstep<1>(a, t, inv_h, true);
-			break;
-		case COP_NGS:
-			s2bSolveContactNgs(a, t);
-			break;
-		case COP_STICKY_BIAS:
-			s2bSolveContactSticky(a, t, inv_h, true);
-			break;
-		case COP_STICKY_RELAX:
-			s2bSolveContactSticky(a, t, inv_h, false);
-			break;
-		case COP_XPBD_POSITIONS:
-			s2bSolveContactXpbdPositions(a, t, a.ctx.h);
-			break;
-		case COP_XPBD_VELOCITIES:
-			s2bSolveContactXpbdVelocities(a, t, a.ctx.h);
-			break;
-		case COP_STORE:
-			s2bStoreContactImpulses(a, t, 1.0f);
-			break;
-		case COP_STORE_SCALED:
-			s2bStoreContactImpulses(a, t, a.xpbdInvH);
-			break;
-		default:
-			break;
+		return;
 	}
+	bool isContact = p >= nJ;
+	int t = isContact ? p - nJ : p;
+	int natural = isContact ? cPerm[t] : jPerm[t];
+	int item = isContact ? nJ + natural : natural;
+	unsigned groupKey = isContact ? cKeys[natural] : jKeys[natural];
+	unsigned long long key = ((unsigned long long)((groupKey << 1) | (isContact ? 1u : 0u))) << 32;
+	unsigned entry = ((unsigned)t << 2) | (isContact ? S2B_INC_CONTACT : 0);
+	itemVal[item] = key | entry;
 }
 
-__device__ __forceinline__ void s2bRunJointOp(int op, const SolveArgs& a, int t, const PassPtrs& p)
+// Besides the sorted list this also hands every constraint its ORDINAL in the lists of its two bodies (k-th of d incident
+// items): what the ticketed Gauss-Seidel passes (solver.cu, "dataflow") wait on instead of a grid barrier.
+__global__ void s2bSortIncidenceKernel(int bodyCapacity, const int* adjStart, const int* adj, const int2* itemBodies,
+									   const unsigned long long* itemVal, unsigned long long* work, int* incList, int2* cFlowA,
+									   int2* cFlowB, int2* jFlowA, int2* jFlowB, int* heavyBodies)
 {
-	switch (op)
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= bodyCapacity)
 	{
-		case JOP_PREPARE_SOFT_WARM:
-			s2bPrepareJoint<JPREP_SOFT>(a, t, p.jointSlots[p.jPerm[t]], true);
-			break;
-		case JOP_PREPARE_SOFT_FLAG:
-			s2bPrepareJoint<JPREP_SOFT>(a, t, p.jointSlots[p.jPerm[t]], a.ctx.warmStart != 0);
-			break;
-		case JOP_PREPARE_RIGID_FLAG:
-			s2bPrepareJoint<JPREP_RIGID>(a, t, p.jointSlots[p.jPerm[t]], a.ctx.warmStart != 0);
-			break;
-		case JOP_PREPARE_RIGID_COLD:
-			s2bPrepareJoint<JPREP_RIGID>(a, t, p.jointSlots[p.jPerm[t]], false);
-			break;
-		case JOP_PREPARE_XPBD:
-			s2bPrepareJoint<JPREP_XPBD>(a, t, p.jointSlots[p.jPerm[t]], false);
-			break;
-		case JOP_WARM_START:
-			s2bWarmStartJoint(a, t);
-			break;
-		case JOP_SOFT_BIAS:
-			s2bSolveJointSoft(a, t, a.ctx.h, a.ctx.inv_h, true);
-			break;
-		case JOP_SOFT_RELAX:
-			s2bSolveJointSoft(a, t, a.ctx.h, a.ctx.inv_h, false);
-			break;
-		case JOP_BAUMGARTE_BIAS:
-			s2bSolveJointBaumgarte(a, t, a.ctx.h, a.ctx.inv_h, true);
-			break;
-		case JOP_BAUMGARTE_RELAX:
-			s2bSolveJointBaumgarte(a, t, a.ctx.h, a.ctx.inv_h, false);
-			break;
-		case JOP_RIGID:
-			s2bSolveJointRigid(a, t, a.ctx.h);
-			break;
-		case JOP_POSITION:
-			s2bSolveJointPosition(a, t);
-			break;
-		case JOP_XPBD:
-			s2bSolveJointXpbd(a, t);
-			break;
-		case JOP_STORE:
-			s2bStoreJointImpulses(a, t);
-			break;
-		default:
-			break;
+		return;
+	}
+	int begin = adjStart[b], end = adjStart[b + 1];
+	int n = end - begin;
+	if (n == 0)
+	{
+		return;
+	}
+	if (heavyBodies != nullptr && n > S2B_HEAVY_DEGREE)
+	{
+		heavyBodies[1 + atomicAdd(heavyBodies, 1)] = b; // the list holds bodyCapacity entries
+	}
+	if (n <= 8)
+	{
+		// the common case (a box touches ~6 others): sort in registers, touch global memory once per entry
+		unsigned long long r[8];
+#pragma unroll
+		for (int k = 0; k < 8; ++k)
+		{
+			r[k] = ~0ull;
+			if (k < n)
+			{
+				int item = adj[begin + k];
+				unsigned long long val = itemVal[item];
+				if (itemBodies[item].x != b)
+				{
+					val |= S2B_INC_SIDE_B;
+				}
+				r[k] = val;
+			}
+		}
+		// odd-even transposition network on 8 keys (padding keys are the largest value and stay at the end)
+#pragma unroll
+		for (int pass = 0; pass < 8; ++pass)
+		{
+#pragma unroll
+			for (int k = pass & 1; k + 1 < 8; k += 2)
+			{
+				unsigned long long lo = r[k] < r[k + 1] ? r[k] : r[k + 1];
+				unsigned long long hi = r[k] < r[k + 1] ? r[k + 1] : r[k];
+				r[k] = lo;
+				r[k + 1] = hi;
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < 8; ++k)
+		{
+			if (k < n)
+			{
+				int e = (int)(unsigned)(r[k] & 0xFFFFFFFFull);
+				incList[begin + k] = e;
+				if (cFlowA != nullptr)
+				{
+					int t = e >> 2;
+					int2 ticket = make_int2(k, n);
+					if (e & S2B_INC_CONTACT)
+					{
+						((e & S2B_INC_SIDE_B) ? cFlowB : cFlowA)[t] = ticket;
+					}
+					else
+					{
+						((e & S2B_INC_SIDE_B) ? jFlowB : jFlowA)[t] = ticket;
+					}
+				}
+			}
+		}
+		return;
+	}
+	unsigned long long* v = work + begin;
+	for (int k = 0; k < n; ++k)
+	{
+		int item = adj[begin + k];
+		unsigned long long val = itemVal[item];
+		if (itemBodies[item].x != b)
+		{
+			val |= S2B_INC_SIDE_B;
+		}
+		v[k] = val;
+	}
+	if (n <= 24)
+	{
+		for (int k = 1; k < n; ++k)
+		{
+			unsigned long long x = v[k];
+			int m = k - 1;
+			while (m >= 0 && v[m] > x)
+			{
+				v[m + 1] = v[m];
+				m -= 1;
+			}
+			v[m + 1] = x;
+		}
+	}
+	else
+	{
+		// heap sort: bodies touching hundreds of constraints (a container wall) stay O(n log n)
+		for (int start = n / 2 - 1; start >= 0; --start)
+		{
+			int root = start;
+			for (;;)
+			{
+				int child = 2 * root + 1;
+				if (child >= n)
+				{
+					break;
+				}
+				if (child + 1 < n && v[child] < v[child + 1])
+				{
+					child += 1;
+				}
+				if (v[root] >= v[child])
+				{
+					break;
+				}
+				unsigned long long tmp = v[root];
+				v[root] = v[child];
+				v[child] = tmp;
+				root = child;
+			}
+		}
+		for (int last = n - 1; last > 0; --last)
+		{
+			unsigned long long tmp = v[0];
+			v[0] = v[last];
+			v[last] = tmp;
+			int root = 0;
+			for (;;)
+			{
+				int child = 2 * root + 1;
+				if (child >= last)
+				{
+					break;
+				}
+				if (child + 1 < last && v[child] < v[child + 1])
+				{
+					child += 1;
+				}
+				if (v[root] >= v[child])
+				{
+					break;
+				}
+				unsigned long long t2 = v[root];
+				v[root] = v[child];
+				v[child] = t2;
+				root = child;
+			}
+		}
+	}
+	for (int k = 0; k < n; ++k)
+	{
+		int e = (int)(unsigned)(v[k] & 0xFFFFFFFFull);
+		incList[begin + k] = e;
+		if (cFlowA != nullptr)
+		{
+			int t = e >> 2;
+			int2 ticket = make_int2(k, n);
+			if (e & S2B_INC_CONTACT)
+			{
+				((e & S2B_INC_SIDE_B) ? cFlowB : cFlowA)[t] = ticket;
+			}
+			else
+			{
+				((e & S2B_INC_SIDE_B) ? jFlowB : jFlowA)[t] = ticket;
+			}
+		}
 	}
 }
 
@@ -921,372 +1181,6 @@ __global__ void s2bSerialPassKernel(SolveArgs a, PassPtrs p, int jointOp, int co
 			for (int t = cBegin; t < cEnd; ++t)
 			{
 				s2bRunContactOp(contactOp, a, t);
-			}
-		}
-	}
-}
-
-// ---- the persistent cooperative kernel ------------------------------------------------------------------------
-
-__device__ __forceinline__ void s2bGridBodyPass(int bodyOp, const SolveArgs& a)
-{
-	int stride = gridDim.x * blockDim.x;
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.bodies.capacity; i += stride)
-	{
-		s2bRunBodyOp(bodyOp, a, i);
-	}
-}
-
-__device__ __forceinline__ void s2bGridFlatPass(int jointOp, int contactOp, const SolveArgs& a, const PassPtrs& p)
-{
-	int nJ = a.counts[CNT_JOINTS], nC = a.counts[CNT_CONTACTS];
-	int stride = gridDim.x * blockDim.x;
-	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nJ + nC; t += stride)
-	{
-		if (t < nJ)
-		{
-			if (jointOp != JOP_NONE)
-			{
-				s2bRunJointOp(jointOp, a, t, p);
-			}
-		}
-		else if (contactOp != COP_NONE)
-		{
-			s2bRunContactOp(contactOp, a, t - nJ);
-		}
-	}
-}
-
-// L1 warm-up for the serial overflow walk: request (prefetch.global.L1) every line an op on this constraint may read
-__device__ __forceinline__ void s2bPrefetchL1(const void* ptr)
-{
-	asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
-}
-
-__device__ __forceinline__ void s2bTouchBody(const SolveArgs& a, int i)
-{
-	s2bPrefetchL1(a.bodies.vel + i);
-	s2bPrefetchL1(a.bodies.pose + i);
-	s2bPrefetchL1(a.bodies.pos + i);
-	if (a.bodies.aux0 != nullptr)
-	{
-		s2bPrefetchL1(a.bodies.aux0 + i);
-	}
-}
-
-__device__ __forceinline__ void s2bTouchContact(const SolveArgs& a, int t)
-{
-	int2 idx = a.cc.idx[t];
-	s2bPrefetchL1(a.cc.nf + t);
-	s2bPrefetchL1(a.cc.src + t);
-#pragma unroll
-	for (int j = 0; j < 2; ++j)
-	{
-		s2bPrefetchL1(a.cc.anchor[j] + t);
-		s2bPrefetchL1(a.cc.pm[j] + t);
-		s2bPrefetchL1(a.cc.lambda[j] + t);
-		if (a.cc.r0[j] != nullptr)
-		{
-			s2bPrefetchL1(a.cc.r0[j] + t);
-		}
-		if (a.cc.sep[j] != nullptr)
-		{
-			s2bPrefetchL1(a.cc.sep[j] + t);
-		}
-		if (a.cc.fanchor[j] != nullptr)
-		{
-			s2bPrefetchL1(a.cc.fanchor[j] + t);
-			s2bPrefetchL1(a.cc.tsep[j] + t);
-		}
-	}
-	s2bTouchBody(a, idx.x);
-	s2bTouchBody(a, idx.y & S2B_CF_INDEX_MASK);
-}
-
-__device__ __forceinline__ void s2bTouchJoint(const SolveArgs& a, int t)
-{
-	int4 head = a.jc.head[t];
-	s2bPrefetchL1(a.jc.anchor + t);
-	s2bPrefetchL1(a.jc.mass + t);
-	s2bPrefetchL1(a.jc.d0ax + t);
-	s2bPrefetchL1(a.jc.lim + t);
-	s2bPrefetchL1(a.jc.motor + t);
-	s2bPrefetchL1(a.jc.coef + t);
-	s2bPrefetchL1(a.jc.pivot + t);
-	s2bPrefetchL1(a.jc.imp + t);
-	s2bPrefetchL1(a.jc.limp + t);
-	if (head.y >= 0)
-	{
-		s2bTouchBody(a, head.y);
-	}
-	s2bTouchBody(a, head.z);
-}
-
-// diagnostic time stamps (s2b_set_solve_trace): code = what just finished (pass kind << 8 | op), stamped by one thread
-__device__ __forceinline__ void s2bTrace(const SolveArgs& a, int code)
-{
-	if (a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
-	{
-		unsigned long long now;
-		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-		unsigned long long n = a.trace[0];
-		if ((int)n + 1 < a.traceCap)
-		{
-			a.trace[1 + n] = ((unsigned long long)code << 48) | (now & 0xFFFFFFFFFFFFull);
-			a.trace[0] = n + 1;
-		}
-	}
-}
-
-__device__ __forceinline__ void s2bGridGroupPass(int jointOp, int contactOp, const SolveArgs& a, const PassPtrs& p, cg::grid_group& grid)
-{
-	int groups = a.counts[CNT_GROUPS];
-	int stride = gridDim.x * blockDim.x;
-	int tid = blockIdx.x * blockDim.x + threadIdx.x;
-	// (Loading the next group's constraint stream between barrier_arrive and barrier_wait was tried: no gain — the pass
-	// time is the barrier plus the dependent body loads, not the stream loads — and it cost registers. See DESIGN.md.)
-	for (int g = 0; g < groups; ++g)
-	{
-		int jBegin = a.jGroupOff[g], cBegin = a.cGroupOff[g];
-		int nj = jointOp != JOP_NONE ? a.jGroupOff[g + 1] - jBegin : 0;
-		int nc = contactOp != COP_NONE ? a.cGroupOff[g + 1] - cBegin : 0;
-		if (nj + nc == 0)
-		{
-			continue; // uniform: every thread reads the same table
-		}
-		for (int t = tid; t < nj + nc; t += stride)
-		{
-			if (t < nj)
-			{
-				s2bRunJointOp(jointOp, a, jBegin + t, p);
-			}
-			else
-			{
-				s2bRunContactOp(contactOp, a, cBegin + (t - nj));
-			}
-		}
-		grid.sync();
-		s2bTrace(a, (PASS_GROUP << 8) | contactOp);
-	}
-	int ovC = contactOp != COP_NONE ? a.counts[CNT_OVERFLOW_C] : 0;
-	int ovJ = jointOp != JOP_NONE ? a.counts[CNT_OVERFLOW_J] : 0;
-	if (ovC + ovJ > 0)
-	{
-		// The overflow group (constraints of bodies with more neighbours than there are colours — a container wall touching
-		// hundreds of boxes) is inherently sequential: one thread walks it. What can be parallel is the memory: the rest of
-		// block 0 first pulls every line that thread is going to touch into this SM's L1, so the walk pays L1 latency per
-		// item instead of several dependent L2 round trips (measured 3.5 us -> ~0.5 us per item).
-		if (blockIdx.x == 0)
-		{
-			int jBegin = a.jGroupOff[S2B_MAX_COLORS], cBegin = a.cGroupOff[S2B_MAX_COLORS];
-			for (int t = threadIdx.x; t < ovJ + ovC; t += blockDim.x)
-			{
-				if (t < ovJ)
-				{
-					s2bTouchJoint(a, jBegin + t);
-				}
-				else
-				{
-					s2bTouchContact(a, cBegin + (t - ovJ));
-				}
-			}
-			__syncthreads();
-			if (threadIdx.x == 0)
-			{
-				for (int t = 0; t < ovJ; ++t)
-				{
-					s2bRunJointOp(jointOp, a, jBegin + t, p);
-				}
-				for (int t = 0; t < ovC; ++t)
-				{
-					s2bRunContactOp(contactOp, a, cBegin + t);
-				}
-			}
-		}
-		grid.sync();
-	}
-}
-
-// ---- ticketed ("dataflow") Gauss-Seidel pass ------------------------------------------------------------------
-// A grid barrier after every colour costs ~1.2 us plus the tail of the slowest block, ten times per pass; on a 100 k-body
-// scene that is most of the solver's time. What a constraint really has to wait for is only the previous constraint that
-// touched each of its two bodies. Every movable body therefore carries a TICKET = number of incident constraints executed
-// on it so far in this launch; the k-th item of a body's (solve-ordered) incidence list of d items runs in pass m when the
-// ticket reads m * d + k, and sets it to m * d + k + 1 when done (release / acquire at GPU scope). The passes keep the
-// stream order (group-major), so the outcome is bit-identical to the barrier version — the colouring now only decides how
-// much runs concurrently — and the whole Gauss-Seidel sweep needs no grid barrier at all.
-// Progress: every thread walks its items in stream order, an item only waits for items earlier in that order, and all
-// blocks of a cooperative launch are resident, so the earliest unfinished item can always run. The work sits INSIDE the
-// polling loop so that a lane that is ready never waits at a reconvergence point for a lane that is still polling.
-
-#define S2B_FLOW_SPIN_LIMIT (1 << 22)
-
-__device__ __forceinline__ int s2bLoadAcquire(const int* p)
-{
-	int v;
-	asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-
-__device__ __forceinline__ void s2bStoreRelaxed(int* p, int v)
-{
-	asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-template <bool JOINT>
-__device__ __forceinline__ void s2bFlowItem(int op, const SolveArgs& a, const PassPtrs& p, int t, int passIndex)
-{
-	int ia, ib;
-	int2 fa, fb;
-	if (JOINT)
-	{
-		int4 head = a.jc.head[t];
-		ia = head.y;
-		ib = head.z;
-		fa = a.jFlowA[t];
-		fb = a.jFlowB[t];
-	}
-	else
-	{
-		int2 idx = a.cc.idx[t];
-		ia = idx.x;
-		ib = idx.y & S2B_CF_INDEX_MASK;
-		fa = a.cFlowA[t];
-		fb = a.cFlowB[t];
-	}
-	int needA = passIndex * fa.y + fa.x, needB = passIndex * fb.y + fb.x;
-	bool done = false;
-	int spins = 0;
-	while (done == false)
-	{
-		bool ready = true;
-		if (fa.x >= 0)
-		{
-			ready = s2bLoadAcquire(a.bodyTicket + ia) == needA;
-		}
-		if (ready && fb.x >= 0)
-		{
-			ready = s2bLoadAcquire(a.bodyTicket + ib) == needB;
-		}
-		if (ready)
-		{
-			if (JOINT)
-			{
-				s2bRunJointOp(op, a, t, p);
-			}
-			else
-			{
-				s2bRunContactOp(op, a, t);
-			}
-			__threadfence();
-			if (fa.x >= 0)
-			{
-				s2bStoreRelaxed(a.bodyTicket + ia, needA + 1);
-			}
-			if (fb.x >= 0)
-			{
-				s2bStoreRelaxed(a.bodyTicket + ib, needB + 1);
-			}
-			done = true;
-		}
-		else if (a.flowSleepNs > 0)
-		{
-			__nanosleep(a.flowSleepNs);
-		}
-		if (done == false && (++spins > S2B_FLOW_SPIN_LIMIT || ((spins & 1023) == 0 && *(volatile int*)a.flowError != 0)))
-		{
-			// never expected; bail out of the whole launch quickly instead of hanging the device
-			a.flowError[0] = 1;
-			done = true;
-		}
-	}
-}
-
-// joints and contacts of every group in stream order, no barrier; a pass with an op of only one kind still walks the other
-// kind (op NONE) to keep the tickets of its bodies moving
-__device__ __forceinline__ void s2bGridFlowPass(int jointOp, int contactOp, const SolveArgs& a, const PassPtrs& p, int passIndex)
-{
-	int groups = a.counts[CNT_GROUPS];
-	int stride = gridDim.x * blockDim.x;
-	int tid = blockIdx.x * blockDim.x + threadIdx.x;
-	int ovC = a.counts[CNT_OVERFLOW_C], ovJ = a.counts[CNT_OVERFLOW_J];
-	for (int g = 0; g <= groups; ++g)
-	{
-		bool overflow = g == groups;
-		if (overflow && ovC + ovJ == 0)
-		{
-			break;
-		}
-		int table = overflow ? S2B_MAX_COLORS : g;
-		int jBegin = a.jGroupOff[table], cBegin = a.cGroupOff[table];
-		int nj = overflow ? ovJ : a.jGroupOff[g + 1] - jBegin;
-		int nc = overflow ? ovC : a.cGroupOff[g + 1] - cBegin;
-		for (int t = tid; t < nj; t += stride)
-		{
-			s2bFlowItem<true>(jointOp, a, p, jBegin + t, passIndex);
-		}
-		for (int t = tid; t < nc; t += stride)
-		{
-			s2bFlowItem<false>(contactOp, a, p, cBegin + t, passIndex);
-		}
-	}
-}
-
-// The whole solver stage of one step: the variant's program from prepare to store, one launch.
-__global__ void __launch_bounds__(S2B_BLOCK) s2bPersistentSolve(SolveArgs a, PassPtrs p, Program prog)
-{
-	cg::grid_group grid = cg::this_grid();
-	s2bTrace(a, 0xFFFF);
-	bool flow = a.bodyTicket != nullptr;
-	bool pendingFlow = false; // a ticketed pass has run since the last grid barrier
-	int flowPasses = 0;
-	for (int s = 0; s < prog.segmentCount; ++s)
-	{
-		for (int r = 0; r < prog.repeat[s]; ++r)
-		{
-			for (int k = 0; k < prog.passCount[s]; ++k)
-			{
-				PassDesc pass = prog.passes[s][k];
-				if (pass.kind == PASS_GROUP)
-				{
-					if (flow)
-					{
-						s2bGridFlowPass(pass.jointOp, pass.contactOp, a, p, flowPasses);
-						flowPasses += 1;
-						pendingFlow = true;
-					}
-					else
-					{
-						s2bGridGroupPass(pass.jointOp, pass.contactOp, a, p, grid);
-					}
-					continue;
-				}
-				if (pendingFlow)
-				{
-					grid.sync(); // body and flat passes read what the ticketed passes wrote
-					pendingFlow = false;
-				}
-				if (pass.kind == PASS_BODY)
-				{
-					s2bGridBodyPass(pass.bodyOp, a);
-					if (a.heavyBodies != nullptr)
-					{
-						if (pass.bodyOp == BOP_INTEGRATE_VELOCITIES_WARM)
-						{
-							s2bGatherHeavyBodies<false>(a, a.ctx.h);
-						}
-						else if (pass.bodyOp == BOP_INTEGRATE_VELOCITIES_WARM_FIXED)
-						{
-							s2bGatherHeavyBodies<true>(a, a.ctx.h);
-						}
-					}
-				}
-				else
-				{
-					s2bGridFlatPass(pass.jointOp, pass.contactOp, a, p);
-				}
-				grid.sync();
-				s2bTrace(a, (pass.kind << 8) | (pass.kind == PASS_BODY ? pass.bodyOp : pass.contactOp));
 			}
 		}
 	}
@@ -1752,96 +1646,108 @@ static void buildWavefront(s2bWorld* w, SolverScratch* s, int nJ, int nC, HostPl
 	S2B_CHECK(cudaStreamSynchronize(st));
 }
 
-void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
+// Gate of the schedule inside the stage's CUDA graph: run the gather + schedule sub-graph only when the set of live
+// constraints changed since it was last built (flag raised by the narrow phase when a manifold gains its first or loses
+// its last point, by body rows whose validity / movability changed, by joint uploads; anything the host knows about —
+// a replaced contact table, other settings — changes the graph signature instead and is rebuilt eagerly).
+__global__ void s2bScheduleGate(cudaGraphConditionalHandle handle, int* dirty)
 {
-	SolverScratch* s = s2bGetSolverScratch(w);
-	cudaStream_t st = w->stream;
-	s2bStepContext ctx = *ctxIn;
+	int v = *dirty;
+	*dirty = 0;
+	cudaGraphSetConditional(handle, v != 0 ? 1u : 0u);
+}
 
-	if (solverType < 0 || solverType > 9)
+// Everything one solver stage needs to know on the host before anything is enqueued.
+struct SolvePlan
+{
+	int solverType = 0;
+	s2bStepContext ctx;
+	Program program;
+	int countedPasses = 0;
+	bool gatherWarm = false, dataflow = false, needInc = false, usePersistent = false;
+	int contactCount = 0, jointCap = 0, bodyCap = 0, maxItems = 0;
+	size_t nC = 1, nJ = 1, nI = 1;
+	VariantColumns cols;
+	int threads = S2B_BLOCK;
+	int grid = 1;	 // blocks of the persistent kernel
+	int regions = 0; // region-local schedule: == grid, or 0
+	HostPlan host;	 // launch-by-launch / wavefront modes
+	int hostNC = 0, hostNJ = 0;
+};
+
+static void verifyProgram(int solverType, const Program& prog)
+{
+	for (int s = 0; s < prog.segmentCount; ++s)
 	{
-		fprintf(stderr, "solver2d-b200: solver type %d is not implemented on the device — there is no CPU fallback\n", solverType);
-		abort();
-	}
-	if (solverType == 9 && (ctx.iterations == 0 || ctx.dt == 0.0f))
-	{
-		return; // s2Solve_XPBD leaves early (reference src/solve_xpbd.c:345-353)
-	}
-	// ---- CUDA graph of the stage ----
-	// A steady scene runs the SAME ~30 launches with the SAME arguments every step (counts live in device memory). The
-	// second consecutive step with an unchanged signature is captured into a graph; after that the stage is one
-	// cudaGraphLaunch until the signature changes (a contact table rebuilt by the pair pass, a re-allocation, other step
-	// parameters). S2B_GRAPH=0 disables it.
-	bool graphable = w->schedule == S2B_SCHEDULE_COLOR && w->persistent != 0 && w->coopSupported != 0 && s->graphDisabled == false &&
-					 s->traceCap == 0 && w->contactCount + w->jointCap > 0 && w->useGraph != 0;
-	std::vector<unsigned char> sig;
-	if (graphable)
-	{
-		auto put = [&sig](const void* ptr, size_t n) {
-			const unsigned char* b = (const unsigned char*)ptr;
-			sig.insert(sig.end(), b, b + n);
-		};
-		unsigned long long epoch = s2bAllocEpoch();
-		int ints[] = {solverType, w->contactCount, w->jointCap, w->bodyCap, w->cur, w->maxColors, w->gatherWarm, w->dataflow, w->sticky ? 1 : 0};
-		put(&ctx, sizeof(ctx));
-		put(ints, sizeof(ints));
-		put(&epoch, sizeof(epoch));
-		put(&w->contactTableVersion, sizeof(w->contactTableVersion));
-		put(&w->gravity, sizeof(w->gravity));
-		if (s->graphExec != nullptr && sig == s->graphSig)
+		for (int k = 0; k < prog.passCount[s]; ++k)
 		{
-			S2B_CHECK(cudaGraphLaunch(s->graphExec, st));
-			w->kernelLaunches += s->graphLaunches;
-			w->solveKernelTimed = true;
-			s->hostCountsValid = false;
-			s->graphReplays += 1;
-			return;
-		}
-	}
-	if (graphable && s->graphExec != nullptr && getenv("S2B_GRAPH_DEBUG") != nullptr)
-	{
-		// which part of the signature moved? layout: ctx | 9 ints | epoch | gravity
-		size_t n = std::min(sig.size(), s->graphSig.size());
-		for (size_t k = 0; k < n; ++k)
-		{
-			if (sig[k] != s->graphSig[k])
+			PassDesc d = prog.passes[s][k];
+			bool ok = (d.bodyOp == BOP_NONE || s2bUsesBodyOp(solverType, d.bodyOp)) && (d.jointOp == JOP_NONE || s2bUsesJointOp(solverType, d.jointOp)) &&
+					  (d.contactOp == COP_NONE || s2bUsesContactOp(solverType, d.contactOp));
+			if (ok == false)
 			{
-				fprintf(stderr, "solver2d-b200: graph signature changed at byte %zu (ctx %zu B, ints from %zu, epoch at %zu)\n", k, sizeof(ctx),
-						sizeof(ctx), sizeof(ctx) + 9 * sizeof(int));
-				break;
+				fprintf(stderr, "solver2d-b200: internal error: program of solver %d uses an operation its kernel was built without (%d/%d/%d)\n",
+						solverType, d.bodyOp, d.jointOp, d.contactOp);
+				abort();
 			}
 		}
 	}
-	bool capturing = graphable && sig == s->graphCandidate;
-	int launchesBefore = w->kernelLaunches;
-	if (capturing)
-	{
-		if (s->graphExec != nullptr)
-		{
-			cudaGraphExecDestroy(s->graphExec);
-			s->graphExec = nullptr;
-		}
-		S2B_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-	}
-	s->graphCandidate = sig;
-	w->capturing = capturing;
+}
 
-	int countedPasses = 0;
+// sizes, modes and scratch of this stage (host only; may allocate, never inside a capture that matters: a re-allocation
+// bumps the allocation epoch and with it the graph signature)
+static void planSolve(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
+{
+	cudaStream_t st = w->stream;
+	int solverType = pl.solverType;
+	const s2bStepContext& ctx = pl.ctx;
 	// per-sub-step warm starting as a per-body gather (warm_gather.cuh); S2B_WARM_GATHER=0 keeps the grouped passes
-	bool gatherWarm = w->gatherWarm != 0 && ctx.warmStart != 0 && (solverType == 7 || solverType == 5 || solverType == 8);
-	Program program = buildProgram(solverType, ctx, gatherWarm, &countedPasses);
-	// ticketed Gauss-Seidel passes instead of a grid barrier per colour (persistent kernel only); S2B_DATAFLOW=0 disables
-	bool dataflow = w->dataflow != 0 && w->persistent != 0 && w->coopSupported != 0;
-	bool needInc = gatherWarm || dataflow;
+	pl.gatherWarm = w->gatherWarm != 0 && ctx.warmStart != 0 && (solverType == 7 || solverType == 5 || solverType == 8);
+	pl.program = buildProgram(solverType, ctx, pl.gatherWarm, &pl.countedPasses);
+	verifyProgram(solverType, pl.program);
+	pl.usePersistent = w->persistent != 0 && w->coopSupported != 0;
+	// ticketed Gauss-Seidel passes instead of grid barriers (persistent kernel only, experimental); S2B_DATAFLOW=1 enables
+	pl.dataflow = w->dataflow != 0 && pl.usePersistent;
+	pl.needInc = pl.gatherWarm || pl.dataflow;
+	pl.contactCount = w->contactCount;
+	pl.jointCap = w->jointCap;
+	pl.bodyCap = w->bodyCap;
+	pl.maxItems = pl.contactCount + pl.jointCap;
+	pl.cols = columnsFor(solverType);
+	int contactCount = pl.contactCount, jointCap = pl.jointCap, bodyCap = pl.bodyCap, maxItems = pl.maxItems;
 
-	int contactCount = w->contactCount;
-	int jointCap = w->jointCap;
-	int bodyCap = w->bodyCap;
-	int maxItems = contactCount + jointCap;
-	VariantColumns cols = columnsFor(solverType);
+	// grid of the persistent kernel
+	pl.threads = S2B_BLOCK;
+	pl.grid = 1;
+	if (pl.usePersistent)
+	{
+		if (w->solveGrid == 0 || w->solveGridSolver != solverType)
+		{
+			int blocksPerSm = 0;
+			S2B_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, s2bPersistentKernel(solverType), S2B_BLOCK, 0));
+			const char* env = getenv("S2B_SOLVE_BLOCKS_PER_SM");
+			int want = env != nullptr ? atoi(env) : 2;
+			w->solveGrid = w->smCount * std::min(std::max(blocksPerSm, 1), std::max(want, 1));
+			w->solveGridSolver = solverType;
+		}
+		const char* env = getenv("S2B_SOLVE_THREADS");
+		if (env != nullptr && atoi(env) >= 32 && atoi(env) <= S2B_BLOCK)
+		{
+			pl.threads = atoi(env) & ~31;
+		}
+		int wanted = std::max(gridFor(std::max(maxItems, bodyCap), pl.threads), 1);
+		pl.grid = std::min(std::min(w->solveGrid, wanted), 511); // 511: region ids share a 16-bit key with the colour
+	}
+	pl.regions = (w->schedule == S2B_SCHEDULE_COLOR && pl.usePersistent && w->useRegions != 0 && pl.dataflow == false && maxItems > 0)
+					 ? pl.grid
+					 : 0;
 
 	// ---- reserve scratch (sizes are upper bounds known on the host: no synchronisation) ----
 	size_t nC = (size_t)std::max(contactCount, 1), nJ = (size_t)std::max(jointCap, 1), nI = (size_t)std::max(maxItems, 1);
+	pl.nC = nC;
+	pl.nJ = nJ;
+	pl.nI = nI;
+	VariantColumns cols = pl.cols;
 	s->counts.reserve(CNT_SIZE, st, false);
 	s->activeFlag.reserve(nC, st, false);
 	s->activeSlots.reserve(nC, st, false);
@@ -1854,6 +1760,8 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 	s->adj.reserve(2 * nI, st, false);
 	s->colorA.reserve(nI, st, false);
 	s->colorB.reserve(nI, st, false);
+	s->colorC.reserve(nI, st, false);
+	s->itemRegion.reserve(nI, st, false);
 	s->sortKeyIn.reserve(2 * nI, st, false);
 	s->sortKeyOut.reserve(2 * nI, st, false);
 	s->sortValIn.reserve(2 * nI, st, false);
@@ -1862,18 +1770,31 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 	s->jGroupOff.reserve(S2B_MAX_COLORS + 2, st, false);
 	s->cPerm.reserve(nC, st, false);
 	s->jPerm.reserve(nJ, st, false);
-	if (needInc)
+	s->heavyBodies.reserve((size_t)bodyCap + 2, st, false);
+	if (pl.regions > 0)
+	{
+		s->bodyKeyIn.reserve((size_t)bodyCap + 1, st, false);
+		s->bodyKeyOut.reserve((size_t)bodyCap + 1, st, false);
+		s->bodyValIn.reserve((size_t)bodyCap + 1, st, false);
+		s->regBodies.reserve((size_t)bodyCap + 1, st, false);
+		s->bodyRegion.reserve((size_t)bodyCap + 1, st, false);
+		s->regBodyStart.reserve((size_t)pl.regions + 2, st, false);
+		s->cRegOff.reserve((size_t)pl.regions * S2B_REG_STRIDE, st, false);
+		s->jRegOff.reserve((size_t)pl.regions * S2B_REG_STRIDE, st, false);
+	}
+	if (pl.needInc)
 	{
 		s->itemVal.reserve(nI, st, false);
 		s->incWork.reserve(2 * nI, st, false);
 		s->incList.reserve(2 * nI, st, false);
-		s->heavyBodies.reserve(S2B_MAX_HEAVY_BODIES + 1, st, false);
 	}
-	if (dataflow)
+	if (pl.dataflow)
 	{
 		s->flow.reserve(2 * nC + 2 * nJ, st, false);
 		s->bodyTicket.reserve((size_t)bodyCap + 2, st, false);
 	}
+	w->solveBarrier.reserve(64, st, true, true);
+	w->schedDirty.reserve(4, st, true, true);
 	// (+2 rows: the bulk-staged colour kernel may read up to two rows past the last constraint)
 	s->idx.reserve(nC + 2, st, false);
 	s->nf.reserve(nC + 2, st, false);
@@ -1908,19 +1829,53 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 	s->jimp.reserve(nJ, st, false);
 	s->jlimp.reserve(nJ, st, false);
 
-	// cub temp storage (compaction, scan, 8-bit sort) sized for the largest use
+	// cub temp storage (compaction, scan, sorts) sized for the largest use
 	size_t tempBytes = 0, need = 0;
 	cub::DeviceSelect::Flagged(nullptr, need, thrust::counting_iterator<int>(0), (int*)nullptr, (int*)nullptr, (int*)nullptr,
 							   (int)nI, st);
 	tempBytes = std::max(tempBytes, need);
 	cub::DeviceScan::ExclusiveSum(nullptr, need, (int*)nullptr, (int*)nullptr, bodyCap + 1, st);
 	tempBytes = std::max(tempBytes, need);
-	cub::DeviceRadixSort::SortPairs(nullptr, need, (unsigned char*)nullptr, (unsigned char*)nullptr, (int*)nullptr,
-									(int*)nullptr, (int)nI, 0, 8, st);
+	cub::DeviceRadixSort::SortPairs(nullptr, need, (unsigned short*)nullptr, (unsigned short*)nullptr, (int*)nullptr, (int*)nullptr, (int)nI, 0,
+									16, st);
+	tempBytes = std::max(tempBytes, need);
+	cub::DeviceRadixSort::SortPairs(nullptr, need, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, bodyCap + 1, 0, 32, st);
 	tempBytes = std::max(tempBytes, need);
 	s->cubTemp.reserve(tempBytes + 256, st, false, false);
+}
+
+static void launchColorKernel(s2bWorld* w, SolverScratch* s, int maxItems, int* color, int maxColors, int indexRounds, int validate)
+{
+	// work counters of the kernel (shared by the primary and the cut colouring)
+	S2B_CHECK(cudaMemsetAsync(s->counts.p + CNT_REMAINING, 0, sizeof(int) * 5, w->stream));
+	if (w->colorGrid == 0)
+	{
+		int blocksPerSm = 0;
+		S2B_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, s2bColorKernel, 256, 0));
+		w->colorGrid = w->smCount * std::min(std::max(blocksPerSm, 1), 2);
+	}
+	int grid = std::min(w->colorGrid, std::max(1, gridFor(maxItems, 256)));
+	int* countsPtr = s->counts.p;
+	const int2* ib = s->itemBodies.p;
+	const int* as = s->adjStart.p;
+	const int* ad = s->adj.p;
+	int* tent = s->colorB.p;
+	void* args[] = {&countsPtr, &ib, &as, &ad, &color, &tent, &maxColors, &indexRounds, &validate};
+	S2B_CHECK(cudaLaunchCooperativeKernel((void*)s2bColorKernel, dim3(grid), dim3(256), args, 0, w->stream));
+	w->kernelLaunches += 1;
+}
+
+// gather + schedule: from the contact / joint tables to the solve order, the group tables, the regions and the incidence
+// lists. Everything here depends only on WHICH constraints are live (and on the settings in the graph signature), not on
+// their values: while that set stands, a replayed graph skips all of it (see s2bSolve).
+static void enqueueSchedule(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
+{
+	cudaStream_t st = w->stream;
+	int contactCount = pl.contactCount, jointCap = pl.jointCap, bodyCap = pl.bodyCap, maxItems = pl.maxItems;
+	size_t nI = pl.nI, nC = pl.nC, nJ = pl.nJ;
 
 	// ---- gather ----
+	S2B_CHECK(cudaMemsetAsync(w->schedDirty.p, 0, sizeof(int), st)); // what follows is the rebuild the flag asks for
 	S2B_CHECK(cudaMemsetAsync(s->counts.p, 0, sizeof(int) * CNT_SIZE, st));
 	{
 		int n = std::max(contactCount, jointCap);
@@ -1945,7 +1900,189 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 		}
 	}
 
-	// ---- argument block ----
+	bool needHostCounts = (w->schedule == S2B_SCHEDULE_WAVEFRONT) || pl.usePersistent == false;
+	s->regions = 0;
+	if (maxItems > 0)
+	{
+		bool wantAdj = w->schedule == S2B_SCHEDULE_COLOR || pl.needInc;
+		if (wantAdj)
+		{
+			S2B_CHECK(cudaMemsetAsync(s->degree.p, 0, sizeof(int) * ((size_t)bodyCap + 1), st));
+			S2B_CHECK(cudaMemsetAsync(s->adjCursor.p, 0, sizeof(int) * ((size_t)bodyCap + 1), st));
+		}
+		S2B_LAUNCH(w, s2bItemEndpoints, gridFor(maxItems, 256), 256, 0, s->counts.p, s->jointSlots.p, s->activeSlots.p,
+				   jointView(w), makeView(w->contacts[w->cur]), bodyView(w), s->itemBodies.p, wantAdj ? s->degree.p : nullptr);
+		if (wantAdj)
+		{
+			size_t tb = s->cubTemp.cap;
+			cub::DeviceScan::ExclusiveSum(s->cubTemp.p, tb, s->degree.p, s->adjStart.p, bodyCap + 1, st);
+			w->kernelLaunches += 2;
+			S2B_LAUNCH(w, s2bFillAdjacency, gridFor(maxItems, 256), 256, 0, s->counts.p, s->itemBodies.p, s->adjStart.p,
+					   s->adjCursor.p, s->adj.p);
+		}
+		S2B_CHECK(cudaMemsetAsync(s->heavyBodies.p, 0, sizeof(int), st));
+
+		if (w->schedule == S2B_SCHEDULE_COLOR)
+		{
+			if (w->coopSupported == 0)
+			{
+				fprintf(stderr, "solver2d-b200: cooperative launch unsupported on this device\n");
+				abort();
+			}
+			// colours: start from the persisted ones; only constraints that appeared this step are uncoloured
+			S2B_LAUNCH(w, s2bSeedColors, gridFor(maxItems, 256), 256, 0, s->counts.p, s->jointSlots.p, s->activeSlots.p, w->jColor.p,
+					   w->contacts[w->cur].color.p, s->colorA.p, w->maxColors);
+			launchColorKernel(w, s, maxItems, s->colorA.p, w->maxColors, S2B_INDEX_PRIORITY_ROUNDS, 1);
+			S2B_LAUNCH(w, s2bStoreColors, gridFor(maxItems, 256), 256, 0, s->counts.p, s->jointSlots.p, s->activeSlots.p, w->jColor.p,
+					   w->contacts[w->cur].color.p, s->colorA.p);
+
+			// regions: Hilbert order of the bodies' centres, equal chunks
+			if (pl.regions > 0)
+			{
+				S2B_LAUNCH(w, s2bBodyBoundsKernel, gridFor(bodyCap, 256), 256, 0, bodyView(w), s->counts.p);
+				S2B_LAUNCH(w, s2bBodyKeysKernel, gridFor(bodyCap, 256), 256, 0, bodyView(w), s->counts.p, s->degree.p, s->bodyKeyIn.p,
+						   s->bodyValIn.p, s->heavyBodies.p);
+				size_t tb = s->cubTemp.cap;
+				cub::DeviceRadixSort::SortPairs(s->cubTemp.p, tb, s->bodyKeyIn.p, s->bodyKeyOut.p, s->bodyValIn.p, s->regBodies.p, bodyCap, 0, 32,
+												st);
+				w->kernelLaunches += 4;
+				S2B_LAUNCH(w, s2bAssignRegionsKernel, gridFor(std::max(bodyCap, pl.regions + 1), 256), 256, 0, s->counts.p, bodyCap, pl.regions,
+						   s->regBodies.p, s->bodyRegion.p, s->regBodyStart.p);
+				s->regions = pl.regions;
+			}
+			S2B_LAUNCH(w, s2bClassifyItemsKernel, gridFor(maxItems, 256), 256, 0, s->counts.p, s->itemBodies.p, s->bodyRegion.p, s->colorA.p,
+					   pl.regions > 0 ? 1 : 0, s->itemRegion.p, s->colorC.p);
+			if (pl.regions > 0)
+			{
+				// the cut set is coloured among itself, from scratch, with hashed priorities (a handful of rounds)
+				launchColorKernel(w, s, maxItems, s->colorC.p, S2B_MAX_COLORS, 0, 0);
+			}
+
+			// solve order: stable 16-bit radix sort of (key, natural index), joints and contacts separately
+			unsigned short* jKeysIn = s->sortKeyIn.p;
+			unsigned short* cKeysIn = s->sortKeyIn.p + nI;
+			unsigned short* jKeysOut = s->sortKeyOut.p;
+			unsigned short* cKeysOut = s->sortKeyOut.p + nI;
+			int* jValsIn = s->sortValIn.p;
+			int* cValsIn = s->sortValIn.p + nI;
+			// entries beyond the live counts keep key 0xFFFF: they sort behind every live entry and are never read
+			S2B_CHECK(cudaMemsetAsync(s->sortKeyIn.p, 0xFF, sizeof(unsigned short) * 2 * nI, st));
+			S2B_LAUNCH(w, s2bMakeSortKeys, gridFor(maxItems, 256), 256, 0, s->counts.p, s->colorA.p, s->itemRegion.p, s->colorC.p, jKeysIn, jValsIn,
+					   cKeysIn, cValsIn);
+			// the sorts run over the host-known upper-bound sizes, so no device count has to be read back
+			size_t tb = s->cubTemp.cap;
+			if (contactCount > 0)
+			{
+				tb = s->cubTemp.cap;
+				cub::DeviceRadixSort::SortPairs(s->cubTemp.p, tb, cKeysIn, cKeysOut, cValsIn, s->cPerm.p, contactCount, 0, 16, st);
+				w->kernelLaunches += 3;
+			}
+			if (jointCap > 0)
+			{
+				tb = s->cubTemp.cap;
+				cub::DeviceRadixSort::SortPairs(s->cubTemp.p, tb, jKeysIn, jKeysOut, jValsIn, s->jPerm.p, jointCap, 0, 16, st);
+				w->kernelLaunches += 3;
+			}
+			int entries = pl.regions * S2B_REG_STRIDE + S2B_MAX_COLORS + 2;
+			S2B_LAUNCH(w, s2bBuildTablesKernel, gridFor(entries, 256), 256, 0, pl.regions, jKeysOut, jointCap, cKeysOut, contactCount, s->jRegOff.p,
+					   s->cRegOff.p, s->jGroupOff.p, s->cGroupOff.p);
+			S2B_LAUNCH(w, s2bFinishGroups, 1, 1, 0, s->counts.p, s->cGroupOff.p, s->jGroupOff.p);
+		}
+
+		if (needHostCounts)
+		{
+			int hostCounts[CNT_SIZE];
+			S2B_CHECK(cudaMemcpyAsync(hostCounts, s->counts.p, sizeof(hostCounts), cudaMemcpyDeviceToHost, st));
+			S2B_CHECK(cudaStreamSynchronize(st));
+			pl.hostNC = hostCounts[CNT_CONTACTS];
+			pl.hostNJ = hostCounts[CNT_JOINTS];
+			if (w->schedule == S2B_SCHEDULE_WAVEFRONT)
+			{
+				buildWavefront(w, s, pl.hostNJ, pl.hostNC, pl.host);
+			}
+			else
+			{
+				pl.host.groups = hostCounts[CNT_GROUPS];
+				pl.host.cOff.resize(S2B_MAX_COLORS + 2);
+				pl.host.jOff.resize(S2B_MAX_COLORS + 2);
+				S2B_CHECK(cudaMemcpy(pl.host.cOff.data(), s->cGroupOff.p, sizeof(int) * (S2B_MAX_COLORS + 2), cudaMemcpyDeviceToHost));
+				S2B_CHECK(cudaMemcpy(pl.host.jOff.data(), s->jGroupOff.p, sizeof(int) * (S2B_MAX_COLORS + 2), cudaMemcpyDeviceToHost));
+			}
+			s->hostContacts = pl.hostNC;
+			s->hostJoints = pl.hostNJ;
+			s->hostGroups = pl.host.groups;
+			s->hostCGroupOff = pl.host.cOff;
+			s->hostJGroupOff = pl.host.jOff;
+			s->hostCountsValid = true;
+		}
+		else
+		{
+			s->hostCountsValid = false;
+		}
+
+		if (contactCount > 0)
+		{
+			S2B_LAUNCH(w, s2bBuildSources, gridFor(contactCount, 256), 256, 0, s->counts.p, s->cPerm.p, s->activeSlots.p, s->src.p);
+		}
+
+		if (pl.needInc)
+		{
+			// incidence lists of the movable bodies in solve order (+ the ticket ordinals of every constraint)
+			if (w->schedule == S2B_SCHEDULE_COLOR)
+			{
+				S2B_LAUNCH(w, s2bItemOrderFromKeysKernel, gridFor(maxItems, 256), 256, 0, s->counts.p, s->cPerm.p, s->jPerm.p, s->sortKeyIn.p,
+						   s->sortKeyIn.p + nI, s->itemVal.p);
+			}
+			else
+			{
+				S2B_LAUNCH(w, s2bItemOrderKernel, gridFor(maxItems, 256), 256, 0, s->counts.p, s->cPerm.p, s->jPerm.p, s->cGroupOff.p,
+						   s->jGroupOff.p, std::max(pl.host.groups, 1), s->itemVal.p);
+			}
+			int2 *cfa = nullptr, *cfb = nullptr, *jfa = nullptr, *jfb = nullptr;
+			if (pl.dataflow)
+			{
+				S2B_CHECK(cudaMemsetAsync(s->flow.p, 0xFF, sizeof(int2) * (2 * nC + 2 * nJ), st));
+				cfa = s->flow.p;
+				cfb = s->flow.p + nC;
+				jfa = s->flow.p + 2 * nC;
+				jfb = s->flow.p + 2 * nC + nJ;
+			}
+			// without regions the hub bodies (gathered by a whole block) are registered here; with regions s2bBodyKeysKernel did it
+			int* heavy = (pl.gatherWarm && pl.usePersistent && pl.regions == 0) ? s->heavyBodies.p : nullptr;
+			S2B_LAUNCH(w, s2bSortIncidenceKernel, gridFor(bodyCap, 128), 128, 0, bodyCap, s->adjStart.p, s->adj.p, s->itemBodies.p,
+					   s->itemVal.p, s->incWork.p, s->incList.p, cfa, cfb, jfa, jfb, heavy);
+		}
+	}
+	else
+	{
+		if (pl.needInc)
+		{
+			S2B_CHECK(cudaMemsetAsync(s->adjStart.p, 0, sizeof(int) * ((size_t)bodyCap + 2), st));
+		}
+		S2B_CHECK(cudaMemsetAsync(s->heavyBodies.p, 0, sizeof(int), st));
+		// no constraints at all: bodies still integrate
+		pl.host.groups = 0;
+		pl.host.cOff.assign(S2B_MAX_COLORS + 2, 0);
+		pl.host.jOff.assign(S2B_MAX_COLORS + 2, 0);
+		S2B_CHECK(cudaMemsetAsync(s->cGroupOff.p, 0, sizeof(int) * (S2B_MAX_COLORS + 2), st));
+		S2B_CHECK(cudaMemsetAsync(s->jGroupOff.p, 0, sizeof(int) * (S2B_MAX_COLORS + 2), st));
+		s->hostContacts = s->hostJoints = s->hostGroups = 0;
+		s->hostCGroupOff = pl.host.cOff;
+		s->hostJGroupOff = pl.host.jOff;
+		s->hostCountsValid = true;
+	}
+}
+
+// the argument block + the iteration itself (persistent kernel or launch by launch) + the work meter
+static void enqueueIterate(s2bWorld* w, SolverScratch* s, SolvePlan& pl, bool capturing)
+{
+	cudaStream_t st = w->stream;
+	int solverType = pl.solverType;
+	const s2bStepContext& ctx = pl.ctx;
+	VariantColumns cols = pl.cols;
+	size_t nC = pl.nC, nJ = pl.nJ;
+	int bodyCap = pl.bodyCap;
+
 	SolveArgs a;
 	memset(&a, 0, sizeof(a));
 	a.bodies = bodyView(w);
@@ -2002,186 +2139,19 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 	a.softJoint = makeSoft(ctx.h, jointHertz, 10.0f);
 
 	PassPtrs pp = {s->jointSlots.p, s->jPerm.p};
-
-	// ---- schedule ----
-	HostPlan plan;
-	bool needHostCounts = (w->schedule == S2B_SCHEDULE_WAVEFRONT) || (w->persistent == 0) || (w->coopSupported == 0);
-	int hostNC = 0, hostNJ = 0;
-
-	if (maxItems > 0)
-	{
-		bool wantAdj = w->schedule == S2B_SCHEDULE_COLOR || needInc;
-		if (wantAdj)
-		{
-			S2B_CHECK(cudaMemsetAsync(s->degree.p, 0, sizeof(int) * ((size_t)bodyCap + 1), st));
-			S2B_CHECK(cudaMemsetAsync(s->adjCursor.p, 0, sizeof(int) * ((size_t)bodyCap + 1), st));
-		}
-		S2B_LAUNCH(w, s2bItemEndpoints, gridFor(maxItems, 256), 256, 0, s->counts.p, s->jointSlots.p, s->activeSlots.p,
-				   jointView(w), makeView(w->contacts[w->cur]), bodyView(w), s->itemBodies.p, wantAdj ? s->degree.p : nullptr);
-
-		if (wantAdj)
-		{
-			size_t tb = s->cubTemp.cap;
-			cub::DeviceScan::ExclusiveSum(s->cubTemp.p, tb, s->degree.p, s->adjStart.p, bodyCap + 1, st);
-			w->kernelLaunches += 2;
-			S2B_LAUNCH(w, s2bFillAdjacency, gridFor(maxItems, 256), 256, 0, s->counts.p, s->itemBodies.p, s->adjStart.p,
-					   s->adjCursor.p, s->adj.p);
-		}
-
-		if (w->schedule == S2B_SCHEDULE_COLOR)
-		{
-			size_t tb = s->cubTemp.cap;
-
-			if (w->coopSupported == 0)
-			{
-				fprintf(stderr, "solver2d-b200: cooperative launch unsupported on this device\n");
-				abort();
-			}
-			{
-				// working colours start from the persisted ones; only constraints that appeared this step are uncoloured
-				S2B_LAUNCH(w, s2bSeedColors, gridFor(maxItems, 256), 256, 0, s->counts.p, s->jointSlots.p, s->activeSlots.p,
-						   w->jColor.p, w->contacts[w->cur].color.p, s->colorA.p, w->maxColors);
-				if (w->colorGrid == 0)
-				{
-					int blocksPerSm = 0;
-					S2B_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, s2bColorKernel, 256, 0));
-					w->colorGrid = w->smCount * std::min(std::max(blocksPerSm, 1), 2);
-				}
-				int grid = std::min(w->colorGrid, std::max(1, gridFor(maxItems, 256)));
-				int* countsPtr = s->counts.p;
-				const int2* ib = s->itemBodies.p;
-				const int* as = s->adjStart.p;
-				const int* ad = s->adj.p;
-				int* ca = s->colorA.p;
-				int* cb = s->colorB.p;
-				int mc = w->maxColors;
-				void* args[] = {&countsPtr, &ib, &as, &ad, &ca, &cb, &mc};
-				S2B_CHECK(cudaLaunchCooperativeKernel((void*)s2bColorKernel, dim3(grid), dim3(256), args, 0, st));
-				w->kernelLaunches += 1;
-				S2B_LAUNCH(w, s2bStoreColors, gridFor(maxItems, 256), 256, 0, s->counts.p, s->jointSlots.p, s->activeSlots.p,
-						   w->jColor.p, w->contacts[w->cur].color.p, s->colorA.p);
-			}
-
-			// colour-major order: 8-bit stable radix sort of (colour, natural index), joints and contacts separately
-			unsigned char* jKeysIn = s->sortKeyIn.p;
-			unsigned char* cKeysIn = s->sortKeyIn.p + nI;
-			unsigned char* jKeysOut = s->sortKeyOut.p;
-			unsigned char* cKeysOut = s->sortKeyOut.p + nI;
-			int* jValsIn = s->sortValIn.p;
-			int* cValsIn = s->sortValIn.p + nI;
-			// entries beyond the live counts keep key 255: they sort behind every live entry and are never read
-			S2B_CHECK(cudaMemsetAsync(s->sortKeyIn.p, 0xFF, 2 * nI, st));
-			S2B_LAUNCH(w, s2bMakeSortKeys, gridFor(maxItems, 256), 256, 0, s->counts.p, s->colorA.p, jKeysIn, jValsIn, cKeysIn,
-					   cValsIn);
-			// the sorts run over the host-known upper-bound sizes, so no device count has to be read back
-			if (contactCount > 0)
-			{
-				tb = s->cubTemp.cap;
-				cub::DeviceRadixSort::SortPairs(s->cubTemp.p, tb, cKeysIn, cKeysOut, cValsIn, s->cPerm.p, contactCount, 0, 8, st);
-				w->kernelLaunches += 3;
-			}
-			if (jointCap > 0)
-			{
-				tb = s->cubTemp.cap;
-				cub::DeviceRadixSort::SortPairs(s->cubTemp.p, tb, jKeysIn, jKeysOut, jValsIn, s->jPerm.p, jointCap, 0, 8, st);
-				w->kernelLaunches += 3;
-			}
-			S2B_LAUNCH(w, s2bGroupOffsets, gridFor(contactCount + 1, 256), 256, 0, s->counts.p, (int)CNT_CONTACTS, cKeysOut,
-					   s->cGroupOff.p);
-			S2B_LAUNCH(w, s2bGroupOffsets, gridFor(jointCap + 1, 256), 256, 0, s->counts.p, (int)CNT_JOINTS, jKeysOut,
-					   s->jGroupOff.p);
-			S2B_LAUNCH(w, s2bFinishGroups, 1, 1, 0, s->counts.p, s->cGroupOff.p, s->jGroupOff.p);
-		}
-
-		if (needHostCounts)
-		{
-			int hostCounts[CNT_SIZE];
-			S2B_CHECK(cudaMemcpyAsync(hostCounts, s->counts.p, sizeof(hostCounts), cudaMemcpyDeviceToHost, st));
-			S2B_CHECK(cudaStreamSynchronize(st));
-			hostNC = hostCounts[CNT_CONTACTS];
-			hostNJ = hostCounts[CNT_JOINTS];
-			if (w->schedule == S2B_SCHEDULE_WAVEFRONT)
-			{
-				buildWavefront(w, s, hostNJ, hostNC, plan);
-			}
-			else
-			{
-				plan.groups = hostCounts[CNT_GROUPS];
-				plan.cOff.resize(S2B_MAX_COLORS + 2);
-				plan.jOff.resize(S2B_MAX_COLORS + 2);
-				S2B_CHECK(cudaMemcpy(plan.cOff.data(), s->cGroupOff.p, sizeof(int) * (S2B_MAX_COLORS + 2), cudaMemcpyDeviceToHost));
-				S2B_CHECK(cudaMemcpy(plan.jOff.data(), s->jGroupOff.p, sizeof(int) * (S2B_MAX_COLORS + 2), cudaMemcpyDeviceToHost));
-			}
-			s->hostContacts = hostNC;
-			s->hostJoints = hostNJ;
-			s->hostGroups = plan.groups;
-			s->hostCGroupOff = plan.cOff;
-			s->hostJGroupOff = plan.jOff;
-			s->hostCountsValid = true;
-		}
-		else
-		{
-			s->hostCountsValid = false;
-		}
-
-		if (contactCount > 0)
-		{
-			S2B_LAUNCH(w, s2bBuildSources, gridFor(contactCount, 256), 256, 0, s->counts.p, s->cPerm.p, s->activeSlots.p,
-					   s->src.p);
-		}
-
-		if (needInc)
-		{
-			// incidence lists of the movable bodies in solve order (+ the ticket ordinals of every constraint)
-			int tableEntries = w->schedule == S2B_SCHEDULE_COLOR ? S2B_MAX_COLORS + 1 : std::max(plan.groups, 1);
-			S2B_LAUNCH(w, s2bItemOrderKernel, gridFor(maxItems, 256), 256, 0, s->counts.p, s->cPerm.p, s->jPerm.p, s->cGroupOff.p,
-					   s->jGroupOff.p, tableEntries, s->itemVal.p);
-			int2 *cfa = nullptr, *cfb = nullptr, *jfa = nullptr, *jfb = nullptr;
-			if (dataflow)
-			{
-				S2B_CHECK(cudaMemsetAsync(s->flow.p, 0xFF, sizeof(int2) * (2 * nC + 2 * nJ), st));
-				cfa = s->flow.p;
-				cfb = s->flow.p + nC;
-				jfa = s->flow.p + 2 * nC;
-				jfb = s->flow.p + 2 * nC + nJ;
-			}
-			int* heavy = nullptr;
-			if (gatherWarm && w->persistent != 0 && w->coopSupported != 0)
-			{
-				S2B_CHECK(cudaMemsetAsync(s->heavyBodies.p, 0, sizeof(int), st));
-				heavy = s->heavyBodies.p;
-			}
-			S2B_LAUNCH(w, s2bSortIncidenceKernel, gridFor(bodyCap, 128), 128, 0, bodyCap, s->adjStart.p, s->adj.p, s->itemBodies.p,
-					   s->itemVal.p, s->incWork.p, s->incList.p, cfa, cfb, jfa, jfb, heavy);
-		}
-	}
-	else
-	{
-		if (needInc)
-		{
-			S2B_CHECK(cudaMemsetAsync(s->adjStart.p, 0, sizeof(int) * ((size_t)bodyCap + 2), st));
-		}
-		// no constraints at all: bodies still integrate
-		plan.groups = 0;
-		plan.cOff.assign(S2B_MAX_COLORS + 2, 0);
-		plan.jOff.assign(S2B_MAX_COLORS + 2, 0);
-		S2B_CHECK(cudaMemsetAsync(s->cGroupOff.p, 0, sizeof(int) * (S2B_MAX_COLORS + 2), st));
-		S2B_CHECK(cudaMemsetAsync(s->jGroupOff.p, 0, sizeof(int) * (S2B_MAX_COLORS + 2), st));
-		needHostCounts = true;
-		s->hostContacts = s->hostJoints = s->hostGroups = 0;
-		s->hostCGroupOff = plan.cOff;
-		s->hostJGroupOff = plan.jOff;
-		s->hostCountsValid = true;
-	}
-
-	// ---- iterate ----
-	// (the group tables may have been re-allocated by the schedule step: take the pointers now)
 	a.cGroupOff = s->cGroupOff.p;
 	a.jGroupOff = s->jGroupOff.p;
-	a.incStart = gatherWarm ? s->adjStart.p : nullptr;
-	a.incList = gatherWarm ? s->incList.p : nullptr;
-	a.heavyBodies = (gatherWarm && maxItems > 0 && w->persistent != 0 && w->coopSupported != 0) ? s->heavyBodies.p : nullptr;
-	if (dataflow)
+	a.incStart = pl.gatherWarm ? s->adjStart.p : nullptr;
+	a.incList = pl.gatherWarm ? s->incList.p : nullptr;
+	// hub bodies: with regions the list drives their body passes (every variant); without, only the block-wide gather
+	a.heavyBodies = (pl.regions > 0 || (pl.gatherWarm && pl.maxItems > 0 && pl.usePersistent)) ? s->heavyBodies.p : nullptr;
+	a.regions = pl.regions;
+	a.regBodyStart = s->regBodyStart.p;
+	a.regBodies = s->regBodies.p;
+	a.jRegOff = s->jRegOff.p;
+	a.cRegOff = s->cRegOff.p;
+	a.barrier = w->solveBarrier.p;
+	if (pl.dataflow)
 	{
 		S2B_CHECK(cudaMemsetAsync(s->bodyTicket.p, 0, sizeof(int) * ((size_t)bodyCap + 2), st));
 		a.bodyTicket = s->bodyTicket.p;
@@ -2192,32 +2162,16 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 		a.jFlowA = s->flow.p + 2 * nC;
 		a.jFlowB = s->flow.p + 2 * nC + nJ;
 	}
-	pp.jPerm = s->jPerm.p;
 	s->lastArgs = a;
 	s->lastJointSlots = pp.jointSlots;
 	s->lastJPerm = pp.jPerm;
 	s->lastArgsValid = true;
-	bool usePersistent = w->persistent != 0 && w->coopSupported != 0;
-	if (usePersistent)
+	if (pl.usePersistent)
 	{
 		// wavefront tables hold CNT_GROUPS levels and no overflow group; the overflow counts are zero so the kernel
 		// never indexes past them
-		if (w->solveGrid == 0)
 		{
-			int blocksPerSm = 0;
-			S2B_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, s2bPersistentSolve, S2B_BLOCK, 0));
-			const char* env = getenv("S2B_SOLVE_BLOCKS_PER_SM");
-			int want = env != nullptr ? atoi(env) : 2;
-			w->solveGrid = w->smCount * std::min(std::max(blocksPerSm, 1), std::max(want, 1));
-		}
-		int threads = S2B_BLOCK;
-		{
-			const char* env = getenv("S2B_SOLVE_THREADS");
-			if (env != nullptr && atoi(env) >= 32 && atoi(env) <= S2B_BLOCK)
-			{
-				threads = atoi(env) & ~31;
-			}
-			env = getenv("S2B_FLOW_SLEEP_NS");
+			const char* env = getenv("S2B_FLOW_SLEEP_NS");
 			a.flowSleepNs = env != nullptr ? atoi(env) : 0;
 		}
 		if (s->traceCap > 0)
@@ -2227,9 +2181,7 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 			a.trace = s->trace.p;
 			a.traceCap = s->traceCap;
 		}
-		int wanted = std::max(gridFor(std::max(maxItems, bodyCap), threads), 1);
-		int grid = std::min(w->solveGrid, wanted);
-		void* args[] = {&a, &pp, &program};
+		void* args[] = {&a, &pp, &pl.program};
 		if (w->solveKernelStart == nullptr)
 		{
 			S2B_CHECK(cudaEventCreate(&w->solveKernelStart));
@@ -2238,51 +2190,216 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 		// (inside a capture the time stamps become external event-record nodes so that they are taken on every replay)
 		unsigned evFlags = capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
 		S2B_CHECK(cudaEventRecordWithFlags(w->solveKernelStart, st, evFlags));
-		S2B_CHECK(cudaLaunchCooperativeKernel((void*)s2bPersistentSolve, dim3(grid), dim3(threads), args, 0, st));
+		S2B_CHECK(cudaLaunchCooperativeKernel(s2bPersistentKernel(solverType), dim3(pl.grid), dim3(pl.threads), args, 0, st));
 		S2B_CHECK(cudaEventRecordWithFlags(w->solveKernelEnd, st, evFlags));
 		w->solveKernelTimed = true;
 		w->kernelLaunches += 1;
 	}
 	else
 	{
-		runProgramLaunchByLaunch(w, a, pp, program, plan, hostNJ, hostNC);
+		runProgramLaunchByLaunch(w, a, pp, pl.program, pl.host, pl.hostNJ, pl.hostNC);
 		w->solveKernelTimed = false;
 	}
 
 	// work meter: constraint-iterations of this step = (contact constraints + joints) x solve passes
 	{
 		w->dWork.reserve(4, st, true);
-		S2B_LAUNCH(w, s2bMeterWork, 1, 1, 0, s->counts.p, countedPasses, w->dWork.p);
+		S2B_LAUNCH(w, s2bMeterWork, 1, 1, 0, s->counts.p, pl.countedPasses, w->dWork.p);
 	}
+}
 
-	if (capturing)
+void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
+{
+	SolverScratch* s = s2bGetSolverScratch(w);
+	cudaStream_t st = w->stream;
+	s2bStepContext ctx = *ctxIn;
+
+	if (solverType < 0 || solverType > 9)
 	{
-		w->capturing = false;
-		cudaGraph_t graph = nullptr;
-		cudaError_t err = cudaStreamEndCapture(st, &graph);
-		if (err == cudaSuccess && graph != nullptr)
+		fprintf(stderr, "solver2d-b200: solver type %d is not implemented on the device — there is no CPU fallback\n", solverType);
+		abort();
+	}
+	if (solverType == 9 && (ctx.iterations == 0 || ctx.dt == 0.0f))
+	{
+		return; // s2Solve_XPBD leaves early (reference src/solve_xpbd.c:345-353)
+	}
+	// ---- CUDA graph of the stage ----
+	// A steady scene runs the SAME ~40 launches with the SAME arguments every step (counts live in device memory). The
+	// second consecutive step with an unchanged signature is captured into a graph; after that the stage is one
+	// cudaGraphLaunch until the signature changes (a contact table rebuilt by the pair pass, a re-allocation, other step
+	// parameters). S2B_GRAPH=0 disables it.
+	bool graphable = w->schedule == S2B_SCHEDULE_COLOR && w->persistent != 0 && w->coopSupported != 0 && s->graphDisabled == false &&
+					 s->traceCap == 0 && w->contactCount + w->jointCap > 0 && w->useGraph != 0;
+	std::vector<unsigned char> sig;
+	if (graphable)
+	{
+		auto put = [&sig](const void* ptr, size_t n) {
+			const unsigned char* b = (const unsigned char*)ptr;
+			sig.insert(sig.end(), b, b + n);
+		};
+		unsigned long long epoch = s2bAllocEpoch();
+		int ints[] = {solverType,	 w->contactCount, w->jointCap, w->bodyCap,		  w->cur,
+					  w->maxColors, w->gatherWarm,	  w->dataflow, w->sticky ? 1 : 0, w->useRegions};
+		put(&ctx, sizeof(ctx));
+		put(ints, sizeof(ints));
+		put(&epoch, sizeof(epoch));
+		put(&w->contactTableVersion, sizeof(w->contactTableVersion));
+		put(&w->scheduleEpoch, sizeof(w->scheduleEpoch));
+		put(&w->gravity, sizeof(w->gravity));
+		if (s->graphExec != nullptr && sig == s->graphSig)
 		{
-			err = cudaGraphInstantiate(&s->graphExec, graph, 0);
-			cudaGraphDestroy(graph);
-		}
-		if (err != cudaSuccess || s->graphExec == nullptr)
-		{
-			// capture not possible on this driver: nothing ran, so run this step eagerly and stop trying
-			(void)cudaGetLastError();
-			fprintf(stderr, "solver2d-b200: CUDA graph capture of the solver stage failed (%s); continuing without graphs\n",
-					cudaGetErrorString(err));
-			s->graphExec = nullptr;
-			s->graphDisabled = true;
-			s->graphCandidate.clear();
-			w->kernelLaunches = launchesBefore;
-			s2bSolve(w, solverType, ctxIn);
+			if (s->scheduleSig != sig)
+			{
+				// the schedule buffers were last built for another configuration (a solve with other settings in between)
+				int one = 1;
+				S2B_CHECK(cudaMemcpyAsync(w->schedDirty.p, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+				s->scheduleSig = sig;
+			}
+			S2B_CHECK(cudaGraphLaunch(s->graphExec, st));
+			w->kernelLaunches += s->graphLaunches;
+			w->solveKernelTimed = true;
+			s->hostCountsValid = false;
+			s->graphReplays += 1;
 			return;
 		}
-		s->graphSig = sig;
-		s->graphLaunches = w->kernelLaunches - launchesBefore;
-		s->graphCaptures += 1;
-		S2B_CHECK(cudaGraphLaunch(s->graphExec, st));
 	}
+	if (graphable && s->graphExec != nullptr && getenv("S2B_GRAPH_DEBUG") != nullptr)
+	{
+		// which part of the signature moved? layout: ctx | 10 ints | epoch | table version | schedule epoch | gravity
+		size_t n = std::min(sig.size(), s->graphSig.size());
+		for (size_t k = 0; k < n; ++k)
+		{
+			if (sig[k] != s->graphSig[k])
+			{
+				fprintf(stderr, "solver2d-b200: graph signature changed at byte %zu (ctx %zu B, ints from %zu, epoch at %zu)\n", k, sizeof(ctx),
+						sizeof(ctx), sizeof(ctx) + 10 * sizeof(int));
+				break;
+			}
+		}
+	}
+
+	SolvePlan pl;
+	pl.solverType = solverType;
+	pl.ctx = ctx;
+	planSolve(w, s, pl);
+	if (graphable)
+	{
+		// planSolve may have (re)allocated: the signature carries the allocation epoch
+		unsigned long long epoch = s2bAllocEpoch();
+		memcpy(sig.data() + sizeof(ctx) + 10 * sizeof(int), &epoch, sizeof(epoch));
+	}
+
+	bool capturing = graphable && sig == s->graphCandidate;
+	int launchesBefore = w->kernelLaunches;
+	s->graphCandidate = sig;
+	s->scheduleSig = sig;
+	if (capturing == false)
+	{
+		enqueueSchedule(w, s, pl);
+		enqueueIterate(w, s, pl, false);
+		return;
+	}
+
+	// ---- build the graph: gate -> IF (gather + schedule) -> iterate ----
+	if (s->graphExec != nullptr)
+	{
+		cudaGraphExecDestroy(s->graphExec);
+		s->graphExec = nullptr;
+	}
+	w->capturing = true;
+	cudaGraph_t graph = nullptr;
+	cudaError_t err = cudaGraphCreate(&graph, 0);
+	cudaGraphNode_t gateNode = nullptr, ifNode = nullptr;
+	cudaGraph_t body = nullptr;
+	bool conditional = getenv("S2B_GRAPH_CONDITIONAL") == nullptr || atoi(getenv("S2B_GRAPH_CONDITIONAL")) != 0;
+	if (err == cudaSuccess && conditional)
+	{
+		cudaGraphConditionalHandle handle;
+		err = cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault);
+		if (err == cudaSuccess)
+		{
+			cudaKernelNodeParams kp = {};
+			int* dirty = w->schedDirty.p;
+			void* args[] = {&handle, &dirty};
+			kp.func = (void*)s2bScheduleGate;
+			kp.gridDim = dim3(1);
+			kp.blockDim = dim3(1);
+			kp.kernelParams = args;
+			err = cudaGraphAddKernelNode(&gateNode, graph, nullptr, 0, &kp);
+		}
+		if (err == cudaSuccess)
+		{
+			cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+			np.conditional.handle = handle;
+			np.conditional.type = cudaGraphCondTypeIf;
+			np.conditional.size = 1;
+			err = cudaGraphAddNode(&ifNode, graph, &gateNode, 1, &np);
+			if (err == cudaSuccess)
+			{
+				body = np.conditional.phGraph_out[0];
+			}
+		}
+		if (err == cudaSuccess)
+		{
+			err = cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+			if (err == cudaSuccess)
+			{
+				enqueueSchedule(w, s, pl);
+				cudaGraph_t out = nullptr;
+				err = cudaStreamEndCapture(st, &out);
+			}
+		}
+		if (err == cudaSuccess)
+		{
+			err = cudaStreamBeginCaptureToGraph(st, graph, &ifNode, nullptr, 1, cudaStreamCaptureModeThreadLocal);
+			if (err == cudaSuccess)
+			{
+				enqueueIterate(w, s, pl, true);
+				cudaGraph_t out = nullptr;
+				err = cudaStreamEndCapture(st, &out);
+			}
+		}
+		w->kernelLaunches += 1; // the gate
+	}
+	else if (err == cudaSuccess)
+	{
+		// plain capture of the whole stage (S2B_GRAPH_CONDITIONAL=0): the schedule is rebuilt on every replay
+		err = cudaStreamBeginCaptureToGraph(st, graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+		if (err == cudaSuccess)
+		{
+			enqueueSchedule(w, s, pl);
+			enqueueIterate(w, s, pl, true);
+			cudaGraph_t out = nullptr;
+			err = cudaStreamEndCapture(st, &out);
+		}
+	}
+	w->capturing = false;
+	if (err == cudaSuccess)
+	{
+		err = cudaGraphInstantiate(&s->graphExec, graph, 0);
+	}
+	if (graph != nullptr)
+	{
+		cudaGraphDestroy(graph);
+	}
+	if (err != cudaSuccess || s->graphExec == nullptr)
+	{
+		// not possible on this driver: nothing ran, so run this step eagerly and stop trying
+		(void)cudaGetLastError();
+		fprintf(stderr, "solver2d-b200: building the CUDA graph of the solver stage failed (%s); continuing without graphs\n",
+				cudaGetErrorString(err));
+		s->graphExec = nullptr;
+		s->graphDisabled = true;
+		s->graphCandidate.clear();
+		w->kernelLaunches = launchesBefore;
+		s2bSolve(w, solverType, ctxIn);
+		return;
+	}
+	s->graphSig = sig;
+	s->graphLaunches = w->kernelLaunches - launchesBefore;
+	s->graphCaptures += 1;
+	// the schedule of the previous (eager) step is still valid unless the flag says otherwise: the gate decides
+	S2B_CHECK(cudaGraphLaunch(s->graphExec, st));
 }
 
 extern "C" void s2b_get_work(s2bWorld* w, uint64_t out[2], int reset)
@@ -2323,11 +2440,18 @@ extern "C" int s2b_download_solve_order(s2bWorld* w, int32_t* items, int maxItem
 	S2B_CHECK(cudaMemcpy(counts, s->counts.p, sizeof(counts), cudaMemcpyDeviceToHost));
 	int nC = counts[CNT_CONTACTS], nJ = counts[CNT_JOINTS], groups = counts[CNT_GROUPS];
 	bool wavefront = w->schedule == S2B_SCHEDULE_WAVEFRONT;
+	int regions = wavefront ? 0 : s->regions;
 	int tableLen = (wavefront ? groups : S2B_MAX_COLORS) + 2;
 	std::vector<int> cOff((size_t)tableLen), jOff((size_t)tableLen), src((size_t)std::max(nC, 1)), jPerm((size_t)std::max(nJ, 1)),
 		jointSlots((size_t)std::max(nJ, 1));
 	S2B_CHECK(cudaMemcpy(cOff.data(), s->cGroupOff.p, sizeof(int) * (size_t)tableLen, cudaMemcpyDeviceToHost));
 	S2B_CHECK(cudaMemcpy(jOff.data(), s->jGroupOff.p, sizeof(int) * (size_t)tableLen, cudaMemcpyDeviceToHost));
+	std::vector<int> cReg((size_t)std::max(regions, 1) * S2B_REG_STRIDE), jReg((size_t)std::max(regions, 1) * S2B_REG_STRIDE);
+	if (regions > 0)
+	{
+		S2B_CHECK(cudaMemcpy(cReg.data(), s->cRegOff.p, sizeof(int) * (size_t)regions * S2B_REG_STRIDE, cudaMemcpyDeviceToHost));
+		S2B_CHECK(cudaMemcpy(jReg.data(), s->jRegOff.p, sizeof(int) * (size_t)regions * S2B_REG_STRIDE, cudaMemcpyDeviceToHost));
+	}
 	if (nC > 0)
 	{
 		S2B_CHECK(cudaMemcpy(src.data(), s->src.p, sizeof(int) * (size_t)nC, cudaMemcpyDeviceToHost));
@@ -2337,12 +2461,13 @@ extern "C" int s2b_download_solve_order(s2bWorld* w, int32_t* items, int maxItem
 		S2B_CHECK(cudaMemcpy(jPerm.data(), s->jPerm.p, sizeof(int) * (size_t)nJ, cudaMemcpyDeviceToHost));
 		S2B_CHECK(cudaMemcpy(jointSlots.data(), s->jointSlots.p, sizeof(int) * (size_t)nJ, cudaMemcpyDeviceToHost));
 	}
-	// group g = joints [jOff[g], jOff[g+1]) then contacts [cOff[g], cOff[g+1]); the serial overflow group (colour
-	// schedule only) sits at table index S2B_MAX_COLORS and is visited last
+	// a group = joints [jb, je) then contacts [cb, ce) of the two streams. Serial order of the region-local schedule
+	// (persistent.cuh): region by region, colour by colour inside a region; then the device-wide groups (cut colours /
+	// colours / wavefront levels); the serial overflow group (colour schedule only, table index S2B_MAX_COLORS) comes last.
 	int written = 0, groupsOut = 0;
-	auto emit = [&](int g) {
+	auto emit = [&](int jb, int je, int cb, int ce) {
 		int size = 0;
-		for (int t = jOff[(size_t)g]; t < jOff[(size_t)g + 1]; ++t, ++size)
+		for (int t = jb; t < je; ++t, ++size)
 		{
 			if (written < maxItems && items != nullptr)
 			{
@@ -2350,7 +2475,7 @@ extern "C" int s2b_download_solve_order(s2bWorld* w, int32_t* items, int maxItem
 			}
 			written += 1;
 		}
-		for (int t = cOff[(size_t)g]; t < cOff[(size_t)g + 1]; ++t, ++size)
+		for (int t = cb; t < ce; ++t, ++size)
 		{
 			if (written < maxItems && items != nullptr)
 			{
@@ -2367,13 +2492,21 @@ extern "C" int s2b_download_solve_order(s2bWorld* w, int32_t* items, int maxItem
 			groupsOut += 1;
 		}
 	};
+	for (int r = 0; r < regions; ++r)
+	{
+		for (int c = 0; c < S2B_MAX_COLORS; ++c)
+		{
+			size_t e = (size_t)r * S2B_REG_STRIDE + c;
+			emit(jReg[e], jReg[e + 1], cReg[e], cReg[e + 1]);
+		}
+	}
 	for (int g = 0; g < groups; ++g)
 	{
-		emit(g);
+		emit(jOff[(size_t)g], jOff[(size_t)g + 1], cOff[(size_t)g], cOff[(size_t)g + 1]);
 	}
 	if (wavefront == false)
 	{
-		emit(S2B_MAX_COLORS);
+		emit(jOff[S2B_MAX_COLORS], jOff[S2B_MAX_COLORS + 1], cOff[S2B_MAX_COLORS], cOff[S2B_MAX_COLORS + 1]);
 	}
 	if (groupCount != nullptr)
 	{
@@ -2397,7 +2530,11 @@ extern "C" void s2b_get_counters(s2bWorld* w, s2bCounters* out)
 		S2B_CHECK(cudaMemcpy(counts, w->scratch->counts.p, sizeof(counts), cudaMemcpyDeviceToHost));
 		out->constraintCount = counts[CNT_CONTACTS];
 		out->jointCount = counts[CNT_JOINTS];
-		out->groupCount = counts[CNT_GROUPS];
+		// colours of the constraint graph under the colour schedule, levels under the wavefront schedule
+		out->groupCount = w->schedule == S2B_SCHEDULE_COLOR ? counts[CNT_COLORS] : counts[CNT_GROUPS];
+		out->cutGroupCount = w->scratch->regions > 0 ? counts[CNT_GROUPS] : 0;
+		out->cutCount = w->scratch->regions > 0 ? counts[CNT_CUT] : 0;
+		out->regionCount = w->scratch->regions;
 		out->overflowCount = counts[CNT_OVERFLOW_C] + counts[CNT_OVERFLOW_J];
 		if (w->scratch->bodyTicket.p != nullptr && w->scratch->flowErrorOffset > 0)
 		{

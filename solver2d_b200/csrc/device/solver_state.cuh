@@ -6,6 +6,9 @@
 
 // threads per block of the solver kernels
 #define S2B_BLOCK 256
+// colours of the constraint graph: 0..S2B_MAX_COLORS-1, or the serial overflow group
+#define S2B_MAX_COLORS 64
+#define S2B_OVERFLOW_KEY 255
 
 // soft-constraint coefficients (reference src/solve_common.c:264-271)
 struct SoftCoef
@@ -25,7 +28,12 @@ enum
 	CNT_REMAINING = 5, // colouring work counters (three rotating slots: 5, 6, 7)
 	CNT_ROUNDS = 8,
 	CNT_UNCOLOURED = 9, // blocks that saw an uncoloured item at the start of the colouring kernel
-	CNT_SIZE = 16
+	CNT_PRIMARY = 10,	// region-local schedule: colours used by interior constraints (0 = no regions)
+	CNT_COLORS = 11,	// colours of the constraint graph (what s2bCounters.groupCount reports under the colour schedule)
+	CNT_OWNED = 12,		// bodies that belong to a region (valid, not a hub)
+	CNT_CUT = 13,		// constraints in the cut set (straddle two regions or touch a hub body)
+	CNT_BOUNDS = 16,	// 4 slots: order-preserving keys of max x, max -x, max y, max -y over the bodies' centres
+	CNT_SIZE = 32
 };
 
 struct SolveArgs
@@ -41,6 +49,13 @@ struct SolveArgs
 	const int* incStart;  // per body: range of its incidence list (warm_gather.cuh); null when the gather is not used
 	const int* incList;	  // incidence entries sorted by solve order
 	const int* heavyBodies; // [0] count, then body indices with more than S2B_HEAVY_DEGREE incident items (null = none split off)
+	// region-local schedule of the persistent kernel (persistent.cuh); regions == 0: every group is device-wide
+	int regions;			 // number of regions = blocks of the persistent kernel
+	const int* regBodyStart; // regions + 1: range of each region in regBodies
+	const int* regBodies;	 // body slots sorted by region (Hilbert order of their centres)
+	const int* jRegOff;		 // regions x (S2B_MAX_COLORS + 1): joint-constraint stream offsets of (region, colour)
+	const int* cRegOff;		 // same for contact constraints
+	unsigned* barrier;		 // [0] monotonic arrival counter of the grid barrier, [32] its value at the start of the next launch
 	// ticketed ("dataflow") Gauss-Seidel passes: null when the passes synchronise with grid barriers instead
 	int* bodyTicket;			   // per body: incident-item executions completed in this launch
 	const int2 *cFlowA, *cFlowB;   // per contact constraint and side: {ordinal in the body's incidence list, its degree} or -1
@@ -74,8 +89,17 @@ struct SolverScratch
 	DevArray<int> adjStart;		  // per body + 1
 	DevArray<int> adjCursor;	  // per body
 	DevArray<int> adj;			  // 2 * items
-	DevArray<int> colorA, colorB; // per item, ping-pong
-	DevArray<unsigned char> sortKeyIn, sortKeyOut;
+	DevArray<int> colorA, colorB; // per item: colour, tentative colour of the speculative rounds
+	DevArray<int> colorC;		  // per item: colour inside the cut set
+	DevArray<int> itemRegion;	  // per item: region it is interior to, or -1 (cut set)
+	DevArray<unsigned short> sortKeyIn, sortKeyOut; // solve-order keys (region x colour | cut colour | overflow), see s2bMakeSortKeys
+	// regions
+	DevArray<unsigned> bodyKeyIn, bodyKeyOut; // Hilbert keys of the bodies' centres
+	DevArray<int> bodyValIn, regBodies;		  // body slots, unsorted / sorted by key
+	DevArray<int> bodyRegion;				  // per body: region or -1 (hub, invalid)
+	DevArray<int> regBodyStart;				  // regions + 1
+	DevArray<int> cRegOff, jRegOff;			  // regions x (S2B_MAX_COLORS + 1)
+	int regions = 0;						  // regions of the last schedule (0: none)
 	DevArray<int> sortValIn, sortValOut;
 	DevArray<int> cGroupOff, jGroupOff; // maxGroups + 2
 	DevArray<int> cPerm;				// solve position -> natural contact-constraint index
@@ -107,6 +131,7 @@ struct SolverScratch
 	// changes: see s2bSolve
 	cudaGraphExec_t graphExec = nullptr;
 	std::vector<unsigned char> graphSig, graphCandidate;
+	std::vector<unsigned char> scheduleSig; // signature the schedule buffers were last built for
 	int graphLaunches = 0;
 	bool graphDisabled = false;
 	int graphReplays = 0, graphCaptures = 0;

@@ -19,7 +19,6 @@
 #define S2B_INC_SIDE_B 2
 // bodies with more incident constraints than this are gathered by a whole block instead of one thread
 #define S2B_HEAVY_DEGREE 48
-#define S2B_MAX_HEAVY_BODIES 1024
 
 // FIXED = false: anchors rotated by the current rotation (s2WarmStartContacts, reference src/solve_common.c:276-326)
 // FIXED = true : prepare-time anchors (s2WarmStartContacts_Fixed, reference src/solve_soft_step.c:16-63)
@@ -229,7 +228,7 @@ template <bool FIXED> __device__ __forceinline__ void s2bGatherHeavyBodies(const
 {
 	__shared__ float sTw0[S2B_BLOCK], sTw1[S2B_BLOCK], sX0[S2B_BLOCK], sY0[S2B_BLOCK], sX1[S2B_BLOCK], sY1[S2B_BLOCK];
 	__shared__ int sNp[S2B_BLOCK];
-	int heavy = min(a.heavyBodies[0], S2B_MAX_HEAVY_BODIES);
+	int heavy = a.heavyBodies[0];
 	for (int hb = blockIdx.x; hb < heavy; hb += gridDim.x)
 	{
 		int i = a.heavyBodies[1 + hb];
@@ -294,224 +293,6 @@ template <bool FIXED> __device__ __forceinline__ void s2bGatherHeavyBodies(const
 		if (threadIdx.x == 0)
 		{
 			a.bodies.vel[i] = make_float4(v.x, v.y, w, invMass);
-		}
-	}
-}
-
-// ---- building the sorted incidence lists (once per step, after the solve order is known) --------------------------
-
-// value of an item in the per-body sort: high word = (group << 1 | isContact), low word = the incidence entry without its
-// side bit, whose top bits are the stream position t. Sorting the 64-bit values orders by (group, joints first, t).
-__global__ void s2bItemOrderKernel(const int* counts, const int* cPerm, const int* jPerm, const int* cGroupOff, const int* jGroupOff,
-								   int tableEntries, unsigned long long* itemVal)
-{
-	int nJ = counts[CNT_JOINTS], nC = counts[CNT_CONTACTS];
-	int p = blockIdx.x * blockDim.x + threadIdx.x;
-	if (p >= nJ + nC)
-	{
-		return;
-	}
-	bool isContact = p >= nJ;
-	int t = isContact ? p - nJ : p;
-	const int* off = isContact ? cGroupOff : jGroupOff;
-	// largest g in [0, tableEntries) with off[g] <= t
-	int lo = 0, hi = tableEntries - 1;
-	while (lo < hi)
-	{
-		int mid = (lo + hi + 1) >> 1;
-		if (off[mid] <= t)
-		{
-			lo = mid;
-		}
-		else
-		{
-			hi = mid - 1;
-		}
-	}
-	int natural = isContact ? cPerm[t] : jPerm[t];
-	int item = isContact ? nJ + natural : natural;
-	unsigned long long key = ((unsigned long long)(unsigned)((lo << 1) | (isContact ? 1 : 0))) << 32;
-	unsigned entry = ((unsigned)t << 2) | (isContact ? S2B_INC_CONTACT : 0);
-	itemVal[item] = key | entry;
-}
-
-// Besides the sorted list this also hands every constraint its ORDINAL in the lists of its two bodies (k-th of d incident
-// items): what the ticketed Gauss-Seidel passes (solver.cu, "dataflow") wait on instead of a grid barrier.
-__global__ void s2bSortIncidenceKernel(int bodyCapacity, const int* adjStart, const int* adj, const int2* itemBodies,
-									   const unsigned long long* itemVal, unsigned long long* work, int* incList, int2* cFlowA,
-									   int2* cFlowB, int2* jFlowA, int2* jFlowB, int* heavyBodies)
-{
-	int b = blockIdx.x * blockDim.x + threadIdx.x;
-	if (b >= bodyCapacity)
-	{
-		return;
-	}
-	int begin = adjStart[b], end = adjStart[b + 1];
-	int n = end - begin;
-	if (n == 0)
-	{
-		return;
-	}
-	if (heavyBodies != nullptr && n > S2B_HEAVY_DEGREE)
-	{
-		int slot = atomicAdd(heavyBodies, 1);
-		if (slot < S2B_MAX_HEAVY_BODIES)
-		{
-			heavyBodies[1 + slot] = b;
-		}
-	}
-	if (n <= 8)
-	{
-		// the common case (a box touches ~6 others): sort in registers, touch global memory once per entry
-		unsigned long long r[8];
-#pragma unroll
-		for (int k = 0; k < 8; ++k)
-		{
-			r[k] = ~0ull;
-			if (k < n)
-			{
-				int item = adj[begin + k];
-				unsigned long long val = itemVal[item];
-				if (itemBodies[item].x != b)
-				{
-					val |= S2B_INC_SIDE_B;
-				}
-				r[k] = val;
-			}
-		}
-		// odd-even transposition network on 8 keys (padding keys are the largest value and stay at the end)
-#pragma unroll
-		for (int pass = 0; pass < 8; ++pass)
-		{
-#pragma unroll
-			for (int k = pass & 1; k + 1 < 8; k += 2)
-			{
-				unsigned long long lo = r[k] < r[k + 1] ? r[k] : r[k + 1];
-				unsigned long long hi = r[k] < r[k + 1] ? r[k + 1] : r[k];
-				r[k] = lo;
-				r[k + 1] = hi;
-			}
-		}
-#pragma unroll
-		for (int k = 0; k < 8; ++k)
-		{
-			if (k < n)
-			{
-				int e = (int)(unsigned)(r[k] & 0xFFFFFFFFull);
-				incList[begin + k] = e;
-				if (cFlowA != nullptr)
-				{
-					int t = e >> 2;
-					int2 ticket = make_int2(k, n);
-					if (e & S2B_INC_CONTACT)
-					{
-						((e & S2B_INC_SIDE_B) ? cFlowB : cFlowA)[t] = ticket;
-					}
-					else
-					{
-						((e & S2B_INC_SIDE_B) ? jFlowB : jFlowA)[t] = ticket;
-					}
-				}
-			}
-		}
-		return;
-	}
-	unsigned long long* v = work + begin;
-	for (int k = 0; k < n; ++k)
-	{
-		int item = adj[begin + k];
-		unsigned long long val = itemVal[item];
-		if (itemBodies[item].x != b)
-		{
-			val |= S2B_INC_SIDE_B;
-		}
-		v[k] = val;
-	}
-	if (n <= 24)
-	{
-		for (int k = 1; k < n; ++k)
-		{
-			unsigned long long x = v[k];
-			int m = k - 1;
-			while (m >= 0 && v[m] > x)
-			{
-				v[m + 1] = v[m];
-				m -= 1;
-			}
-			v[m + 1] = x;
-		}
-	}
-	else
-	{
-		// heap sort: bodies touching hundreds of constraints (a container wall) stay O(n log n)
-		for (int start = n / 2 - 1; start >= 0; --start)
-		{
-			int root = start;
-			for (;;)
-			{
-				int child = 2 * root + 1;
-				if (child >= n)
-				{
-					break;
-				}
-				if (child + 1 < n && v[child] < v[child + 1])
-				{
-					child += 1;
-				}
-				if (v[root] >= v[child])
-				{
-					break;
-				}
-				unsigned long long tmp = v[root];
-				v[root] = v[child];
-				v[child] = tmp;
-				root = child;
-			}
-		}
-		for (int last = n - 1; last > 0; --last)
-		{
-			unsigned long long tmp = v[0];
-			v[0] = v[last];
-			v[last] = tmp;
-			int root = 0;
-			for (;;)
-			{
-				int child = 2 * root + 1;
-				if (child >= last)
-				{
-					break;
-				}
-				if (child + 1 < last && v[child] < v[child + 1])
-				{
-					child += 1;
-				}
-				if (v[root] >= v[child])
-				{
-					break;
-				}
-				unsigned long long t2 = v[root];
-				v[root] = v[child];
-				v[child] = t2;
-				root = child;
-			}
-		}
-	}
-	for (int k = 0; k < n; ++k)
-	{
-		int e = (int)(unsigned)(v[k] & 0xFFFFFFFFull);
-		incList[begin + k] = e;
-		if (cFlowA != nullptr)
-		{
-			int t = e >> 2;
-			int2 ticket = make_int2(k, n);
-			if (e & S2B_INC_CONTACT)
-			{
-				((e & S2B_INC_SIDE_B) ? cFlowB : cFlowA)[t] = ticket;
-			}
-			else
-			{
-				((e & S2B_INC_SIDE_B) ? jFlowB : jFlowA)[t] = ticket;
-			}
 		}
 	}
 }

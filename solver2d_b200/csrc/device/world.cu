@@ -10,7 +10,7 @@
 // scatter kernels
 // ---------------------------------------------------------------------------------------------------------------
 
-__global__ void s2bScatterBodies(const s2bBodyRow* __restrict__ rows, int count, BodyView b)
+__global__ void s2bScatterBodies(const s2bBodyRow* __restrict__ rows, int count, BodyView b, int* schedDirty)
 {
 	int t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= count)
@@ -19,6 +19,15 @@ __global__ void s2bScatterBodies(const s2bBodyRow* __restrict__ rows, int count,
 	}
 	s2bBodyRow r = rows[t];
 	int i = r.index;
+	{
+		// the solve schedule (conflict graph, regions) depends on which bodies exist and which of them can move
+		bool wasValid = (b.flags[i] & S2B_BODY_VALID) != 0, isValid = (r.flags & S2B_BODY_VALID) != 0;
+		bool wasMovable = b.vel[i].w != 0.0f || b.prm[i].w != 0.0f, isMovable = r.invMass != 0.0f || r.invI != 0.0f;
+		if (wasValid != isValid || (isValid && wasMovable != isMovable))
+		{
+			*schedDirty = 1;
+		}
+	}
 	b.vel[i] = make_float4(r.linearVelocity[0], r.linearVelocity[1], r.angularVelocity, r.invMass);
 	b.pose[i] = make_float4(0.0f, 0.0f, r.rot[0], r.rot[1]);
 	b.pos[i] = make_float4(r.position[0], r.position[1], r.invI, r.I);
@@ -57,7 +66,7 @@ __global__ void s2bScatterShapes(const s2bShapeRow* __restrict__ rows, int count
 	}
 }
 
-__global__ void s2bScatterJoints(const s2bJointRow* __restrict__ rows, int count, JointView j)
+__global__ void s2bScatterJoints(const s2bJointRow* __restrict__ rows, int count, JointView j, int* schedDirty)
 {
 	int t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= count)
@@ -66,6 +75,16 @@ __global__ void s2bScatterJoints(const s2bJointRow* __restrict__ rows, int count
 	}
 	const s2bJointRow* r = rows + t;
 	int i = r->index;
+	{
+		// a joint that appears, disappears or changes its bodies / kind changes the solve schedule; a new target, motor
+		// speed or limit does not
+		int4 old = j.head[i];
+		if (((old.x ^ r->flags) & (S2B_ROW_VALID | 0xE)) != 0 || ((r->flags & S2B_ROW_VALID) != 0 && (old.y != r->bodyA || old.z != r->bodyB)))
+		{
+			*schedDirty = 1;
+			j.color[i] = -1; // (an unchanged joint keeps the colour it was last solved with)
+		}
+	}
 	j.head[i] = make_int4(r->flags, r->bodyA, r->bodyB, 0);
 	j.anchors[i] = make_float4(r->localOriginAnchorA[0], r->localOriginAnchorA[1], r->localOriginAnchorB[0],
 							   r->localOriginAnchorB[1]);
@@ -74,7 +93,6 @@ __global__ void s2bScatterJoints(const s2bJointRow* __restrict__ rows, int count
 	j.target[i] = make_float4(r->target[0], r->target[1], 0.0f, 0.0f);
 	j.imp[i] = make_float4(r->impulse[0], r->impulse[1], r->motorImpulse, 0.0f);
 	j.limp[i] = make_float4(r->lowerImpulse, r->upperImpulse, 0.0f, 0.0f);
-	j.color[i] = -1;
 }
 
 __device__ __forceinline__ int s2bPackCache(const s2bContactRow* r)
@@ -326,6 +344,11 @@ extern "C" s2bWorld* s2b_world_create(int cudaDevice, int solverType)
 		{
 			w->useGraph = atoi(env) != 0 ? 1 : 0;
 		}
+		env = getenv("S2B_REGIONS");
+		if (env != nullptr)
+		{
+			w->useRegions = atoi(env) != 0 ? 1 : 0;
+		}
 		env = getenv("S2B_DATAFLOW");
 		if (env != nullptr)
 		{
@@ -334,6 +357,8 @@ extern "C" s2bWorld* s2b_world_create(int cudaDevice, int solverType)
 	}
 	w->solverType = solverType;
 	w->sticky = (solverType == 6); // s2_solverTGS_Sticky
+	w->schedDirty.reserve(4, w->stream, true, true);
+	w->solveBarrier.reserve(64, w->stream, true, true);
 	S2B_CHECK(cudaMallocHost((void**)&w->hostMail, MAIL_COUNT * sizeof(int)));
 	memset(w->hostMail, 0, MAIL_COUNT * sizeof(int));
 	S2B_CHECK(cudaMalloc((void**)&w->devMail, MAIL_COUNT * sizeof(int)));
@@ -394,6 +419,8 @@ extern "C" void s2b_world_destroy(s2bWorld* w)
 	w->contacts[0].release();
 	w->contacts[1].release();
 	w->dMovedFlag.release();
+	w->solveBarrier.release();
+	w->schedDirty.release();
 	w->l2Flush.release();
 	w->dWork.release();
 	if (w->solveKernelStart != nullptr)
@@ -419,31 +446,43 @@ extern "C" void s2b_set_gravity(s2bWorld* w, float gx, float gy)
 extern "C" void s2b_set_schedule(s2bWorld* w, int schedule)
 {
 	w->schedule = schedule;
+	w->scheduleEpoch += 1;
 }
 
 extern "C" void s2b_set_max_colors(s2bWorld* w, int maxColors)
 {
 	w->maxColors = maxColors < 1 ? 1 : (maxColors > 64 ? 64 : maxColors);
+	w->scheduleEpoch += 1;
 }
 
 extern "C" void s2b_set_persistent(s2bWorld* w, int enable)
 {
 	w->persistent = enable;
+	w->scheduleEpoch += 1;
 }
 
 extern "C" void s2b_set_warm_gather(s2bWorld* w, int enable)
 {
 	w->gatherWarm = enable;
+	w->scheduleEpoch += 1;
 }
 
 extern "C" void s2b_set_graph(s2bWorld* w, int enable)
 {
 	w->useGraph = enable;
+	w->scheduleEpoch += 1;
 }
 
 extern "C" void s2b_set_dataflow(s2bWorld* w, int enable)
 {
 	w->dataflow = enable;
+	w->scheduleEpoch += 1;
+}
+
+extern "C" void s2b_set_regions(s2bWorld* w, int enable)
+{
+	w->useRegions = enable;
+	w->scheduleEpoch += 1;
 }
 
 static void reserveBodies(s2bWorld* w, int cap)
@@ -509,7 +548,7 @@ extern "C" void s2b_upload_bodies(s2bWorld* w, const s2bBodyRow* rows, int count
 		return;
 	}
 	s2bBodyRow* d = (s2bBodyRow*)stageRows(w, rows, sizeof(s2bBodyRow) * (size_t)count);
-	S2B_LAUNCH(w, s2bScatterBodies, gridFor(count, 128), 128, 0, d, count, bodyView(w));
+	S2B_LAUNCH(w, s2bScatterBodies, gridFor(count, 128), 128, 0, d, count, bodyView(w), w->schedDirty.p);
 	S2B_CHECK(cudaFreeAsync(d, w->stream));
 	// the staging copy reads pageable host memory: make sure it is consumed before the caller reuses the buffer
 	S2B_CHECK(cudaStreamSynchronize(w->stream));
@@ -539,7 +578,7 @@ extern "C" void s2b_upload_joints(s2bWorld* w, const s2bJointRow* rows, int coun
 		return;
 	}
 	s2bJointRow* d = (s2bJointRow*)stageRows(w, rows, sizeof(s2bJointRow) * (size_t)count);
-	S2B_LAUNCH(w, s2bScatterJoints, gridFor(count, 128), 128, 0, d, count, jointView(w));
+	S2B_LAUNCH(w, s2bScatterJoints, gridFor(count, 128), 128, 0, d, count, jointView(w), w->schedDirty.p);
 	S2B_CHECK(cudaFreeAsync(d, w->stream));
 	S2B_CHECK(cudaStreamSynchronize(w->stream));
 }

@@ -57,7 +57,8 @@ class Counters(C.Structure):
                 ("contactCount", C.c_int32), ("constraintCount", C.c_int32), ("jointCount", C.c_int32),
                 ("groupCount", C.c_int32), ("overflowCount", C.c_int32), ("treeHeight", C.c_int32),
                 ("movedCount", C.c_int32), ("pairPassCount", C.c_int32), ("kernelLaunches", C.c_int32),
-                ("graphReplays", C.c_int32), ("graphCaptures", C.c_int32), ("scratchBytes", C.c_int64)]
+                ("graphReplays", C.c_int32), ("graphCaptures", C.c_int32), ("scratchBytes", C.c_int64),
+                ("regionCount", C.c_int32), ("cutCount", C.c_int32), ("cutGroupCount", C.c_int32), ("reserved0", C.c_int32)]
 
 
 SCHEDULE_COLOR, SCHEDULE_WAVEFRONT = 0, 1
@@ -74,7 +75,7 @@ ABI_SYMBOLS = [
     "s2b_download_all_bodies", "s2b_download_shape_boxes", "s2b_download_joints", "s2b_download_contacts",
     "s2b_download_solve_order", "s2b_get_counters", "s2b_pack_body_state", "s2b_timed_steps", "s2b_last_stage_ms",
     "s2b_flush_l2", "s2b_time_color_kernel", "s2b_version", "s2b_abi_sizes", "s2b_upload_forces", "s2b_host_alloc",
-    "s2b_host_free", "s2b_sync_body_state", "s2b_set_warm_gather", "s2b_eval_atan2", "s2b_set_dataflow", "s2b_set_graph", "s2b_get_stream", "s2b_add_forces", "s2b_download_transforms",
+    "s2b_host_free", "s2b_sync_body_state", "s2b_set_warm_gather", "s2b_eval_atan2", "s2b_set_dataflow", "s2b_set_regions", "s2b_set_graph", "s2b_get_stream", "s2b_add_forces", "s2b_download_transforms",
 ]
 
 
@@ -112,7 +113,7 @@ class Device:
         L.s2b_world_create.argtypes = [C.c_int, C.c_int]
         L.s2b_world_destroy.argtypes = [vp]
         L.s2b_set_gravity.argtypes = [vp, C.c_float, C.c_float]
-        for name in ("s2b_set_schedule", "s2b_set_max_colors", "s2b_set_persistent", "s2b_set_warm_gather", "s2b_set_dataflow", "s2b_set_graph"):
+        for name in ("s2b_set_schedule", "s2b_set_max_colors", "s2b_set_persistent", "s2b_set_warm_gather", "s2b_set_dataflow", "s2b_set_regions", "s2b_set_graph"):
             getattr(L, name).argtypes = [vp, C.c_int]
         for name in ("s2b_upload_bodies", "s2b_upload_shapes", "s2b_upload_joints"):
             getattr(L, name).argtypes = [vp, vp, C.c_int, C.c_int]
@@ -217,6 +218,10 @@ class DeviceWorld:
 
     def set_dataflow(self, enable: bool):
         self.L.s2b_set_dataflow(self.h, 1 if enable else 0)
+
+    def set_regions(self, enable: bool):
+        """Region-local schedule of the persistent kernel (default on): see DESIGN.md §3.1."""
+        self.L.s2b_set_regions(self.h, 1 if enable else 0)
 
     def set_warm_gather(self, enable: bool):
         self.L.s2b_set_warm_gather(self.h, 1 if enable else 0)

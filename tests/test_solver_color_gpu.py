@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 DT = 1.0 / 60.0
 
 
-def _case(reference, dev, recipe, solver, warm, vel, pos, persistent, max_colors=None, warm_start=True, warm_gather=True, dataflow=False, **kw):
+def _case(reference, dev, recipe, solver, warm, vel, pos, persistent, max_colors=None, warm_start=True, warm_gather=True, dataflow=False,
+          regions=True, **kw):
     R = reference
     O = port.load()
     sc = recipe(R, solver, **kw)
@@ -33,6 +34,7 @@ def _case(reference, dev, recipe, solver, warm, vel, pos, persistent, max_colors
     dw.set_persistent(persistent)
     dw.set_warm_gather(warm_gather)
     dw.set_dataflow(dataflow)
+    dw.set_regions(regions)
     if max_colors is not None:
         dw.set_max_colors(max_colors)
     dw.solve(ctx)
@@ -147,6 +149,25 @@ def test_grouped_warm_start_path_still_matches(reference, dev, solver):
     assert c.jointCount == 19
     c = _case(reference, dev, scenes.pyramid, solver, 30, 4, 2, True, warm_gather=False, max_colors=3, base_count=14)
     assert c.overflowCount > 0
+
+
+@pytest.mark.parametrize("solver", VARIANTS)
+def test_device_wide_colour_steps_still_match(reference, dev, solver):
+    """The persistent kernel runs the constraints interior to a block's region between block barriers and only the cut set
+    in device-wide steps (default). With regions off every colour is one device-wide step; both orders are replayed by
+    the oracle bit for bit."""
+    c = _case(reference, dev, scenes.limited_chains, solver, 40, 4, 2, True, regions=False)
+    assert c.jointCount == 19 and c.regionCount == 0
+    warm = 2 if solver == "Jacobi" else 30
+    c = _case(reference, dev, scenes.pyramid, solver, warm, 4, 2, True, regions=False, max_colors=3, base_count=14)
+    assert c.overflowCount > 0
+
+
+def test_region_schedule_has_a_cut_set(reference, dev):
+    """A pyramid large enough for several blocks: most constraints are interior to a region, the rest form a cut set with
+    only a few colours (= device-wide steps per sweep)."""
+    c = _case(reference, dev, scenes.pyramid, "TGS_Soft", 5, 4, 2, True, base_count=60)
+    assert c.regionCount >= 4 and 0 < c.cutCount < c.constraintCount // 2 and 1 <= c.cutGroupCount <= 8
 
 
 @pytest.mark.parametrize("solver", VARIANTS)

@@ -29,11 +29,15 @@ dt = np.diff(ns)
 names = {0: "body", 1: "flat", 2: "group"}
 agg = {}
 for c, d in zip(code[1:], dt):
-    key = (names.get(int(c) >> 8, "?"), int(c) & 0xFF)
+    kind = int(c) >> 8
+    # an interval ends at a grid barrier and is labelled with the LAST phase before it (region-local phases that ran since
+    # the previous barrier are inside the same interval); bit 7: device-wide step (cut colour), bits 7+6: overflow group
+    key = (names.get(kind & 0x3F, "?") + ("/cut" if (kind & 0xC0) == 0x80 else "/ovf" if (kind & 0xC0) == 0xC0 else ""), int(c) & 0xFF)
     agg.setdefault(key, []).append(int(d))
 print("stamps", n, "total us", (ns[-1] - ns[0]) / 1e3)
 for key, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
-    print(f"{key[0]:6s} op {key[1]:3d}: n={len(v):3d} total {sum(v)/1e3:8.1f} us  mean {np.mean(v)/1e3:6.2f} us  min {min(v)/1e3:6.2f}  max {max(v)/1e3:6.2f}")
+    print(f"{key[0]:9s} op {key[1]:3d}: n={len(v):3d} total {sum(v)/1e3:8.1f} us  mean {np.mean(v)/1e3:6.2f} us  min {min(v)/1e3:6.2f}  max {max(v)/1e3:6.2f}")
 print("sequence (us):", [round(float(d) / 1e3, 2) for d in dt[:60]])
 c = dw.counters()
-print("constraints", c.constraintCount, "groups", c.groupCount, "overflow", c.overflowCount, "stage ms", dw.stage_ms())
+print("constraints", c.constraintCount, "colours", c.groupCount, "overflow", c.overflowCount, "regions", c.regionCount, "cut", c.cutCount,
+      "cut colours", c.cutGroupCount, "stage ms", dw.stage_ms(), "kernel ms", dev.lib.s2b_last_solve_kernel_ms(dw.h) if hasattr(dev.lib, "s2b_last_solve_kernel_ms") else None)
