@@ -203,10 +203,12 @@ S2B_API void s2b_set_warm_gather(s2bWorld* world, int enable);
 // Replay the solver stage (set-up kernels + persistent kernel, ~30 launches) as ONE CUDA graph launch while its inputs'
 // shapes and addresses are unchanged (1, default) or always launch kernel by kernel (0).
 S2B_API void s2b_set_graph(s2bWorld* world, int enable);
-// Region-local schedule of the persistent kernel (1, default): bodies are partitioned into one region per thread block,
-// constraints interior to a region run between block barriers, only the cut set needs grid barriers.
-// 0 = one device-wide step per colour (cross-check; same bits against the oracle replayed in the reported order).
-S2B_API void s2b_set_regions(s2bWorld* world, int enable);
+// Region-local schedule of the persistent kernel: bodies are partitioned into one region per thread block, constraints
+// interior to a region run between block barriers, only the cut set needs grid barriers.
+// mode 0 = never: one device-wide step per colour; 1 (default) = when the cut set needs at most 3 colours (islands,
+// batched worlds, chains, anything that fits one block), decided on the device whenever the schedule is built; 2 = always.
+// Whatever order results is reported by s2b_download_solve_order and replayed bit for bit by the oracle.
+S2B_API void s2b_set_regions(s2bWorld* world, int mode);
 // Gauss-Seidel passes of the persistent kernel synchronised by one grid barrier per colour (0, default) or by per-body
 // tickets (1: a constraint waits only for the previous constraint on each of its bodies; no barrier inside a sweep).
 // Same bits either way; the ticketed form measured SLOWER on B200 (75 k pollers saturate L2), kept as an experiment.

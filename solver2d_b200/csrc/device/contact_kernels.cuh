@@ -82,6 +82,29 @@ __device__ __forceinline__ void s2bFinalizePosition(const SolveArgs& a, int i)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// The warm-start rows of one constraint (ConstraintView::warmP / warmAnchor, read by the per-body gather).
+// s2bWriteWarmImpulses: by whichever pass leaves the impulses the next gather applies — prepare, and the last solve /
+// relax pass of a sub-step. s2bWriteWarmAnchors: by prepare; anchors[j] = side A anchor in .xy, side B in .zw.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void s2bWriteWarmImpulses(const SolveArgs& a, int t, s2Vec2 normal, s2Vec2 tangent, int pointCount, float2 lam0,
+													 float2 lam1)
+{
+	s2Vec2 P0 = s2Add(s2MulSV(lam0.x, normal), s2MulSV(lam0.y, tangent));
+	s2Vec2 P1 = s2Add(s2MulSV(lam1.x, normal), s2MulSV(lam1.y, tangent));
+	if (pointCount != 2)
+	{
+		P1.x = __int_as_float(0x7FC00000); // NaN: no second point
+	}
+	a.cc.warmP[t] = make_float4(P0.x, P0.y, P1.x, P1.y);
+}
+
+__device__ __forceinline__ void s2bWriteWarmAnchors(const SolveArgs& a, int t, float4 anchors0, float4 anchors1)
+{
+	a.cc.warmAnchor[(size_t)t * 2] = make_float4(anchors0.x, anchors0.y, anchors1.x, anchors1.y);
+	a.cc.warmAnchor[(size_t)t * 2 + 1] = make_float4(anchors0.z, anchors0.w, anchors1.z, anchors1.w);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // contact constraints: prepare
 // ---------------------------------------------------------------------------------------------------------------
 
@@ -125,6 +148,8 @@ template <int KIND> __device__ __forceinline__ void s2bPrepareContact(const Solv
 	}
 	cc.idx[t] = make_int2(bodies.x, (int)((unsigned)bodies.y | flags));
 	cc.nf[t] = make_float4(normal.x, normal.y, mnf.z, iA);
+	float2 warmLam[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+	float4 warmAnchor[2] = {make_float4(0.0f, 0.0f, 0.0f, 0.0f), make_float4(0.0f, 0.0f, 0.0f, 0.0f)};
 
 #pragma unroll
 	for (int j = 0; j < 2; ++j)
@@ -159,6 +184,9 @@ template <int KIND> __device__ __forceinline__ void s2bPrepareContact(const Solv
 			cc.anchor[j][t] = make_float4(lA.x, lA.y, lB.x, lB.y);
 			cc.pm[j][t] = make_float4(adjustedSeparation, normalMass, tangentMass, j == 0 ? iB : 0.0f);
 			cc.lambda[j][t] = make_float2(normalImpulse, tangentImpulse);
+			warmLam[j] = make_float2(normalImpulse, tangentImpulse);
+			// SoftStep warm starts at the prepare-time world anchors (reference src/solve_soft_step.c:16-63)
+			warmAnchor[j] = a.solverType == 5 ? make_float4(rA.x, rA.y, rB.x, rB.y) : make_float4(lA.x, lA.y, lB.x, lB.y);
 			if (cc.r0[j] != nullptr)
 			{
 				cc.r0[j][t] = make_float4(rA.x, rA.y, rB.x, rB.y);
@@ -182,6 +210,11 @@ template <int KIND> __device__ __forceinline__ void s2bPrepareContact(const Solv
 				cc.sep[j][t] = 0.0f;
 			}
 		}
+	}
+	if (cc.warmP != nullptr)
+	{
+		s2bWriteWarmImpulses(a, t, normal, tangent, pointCount, warmLam[0], warmLam[1]);
+		s2bWriteWarmAnchors(a, t, warmAnchor[0], warmAnchor[1]);
 	}
 }
 
@@ -303,7 +336,8 @@ __device__ __forceinline__ ContactStream s2bLoadContactStream(const SolveArgs& a
 	return cs;
 }
 
-__device__ __forceinline__ void s2bSolveContactTgsSoftStream(const SolveArgs& a, int t, const ContactStream& cs, float inv_h, bool useBias)
+__device__ __forceinline__ void s2bSolveContactTgsSoftStream(const SolveArgs& a, int t, const ContactStream& cs, float inv_h, bool useBias,
+															 bool writeWarm = false)
 {
 	const ConstraintView& cc = a.cc;
 	int2 idx = cs.idx;
@@ -413,14 +447,19 @@ __device__ __forceinline__ void s2bSolveContactTgsSoftStream(const SolveArgs& a,
 	{
 		cc.lambda[1][t] = lam[1];
 	}
+	if (writeWarm && cc.warmP != nullptr)
+	{
+		s2bWriteWarmImpulses(a, t, normal, tangent, pointCount, lam[0], lam[1]);
+	}
 	BodyPair bp = {ia, ib, velA, velB, (mA != 0.0f) || (iA != 0.0f), (mB != 0.0f) || (iB != 0.0f)};
 	s2bStoreVelocities(a, bp, vA, wA, vB, wB);
 }
 
-__device__ __forceinline__ void s2bSolveContactTgsSoft(const SolveArgs& a, int t, float inv_h, bool useBias)
+// writeWarm: this is the last pass that changes the impulses before the next sub-step's warm-start gather
+__device__ __forceinline__ void s2bSolveContactTgsSoft(const SolveArgs& a, int t, float inv_h, bool useBias, bool writeWarm = false)
 {
 	ContactStream cs = s2bLoadContactStream(a, t);
-	s2bSolveContactTgsSoftStream(a, t, cs, inv_h, useBias);
+	s2bSolveContactTgsSoftStream(a, t, cs, inv_h, useBias, writeWarm);
 }
 
 // ===============================================================================================================
@@ -690,7 +729,8 @@ __device__ __forceinline__ void s2bSolveContactPgs(const SolveArgs& a, int t)
 //   KIND 0  s2SolveContacts_TGS_Fixed (reference src/solve_soft_step.c:66-177): soft, clamp -0.5*maxBaumgarte, velocity
 //           and impulse applied at the FIXED prepare-time anchors
 //   KIND 1  s2SolveContacts_TGS       (reference src/solve_tgs_ngs.c:91-201): rigid, speculative bias only, current anchors
-template <int KIND> __device__ __forceinline__ void s2bSolveContactSubstep(const SolveArgs& a, int t, float inv_h, bool useBias)
+template <int KIND>
+__device__ __forceinline__ void s2bSolveContactSubstep(const SolveArgs& a, int t, float inv_h, bool useBias, bool writeWarm = false)
 {
 	ContactLoad c = s2bLoadContact(a, t);
 	const SoftCoef soft = c.staticSoft ? a.softStatic : a.softDynamic;
@@ -798,6 +838,10 @@ template <int KIND> __device__ __forceinline__ void s2bSolveContactSubstep(const
 	if (c.pointCount == 2)
 	{
 		a.cc.lambda[1][t] = lam[1];
+	}
+	if (writeWarm && a.cc.warmP != nullptr)
+	{
+		s2bWriteWarmImpulses(a, t, normal, tangent, c.pointCount, lam[0], lam[1]);
 	}
 	s2bStoreContactVelocities(a, c, vA, wA, vB, wB);
 }

@@ -517,7 +517,7 @@ template <int SOLVER> __global__ void __launch_bounds__(S2B_BLOCK) s2bPersistent
 	li.groups = a.counts[CNT_GROUPS];
 	li.ovJ = a.counts[CNT_OVERFLOW_J];
 	li.ovC = a.counts[CNT_OVERFLOW_C];
-	li.regions = a.regions > 0;
+	li.regions = a.regions > 0 && a.counts[CNT_REGIONS_ON] != 0;
 	li.hubs = (li.regions && a.heavyBodies != nullptr) ? a.heavyBodies[0] : 0;
 	li.bodyBegin = li.bodyEnd = 0;
 	if (li.regions)

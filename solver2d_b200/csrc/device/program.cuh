@@ -361,13 +361,13 @@ template <int SOLVER> __device__ __forceinline__ void s2bRunContactOpT(int op, c
 		case COP_TGS_SOFT_BIAS:
 			if constexpr (s2bUsesContactOp(SOLVER, COP_TGS_SOFT_BIAS))
 			{
-				s2bSolveContactTgsSoft(a, t, inv_h, true);
+				s2bSolveContactTgsSoft(a, t, inv_h, true, a.ctx.extraIterations == 0);
 			}
 			break;
 		case COP_TGS_SOFT_RELAX:
 			if constexpr (s2bUsesContactOp(SOLVER, COP_TGS_SOFT_RELAX))
 			{
-				s2bSolveContactTgsSoft(a, t, inv_h, false);
+				s2bSolveContactTgsSoft(a, t, inv_h, false, true);
 			}
 			break;
 		case COP_PGS_BAUMGARTE:
@@ -409,19 +409,19 @@ template <int SOLVER> __device__ __forceinline__ void s2bRunContactOpT(int op, c
 		case COP_SOFTSTEP_BIAS:
 			if constexpr (s2bUsesContactOp(SOLVER, COP_SOFTSTEP_BIAS))
 			{
-				s2bSolveContactSubstep<0>(a, t, inv_h, true);
+				s2bSolveContactSubstep<0>(a, t, inv_h, true, a.ctx.extraIterations == 0);
 			}
 			break;
 		case COP_SOFTSTEP_RELAX:
 			if constexpr (s2bUsesContactOp(SOLVER, COP_SOFTSTEP_RELAX))
 			{
-				s2bSolveContactSubstep<0>(a, t, inv_h, false);
+				s2bSolveContactSubstep<0>(a, t, inv_h, false, true);
 			}
 			break;
 		case COP_TGS:
 			if constexpr (s2bUsesContactOp(SOLVER, COP_TGS))
 			{
-				s2bSolveContactSubstep<1>(a, t, inv_h, true);
+				s2bSolveContactSubstep<1>(a, t, inv_h, true, true);
 			}
 			break;
 		case COP_NGS:

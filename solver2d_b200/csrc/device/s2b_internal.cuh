@@ -208,6 +208,13 @@ struct ConstraintView
 	float4* r0[2];	  // prepare-time world anchors rA0.xy rB0.xy (fixed-anchor variants, XPBD)
 	float* sep[2];	  // prepare-time separation (PGS family, NGS)
 	int* src;		  // contact slot this constraint came from
+	// warm-start gather (warm_gather.cuh): what one body needs from one incident constraint, in two 16-byte rows instead of
+	// six scattered columns. warmP[t] = {P0.x, P0.y, P1.x, P1.y}, P = lambda_n * n + lambda_t * t per point, rewritten by
+	// whichever pass last changes the impulses before the next gather (P1.x = NaN: one-point manifold);
+	// warmAnchor[t * 2 + side] = {anchor0.xy, anchor1.xy} of that side, written by prepare (COM-relative local anchors;
+	// prepare-time world anchors for SoftStep). Null when the variant does not gather.
+	float4* warmP;
+	float4* warmAnchor;
 	// sticky extras
 	float4* fanchor[2]; // COM-relative local friction anchors A.xy B.xy
 	float2* tsep[2];	// tangentSeparation, spare
@@ -292,7 +299,10 @@ struct s2bWorld
 	int useGraph = 1;		// replay the solver stage as a CUDA graph when nothing changed; s2b_set_graph / S2B_GRAPH=0 disable
 	bool capturing = false;
 	unsigned long long contactTableVersion = 0; // bumped whenever the contact table is replaced (pair pass commit, upload) // a stream capture of the solver stage is in progress
-	int useRegions = 1; // region-local schedule of the persistent kernel (persistent.cuh); s2b_set_regions / S2B_REGIONS=0 disable it
+	// region-local schedule of the persistent kernel (persistent.cuh): 0 off, 1 when the cut set needs at most regionCutLimit
+	// colours (decided on the device every time the schedule is built), 2 always; s2b_set_regions / S2B_REGIONS
+	int useRegions = 1;
+	int regionCutLimit = 3; // S2B_REGION_CUT_LIMIT
 	int dataflow = 0;	// ticketed Gauss-Seidel passes in the persistent kernel (experimental, slower on B200: DESIGN.md §3.1);
 						// s2b_set_dataflow / S2B_DATAFLOW=1 enable it
 	int gatherWarm = 1; // per-body warm-start gather (warm_gather.cuh); s2b_set_warm_gather / S2B_WARM_GATHER=0 disable it

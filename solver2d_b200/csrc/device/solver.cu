@@ -100,6 +100,8 @@ void s2bFreeSolverScratch(s2bWorld* w)
 		s->sep[p].release();
 	}
 	s->src.release();
+	s->warmP.release();
+	s->warmAnchor.release();
 	s->jhead.release();
 	s->janchor.release();
 	s->jmass.release();
@@ -723,18 +725,58 @@ __global__ void s2bClassifyItemsKernel(int* counts, const int2* itemBodies, cons
 #define S2B_KEY_OVERFLOW 0xFFFE
 #define S2B_KEY_DEAD 0xFFFF
 
-__global__ void s2bMakeSortKeys(const int* counts, const int* color, const int* itemRegion, const int* cutColor, unsigned short* jKeys,
-								int* jVals, unsigned short* cKeys, int* cVals)
+// colours used by the cut set (largest cut colour + 1)
+__global__ void s2bCutColorCountKernel(int* counts, const int* cutColor)
+{
+	int n = counts[CNT_JOINTS] + counts[CNT_CONTACTS];
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	int c = 0;
+	if (i < n)
+	{
+		int cc = cutColor[i];
+		c = (cc >= 0 && cc < S2B_MAX_COLORS) ? cc + 1 : 0;
+	}
+	for (int d = 16; d > 0; d >>= 1)
+	{
+		c = max(c, __shfl_xor_sync(0xFFFFFFFFu, c, d));
+	}
+	if ((threadIdx.x & 31) == 0 && c > 0)
+	{
+		atomicMax(counts + CNT_CUT_COLORS, c);
+	}
+}
+
+// Regions pay when the cut set needs few colours: a sweep then costs (cut colours) device-wide steps + 7 block-local ones
+// instead of one device-wide step per colour. Islands, batched worlds, bridges, anything that fits one block: 0-3 cut
+// colours. A single dense pile cut along the jagged border of Hilbert chunks has boundary bodies with 3-6 cut constraints
+// and needs 6 — as many as the pile has colours — so there the plain colour-major order is kept (measured).
+// The decision is taken here, on the device, from the cut colouring; every later kernel reads CNT_REGIONS_ON.
+__global__ void s2bMakeSortKeys(int* counts, const int* color, const int* itemRegion, const int* cutColor, int regionCutLimit,
+								unsigned short* jKeys, int* jVals, unsigned short* cKeys, int* cVals)
 {
 	int nJ = counts[CNT_JOINTS], nC = counts[CNT_CONTACTS];
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	bool regionsOn = regionCutLimit >= 0 && counts[CNT_CUT_COLORS] <= regionCutLimit;
+	if (i == 0)
+	{
+		counts[CNT_REGIONS_ON] = regionsOn ? 1 : 0;
+		if (regionsOn == false)
+		{
+			counts[CNT_PRIMARY] = 0;
+		}
+	}
 	if (i >= nJ + nC)
 	{
 		return;
 	}
-	int region = itemRegion[i];
+	int region = regionsOn ? itemRegion[i] : -1;
 	int key;
-	if (region >= 0)
+	if (regionsOn == false)
+	{
+		int c = color[i];
+		key = (c >= 0 && c < S2B_MAX_COLORS) ? S2B_KEY_CUT + c : S2B_KEY_OVERFLOW;
+	}
+	else if (region >= 0)
 	{
 		key = region * S2B_MAX_COLORS + color[i];
 	}
@@ -1799,6 +1841,11 @@ static void planSolve(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 	s->idx.reserve(nC + 2, st, false);
 	s->nf.reserve(nC + 2, st, false);
 	s->src.reserve(nC, st, false);
+	if (pl.gatherWarm)
+	{
+		s->warmP.reserve(nC, st, false);
+		s->warmAnchor.reserve(2 * nC, st, false);
+	}
 	for (int p = 0; p < 2; ++p)
 	{
 		s->anchor[p].reserve(nC + 2, st, false);
@@ -1952,10 +1999,13 @@ static void enqueueSchedule(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 			}
 			S2B_LAUNCH(w, s2bClassifyItemsKernel, gridFor(maxItems, 256), 256, 0, s->counts.p, s->itemBodies.p, s->bodyRegion.p, s->colorA.p,
 					   pl.regions > 0 ? 1 : 0, s->itemRegion.p, s->colorC.p);
+			int regionCutLimit = -1;
 			if (pl.regions > 0)
 			{
 				// the cut set is coloured among itself, from scratch, with hashed priorities (a handful of rounds)
 				launchColorKernel(w, s, maxItems, s->colorC.p, S2B_MAX_COLORS, 0, 0);
+				S2B_LAUNCH(w, s2bCutColorCountKernel, gridFor(maxItems, 256), 256, 0, s->counts.p, s->colorC.p);
+				regionCutLimit = w->useRegions >= 2 ? S2B_MAX_COLORS : w->regionCutLimit;
 			}
 
 			// solve order: stable 16-bit radix sort of (key, natural index), joints and contacts separately
@@ -1967,8 +2017,8 @@ static void enqueueSchedule(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 			int* cValsIn = s->sortValIn.p + nI;
 			// entries beyond the live counts keep key 0xFFFF: they sort behind every live entry and are never read
 			S2B_CHECK(cudaMemsetAsync(s->sortKeyIn.p, 0xFF, sizeof(unsigned short) * 2 * nI, st));
-			S2B_LAUNCH(w, s2bMakeSortKeys, gridFor(maxItems, 256), 256, 0, s->counts.p, s->colorA.p, s->itemRegion.p, s->colorC.p, jKeysIn, jValsIn,
-					   cKeysIn, cValsIn);
+			S2B_LAUNCH(w, s2bMakeSortKeys, gridFor(maxItems, 256), 256, 0, s->counts.p, s->colorA.p, s->itemRegion.p, s->colorC.p, regionCutLimit,
+					   jKeysIn, jValsIn, cKeysIn, cValsIn);
 			// the sorts run over the host-known upper-bound sizes, so no device count has to be read back
 			size_t tb = s->cubTemp.cap;
 			if (contactCount > 0)
@@ -2091,6 +2141,8 @@ static void enqueueIterate(s2bWorld* w, SolverScratch* s, SolvePlan& pl, bool ca
 	a.cc.idx = s->idx.p;
 	a.cc.nf = s->nf.p;
 	a.cc.src = s->src.p;
+	a.cc.warmP = pl.gatherWarm ? s->warmP.p : nullptr;
+	a.cc.warmAnchor = pl.gatherWarm ? s->warmAnchor.p : nullptr;
 	for (int p = 0; p < 2; ++p)
 	{
 		a.cc.anchor[p] = s->anchor[p].p;
@@ -2239,7 +2291,7 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 		};
 		unsigned long long epoch = s2bAllocEpoch();
 		int ints[] = {solverType,	 w->contactCount, w->jointCap, w->bodyCap,		  w->cur,
-					  w->maxColors, w->gatherWarm,	  w->dataflow, w->sticky ? 1 : 0, w->useRegions};
+					  w->maxColors, w->gatherWarm,	  w->dataflow, w->sticky ? 1 : 0, w->useRegions * 256 + w->regionCutLimit};
 		put(&ctx, sizeof(ctx));
 		put(ints, sizeof(ints));
 		put(&epoch, sizeof(epoch));
@@ -2440,7 +2492,7 @@ extern "C" int s2b_download_solve_order(s2bWorld* w, int32_t* items, int maxItem
 	S2B_CHECK(cudaMemcpy(counts, s->counts.p, sizeof(counts), cudaMemcpyDeviceToHost));
 	int nC = counts[CNT_CONTACTS], nJ = counts[CNT_JOINTS], groups = counts[CNT_GROUPS];
 	bool wavefront = w->schedule == S2B_SCHEDULE_WAVEFRONT;
-	int regions = wavefront ? 0 : s->regions;
+	int regions = (wavefront || counts[CNT_REGIONS_ON] == 0) ? 0 : s->regions;
 	int tableLen = (wavefront ? groups : S2B_MAX_COLORS) + 2;
 	std::vector<int> cOff((size_t)tableLen), jOff((size_t)tableLen), src((size_t)std::max(nC, 1)), jPerm((size_t)std::max(nJ, 1)),
 		jointSlots((size_t)std::max(nJ, 1));
@@ -2532,9 +2584,10 @@ extern "C" void s2b_get_counters(s2bWorld* w, s2bCounters* out)
 		out->jointCount = counts[CNT_JOINTS];
 		// colours of the constraint graph under the colour schedule, levels under the wavefront schedule
 		out->groupCount = w->schedule == S2B_SCHEDULE_COLOR ? counts[CNT_COLORS] : counts[CNT_GROUPS];
-		out->cutGroupCount = w->scratch->regions > 0 ? counts[CNT_GROUPS] : 0;
+		// (cut statistics are reported whenever regions were tried; regionCount says whether the solve order used them)
+		out->cutGroupCount = w->scratch->regions > 0 ? counts[CNT_CUT_COLORS] : 0;
 		out->cutCount = w->scratch->regions > 0 ? counts[CNT_CUT] : 0;
-		out->regionCount = w->scratch->regions;
+		out->regionCount = counts[CNT_REGIONS_ON] != 0 ? w->scratch->regions : 0;
 		out->overflowCount = counts[CNT_OVERFLOW_C] + counts[CNT_OVERFLOW_J];
 		if (w->scratch->bodyTicket.p != nullptr && w->scratch->flowErrorOffset > 0)
 		{

@@ -32,6 +32,8 @@ enum
 	CNT_COLORS = 11,	// colours of the constraint graph (what s2bCounters.groupCount reports under the colour schedule)
 	CNT_OWNED = 12,		// bodies that belong to a region (valid, not a hub)
 	CNT_CUT = 13,		// constraints in the cut set (straddle two regions or touch a hub body)
+	CNT_CUT_COLORS = 14, // colours the cut set needed
+	CNT_REGIONS_ON = 15, // 1: the solve order is region-major (persistent.cuh); 0: one device-wide group per colour
 	CNT_BOUNDS = 16,	// 4 slots: order-preserving keys of max x, max -x, max y, max -y over the bodies' centres
 	CNT_SIZE = 32
 };
@@ -122,6 +124,7 @@ struct SolverScratch
 	DevArray<float2> lambda[2], tsep[2];
 	DevArray<float> sep[2];
 	DevArray<int> src;
+	DevArray<float4> warmP, warmAnchor; // ConstraintView::warmP (1 per constraint), ::warmAnchor (2 per constraint)
 
 	// joint constraint columns
 	DevArray<int4> jhead;

@@ -20,125 +20,7 @@
 // bodies with more incident constraints than this are gathered by a whole block instead of one thread
 #define S2B_HEAVY_DEGREE 48
 
-// FIXED = false: anchors rotated by the current rotation (s2WarmStartContacts, reference src/solve_common.c:276-326)
-// FIXED = true : prepare-time anchors (s2WarmStartContacts_Fixed, reference src/solve_soft_step.c:16-63)
-template <bool FIXED> __device__ __forceinline__ void s2bIntegrateVelocityWarm(const SolveArgs& a, int i, float h)
-{
-	unsigned f = a.bodies.flags[i];
-	if ((f & S2B_BODY_VALID) == 0)
-	{
-		return;
-	}
-	float4 vel = a.bodies.vel[i];
-	float4 prm = a.bodies.prm[i];
-	float invMass = vel.w, invI = prm.w;
-	s2Vec2 v = V2(vel.x, vel.y);
-	float w = vel.z;
-	bool dynamic = S2B_BODY_TYPE(f) == S2B_BODY_DYNAMIC;
-
-	// s2IntegrateVelocities (reference src/solve_common.c:10-45)
-	if (dynamic)
-	{
-		float4 frc = a.bodies.frc[i];
-		s2Vec2 gravity = V2(a.gravity.x, a.gravity.y);
-		v = s2Add(v, s2MulSV(h * invMass, s2MulAdd(V2(frc.x, frc.y), frc.w * prm.z, gravity)));
-		w = w + h * invI * frc.z;
-		v = s2MulSV(1.0f / (1.0f + h * prm.x), v);
-		w *= 1.0f / (1.0f + h * prm.y);
-	}
-
-	int begin = a.incStart[i], end = a.incStart[i + 1];
-	if (begin == end)
-	{
-		if (dynamic)
-		{
-			a.bodies.vel[i] = make_float4(v.x, v.y, w, invMass);
-		}
-		return;
-	}
-	if (a.heavyBodies != nullptr && end - begin > S2B_HEAVY_DEGREE)
-	{
-		return; // a hub body (container wall ...): gathered by a whole block, s2bGatherHeavyBodies
-	}
-
-	float4 pose = a.bodies.pose[i];
-	s2Rot q = R2(pose.z, pose.w);
-	for (int k = begin; k < end; ++k)
-	{
-		int e = a.incList[k];
-		int t = e >> 2;
-		bool sideB = (e & S2B_INC_SIDE_B) != 0;
-		if (e & S2B_INC_CONTACT)
-		{
-			int2 idx = a.cc.idx[t];
-			float4 nf = a.cc.nf[t];
-			s2Vec2 normal = V2(nf.x, nf.y);
-			s2Vec2 tangent = s2RightPerp(normal);
-			int pointCount = (idx.y & S2B_CF_TWO_POINTS) ? 2 : 1;
-#pragma unroll
-			for (int j = 0; j < 2; ++j)
-			{
-				if (j < pointCount)
-				{
-					float4 la = FIXED ? a.cc.r0[j][t] : a.cc.anchor[j][t];
-					float2 l = a.cc.lambda[j][t];
-					s2Vec2 local = sideB ? V2(la.z, la.w) : V2(la.x, la.y);
-					s2Vec2 r = FIXED ? local : s2RotateVector(q, local);
-					s2Vec2 P = s2Add(s2MulSV(l.x, normal), s2MulSV(l.y, tangent));
-					if (sideB)
-					{
-						w += invI * s2Cross(r, P);
-						v = s2MulAdd(v, invMass, P);
-					}
-					else
-					{
-						w -= invI * s2Cross(r, P);
-						v = s2MulAdd(v, -invMass, P);
-					}
-				}
-			}
-		}
-		else
-		{
-			int4 head = a.jc.head[t];
-			float4 anchor = a.jc.anchor[t];
-			float4 imp = a.jc.imp[t];
-			s2Vec2 P = V2(imp.x, imp.y);
-			if (S2B_JOINT_TYPE(head.x) == S2B_JOINT_MOUSE)
-			{
-				// s2WarmStartMouse (reference src/mouse_joint.c:85-107): body B only
-				s2Vec2 rB = s2RotateVector(q, V2(anchor.z, anchor.w));
-				v = s2MulAdd(v, invMass, P);
-				w += invI * (s2Cross(rB, P) + imp.z);
-			}
-			else
-			{
-				// s2WarmStartRevolute (reference src/revolute_joint.c:107-150)
-				float4 limp = a.jc.limp[t];
-				float axialImpulse = imp.z + limp.x - limp.y;
-				if (sideB)
-				{
-					s2Vec2 rB = s2RotateVector(q, V2(anchor.z, anchor.w));
-					v = s2MulAdd(v, invMass, P);
-					w += invI * (s2Cross(rB, P) + axialImpulse);
-				}
-				else
-				{
-					s2Vec2 rA = s2RotateVector(q, V2(anchor.x, anchor.y));
-					v = s2MulSub(v, invMass, P);
-					w -= invI * (s2Cross(rA, P) + axialImpulse);
-				}
-			}
-		}
-	}
-	a.bodies.vel[i] = make_float4(v.x, v.y, w, invMass);
-}
-
-// ---- hub bodies -----------------------------------------------------------------------------------------------------
-// A container touching hundreds of boxes has hundreds of incident constraints; one thread walking them is ~0.6 us per entry.
-// The terms tw = -/+ invI * (cross(r, P) [+ axial]) and tv = (-/+ invM) * P do not involve v or w, so a whole block forms them
-// in parallel (shared memory) and ONE thread then adds them to v, w in list order: the same float operations in the same
-// order as the serial walk, hence the same bits.
+// the terms one incidence entry contributes to its body: (tw0, tv0) of point 0 / the joint, (tw1, tv1) of point 1
 struct GatherTerms
 {
 	int np;
@@ -157,21 +39,18 @@ __device__ __forceinline__ GatherTerms s2bGatherTermsOf(const SolveArgs& a, int 
 	bool sideB = (e & S2B_INC_SIDE_B) != 0;
 	if (e & S2B_INC_CONTACT)
 	{
-		int2 idx = a.cc.idx[t];
-		float4 nf = a.cc.nf[t];
-		s2Vec2 normal = V2(nf.x, nf.y);
-		s2Vec2 tangent = s2RightPerp(normal);
-		g.np = (idx.y & S2B_CF_TWO_POINTS) ? 2 : 1;
+		// two 16-byte rows: the impulse vectors of both points, this side's anchors (contact_kernels.cuh, s2bWriteWarm*)
+		float4 imp = a.cc.warmP[t];
+		float4 anchors = a.cc.warmAnchor[(size_t)t * 2 + (sideB ? 1 : 0)];
+		g.np = imp.z == imp.z ? 2 : 1;
 #pragma unroll
 		for (int j = 0; j < 2; ++j)
 		{
 			if (j < g.np)
 			{
-				float4 la = FIXED ? a.cc.r0[j][t] : a.cc.anchor[j][t];
-				float2 l = a.cc.lambda[j][t];
-				s2Vec2 local = sideB ? V2(la.z, la.w) : V2(la.x, la.y);
+				s2Vec2 local = j == 0 ? V2(anchors.x, anchors.y) : V2(anchors.z, anchors.w);
 				s2Vec2 r = FIXED ? local : s2RotateVector(q, local);
-				s2Vec2 P = s2Add(s2MulSV(l.x, normal), s2MulSV(l.y, tangent));
+				s2Vec2 P = j == 0 ? V2(imp.x, imp.y) : V2(imp.z, imp.w);
 				float c = invI * s2Cross(r, P);
 				float tw = sideB ? c : -c;
 				s2Vec2 tv = s2MulSV(sideB ? invMass : -invMass, P);
@@ -223,6 +102,95 @@ __device__ __forceinline__ GatherTerms s2bGatherTermsOf(const SolveArgs& a, int 
 	return g;
 }
 
+// FIXED = false: anchors rotated by the current rotation (s2WarmStartContacts, reference src/solve_common.c:276-326)
+// FIXED = true : prepare-time anchors (s2WarmStartContacts_Fixed, reference src/solve_soft_step.c:16-63)
+template <bool FIXED> __device__ __forceinline__ void s2bIntegrateVelocityWarm(const SolveArgs& a, int i, float h)
+{
+	unsigned f = a.bodies.flags[i];
+	if ((f & S2B_BODY_VALID) == 0)
+	{
+		return;
+	}
+	float4 vel = a.bodies.vel[i];
+	float4 prm = a.bodies.prm[i];
+	float invMass = vel.w, invI = prm.w;
+	s2Vec2 v = V2(vel.x, vel.y);
+	float w = vel.z;
+	bool dynamic = S2B_BODY_TYPE(f) == S2B_BODY_DYNAMIC;
+
+	// s2IntegrateVelocities (reference src/solve_common.c:10-45)
+	if (dynamic)
+	{
+		float4 frc = a.bodies.frc[i];
+		s2Vec2 gravity = V2(a.gravity.x, a.gravity.y);
+		v = s2Add(v, s2MulSV(h * invMass, s2MulAdd(V2(frc.x, frc.y), frc.w * prm.z, gravity)));
+		w = w + h * invI * frc.z;
+		v = s2MulSV(1.0f / (1.0f + h * prm.x), v);
+		w *= 1.0f / (1.0f + h * prm.y);
+	}
+
+	int begin = a.incStart[i], end = a.incStart[i + 1];
+	if (begin == end)
+	{
+		if (dynamic)
+		{
+			a.bodies.vel[i] = make_float4(v.x, v.y, w, invMass);
+		}
+		return;
+	}
+	if (a.heavyBodies != nullptr && end - begin > S2B_HEAVY_DEGREE)
+	{
+		return; // a hub body (container wall ...): gathered by a whole block, s2bGatherHeavyBodies
+	}
+
+	float4 pose = a.bodies.pose[i];
+	s2Rot q = R2(pose.z, pose.w);
+	// The terms do not depend on v, w: four entries at a time, their (independent) load chains — incidence entry ->
+	// constraint row — in flight together, then added to v, w in list order (same float operations, same order as the
+	// constraint-by-constraint pass, and the same code as the block-wide hub gather below).
+	for (int k0 = begin; k0 < end; k0 += 4)
+	{
+		int e[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+		{
+			e[u] = k0 + u < end ? a.incList[k0 + u] : -1;
+		}
+		GatherTerms g[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+		{
+			g[u].np = 0;
+			g[u].tw0 = g[u].tw1 = 0.0f;
+			g[u].tv0 = g[u].tv1 = V2(0.0f, 0.0f);
+			if (e[u] != -1)
+			{
+				g[u] = s2bGatherTermsOf<FIXED>(a, e[u], q, invMass, invI);
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+		{
+			if (g[u].np >= 1)
+			{
+				w = w + g[u].tw0;
+				v = V2(v.x + g[u].tv0.x, v.y + g[u].tv0.y);
+			}
+			if (g[u].np == 2)
+			{
+				w = w + g[u].tw1;
+				v = V2(v.x + g[u].tv1.x, v.y + g[u].tv1.y);
+			}
+		}
+	}
+	a.bodies.vel[i] = make_float4(v.x, v.y, w, invMass);
+}
+
+// ---- hub bodies -----------------------------------------------------------------------------------------------------
+// A container touching hundreds of boxes has hundreds of incident constraints; one thread walking them is ~0.6 us per entry.
+// The terms tw = -/+ invI * (cross(r, P) [+ axial]) and tv = (-/+ invM) * P do not involve v or w, so a whole block forms them
+// in parallel (shared memory) and ONE thread then adds them to v, w in list order: the same float operations in the same
+// order as the serial walk, hence the same bits.
 // called by every block of the persistent kernel after the per-thread gather; block b takes hub bodies b, b + gridDim, ...
 template <bool FIXED> __device__ __forceinline__ void s2bGatherHeavyBodies(const SolveArgs& a, float h)
 {

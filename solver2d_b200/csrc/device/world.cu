@@ -347,7 +347,12 @@ extern "C" s2bWorld* s2b_world_create(int cudaDevice, int solverType)
 		env = getenv("S2B_REGIONS");
 		if (env != nullptr)
 		{
-			w->useRegions = atoi(env) != 0 ? 1 : 0;
+			w->useRegions = atoi(env) < 0 ? 0 : (atoi(env) > 2 ? 2 : atoi(env));
+		}
+		env = getenv("S2B_REGION_CUT_LIMIT");
+		if (env != nullptr)
+		{
+			w->regionCutLimit = atoi(env) < 0 ? 0 : (atoi(env) > 64 ? 64 : atoi(env));
 		}
 		env = getenv("S2B_DATAFLOW");
 		if (env != nullptr)

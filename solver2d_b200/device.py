@@ -219,9 +219,10 @@ class DeviceWorld:
     def set_dataflow(self, enable: bool):
         self.L.s2b_set_dataflow(self.h, 1 if enable else 0)
 
-    def set_regions(self, enable: bool):
-        """Region-local schedule of the persistent kernel (default on): see DESIGN.md §3.1."""
-        self.L.s2b_set_regions(self.h, 1 if enable else 0)
+    def set_regions(self, mode):
+        """Region-local schedule of the persistent kernel: 0 / False never, 1 when the cut set needs few colours (default),
+        2 / True always. See DESIGN.md §3.1."""
+        self.L.s2b_set_regions(self.h, 2 if mode is True else (0 if mode is False else int(mode)))
 
     def set_warm_gather(self, enable: bool):
         self.L.s2b_set_warm_gather(self.h, 1 if enable else 0)
