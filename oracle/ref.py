@@ -79,6 +79,10 @@ class Reference(capi.Solver2D):
         L.s2ref_step_finalize.argtypes = [C.c_int]
         L.s2ref_set_contact_impulses.restype = None
         L.s2ref_set_contact_impulses.argtypes = [C.c_int, C.c_int] + [C.c_float] * 4
+        for name in ("s2ref_load_contact_impulses", "s2ref_load_joint_impulses"):
+            fn = getattr(L, name)
+            fn.restype = None
+            fn.argtypes = [C.c_int, fp]
         L.s2ref_timed_steps.restype = C.c_double
         L.s2ref_timed_steps.argtypes = [capi.WorldId, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
         L.s2ref_timed_e2e_steps.restype = C.c_double
@@ -116,6 +120,16 @@ class Reference(capi.Solver2D):
     def load_body_state(self, wid, f):
         f = np.ascontiguousarray(f, dtype=np.float32)
         self.lib.s2ref_load_body_state(wid.index, f.ctypes.data_as(C.POINTER(C.c_float)))
+
+    def load_contact_impulses(self, wid, f):
+        """f: (contactCap, 4) = normal / tangent impulse of both points, by pool slot."""
+        f = np.ascontiguousarray(f, dtype=np.float32)
+        self.lib.s2ref_load_contact_impulses(wid.index, f.ctypes.data_as(C.POINTER(C.c_float)))
+
+    def load_joint_impulses(self, wid, f):
+        """f: (jointCap, 5) = impulse.xy, motor, lower, upper impulse, by pool slot."""
+        f = np.ascontiguousarray(f, dtype=np.float32)
+        self.lib.s2ref_load_joint_impulses(wid.index, f.ctypes.data_as(C.POINTER(C.c_float)))
 
     def step_collide(self, wid):
         self.lib.s2ref_step_collide(wid.index)

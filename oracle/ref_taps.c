@@ -430,6 +430,56 @@ TAP_EXPORT void s2ref_set_contact_impulses(int worldIndex, int contactIndex, flo
 	m->points[1].tangentImpulse = t1;
 }
 
+// Bulk forms of the impulse setters: what a solver stage leaves in the manifolds / joints (warm-start state of the next
+// step), written from arrays indexed by pool slot. Used by the multi-step parity test, which lets the ORDER-PERMUTED
+// oracle advance the reference world so that every step of the free-running device schedule can be checked bit for bit.
+// f: contactCapacity x 4 floats {normalImpulse0, tangentImpulse0, normalImpulse1, tangentImpulse1}
+TAP_EXPORT void s2ref_load_contact_impulses(int worldIndex, const float* f)
+{
+	s2World* w = s2GetWorldFromIndex((int16_t)worldIndex);
+	int cap = w->contactPool.capacity;
+	for (int i = 0; i < cap; ++i)
+	{
+		s2Contact* c = w->contacts + i;
+		if (s2IsFree(&c->object))
+		{
+			continue;
+		}
+		c->manifold.points[0].normalImpulse = f[4 * i + 0];
+		c->manifold.points[0].tangentImpulse = f[4 * i + 1];
+		c->manifold.points[1].normalImpulse = f[4 * i + 2];
+		c->manifold.points[1].tangentImpulse = f[4 * i + 3];
+	}
+}
+
+// f: jointCapacity x 5 floats {impulse.x, impulse.y, motorImpulse, lowerImpulse, upperImpulse}
+TAP_EXPORT void s2ref_load_joint_impulses(int worldIndex, const float* f)
+{
+	s2World* w = s2GetWorldFromIndex((int16_t)worldIndex);
+	int cap = w->jointPool.capacity;
+	for (int i = 0; i < cap; ++i)
+	{
+		s2Joint* j = w->joints + i;
+		if (s2IsFree(&j->object))
+		{
+			continue;
+		}
+		const float* o = f + 5 * i;
+		if (j->type == s2_revoluteJoint)
+		{
+			j->revoluteJoint.impulse = (s2Vec2){o[0], o[1]};
+			j->revoluteJoint.motorImpulse = o[2];
+			j->revoluteJoint.lowerImpulse = o[3];
+			j->revoluteJoint.upperImpulse = o[4];
+		}
+		else
+		{
+			j->mouseJoint.impulse = (s2Vec2){o[0], o[1]};
+			j->mouseJoint.motorImpulse = o[2];
+		}
+	}
+}
+
 // Time N reference steps with CLOCK_MONOTONIC inside C (bench.py's reference arm; avoids ctypes overhead in the loop).
 #include <time.h>
 TAP_EXPORT double s2ref_timed_steps(s2WorldId worldId, int steps, float timeStep, int velIters, int posIters, int warmStart)
