@@ -186,6 +186,114 @@ def aggregate_over_ranks(dist, device, total_ms, e2e_time, work, e2e_work):
     return total_ms_max, e2e_time_max, work_all, e2e_work_all
 
 
+def measure_field(args, P, dev, dist, rank: int, world_size: int, local_rank: int, shard: bool):
+    """SURVEY §8d config 5 / north_star: `--field-count` independent pyramid worlds of `--field-base` rows. shard=True: world k
+    lives on rank k mod N (rank r batches worlds r, r+N, ... into ONE s2World: disconnected islands of one constraint graph,
+    one set of launches), no data-path collective; the one NCCL all-gather of packed body state per step runs on a side
+    stream behind the step. shard=False: this rank steps all the worlds alone (the 1-GPU point of the strong-scaling curve).
+    Returns (device ms over the timed steps, constraint-iterations done, boxes, constraints) of THIS rank."""
+    import torch
+    from solver2d_b200 import device, scenes
+    L = P.lib
+    mine = len(range(rank, args.field_count, world_size)) if shard else args.field_count
+    sc = scenes.pyramid_field(P, "TGS_Soft", count=mine, base_count=args.field_base, first=0)
+    dw = device.DeviceWorld.attach(dev, sc.world)
+    nb = len(sc.bodies)
+    gather_in = gather_out = ext_stream = side_stream = None
+    state = {"done": None}
+    if dist is not None and shard:
+        most = len(range(0, args.field_count, world_size)) * (args.field_base * (args.field_base + 1) // 2 + 1)
+        gather_in = torch.zeros((most + 8) * 8, dtype=torch.float32, device="cuda")
+        gather_out = torch.empty(world_size * (most + 8) * 8, dtype=torch.float32, device="cuda")
+        L.s2b_get_stream.restype = C.c_void_p
+        L.s2b_get_stream.argtypes = [C.c_void_p]
+        ext_stream = torch.cuda.ExternalStream(int(L.s2b_get_stream(dw.h)), device=torch.device("cuda", local_rank))
+        side_stream = torch.cuda.Stream(device=torch.device("cuda", local_rank))
+
+    def exchange():
+        if gather_in is None:
+            return
+        if state["done"] is not None:
+            ext_stream.wait_event(state["done"])
+        L.s2b_pack_body_state(dw.h, 0, nb, C.c_void_p(gather_in.data_ptr()))
+        packed = torch.cuda.Event()
+        packed.record(ext_stream)
+        side_stream.wait_event(packed)
+        with torch.cuda.stream(side_stream):
+            dist.all_gather_into_tensor(gather_out, gather_in)
+            done = torch.cuda.Event()
+            done.record(side_stream)
+        state["done"] = done
+
+    for _ in range(max(args.warmup, 3)):
+        sc.step(DT, args.substeps, args.relax, True)
+        exchange()
+    dw.sync()
+    out = (C.c_uint64 * 2)()
+    L.s2b_get_work(dw.h, out, 1)
+    if dist is not None and shard:
+        dist.barrier()
+    torch.cuda.synchronize()
+    total_ms = 0.0
+    if gather_in is None:
+        for _ in range(args.steps):
+            total_ms += float(L.s2World_TimedSteps(sc.world, 1, DT, args.substeps, args.relax, True, 1 if args.flush_l2 else 0))
+    else:
+        pairs = []
+        for _ in range(args.steps):
+            if args.flush_l2:
+                L.s2b_flush_l2(dw.h)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(ext_stream)
+            sc.step(DT, args.substeps, args.relax, True)
+            exchange()
+            e1.record(ext_stream)
+            pairs.append((e0, e1))
+        tail = torch.cuda.Event(enable_timing=True)
+        ext_stream.wait_event(state["done"])
+        tail.record(ext_stream)
+        torch.cuda.synchronize()
+        total_ms = sum(a.elapsed_time(b) for a, b in pairs) + pairs[-1][1].elapsed_time(tail)
+    torch.cuda.synchronize()
+    L.s2b_get_work(dw.h, out, 1)
+    c = dw.counters()
+    res = (total_ms, int(out[0]), nb - mine, c.constraintCount, c.regionCount, c.cutCount)
+    sc.destroy()
+    return res
+
+
+def field_report(args, P, dev, dist, rank: int, world_size: int, local_rank: int) -> dict | None:
+    """The sharded config-5 numbers attached to the bench line (key "field"). At N > 1 rank 0 also steps the whole field
+    alone afterwards: the 1-GPU point the strong-scaling efficiency is quoted against, measured in the same run."""
+    import torch
+    ms, work, boxes, constraints, regions, cut = measure_field(args, P, dev, dist, rank, world_size, local_rank, True)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    w = torch.tensor([float(work), float(boxes), float(constraints)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    ms_max = float(t.item())
+    work_all, boxes_all, constraints_all = w.tolist()
+    rep = None
+    if rank == 0:
+        rep = {"workload": f"field{args.field_count}x_pyramid{args.field_base}_tgs_soft_s{args.substeps}_e{args.relax}",
+               "value": work_all / (ms_max * 1e-3), "unit": "constraint-iters/s", "ms_per_step": ms_max / args.steps,
+               "scaling": "strong", "worlds_per_rank": len(range(0, args.field_count, world_size)), "boxes": int(boxes_all),
+               "contact_constraints": int(constraints_all), "regions_rank0": regions, "cut_constraints_rank0": cut,
+               "partition": "world k -> rank k mod N, a rank's worlds batched into one s2World; no data-path collective; "
+                            "one NCCL all-gather of packed body state per step on a side stream" if world_size > 1 else
+                            "all worlds batched into one s2World on one GPU"}
+    if world_size > 1:
+        if rank == 0 and not args.no_field_n1:
+            ms1, work1, *_ = measure_field(args, P, dev, None, 0, 1, local_rank, False)
+            rep["n1_value_same_run"] = work1 / (ms1 * 1e-3)
+            rep["n1_ms_per_step_same_run"] = ms1 / args.steps
+            rep["efficiency_vs_n1"] = rep["value"] / (world_size * rep["n1_value_same_run"])
+        dist.barrier()
+    return rep
+
+
 def run_ours(args, rank: int, world_size: int, local_rank: int):
     os.environ["S2B_DEVICE"] = str(local_rank)  # worlds of this process live on its own GPU
     import torch
@@ -395,9 +503,12 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
                     "host_ms_per_step": {"apply_forces": 1e3 * e2e_parts[0] / e2e_steps, "step_call": 1e3 * e2e_parts[1] / e2e_steps,
                                          "get_transforms_incl_wait": 1e3 * e2e_parts[2] / e2e_steps}},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "s2bPersistentTgsSoft (whole solver stage of one step)", "bound": "hbm",
+            "roofline": {"kernel": "s2bPersistentSolveT<7> (TGS_Soft instantiation; the whole solver stage of one step)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                         "traffic": _traffic("persistent_solve"), "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms, "peak_source": peak_src},
+                         "traffic": _traffic("persistent_solve"),
+                         "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` "
+                                           "capture of this workload (committed), not measured in this run",
+                         "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms, "peak_source": peak_src},
             "clocks": clocks,
             "wall_s_timed_region": wall,
         }
@@ -418,11 +529,22 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
                 line["roofline_colour_kernel"] = {"error": repr(e)}
         if not args.no_cpu_baseline and world_size == 1:
             line["cpu_baseline"] = cpu_baseline(args)
+    sc.destroy()
+    sc = None
+    # config 5 (the configuration that shards): every rank takes part, rank 0 reports
+    field = None
+    if not args.no_field and args.workload == "pyramid":
+        try:
+            field = field_report(args, P, dev, dist, rank, world_size, local_rank)
+        except Exception as e:  # additional evidence, never a reason to lose the bench line
+            field = {"error": repr(e)}
+    if rank == 0:
+        if field is not None:
+            line["field"] = field
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
-    sc.destroy()
 
 
 def cpu_baseline(args) -> dict:
@@ -458,6 +580,9 @@ def main():
     ap.add_argument("--workload", choices=["pyramid", "field"], default="pyramid",
                     help="pyramid = headline (replica per rank); field = config 5: --field-count worlds of --base rows, sharded over ranks")
     ap.add_argument("--field-count", type=int, default=256)
+    ap.add_argument("--field-base", type=int, default=45, help="rows of each world of the sharded config-5 measurement (45 -> 1 035 boxes)")
+    ap.add_argument("--no-field", action="store_true", help="skip the sharded config-5 measurement attached as key 'field'")
+    ap.add_argument("--no-field-n1", action="store_true", help="at N > 1: skip rank 0's single-GPU run of the whole field")
     ap.add_argument("--substeps", type=int, default=4)
     ap.add_argument("--relax", type=int, default=2)
     ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false")

@@ -45,24 +45,27 @@ def _case(reference, dev, recipe, solver, warm, vel, pos, persistent, max_colors
     counters = dw.counters()
     dw.destroy()
 
-    # validity of the colouring: within a parallel group no movable body appears twice
+    # validity of the schedule: within a parallel group no movable body appears twice
     movable = (bodies["invMass"] != 0) | (bodies["invI"] != 0)
-    start = 0
     parallel_groups = len(group_sizes) - (1 if counters.overflowCount > 0 else 0)
-    for g, size in enumerate(group_sizes):
-        seen = set()
-        for it in order[start:start + size]:
-            if it >= 0:
-                ends = [contacts["bodyA"][it], contacts["bodyB"][it]]
-            else:
-                j = joints[-1 - it]
-                ends = [j["bodyB"]] if ((j["flags"] >> 1) & 7) == 1 else [j["bodyA"], j["bodyB"]]
-            for b in ends:
-                if movable[b] and g < parallel_groups:
-                    assert b not in seen, f"body {b} twice in group {g}"
-                    seen.add(b)
-        start += size
-    assert start == len(order)
+    is_contact = order >= 0
+    ends_a = np.where(is_contact, contacts["bodyA"][np.where(is_contact, order, 0)], -1)
+    ends_b = np.where(is_contact, contacts["bodyB"][np.where(is_contact, order, 0)], -1)
+    if len(joints):
+        jslot = np.where(is_contact, 0, -1 - order)
+        jtype = (joints["flags"][jslot] >> 1) & 7
+        ends_a = np.where(is_contact, ends_a, np.where(jtype == 1, -1, joints["bodyA"][jslot]))  # a mouse joint acts on B only
+        ends_b = np.where(is_contact, ends_b, joints["bodyB"][jslot])
+    group_of = np.repeat(np.arange(len(group_sizes)), group_sizes)
+    assert len(group_of) == len(order)
+    for ends in (ends_a, ends_b):
+        pass
+    both = np.concatenate([np.stack([group_of, ends_a], 1), np.stack([group_of, ends_b], 1)])
+    both = both[(both[:, 1] >= 0) & (both[:, 0] < parallel_groups)]
+    both = both[movable[both[:, 1]]]
+    packed = both[:, 0].astype(np.int64) * (len(bodies) + 1) + both[:, 1]
+    uniq, cnt = np.unique(packed, return_counts=True)
+    assert (cnt == 1).all(), f"a movable body appears twice in a parallel group: group {uniq[cnt > 1][0] // (len(bodies) + 1)}"
 
     ob, oc, oj = O.solve(capi.SOLVER[solver], bodies, contacts, joints, ctx, order=order)
     valid = (bodies["flags"] & 1) == 1
@@ -189,3 +192,31 @@ def test_full_size_configs_match_permuted_oracle(reference, dev, base, vel):
     c = _case(reference, dev, scenes.pyramid, "TGS_Soft", 3, vel, 2, True, base_count=base)
     assert c.constraintCount == 3 * (base * (base + 1) // 2) - 2 * base + (base - 1) - (base - 1) or c.constraintCount > 100000
     assert c.overflowCount == 0 and c.groupCount <= 16
+
+
+# ---- BASELINE.json configs 3, 4, 5 at their full sizes: one solver stage of the production schedule against the oracle
+# replayed in the device's order, every body and every impulse, tolerance 0 ----------------------------------------------
+
+@pytest.mark.parametrize("solver", ["PGS", "PGS_NGS", "TGS_NGS", "XPBD", "Jacobi", "TGS_Soft"])
+def test_config3_tumbler_full_size(reference, dev, solver):
+    """Config 3: the solver-variant sweep on the 10 000-box motorised tumbler, after the boxes have fallen against the
+    container (a hub body with hundreds of contacts: overflow group, block-wide warm-start gather)."""
+    # the lattice needs ~1.7 s to reach the container floor and ~4 s to pile up; the reference's Jacobi variant blows a
+    # pile apart, so it is sampled while the pile forms
+    warm = 150 if solver == "Jacobi" else 240
+    c = _case(reference, dev, scenes.tumbler, solver, warm, 4, 2, True, grid=100)
+    print(f"config 3 {solver}: contact constraints {c.constraintCount}, colours {c.groupCount}, overflow {c.overflowCount}")
+    assert c.jointCount == 1 and c.constraintCount > (500 if solver == "Jacobi" else 9000)
+
+
+def test_config4_joints_and_contacts_full_size(reference, dev):
+    """Config 4: 25 bridges x 160 planks = 4 025 revolute joints with the 73 x 73 box lattice landed on them."""
+    c = _case(reference, dev, scenes.joint_contact_stress, "TGS_Soft", 420, 4, 2, True)
+    print(f"config 4: joints {c.jointCount}, contact constraints {c.constraintCount}, colours {c.groupCount}, overflow {c.overflowCount}")
+    assert c.jointCount == 4025 and c.constraintCount > 8000
+
+
+def test_config5_field_full_size(reference, dev):
+    """Config 5: 256 independent 1 035-box pyramid worlds batched into one constraint graph (264 960 boxes)."""
+    c = _case(reference, dev, scenes.pyramid_field, "TGS_Soft", 2, 4, 2, True, count=256, base_count=45)
+    assert c.constraintCount > 700000 and c.overflowCount == 0
