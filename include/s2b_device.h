@@ -293,6 +293,13 @@ S2B_API int s2b_download_contacts(s2bWorld* world, s2bContactRow* rows, int maxC
 S2B_API int s2b_download_solve_order(s2bWorld* world, int32_t* items, int maxItems, int32_t* groupSizes, int maxGroups,
 							 int32_t* groupCount);
 S2B_API void s2b_get_counters(s2bWorld* world, s2bCounters* out);
+// Islands = connected components of the constraint graph of the last s2b_solve over the movable bodies (contacts with at
+// least one point and joints connect; static and kinematic bodies do not — two piles on one ground are two islands). The
+// reference reserves an island pool it never fills (reference src/world.h:31, src/contact.c:21-38). islandOfBody[i] = label
+// of body slot i = the smallest body slot of its island, -1 for free slots; returns the number of islands (bodies without
+// constraints count as islands of one). What shards a world across GPUs (island -> rank) and what the region-local solver
+// schedule keeps whole inside one thread block. Synchronises.
+S2B_API int s2b_download_islands(s2bWorld* world, int32_t* islandOfBody, int capacity);
 
 // Packed per-body state {origin.x, origin.y, rot.s, rot.c, v.x, v.y, w, 0} for slots [first, first+count) written to
 // a DEVICE buffer (32 B/body) — the payload of the per-step NCCL all-gather in the multi-world configuration.

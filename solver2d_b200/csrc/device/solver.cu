@@ -68,6 +68,12 @@ void s2bFreeSolverScratch(s2bWorld* w)
 	s->bodyKeyIn.release();
 	s->bodyKeyOut.release();
 	s->bodyValIn.release();
+	s->bodySorted.release();
+	s->island.release();
+	s->islandParent.release();
+	s->islandSize.release();
+	s->islandStart.release();
+	s->regCount.release();
 	s->regBodies.release();
 	s->bodyRegion.release();
 	s->regBodyStart.release();
@@ -593,9 +599,113 @@ __device__ __forceinline__ unsigned s2bHilbert16(unsigned x, unsigned y)
 	return d;
 }
 
-// sort key of every body slot: its Hilbert position, or 0xFFFFFFFF for slots that belong to no region (free slots, hub
-// bodies). Hub bodies are appended to the hub list (order irrelevant: each is processed on its own).
-__global__ void s2bBodyKeysKernel(BodyView bodies, int* counts, const int* degree, unsigned* keys, int* vals, int* hubs)
+// ---- islands: connected components of the constraint graph over the movable bodies (union-find) -------------------
+// The reference reserves an island pool it never fills (reference src/world.h:31, design note src/contact.c:21-38); here
+// the islands are what keeps the region schedule cheap: an island that fits a block stays whole in ONE region, so a world
+// made of many small islands (batched worlds, bridges, rag dolls, debris) has no cut set at all and its Gauss-Seidel sweeps
+// need no grid barrier. Lock-free union by index (hook the larger root under the smaller with atomicCAS, path halving on
+// the way — the ECL-CC scheme): one pass over the items, one flatten pass; the label of an island is its smallest body slot,
+// so the result does not depend on thread timing.
+
+__device__ __forceinline__ int s2bIslandFind(int* parent, int x)
+{
+	volatile int* vp = parent;
+	int p = vp[x];
+	while (p != x)
+	{
+		int gp = vp[p];
+		if (gp != p)
+		{
+			vp[x] = gp; // path halving: gp is an ancestor of x whatever other threads do meanwhile (parents only decrease)
+		}
+		x = p;
+		p = gp;
+	}
+	return x;
+}
+
+__global__ void s2bIslandInitKernel(int bodyCapacity, int* parent)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < bodyCapacity)
+	{
+		parent[i] = i;
+	}
+}
+
+__global__ void s2bIslandHookKernel(const int* counts, const int2* itemBodies, int* parent)
+{
+	int n = counts[CNT_JOINTS] + counts[CNT_CONTACTS];
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+	{
+		return;
+	}
+	int2 e = itemBodies[i]; // movable endpoints only: a static body (the ground) does not connect what rests on it
+	if (e.x < 0 || e.y < 0)
+	{
+		return;
+	}
+	int a = e.x, b = e.y;
+	for (;;)
+	{
+		a = s2bIslandFind(parent, a);
+		b = s2bIslandFind(parent, b);
+		if (a == b)
+		{
+			break;
+		}
+		int hi = max(a, b), lo = min(a, b);
+		int old = atomicCAS(parent + hi, hi, lo);
+		if (old == hi)
+		{
+			break;
+		}
+		a = old; // someone hooked `hi` meanwhile: continue from where it points now
+		b = lo;
+	}
+}
+
+// label of every body slot = smallest body slot of its island; island sizes counted at the label. The forest is final
+// when this runs and is only READ here (a find that compresses paths would race with the label writes of other threads).
+__global__ void s2bIslandFlattenKernel(BodyView bodies, const int* parent, int* label, int* islandSize)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= bodies.capacity)
+	{
+		return;
+	}
+	int root = i;
+	for (int p = parent[root]; p != root; p = parent[root])
+	{
+		root = p;
+	}
+	label[i] = root;
+	if (bodies.flags[i] & S2B_BODY_VALID)
+	{
+		atomicAdd(islandSize + root, 1);
+	}
+}
+
+__device__ __forceinline__ unsigned s2bHilbertOfBody(const BodyView& bodies, const int* counts, int i)
+{
+	const unsigned* b = (const unsigned*)(counts + CNT_BOUNDS);
+	float maxX = s2bFromOrderedKey(b[0]), minX = -s2bFromOrderedKey(b[1]);
+	float maxY = s2bFromOrderedKey(b[2]), minY = -s2bFromOrderedKey(b[3]);
+	float extent = fmaxf(maxX - minX, maxY - minY);
+	float scale = extent > 0.0f ? 65535.0f / extent : 0.0f;
+	float4 pos = bodies.pos[i];
+	float fx = (pos.x - minX) * scale, fy = (pos.y - minY) * scale;
+	unsigned qx = fx >= 0.0f ? (fx < 65535.0f ? (unsigned)fx : 65535u) : 0u;
+	unsigned qy = fy >= 0.0f ? (fy < 65535.0f ? (unsigned)fy : 65535u) : 0u;
+	return s2bHilbert16(qx, qy);
+}
+
+// Sort key of every body slot: (Hilbert position of its ISLAND's label body) << 32 | its own Hilbert position — islands are
+// contiguous in the sorted order and laid out along the curve inside — or all ones for slots that belong to no region
+// (free slots, hub bodies). Hub bodies are appended to the hub list (order irrelevant: each is processed on its own).
+__global__ void s2bBodyKeysKernel(BodyView bodies, int* counts, const int* degree, const int* island, unsigned long long* keys, int* vals,
+								  int* hubs)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= bodies.capacity)
@@ -603,7 +713,7 @@ __global__ void s2bBodyKeysKernel(BodyView bodies, int* counts, const int* degre
 		return;
 	}
 	vals[i] = i;
-	unsigned key = 0xFFFFFFFFu;
+	unsigned long long key = ~0ull;
 	if (bodies.flags[i] & S2B_BODY_VALID)
 	{
 		if (degree[i] > S2B_HEAVY_DEGREE)
@@ -612,37 +722,88 @@ __global__ void s2bBodyKeysKernel(BodyView bodies, int* counts, const int* degre
 		}
 		else
 		{
-			const unsigned* b = (const unsigned*)(counts + CNT_BOUNDS);
-			float maxX = s2bFromOrderedKey(b[0]), minX = -s2bFromOrderedKey(b[1]);
-			float maxY = s2bFromOrderedKey(b[2]), minY = -s2bFromOrderedKey(b[3]);
-			float extent = fmaxf(maxX - minX, maxY - minY);
-			float scale = extent > 0.0f ? 65535.0f / extent : 0.0f;
-			float4 pos = bodies.pos[i];
-			float fx = (pos.x - minX) * scale, fy = (pos.y - minY) * scale;
-			unsigned qx = fx >= 0.0f ? (fx < 65535.0f ? (unsigned)fx : 65535u) : 0u;
-			unsigned qy = fy >= 0.0f ? (fy < 65535.0f ? (unsigned)fy : 65535u) : 0u;
-			key = min(s2bHilbert16(qx, qy), 0xFFFFFFFEu);
+			unsigned own = s2bHilbertOfBody(bodies, counts, i);
+			unsigned isl = s2bHilbertOfBody(bodies, counts, island[i]);
+			key = ((unsigned long long)isl << 32) | own;
+			if (key == ~0ull)
+			{
+				key -= 1;
+			}
 			atomicAdd(counts + CNT_OWNED, 1);
 		}
 	}
 	keys[i] = key;
 }
 
-// region of every body from its rank in the sorted order: equal chunks of the owned bodies
-__global__ void s2bAssignRegionsKernel(const int* counts, int bodyCapacity, int regions, const int* sortedBodies, int* bodyRegion,
-									   int* regBodyStart)
+// first rank of every island in the sorted order (at the island's label)
+__global__ void s2bIslandStartKernel(const int* counts, const int* sortedBodies, const int* island, int* islandStart)
 {
 	int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < counts[CNT_OWNED])
+	{
+		atomicMin(islandStart + island[sortedBodies[k]], k);
+	}
+}
+
+// Region of every body. The owned bodies are cut into `regions` chunks of equal size along the sorted order; an island of
+// at most two chunks goes WHOLE to the region its first body falls in (a block walks up to ~600 bodies per colour step at no
+// extra cost and twice that in two waves, cheaper than any cut set); larger islands are split along the curve.
+__global__ void s2bAssignRegionsKernel(const int* counts, int bodyCapacity, int regions, const int* sortedBodies, const int* island,
+									   const int* islandStart, const int* islandSize, int* bodyRegion, int* regCount)
+{
+	int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= bodyCapacity)
+	{
+		return;
+	}
 	int owned = counts[CNT_OWNED];
 	int chunk = max((owned + regions - 1) / regions, 1);
-	if (k < bodyCapacity)
+	int body = sortedBodies[k];
+	int region = -1;
+	if (k < owned)
 	{
-		bodyRegion[sortedBodies[k]] = k < owned ? k / chunk : -1;
+		int label = island[body];
+		int rank = islandSize[label] <= 2 * chunk ? islandStart[label] : k;
+		region = min(rank / chunk, regions - 1);
+		atomicAdd(regCount + region, 1);
 	}
-	if (k <= regions)
+	bodyRegion[body] = region;
+}
+
+// regBodyStart = exclusive scan of the region sizes (one block; regions <= 511); the cursors start at the same offsets
+__global__ void __launch_bounds__(512) s2bRegionOffsetsKernel(int regions, const int* regCount, int* regBodyStart, int* regCursor)
+{
+	__shared__ int s[512];
+	int t = threadIdx.x;
+	s[t] = t < regions ? regCount[t] : 0;
+	__syncthreads();
+	for (int d = 1; d < 512; d <<= 1)
 	{
-		long long start = (long long)k * chunk;
-		regBodyStart[k] = start < owned ? (int)start : owned;
+		int v = t >= d ? s[t - d] : 0;
+		__syncthreads();
+		s[t] += v;
+		__syncthreads();
+	}
+	if (t < regions)
+	{
+		int begin = s[t] - regCount[t];
+		regBodyStart[t] = begin;
+		regCursor[t] = begin;
+		if (t == regions - 1)
+		{
+			regBodyStart[regions] = s[t];
+		}
+	}
+}
+
+// body lists of the regions (order inside a region is irrelevant: body passes treat every body on its own)
+__global__ void s2bFillRegionBodiesKernel(const int* counts, const int* sortedBodies, const int* bodyRegion, int* regCursor, int* regBodies)
+{
+	int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < counts[CNT_OWNED])
+	{
+		int body = sortedBodies[k];
+		regBodies[atomicAdd(regCursor + bodyRegion[body], 1)] = body;
 	}
 }
 
@@ -1818,6 +1979,12 @@ static void planSolve(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 		s->bodyKeyIn.reserve((size_t)bodyCap + 1, st, false);
 		s->bodyKeyOut.reserve((size_t)bodyCap + 1, st, false);
 		s->bodyValIn.reserve((size_t)bodyCap + 1, st, false);
+		s->bodySorted.reserve((size_t)bodyCap + 1, st, false);
+		s->island.reserve((size_t)bodyCap + 1, st, false);
+		s->islandParent.reserve((size_t)bodyCap + 1, st, false);
+		s->islandSize.reserve((size_t)bodyCap + 1, st, false);
+		s->islandStart.reserve((size_t)bodyCap + 1, st, false);
+		s->regCount.reserve(1024, st, false);
 		s->regBodies.reserve((size_t)bodyCap + 1, st, false);
 		s->bodyRegion.reserve((size_t)bodyCap + 1, st, false);
 		s->regBodyStart.reserve((size_t)pl.regions + 2, st, false);
@@ -1886,7 +2053,8 @@ static void planSolve(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 	cub::DeviceRadixSort::SortPairs(nullptr, need, (unsigned short*)nullptr, (unsigned short*)nullptr, (int*)nullptr, (int*)nullptr, (int)nI, 0,
 									16, st);
 	tempBytes = std::max(tempBytes, need);
-	cub::DeviceRadixSort::SortPairs(nullptr, need, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, bodyCap + 1, 0, 32, st);
+	cub::DeviceRadixSort::SortPairs(nullptr, need, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr,
+									bodyCap + 1, 0, 64, st);
 	tempBytes = std::max(tempBytes, need);
 	s->cubTemp.reserve(tempBytes + 256, st, false, false);
 }
@@ -1986,15 +2154,26 @@ static void enqueueSchedule(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 			// regions: Hilbert order of the bodies' centres, equal chunks
 			if (pl.regions > 0)
 			{
+				// islands (union-find over the items), then Hilbert order with the island as the major key
+				S2B_LAUNCH(w, s2bIslandInitKernel, gridFor(bodyCap, 256), 256, 0, bodyCap, s->islandParent.p);
+				S2B_LAUNCH(w, s2bIslandHookKernel, gridFor(maxItems, 256), 256, 0, s->counts.p, s->itemBodies.p, s->islandParent.p);
+				S2B_CHECK(cudaMemsetAsync(s->islandSize.p, 0, sizeof(int) * ((size_t)bodyCap + 1), st));
+				S2B_CHECK(cudaMemsetAsync(s->islandStart.p, 0x7F, sizeof(int) * ((size_t)bodyCap + 1), st));
+				S2B_CHECK(cudaMemsetAsync(s->regCount.p, 0, sizeof(int) * 512, st));
+				S2B_LAUNCH(w, s2bIslandFlattenKernel, gridFor(bodyCap, 256), 256, 0, bodyView(w), s->islandParent.p, s->island.p, s->islandSize.p);
 				S2B_LAUNCH(w, s2bBodyBoundsKernel, gridFor(bodyCap, 256), 256, 0, bodyView(w), s->counts.p);
-				S2B_LAUNCH(w, s2bBodyKeysKernel, gridFor(bodyCap, 256), 256, 0, bodyView(w), s->counts.p, s->degree.p, s->bodyKeyIn.p,
+				S2B_LAUNCH(w, s2bBodyKeysKernel, gridFor(bodyCap, 256), 256, 0, bodyView(w), s->counts.p, s->degree.p, s->island.p, s->bodyKeyIn.p,
 						   s->bodyValIn.p, s->heavyBodies.p);
 				size_t tb = s->cubTemp.cap;
-				cub::DeviceRadixSort::SortPairs(s->cubTemp.p, tb, s->bodyKeyIn.p, s->bodyKeyOut.p, s->bodyValIn.p, s->regBodies.p, bodyCap, 0, 32,
+				cub::DeviceRadixSort::SortPairs(s->cubTemp.p, tb, s->bodyKeyIn.p, s->bodyKeyOut.p, s->bodyValIn.p, s->bodySorted.p, bodyCap, 0, 64,
 												st);
-				w->kernelLaunches += 4;
-				S2B_LAUNCH(w, s2bAssignRegionsKernel, gridFor(std::max(bodyCap, pl.regions + 1), 256), 256, 0, s->counts.p, bodyCap, pl.regions,
-						   s->regBodies.p, s->bodyRegion.p, s->regBodyStart.p);
+				w->kernelLaunches += 10;
+				S2B_LAUNCH(w, s2bIslandStartKernel, gridFor(bodyCap, 256), 256, 0, s->counts.p, s->bodySorted.p, s->island.p, s->islandStart.p);
+				S2B_LAUNCH(w, s2bAssignRegionsKernel, gridFor(bodyCap, 256), 256, 0, s->counts.p, bodyCap, pl.regions, s->bodySorted.p, s->island.p,
+						   s->islandStart.p, s->islandSize.p, s->bodyRegion.p, s->regCount.p);
+				S2B_LAUNCH(w, s2bRegionOffsetsKernel, 1, 512, 0, pl.regions, s->regCount.p, s->regBodyStart.p, s->regCount.p + 512);
+				S2B_LAUNCH(w, s2bFillRegionBodiesKernel, gridFor(bodyCap, 256), 256, 0, s->counts.p, s->bodySorted.p, s->bodyRegion.p,
+						   s->regCount.p + 512, s->regBodies.p);
 				s->regions = pl.regions;
 			}
 			S2B_LAUNCH(w, s2bClassifyItemsKernel, gridFor(maxItems, 256), 256, 0, s->counts.p, s->itemBodies.p, s->bodyRegion.p, s->colorA.p,
@@ -2565,6 +2744,54 @@ extern "C" int s2b_download_solve_order(s2bWorld* w, int32_t* items, int maxItem
 		*groupCount = groupsOut;
 	}
 	return written;
+}
+
+// Islands of the constraint graph of the last solve (see s2bIslandHookKernel): label per body slot = smallest body slot of
+// its island (a body without constraints, or a static body, is an island of its own); -1 for free slots.
+extern "C" int s2b_download_islands(s2bWorld* w, int32_t* islandOfBody, int capacity)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	S2bEpochFreeze freeze; // scratch of this query is not referenced by the solver's graph
+	SolverScratch* s = s2bGetSolverScratch(w);
+	cudaStream_t st = w->stream;
+	int bodyCap = w->bodyCap;
+	if (bodyCap <= 0 || s->counts.p == nullptr)
+	{
+		return 0;
+	}
+	int maxItems = w->contactCount + w->jointCap;
+	DevArray<int> parent, label, size;
+	parent.reserve((size_t)bodyCap + 1, st, false);
+	label.reserve((size_t)bodyCap + 1, st, false);
+	size.reserve((size_t)bodyCap + 1, st, false, true);
+	S2B_LAUNCH(w, s2bIslandInitKernel, gridFor(bodyCap, 256), 256, 0, bodyCap, parent.p);
+	if (maxItems > 0 && s->itemBodies.p != nullptr)
+	{
+		S2B_LAUNCH(w, s2bIslandHookKernel, gridFor(maxItems, 256), 256, 0, s->counts.p, s->itemBodies.p, parent.p);
+	}
+	S2B_LAUNCH(w, s2bIslandFlattenKernel, gridFor(bodyCap, 256), 256, 0, bodyView(w), parent.p, label.p, size.p);
+	std::vector<int> host((size_t)bodyCap);
+	std::vector<uint8_t> flags((size_t)bodyCap);
+	S2B_CHECK(cudaMemcpyAsync(host.data(), label.p, sizeof(int) * (size_t)bodyCap, cudaMemcpyDeviceToHost, st));
+	S2B_CHECK(cudaMemcpyAsync(flags.data(), w->bFlags.p, (size_t)bodyCap, cudaMemcpyDeviceToHost, st));
+	S2B_CHECK(cudaStreamSynchronize(st));
+	parent.release();
+	label.release();
+	size.release();
+	int islands = 0;
+	for (int i = 0; i < bodyCap; ++i)
+	{
+		bool valid = (flags[(size_t)i] & S2B_BODY_VALID) != 0;
+		if (valid && host[(size_t)i] == i)
+		{
+			islands += 1;
+		}
+		if (i < capacity && islandOfBody != nullptr)
+		{
+			islandOfBody[i] = valid ? host[(size_t)i] : -1;
+		}
+	}
+	return islands;
 }
 
 extern "C" void s2b_get_counters(s2bWorld* w, s2bCounters* out)

@@ -96,8 +96,13 @@ struct SolverScratch
 	DevArray<int> itemRegion;	  // per item: region it is interior to, or -1 (cut set)
 	DevArray<unsigned short> sortKeyIn, sortKeyOut; // solve-order keys (region x colour | cut colour | overflow), see s2bMakeSortKeys
 	// regions
-	DevArray<unsigned> bodyKeyIn, bodyKeyOut; // Hilbert keys of the bodies' centres
-	DevArray<int> bodyValIn, regBodies;		  // body slots, unsorted / sorted by key
+	DevArray<unsigned long long> bodyKeyIn, bodyKeyOut; // (island, Hilbert position) keys of the bodies
+	DevArray<int> bodyValIn, bodySorted;	  // body slots, unsorted / sorted by key
+	DevArray<int> regBodies;				  // body slots grouped by region
+	DevArray<int> islandParent;				  // union-find forest over the body slots
+	DevArray<int> island;					  // per body: label of its island (smallest body slot in it)
+	DevArray<int> islandSize, islandStart;	  // per label: bodies in the island, its first rank in the sorted order
+	DevArray<int> regCount;					  // [0, 512): bodies per region; [512, 1024): fill cursors
 	DevArray<int> bodyRegion;				  // per body: region or -1 (hub, invalid)
 	DevArray<int> regBodyStart;				  // regions + 1
 	DevArray<int> cRegOff, jRegOff;			  // regions x (S2B_MAX_COLORS + 1)

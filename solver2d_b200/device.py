@@ -73,7 +73,7 @@ ABI_SYMBOLS = [
     "s2b_upload_joint_pairs", "s2b_mark_pairs_dirty", "s2b_set_contact_order", "s2b_update_pairs",
     "s2b_update_contacts", "s2b_solve", "s2b_finalize", "s2b_step", "s2b_sync", "s2b_download_bodies",
     "s2b_download_all_bodies", "s2b_download_shape_boxes", "s2b_download_joints", "s2b_download_contacts",
-    "s2b_download_solve_order", "s2b_get_counters", "s2b_pack_body_state", "s2b_timed_steps", "s2b_last_stage_ms",
+    "s2b_download_solve_order", "s2b_download_islands", "s2b_get_counters", "s2b_pack_body_state", "s2b_timed_steps", "s2b_last_stage_ms",
     "s2b_flush_l2", "s2b_time_color_kernel", "s2b_version", "s2b_abi_sizes", "s2b_upload_forces", "s2b_host_alloc",
     "s2b_host_free", "s2b_sync_body_state", "s2b_set_warm_gather", "s2b_eval_atan2", "s2b_set_dataflow", "s2b_set_regions", "s2b_set_graph", "s2b_get_stream", "s2b_add_forces", "s2b_download_transforms",
 ]
@@ -284,6 +284,15 @@ class DeviceWorld:
         flags = np.zeros(cap, dtype=np.int32)
         self.L.s2b_download_shape_boxes(self.h, aabb.ctypes.data, fat.ctypes.data, flags.ctypes.data, cap)
         return aabb, fat, flags
+
+    def islands(self, capacity: int | None = None):
+        """(labels, count): labels[i] = island of body slot i (smallest body slot of the island, -1 for free slots)."""
+        cap = self.body_cap if capacity is None else capacity
+        labels = np.full(max(cap, 1), -1, dtype=np.int32)
+        self.L.s2b_download_islands.restype = C.c_int
+        self.L.s2b_download_islands.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        n = self.L.s2b_download_islands(self.h, labels.ctypes.data, cap)
+        return labels[:cap], int(n)
 
     def solve_order(self, max_items: int, max_groups: int = 70000):
         """(items, group_sizes): items >= 0 contact slot, < 0 joint slot (-1 - k), in the order the last solve visited them."""

@@ -31,6 +31,7 @@ class Scene:
     bodies: list = field(default_factory=list)
     joints: list = field(default_factory=list)
     name: str = ""
+    piles: dict = field(default_factory=dict)
 
     def step(self, dt=1.0 / 60.0, vel_iters=4, pos_iters=2, warm_start=True):
         self.lib.s2World_Step(self.world, dt, vel_iters, pos_iters, warm_start)
@@ -369,6 +370,47 @@ def pyramid_rows(base_count: int):
     m = np.float32(0.1)  # s2_aabbMargin
     shapes["fatAABB"] = np.stack([cx - hw - m, cy - hh - m, cx + hw + m, cy + hh + m], axis=1)
     return bodies, shapes
+
+
+def pyramid_field_interleaved(lib: capi.Solver2D, solver="TGS_Soft", count=12, base_count=8, pitch=None, only=None) -> Scene:
+    """The same piles as :func:`pyramid_field`, but created ROUND-ROBIN — body k of every pile before body k + 1 of any — so
+    that the islands are thoroughly interleaved in every pool and table (slots, proxy ids, contact keys). Within one pile
+    the creation order is the pyramid recipe's, so each pile evolves bit for bit like a world that holds it alone
+    (``only=k`` builds exactly that world, at the same position). ``Scene.bodies`` lists pile 0's bodies first (ground,
+    then boxes), then pile 1's ... — ``Scene.piles[k]`` is the slice of pile k."""
+    world = lib.create_world(solver)
+    sc = Scene(lib, world, name=f"field{count}x{base_count}i")
+    h = 0.5
+    if pitch is None:
+        pitch = float(base_count + 6)
+    box = lib.s2MakeSquare(h)
+    ground = lib.s2MakeBox(0.5 * base_count + 2.0, 1.0)
+    sd = default_shape_def()
+    sd.density = 1.0
+    which = list(range(count)) if only is None else [only]
+    cells = [(i, j) for i in range(base_count) for j in range(i, base_count)]
+    per_pile = {k: [] for k in which}
+    for k in which:
+        bd = default_body_def()
+        bd.position = Vec2(k * pitch, -1.0)
+        gid = lib.s2CreateBody(world, C.byref(bd))
+        lib.s2CreatePolygonShape(gid, C.byref(sd), C.byref(ground))
+        per_pile[k].append(gid)
+    bd = default_body_def()
+    bd.type = capi.DYNAMIC_BODY
+    for (i, j) in cells:
+        y = (2.0 * i + 1.0) * h
+        x = (i + 1.0) * h + 2.0 * (j - i) * h - h * base_count
+        for k in which:
+            bd.position = Vec2(k * pitch + x, y)
+            bid = lib.s2CreateBody(world, C.byref(bd))
+            lib.s2CreatePolygonShape(bid, C.byref(sd), C.byref(box))
+            per_pile[k].append(bid)
+    sc.piles = {}
+    for k in which:
+        sc.piles[k] = slice(len(sc.bodies), len(sc.bodies) + len(per_pile[k]))
+        sc.bodies.extend(per_pile[k])
+    return sc
 
 
 def pyramid_field(lib: capi.Solver2D, solver="TGS_Soft", count=256, base_count=45, first=0, pitch=None) -> Scene:

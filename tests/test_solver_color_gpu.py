@@ -49,8 +49,12 @@ def _case(reference, dev, recipe, solver, warm, vel, pos, persistent, max_colors
     movable = (bodies["invMass"] != 0) | (bodies["invI"] != 0)
     parallel_groups = len(group_sizes) - (1 if counters.overflowCount > 0 else 0)
     is_contact = order >= 0
-    ends_a = np.where(is_contact, contacts["bodyA"][np.where(is_contact, order, 0)], -1)
-    ends_b = np.where(is_contact, contacts["bodyB"][np.where(is_contact, order, 0)], -1)
+    if len(contacts):
+        ends_a = np.where(is_contact, contacts["bodyA"][np.where(is_contact, order, 0)], -1)
+        ends_b = np.where(is_contact, contacts["bodyB"][np.where(is_contact, order, 0)], -1)
+    else:
+        ends_a = np.full(len(order), -1)
+        ends_b = np.full(len(order), -1)
     if len(joints):
         jslot = np.where(is_contact, 0, -1 - order)
         jtype = (joints["flags"][jslot] >> 1) & 7
@@ -58,8 +62,6 @@ def _case(reference, dev, recipe, solver, warm, vel, pos, persistent, max_colors
         ends_b = np.where(is_contact, ends_b, joints["bodyB"][jslot])
     group_of = np.repeat(np.arange(len(group_sizes)), group_sizes)
     assert len(group_of) == len(order)
-    for ends in (ends_a, ends_b):
-        pass
     both = np.concatenate([np.stack([group_of, ends_a], 1), np.stack([group_of, ends_b], 1)])
     both = both[(both[:, 1] >= 0) & (both[:, 0] < parallel_groups)]
     both = both[movable[both[:, 1]]]
