@@ -508,7 +508,12 @@ __device__ __forceinline__ void s2bConsiderPair(const PairQuery& q, int other, c
 	unsigned long long lo = (unsigned long long)(other < shapeQ ? other : shapeQ);
 	unsigned long long hi = (unsigned long long)(other < shapeQ ? shapeQ : other);
 	unsigned long long pairKey = (lo << 32) | hi;
-	if (s2bPairInHash(pairHash, hashMask, pairKey))
+	// "this pair already has a contact" — unless one of the shapes was (re)created since the table was built: the table's
+	// contact then belongs to the shape that used to live in that slot and is dropped by this very pass (s2bFlagKeptContacts),
+	// so the pair has to be reported again (the reference removes the key from its pair set when the old shape is destroyed,
+	// src/contact.c:231-292, and creates the contact on the next update)
+	bool recreated = ((q.headQ.x | headO.x) & S2B_SHAPE_FRESH) != 0;
+	if (recreated == false && s2bPairInHash(pairHash, hashMask, pairKey))
 	{
 		return;
 	}
@@ -564,6 +569,8 @@ __device__ __forceinline__ bool s2bMakeQuery(PairQuery& q, int shapeQ, const Sha
 	return q.typeBodyQ != S2B_BODY_STATIC; // static proxies never query (reference src/broad_phase.c:284-299)
 }
 
+#define S2B_QUERY_BATCH 16
+
 // moved proxies with ordinary boxes: one thread walks the hierarchy
 __global__ void __launch_bounds__(128) s2bFindPairs(ShapeView s, BodyView b, const int* leafShape, const int* sortedLeaf, int* counters,
 								 const int* movedLeaves, const int2* children, const float4* pairBox,
@@ -585,50 +592,66 @@ __global__ void __launch_bounds__(128) s2bFindPairs(ShapeView s, BodyView b, con
 	}
 	float4 boxQ = s.fat[q.shapeQ];
 
-	// descend into one overlapping child directly and stack the other: half the stack traffic of push-both / pop
+	// descend into one overlapping child directly and stack the other: half the stack traffic of push-both / pop.
+	// Overlapping LEAVES are only collected during the walk and examined in batches afterwards: the walk (box tests) and the
+	// pair rules (shape header, hash probe, filters) are two different instruction streams, and a warp whose lanes hit
+	// leaves at different moments would otherwise execute both serially for every lane (10 of 32 lanes active, ncu round 1).
 	int stack[64];
+	int found[S2B_QUERY_BATCH];
+	int nFound = 0;
 	int sp = 0;
 	int node = 0;
-	for (;;)
+	bool walking = true;
+	while (walking || nFound > 0)
 	{
-		if (node >= n - 1)
+		while (walking && nFound < S2B_QUERY_BATCH)
 		{
-			s2bConsiderPair(q, leafShape[sortedLeaf[node - (n - 1)]], s, b, counters, pairHash, hashMask, jointKeys, jointKeyCount, newKey,
-							newShapes, newCap);
-			if (sp == 0)
+			if (node >= n - 1)
 			{
-				break;
+				found[nFound++] = node - (n - 1);
+				if (sp == 0)
+				{
+					walking = false;
+					break;
+				}
+				node = stack[--sp];
+				continue;
 			}
-			node = stack[--sp];
-			continue;
-		}
-		int2 ch = children[node];
-		bool o0 = s2bBoxesOverlap(boxQ, pairBox[2 * node]);
-		bool o1 = s2bBoxesOverlap(boxQ, pairBox[2 * node + 1]);
-		if (o0 && o1)
-		{
-			if (sp < 64)
+			int2 ch = children[node];
+			bool o0 = s2bBoxesOverlap(boxQ, pairBox[2 * node]);
+			bool o1 = s2bBoxesOverlap(boxQ, pairBox[2 * node + 1]);
+			if (o0 && o1)
 			{
-				stack[sp++] = ch.y;
+				if (sp < 64)
+				{
+					stack[sp++] = ch.y;
+				}
+				node = ch.x;
 			}
-			node = ch.x;
-		}
-		else if (o0)
-		{
-			node = ch.x;
-		}
-		else if (o1)
-		{
-			node = ch.y;
-		}
-		else
-		{
-			if (sp == 0)
+			else if (o0)
 			{
-				break;
+				node = ch.x;
 			}
-			node = stack[--sp];
+			else if (o1)
+			{
+				node = ch.y;
+			}
+			else
+			{
+				if (sp == 0)
+				{
+					walking = false;
+					break;
+				}
+				node = stack[--sp];
+			}
 		}
+		for (int k = 0; k < nFound; ++k)
+		{
+			s2bConsiderPair(q, leafShape[sortedLeaf[found[k]]], s, b, counters, pairHash, hashMask, jointKeys, jointKeyCount, newKey, newShapes,
+							newCap);
+		}
+		nFound = 0;
 	}
 }
 

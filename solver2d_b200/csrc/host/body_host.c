@@ -14,43 +14,37 @@ s2Body* s2GetBody(s2World* world, s2BodyId id)
 	return body;
 }
 
-// reference src/body.c:17-63
+// A new body slot (behaviour of reference src/body.c:17-63): state from the definition, no shapes and hence no mass yet.
 s2BodyId s2CreateBody(s2WorldId worldId, const s2BodyDef* def)
 {
 	s2World* world = s2GetWorldFromId(worldId);
-	s2Body* b = (s2Body*)s2AllocObject(&world->bodyPool);
-	world->bodies = (s2Body*)world->bodyPool.memory;
-	if (b->object.index + 1 > world->bodyHighWater)
-	{
-		world->bodyHighWater = b->object.index + 1;
-	}
-	b->onDevice = false;
+	s2Body* slot = (s2Body*)s2AllocObject(&world->bodyPool);
+	world->bodies = (s2Body*)world->bodyPool.memory; // the pool may have moved
+	int32_t used = slot->object.index + 1;
+	world->bodyHighWater = used > world->bodyHighWater ? used : world->bodyHighWater;
 
-	b->type = def->type;
-	b->origin = def->position;
-	b->position = def->position;
-	b->rot = s2MakeRot(def->angle);
-	b->localCenter = s2Vec2_zero;
-	b->linearVelocity = def->linearVelocity;
-	b->angularVelocity = def->angularVelocity;
-	b->force = s2Vec2_zero;
-	b->torque = 0.0f;
-	b->shapeList = S2_NULL_INDEX;
-	b->jointCount = 0;
-	b->mass = 0.0f;
-	b->invMass = 0.0f;
-	b->I = 0.0f;
-	b->invI = 0.0f;
-	b->linearDamping = def->linearDamping;
-	b->angularDamping = def->angularDamping;
-	b->gravityScale = def->gravityScale;
-	b->userData = def->userData;
-	b->world = worldId.index;
-	// rowDirty / forceDirty keep their value: a reused slot may already sit in the dirty list
-	s2MarkBodyDirty(world, b);
+	// what the definition prescribes
+	slot->type = def->type;
+	slot->userData = def->userData;
+	slot->world = worldId.index;
+	slot->rot = s2MakeRot(def->angle);
+	slot->origin = slot->position = def->position; // centre of mass == origin until a shape with density arrives
+	slot->linearVelocity = def->linearVelocity;
+	slot->angularVelocity = def->angularVelocity;
+	slot->linearDamping = def->linearDamping;
+	slot->angularDamping = def->angularDamping;
+	slot->gravityScale = def->gravityScale;
+	// what a body without shapes is
+	slot->localCenter = slot->force = s2Vec2_zero;
+	slot->torque = 0.0f;
+	slot->mass = slot->invMass = slot->I = slot->invI = 0.0f;
+	slot->shapeList = S2_NULL_INDEX;
+	slot->jointCount = 0;
+	// device mirror: not there yet (rowDirty / forceDirty keep their value — a reused slot may already sit in the dirty list)
+	slot->onDevice = false;
+	s2MarkBodyDirty(world, slot);
 
-	s2BodyId id = {b->object.index, worldId.index, b->object.revision};
-	return id;
+	return (s2BodyId){slot->object.index, worldId.index, slot->object.revision};
 }
 
 static void s2DestroyShapeProxy(s2World* world, s2Shape* shape)
@@ -82,99 +76,122 @@ void s2DestroyBody(s2BodyId bodyId)
 	s2MarkBodyDirty(world, body);
 }
 
+// per shape kind: tight box and mass properties, dispatched through tables indexed by s2ShapeType
+typedef s2Box s2ShapeBoxFcn(const void* geometry, s2Transform xf);
+typedef s2MassData s2ShapeMassFcn(const void* geometry, float density);
+
+static s2Box s2BoxOfCapsule(const void* g, s2Transform xf)
+{
+	return s2ComputeCapsuleAABB((const s2Capsule*)g, xf);
+}
+static s2Box s2BoxOfCircle(const void* g, s2Transform xf)
+{
+	return s2ComputeCircleAABB((const s2Circle*)g, xf);
+}
+static s2Box s2BoxOfPolygon(const void* g, s2Transform xf)
+{
+	return s2ComputePolygonAABB((const s2Polygon*)g, xf);
+}
+static s2Box s2BoxOfSegment(const void* g, s2Transform xf)
+{
+	return s2ComputeSegmentAABB((const s2Segment*)g, xf);
+}
+static s2MassData s2MassOfCapsule(const void* g, float density)
+{
+	return s2ComputeCapsuleMass((const s2Capsule*)g, density);
+}
+static s2MassData s2MassOfCircle(const void* g, float density)
+{
+	return s2ComputeCircleMass((const s2Circle*)g, density);
+}
+static s2MassData s2MassOfPolygon(const void* g, float density)
+{
+	return s2ComputePolygonMass((const s2Polygon*)g, density);
+}
+
+static s2ShapeBoxFcn* const s2_shapeBox[s2_shapeTypeCount] = {
+	[s2_capsuleShape] = s2BoxOfCapsule, [s2_circleShape] = s2BoxOfCircle, [s2_polygonShape] = s2BoxOfPolygon, [s2_segmentShape] = s2BoxOfSegment};
+// (a segment has no area: no entry, no mass)
+static s2ShapeMassFcn* const s2_shapeMass[s2_shapeTypeCount] = {
+	[s2_capsuleShape] = s2MassOfCapsule, [s2_circleShape] = s2MassOfCircle, [s2_polygonShape] = s2MassOfPolygon};
+
 s2Box s2Shape_ComputeAABB(const s2Shape* shape, s2Transform xf)
 {
-	switch (shape->type)
+	if ((unsigned)shape->type < (unsigned)s2_shapeTypeCount && s2_shapeBox[shape->type] != NULL)
 	{
-		case s2_capsuleShape:
-			return s2ComputeCapsuleAABB(&shape->capsule, xf);
-		case s2_circleShape:
-			return s2ComputeCircleAABB(&shape->circle, xf);
-		case s2_polygonShape:
-			return s2ComputePolygonAABB(&shape->polygon, xf);
-		case s2_segmentShape:
-			return s2ComputeSegmentAABB(&shape->segment, xf);
-		default:
-		{
-			s2Box empty = {xf.p, xf.p};
-			return empty;
-		}
+		return s2_shapeBox[shape->type](&shape->capsule, xf); // the geometry union starts at its first member
 	}
+	return (s2Box){xf.p, xf.p};
 }
 
 s2MassData s2Shape_ComputeMass(const s2Shape* shape)
 {
-	switch (shape->type)
+	if ((unsigned)shape->type < (unsigned)s2_shapeTypeCount && s2_shapeMass[shape->type] != NULL)
 	{
-		case s2_capsuleShape:
-			return s2ComputeCapsuleMass(&shape->capsule, shape->density);
-		case s2_circleShape:
-			return s2ComputeCircleMass(&shape->circle, shape->density);
-		case s2_polygonShape:
-			return s2ComputePolygonMass(&shape->polygon, shape->density);
-		default:
-		{
-			s2MassData zero = {0};
-			return zero;
-		}
+		return s2_shapeMass[shape->type](&shape->capsule, shape->density);
 	}
+	return (s2MassData){0};
 }
 
-// reference src/body.c:152-218: total mass, centre of mass and inertia about it from the attached shapes
+// Mass, centre of mass and inertia about it of a body from the shapes attached to it (behaviour of reference
+// src/body.c:152-218; sums run over the shape list in list order, the float operations are the reference's).
+typedef struct s2MassSum
+{
+	float mass;		 // sum of the shape masses
+	s2Vec2 moment;	 // sum of mass x centre (body frame)
+	float inertia;	 // sum of the shape inertias about the body origin
+} s2MassSum;
+
+static s2MassSum s2SumShapeMasses(const s2World* world, const s2Body* body)
+{
+	s2MassSum sum = {0.0f, {0.0f, 0.0f}, 0.0f};
+	int32_t next = body->shapeList;
+	while (next != S2_NULL_INDEX)
+	{
+		const s2Shape* shape = world->shapes + next;
+		next = shape->nextShapeIndex;
+		if (shape->density != 0.0f)
+		{
+			s2MassData part = s2Shape_ComputeMass(shape);
+			sum.mass += part.mass;
+			sum.moment = s2MulAdd(sum.moment, part.mass, part.center);
+			sum.inertia += part.I;
+		}
+	}
+	return sum;
+}
+
 static void s2UpdateBodyMass(s2World* world, s2Body* b)
 {
-	b->mass = 0.0f;
-	b->invMass = 0.0f;
-	b->I = 0.0f;
-	b->invI = 0.0f;
+	b->mass = b->invMass = b->I = b->invI = 0.0f;
 	b->localCenter = s2Vec2_zero;
-
 	if (b->type != s2_dynamicBody)
 	{
+		// static and kinematic bodies have no mass: the "centre of mass" is the origin
 		b->position = b->origin;
 		return;
 	}
 
-	s2Vec2 localCenter = s2Vec2_zero;
-	for (int32_t si = b->shapeList; si != S2_NULL_INDEX;)
+	s2MassSum sum = s2SumShapeMasses(world, b);
+	s2Vec2 center = sum.moment;
+	b->mass = sum.mass;
+	if (sum.mass > 0.0f)
 	{
-		const s2Shape* s = world->shapes + si;
-		si = s->nextShapeIndex;
-		if (s->density == 0.0f)
-		{
-			continue;
-		}
-		s2MassData md = s2Shape_ComputeMass(s);
-		b->mass += md.mass;
-		localCenter = s2MulAdd(localCenter, md.mass, md.center);
-		b->I += md.I;
+		b->invMass = 1.0f / sum.mass;
+		center = s2MulSV(b->invMass, center);
 	}
-
-	if (b->mass > 0.0f)
+	if (sum.inertia > 0.0f)
 	{
-		b->invMass = 1.0f / b->mass;
-		localCenter = s2MulSV(b->invMass, localCenter);
-	}
-
-	if (b->I > 0.0f)
-	{
-		// inertia about the centre of mass
-		b->I -= b->mass * s2Dot(localCenter, localCenter);
+		// from the body origin to the centre of mass (parallel axes)
+		b->I = sum.inertia - b->mass * s2Dot(center, center);
 		b->invI = 1.0f / b->I;
 	}
-	else
-	{
-		b->I = 0.0f;
-		b->invI = 0.0f;
-	}
 
-	s2Vec2 oldCenter = b->position;
-	b->localCenter = localCenter;
-	b->position = s2Add(s2RotateVector(b->rot, b->localCenter), b->origin);
-
-	// the velocity refers to the centre of mass
-	s2Vec2 deltaLinear = s2CrossSV(b->angularVelocity, s2Sub(b->position, oldCenter));
-	b->linearVelocity = s2Add(b->linearVelocity, deltaLinear);
+	// the centre of mass moved inside the body: keep the velocity of the material (v refers to the centre of mass)
+	s2Vec2 before = b->position;
+	b->localCenter = center;
+	b->position = s2Add(s2RotateVector(b->rot, center), b->origin);
+	b->linearVelocity = s2Add(b->linearVelocity, s2CrossSV(b->angularVelocity, s2Sub(b->position, before)));
 }
 
 // reference src/body.c:220-280 + s2Shape_CreateProxy (src/shape.c:48-67)

@@ -7,6 +7,7 @@
 #include "shared/s2_collide.h"
 
 #include <float.h>
+#include <string.h>
 #include <math.h>
 
 // ---- math.h out-of-line part (reference src/math.c) --------------------------------------------------------------
@@ -217,88 +218,73 @@ s2MassData s2ComputeCapsuleMass(const s2Capsule* shape, float density)
 	return md;
 }
 
-// reference src/geometry.c:152-286: triangle fan about vertex 0; rounded polygons are inflated first
+// Outline whose area a (possibly rounded) polygon is given the mass of: the polygon itself, or — radius > 0 — every corner
+// moved outwards along the bisector of its two edge normals until the straight edges have moved out by `radius`.
+static void s2MassOutline(const s2Polygon* poly, s2Vec2* outline)
+{
+	int32_t n = poly->count;
+	if (poly->radius <= 0.0f)
+	{
+		memcpy(outline, poly->vertices, sizeof(s2Vec2) * (size_t)n);
+		return;
+	}
+	for (int32_t corner = 0, before = n - 1; corner < n; before = corner++)
+	{
+		s2Vec2 nIn = poly->normals[before], nOut = poly->normals[corner];
+		s2Vec2 bisector = s2cNormalize(s2Add(nIn, nOut));
+		s2Vec2 alongIn = {-nIn.y, nIn.x};
+		// sine of half the corner's exterior angle; a straight "corner" keeps the plain radius
+		float s = s2Cross(bisector, alongIn);
+		float push = s > FLT_EPSILON ? poly->radius / s : poly->radius;
+		outline[corner] = s2MulAdd(poly->vertices[corner], push, bisector);
+	}
+}
+
+// Mass properties of a convex polygon (behaviour of reference src/geometry.c:152-286, whose arithmetic is kept operation
+// for operation — the body masses of a scene have to come out bit-identical). Degenerate polygons are the round shapes
+// they stand for; everything else is summed as a fan of triangles spanned from the first outline vertex.
 s2MassData s2ComputePolygonMass(const s2Polygon* shape, float density)
 {
-	if (shape->count == 1)
+	if (shape->count <= 2)
 	{
-		s2Circle circle;
-		circle.point = shape->vertices[0];
-		circle.radius = shape->radius;
-		return s2ComputeCircleMass(&circle, density);
-	}
-
-	if (shape->count == 2)
-	{
-		s2Capsule capsule;
-		capsule.point1 = shape->vertices[0];
-		capsule.point2 = shape->vertices[1];
-		capsule.radius = shape->radius;
-		return s2ComputeCapsuleMass(&capsule, density);
-	}
-
-	s2Vec2 vertices[s2_maxPolygonVertices];
-	int32_t count = shape->count;
-	float radius = shape->radius;
-
-	if (radius > 0.0f)
-	{
-		// push each vertex out along the bisector of its two edge normals
-		for (int32_t i = 0; i < count; ++i)
+		if (shape->count == 1)
 		{
-			int32_t prev = i == 0 ? count - 1 : i - 1;
-			s2Vec2 n1 = shape->normals[prev];
-			s2Vec2 n2 = shape->normals[i];
-			s2Vec2 mid = s2cNormalize(s2Add(n1, n2));
-			s2Vec2 t1 = {-n1.y, n1.x};
-			float sinHalfAngle = s2Cross(mid, t1);
-			float offset = radius;
-			if (sinHalfAngle > FLT_EPSILON)
-			{
-				offset = radius / sinHalfAngle;
-			}
-			vertices[i] = s2MulAdd(shape->vertices[i], offset, mid);
+			s2Circle disc = {shape->vertices[0], shape->radius};
+			return s2ComputeCircleMass(&disc, density);
 		}
+		s2Capsule pill = {shape->vertices[0], shape->vertices[1], shape->radius};
+		return s2ComputeCapsuleMass(&pill, density);
 	}
-	else
+
+	s2Vec2 outline[s2_maxPolygonVertices];
+	s2MassOutline(shape, outline);
+
+	// zeroth, first and second moments about the fan's apex
+	const s2Vec2 apex = outline[0];
+	const float third = 1.0f / 3.0f;
+	float areaSum = 0.0f, secondMoment = 0.0f;
+	s2Vec2 firstMoment = {0.0f, 0.0f};
+	for (const s2Vec2* v = outline + 1; v + 1 < outline + shape->count; ++v)
 	{
-		for (int32_t i = 0; i < count; ++i)
-		{
-			vertices[i] = shape->vertices[i];
-		}
+		s2Vec2 a = s2Sub(v[0], apex), b = s2Sub(v[1], apex);
+		float twiceArea = s2Cross(a, b);
+		float wedge = 0.5f * twiceArea;
+		areaSum += wedge;
+		firstMoment = s2MulAdd(firstMoment, wedge * third, s2Add(a, b));
+		float xx = a.x * a.x + b.x * a.x + b.x * b.x;
+		float yy = a.y * a.y + b.y * a.y + b.y * b.y;
+		secondMoment += (0.25f * third * twiceArea) * (xx + yy);
 	}
 
-	s2Vec2 center = {0.0f, 0.0f};
-	float area = 0.0f;
-	float I = 0.0f;
-	s2Vec2 r = vertices[0];
-	const float inv3 = 1.0f / 3.0f;
-
-	for (int32_t i = 1; i < count - 1; ++i)
-	{
-		s2Vec2 e1 = s2Sub(vertices[i], r);
-		s2Vec2 e2 = s2Sub(vertices[i + 1], r);
-		float D = s2Cross(e1, e2);
-		float triangleArea = 0.5f * D;
-		area += triangleArea;
-		center = s2MulAdd(center, triangleArea * inv3, s2Add(e1, e2));
-
-		float ex1 = e1.x, ey1 = e1.y;
-		float ex2 = e2.x, ey2 = e2.y;
-		float intx2 = ex1 * ex1 + ex2 * ex1 + ex2 * ex2;
-		float inty2 = ey1 * ey1 + ey2 * ey1 + ey2 * ey2;
-		I += (0.25f * inv3 * D) * (intx2 + inty2);
-	}
-
-	s2MassData md;
-	md.mass = density * area;
-	float invArea = 1.0f / area;
-	center.x *= invArea;
-	center.y *= invArea;
-	md.center = s2Add(r, center);
-	md.I = density * I;
-	md.I += md.mass * (s2Dot(md.center, md.center) - s2Dot(center, center));
-	return md;
+	s2MassData out;
+	out.mass = density * areaSum;
+	float perArea = 1.0f / areaSum;
+	s2Vec2 centroidFromApex = {firstMoment.x * perArea, firstMoment.y * perArea};
+	out.center = s2Add(apex, centroidFromApex);
+	// inertia about the apex, shifted to the shape's origin (parallel axes, through the centroid)
+	out.I = density * secondMoment;
+	out.I += out.mass * (s2Dot(out.center, out.center) - s2Dot(centroidFromApex, centroidFromApex));
+	return out;
 }
 
 // ---- bounding boxes (reference src/geometry.c:288-341) ------------------------------------------------------------

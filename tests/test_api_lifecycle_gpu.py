@@ -275,3 +275,44 @@ def test_edge_cases_match_reference(reference, dev):
     assert P.s2World_GetStatistics(sp.world).bodyCount == R.s2World_GetStatistics(sr.world).bodyCount == 309
     R.s2DestroyWorld(sr.world)
     P.s2DestroyWorld(sp.world)
+
+
+def test_body_recreated_in_the_same_slot_at_the_same_place(reference, dev):
+    """A resting box is destroyed and a new one is created where it stood: the new body re-uses the body and shape slots
+    (and the proxy id) of the old one, so the contact table still holds the OLD shape's pairs under the same keys when the
+    next pair pass runs. The pass has to drop those and report the pairs of the new shape in the same pass (the reference
+    removes the keys on destroy and re-creates the contacts on its next update); otherwise the new box has no contacts
+    until it leaves its fat AABB and sinks into its neighbours."""
+    R = reference
+    P = capi.Solver2D(device.LIB_PATH)
+
+    def script(lib):
+        sc = scenes.vertical_stack(lib, "TGS_Soft", count=4, columns=3)
+        for _ in range(40):
+            sc.step(DT, 4, 2, True)
+        # replace the second box of the middle column by a new one at the same place, at rest
+        victim = sc.bodies[1 + 4 + 1]
+        pos = lib.s2Body_GetPosition(victim)
+        lib.s2DestroyBody(victim)
+        bd = default_body_def()
+        bd.type = capi.DYNAMIC_BODY
+        bd.position = Vec2(pos.x, pos.y)
+        bid = lib.s2CreateBody(sc.world, C.byref(bd))
+        sd = default_shape_def()
+        box = lib.s2MakeSquare(0.5)
+        lib.s2CreatePolygonShape(bid, C.byref(sd), C.byref(box))
+        sc.bodies[1 + 4 + 1] = bid
+        counts, ys = [], []
+        for _ in range(30):
+            sc.step(DT, 4, 2, True)
+            counts.append(lib.s2World_GetStatistics(sc.world).contactCount)
+            ys.append(lib.s2Body_GetPosition(bid).y)
+        return sc, counts, ys
+
+    sr, cr, yr = script(R)
+    sp, cp, yp = script(P)
+    assert cp == cr, f"contact counts after re-creating the body: device {cp[:6]}... reference {cr[:6]}..."
+    assert max(abs(a - b) for a, b in zip(yr, yp)) < 2e-3, "the re-created box does not rest where the reference's does"
+    assert min(yp) > yr[0] - 0.02, "the re-created box sank into its neighbour"
+    sr.destroy()
+    sp.destroy()
