@@ -82,11 +82,11 @@ __global__ void __launch_bounds__(S2B_NP_BLOCK) s2bUpdateContactsKernel(ContactV
 	xfB.q.s = poseB.z;
 	xfB.q.c = poseB.w;
 
-	// previous manifold state
+	// previous manifold state (scalars, not arrays: a dynamically indexed array would live on the local stack)
 	int4 info = c.info[i];
 	int oldCount = S2B_CI_COUNT(info.x);
-	int oldId[2] = {info.y & 0xFFFF, (info.y >> 16) & 0xFFFF};
-	float4 oldImp[2] = {c.impulse[0][i], c.impulse[1][i]};
+	int oldId0 = info.y & 0xFFFF, oldId1 = (info.y >> 16) & 0xFFFF;
+	float4 oldImp0 = c.impulse[0][i], oldImp1 = c.impulse[1][i];
 
 	s2DistanceCache cache;
 	cache.metric = __int_as_float(info.w);
@@ -129,43 +129,36 @@ __global__ void __launch_bounds__(S2B_NP_BLOCK) s2bUpdateContactsKernel(ContactV
 		s2cCollidePolygonsLocal(&m, polyA, xfA, polyB, xf, &cache);
 	}
 
-	// s2UpdateContact: match old ids to new ids and carry the impulses (reference src/contact.c:317-358)
+	// s2UpdateContact: match old ids to new ids and carry the impulses (reference src/contact.c:317-358). A new point takes
+	// the impulses of the FIRST old point with the same feature id.
 	int pointCount = m.pointCount;
-	bool frictionPersisted = pointCount == oldCount;
-	int flags = pointCount & 0x3;
-	float4 newImp[2];
-	int newId[2] = {0, 0};
-	int matched[2] = {-1, -1};
-	for (int p = 0; p < 2; ++p)
+	int newId0 = pointCount > 0 ? m.points[0].id : 0, newId1 = pointCount > 1 ? m.points[1].id : 0;
+	int matched0 = pointCount > 0 ? ((oldCount > 0 && oldId0 == newId0) ? 0 : ((oldCount > 1 && oldId1 == newId0) ? 1 : -1)) : -1;
+	int matched1 = pointCount > 1 ? ((oldCount > 0 && oldId0 == newId1) ? 0 : ((oldCount > 1 && oldId1 == newId1) ? 1 : -1)) : -1;
+	float4 newImp0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), newImp1 = newImp0;
+	if (pointCount > 0)
 	{
-		newImp[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-		if (p < pointCount)
+		newImp0.x = m.points[0].separation;
+		if (matched0 >= 0)
 		{
-			int id2 = m.points[p].id;
-			newId[p] = id2;
-			newImp[p].x = m.points[p].separation;
-			bool persisted = false;
-			for (int j = 0; j < oldCount; ++j)
-			{
-				if (oldId[j] == id2)
-				{
-					newImp[p].y = oldImp[j].y;
-					newImp[p].z = oldImp[j].z;
-					matched[p] = j;
-					persisted = true;
-					break;
-				}
-			}
-			if (persisted)
-			{
-				flags |= (p == 0 ? S2B_CI_PERSISTED0 : S2B_CI_PERSISTED1);
-			}
-			else
-			{
-				frictionPersisted = false;
-			}
+			newImp0.y = matched0 == 0 ? oldImp0.y : oldImp1.y;
+			newImp0.z = matched0 == 0 ? oldImp0.z : oldImp1.z;
 		}
 	}
+	if (pointCount > 1)
+	{
+		newImp1.x = m.points[1].separation;
+		if (matched1 >= 0)
+		{
+			newImp1.y = matched1 == 0 ? oldImp0.y : oldImp1.y;
+			newImp1.z = matched1 == 0 ? oldImp0.z : oldImp1.z;
+		}
+	}
+	int flags = pointCount & 0x3;
+	flags |= matched0 >= 0 ? S2B_CI_PERSISTED0 : 0;
+	flags |= matched1 >= 0 ? S2B_CI_PERSISTED1 : 0;
+	// friction anchors persist only when the point count is unchanged and every point was matched
+	bool frictionPersisted = pointCount == oldCount && (pointCount < 1 || matched0 >= 0) && (pointCount < 2 || matched1 >= 0);
 	if (frictionPersisted)
 	{
 		flags |= S2B_CI_FRICTION_PERSISTED;
@@ -174,19 +167,13 @@ __global__ void __launch_bounds__(S2B_NP_BLOCK) s2bUpdateContactsKernel(ContactV
 	if (sticky)
 	{
 		// friction anchors / normals follow their point (reference src/contact.c:339-342); unmatched points start at 0
-		float4 oldFA[2] = {c.fanchor[0][i], c.fanchor[1][i]};
-		float4 oldFN[2] = {c.fnormal[0][i], c.fnormal[1][i]};
-		for (int p = 0; p < 2; ++p)
-		{
-			float4 fa = make_float4(0.0f, 0.0f, 0.0f, 0.0f), fn = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-			if (p < pointCount && matched[p] >= 0)
-			{
-				fa = oldFA[matched[p]];
-				fn = oldFN[matched[p]];
-			}
-			c.fanchor[p][i] = fa;
-			c.fnormal[p][i] = fn;
-		}
+		float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		float4 oldFA0 = c.fanchor[0][i], oldFA1 = c.fanchor[1][i];
+		float4 oldFN0 = c.fnormal[0][i], oldFN1 = c.fnormal[1][i];
+		c.fanchor[0][i] = matched0 < 0 ? zero : (matched0 == 0 ? oldFA0 : oldFA1);
+		c.fnormal[0][i] = matched0 < 0 ? zero : (matched0 == 0 ? oldFN0 : oldFN1);
+		c.fanchor[1][i] = matched1 < 0 ? zero : (matched1 == 0 ? oldFA0 : oldFA1);
+		c.fnormal[1][i] = matched1 < 0 ? zero : (matched1 == 0 ? oldFN0 : oldFN1);
 	}
 
 	int cacheBits = cache.count & 0x3;
@@ -195,7 +182,7 @@ __global__ void __launch_bounds__(S2B_NP_BLOCK) s2bUpdateContactsKernel(ContactV
 		cacheBits |= (cache.indexA[k] & 0x7) << (2 + 3 * k);
 		cacheBits |= (cache.indexB[k] & 0x7) << (11 + 3 * k);
 	}
-	c.info[i] = make_int4(flags, (newId[0] & 0xFFFF) | ((newId[1] & 0xFFFF) << 16), cacheBits, __float_as_int(cache.metric));
+	c.info[i] = make_int4(flags, (newId0 & 0xFFFF) | ((newId1 & 0xFFFF) << 16), cacheBits, __float_as_int(cache.metric));
 	float4 nf = c.nf[i];
 	c.nf[i] = make_float4(m.normal.x, m.normal.y, nf.z, nf.w);
 	if (pointCount == 0)
@@ -206,12 +193,10 @@ __global__ void __launch_bounds__(S2B_NP_BLOCK) s2bUpdateContactsKernel(ContactV
 	{
 		*schedDirty = 1; // the set of live constraints changed: the solve schedule has to be rebuilt (solver.cu, s2bScheduleGate)
 	}
-	for (int p = 0; p < 2; ++p)
-	{
-		c.anchor[p][i] = make_float4(m.points[p].localAnchorA.x, m.points[p].localAnchorA.y, m.points[p].localAnchorB.x,
-									 m.points[p].localAnchorB.y);
-		c.impulse[p][i] = newImp[p];
-	}
+	c.anchor[0][i] = make_float4(m.points[0].localAnchorA.x, m.points[0].localAnchorA.y, m.points[0].localAnchorB.x, m.points[0].localAnchorB.y);
+	c.anchor[1][i] = make_float4(m.points[1].localAnchorA.x, m.points[1].localAnchorA.y, m.points[1].localAnchorB.x, m.points[1].localAnchorB.y);
+	c.impulse[0][i] = newImp0;
+	c.impulse[1][i] = newImp1;
 }
 
 void s2bNarrowphaseUpdate(s2bWorld* w)

@@ -178,101 +178,92 @@ S2C_FN void s2cSolveSimplex2(s2cSimplex* s)
 	s->count = 2;
 }
 
-// s2SolveSimplex3 (reference src/distance.c:336-446): closest point of a triangle to the origin (Voronoi regions)
+// Un-normalised barycentric coordinates of the origin's projection on the line through p and q: {weight of p, weight of q}.
+// Both positive: the projection lies between them; weight of q <= 0: at or before p; weight of p <= 0: at or past q.
+typedef struct s2cLineWeights
+{
+	float atFirst, atSecond;
+} s2cLineWeights;
+
+S2C_FN s2cLineWeights s2cProjectOriginOnLine(s2Vec2 p, s2Vec2 q)
+{
+	s2Vec2 along = s2Sub(q, p);
+	s2cLineWeights w;
+	w.atFirst = s2Dot(q, along);
+	w.atSecond = -s2Dot(p, along);
+	return w;
+}
+
+// the reduced simplex is an edge: vertices `first` and `second` of the triangle end up in slots 0 and 1
+#define S2C_REDUCE_TO_EDGE(s, first, second, weights)                                                                      \
+	do                                                                                                                    \
+	{                                                                                                                     \
+		float scale__ = 1.0f / ((weights).atFirst + (weights).atSecond);                                                 \
+		(s)->v[first].a = (weights).atFirst * scale__;                                                                   \
+		(s)->v[second].a = (weights).atSecond * scale__;                                                                 \
+		(s)->count = 2;                                                                                                   \
+	} while (0)
+
+// Closest point of the triangle (w1, w2, w3) of a GJK simplex to the origin, by Voronoi region (behaviour and region
+// order of reference src/distance.c:336-446: a point on a region boundary goes to the first region listed). The triangle's
+// vertices are addressed with literal indices only — on the device the simplex lives in registers.
 S2C_FN void s2cSolveSimplex3(s2cSimplex* s)
 {
-	s2Vec2 w1 = s->v[0].w;
-	s2Vec2 w2 = s->v[1].w;
-	s2Vec2 w3 = s->v[2].w;
+	s2Vec2 p1 = s->v[0].w, p2 = s->v[1].w, p3 = s->v[2].w;
+	s2cLineWeights side12 = s2cProjectOriginOnLine(p1, p2);
+	s2cLineWeights side13 = s2cProjectOriginOnLine(p1, p3);
+	s2cLineWeights side23 = s2cProjectOriginOnLine(p2, p3);
 
-	s2Vec2 e12 = s2Sub(w2, w1);
-	float w1e12 = s2Dot(w1, e12);
-	float w2e12 = s2Dot(w2, e12);
-	float d12_1 = w2e12;
-	float d12_2 = -w1e12;
+	// signed areas of the three sub-triangles the origin spans with the sides, scaled by the triangle's own signed area so
+	// that their signs do not depend on the winding
+	float winding = s2Cross(s2Sub(p2, p1), s2Sub(p3, p1));
+	float area1 = winding * s2Cross(p2, p3);
+	float area2 = winding * s2Cross(p3, p1);
+	float area3 = winding * s2Cross(p1, p2);
 
-	s2Vec2 e13 = s2Sub(w3, w1);
-	float w1e13 = s2Dot(w1, e13);
-	float w3e13 = s2Dot(w3, e13);
-	float d13_1 = w3e13;
-	float d13_2 = -w1e13;
-
-	s2Vec2 e23 = s2Sub(w3, w2);
-	float w2e23 = s2Dot(w2, e23);
-	float w3e23 = s2Dot(w3, e23);
-	float d23_1 = w3e23;
-	float d23_2 = -w2e23;
-
-	float n123 = s2Cross(e12, e13);
-
-	float d123_1 = n123 * s2Cross(w2, w3);
-	float d123_2 = n123 * s2Cross(w3, w1);
-	float d123_3 = n123 * s2Cross(w1, w2);
-
-	// vertex 1
-	if (d12_2 <= 0.0f && d13_2 <= 0.0f)
+	if (side12.atSecond <= 0.0f && side13.atSecond <= 0.0f)
 	{
+		// corner p1
 		s->v[0].a = 1.0f;
 		s->count = 1;
-		return;
 	}
-
-	// edge 12
-	if (d12_1 > 0.0f && d12_2 > 0.0f && d123_3 <= 0.0f)
+	else if (side12.atFirst > 0.0f && side12.atSecond > 0.0f && area3 <= 0.0f)
 	{
-		float inv_d12 = 1.0f / (d12_1 + d12_2);
-		s->v[0].a = d12_1 * inv_d12;
-		s->v[1].a = d12_2 * inv_d12;
-		s->count = 2;
-		return;
+		S2C_REDUCE_TO_EDGE(s, 0, 1, side12);
 	}
-
-	// edge 13
-	if (d13_1 > 0.0f && d13_2 > 0.0f && d123_2 <= 0.0f)
+	else if (side13.atFirst > 0.0f && side13.atSecond > 0.0f && area2 <= 0.0f)
 	{
-		float inv_d13 = 1.0f / (d13_1 + d13_2);
-		s->v[0].a = d13_1 * inv_d13;
-		s->v[2].a = d13_2 * inv_d13;
-		s->count = 2;
+		S2C_REDUCE_TO_EDGE(s, 0, 2, side13);
 		s->v[1] = s->v[2];
-		return;
 	}
-
-	// vertex 2
-	if (d12_1 <= 0.0f && d23_2 <= 0.0f)
+	else if (side12.atFirst <= 0.0f && side23.atSecond <= 0.0f)
 	{
+		// corner p2
 		s->v[1].a = 1.0f;
 		s->count = 1;
 		s->v[0] = s->v[1];
-		return;
 	}
-
-	// vertex 3
-	if (d13_1 <= 0.0f && d23_1 <= 0.0f)
+	else if (side13.atFirst <= 0.0f && side23.atFirst <= 0.0f)
 	{
+		// corner p3
 		s->v[2].a = 1.0f;
 		s->count = 1;
 		s->v[0] = s->v[2];
-		return;
 	}
-
-	// edge 23
-	if (d23_1 > 0.0f && d23_2 > 0.0f && d123_1 <= 0.0f)
+	else if (side23.atFirst > 0.0f && side23.atSecond > 0.0f && area1 <= 0.0f)
 	{
-		float inv_d23 = 1.0f / (d23_1 + d23_2);
-		s->v[1].a = d23_1 * inv_d23;
-		s->v[2].a = d23_2 * inv_d23;
-		s->count = 2;
+		S2C_REDUCE_TO_EDGE(s, 1, 2, side23);
 		s->v[0] = s->v[2];
-		return;
 	}
-
-	// interior
-	float inv_d123 = 1.0f / (d123_1 + d123_2 + d123_3);
-	s->v[0].a = d123_1 * inv_d123;
-	s->v[1].a = d123_2 * inv_d123;
-	s->v[2].a = d123_3 * inv_d123;
-	s->count = 3;
+	else
+	{
+		// the origin is inside
+		float scale = 1.0f / (area1 + area2 + area3);
+		s->v[0].a = area1 * scale;
+		s->v[1].a = area2 * scale;
+		s->v[2].a = area3 * scale;
+		s->count = 3;
+	}
 }
 
 // s2ShapeDistance (reference src/distance.c:485-636) over raw vertex arrays. The simplex cache is input/output.
@@ -481,64 +472,64 @@ S2C_FN s2DistanceOutput s2cShapeDistance(s2DistanceCache* cache, const s2Vec2* v
 	return output;
 }
 
-// s2SegmentDistance (reference src/distance.c:14-98, Ericson 5.1.9)
-S2C_FN s2SegmentDistanceResult s2cSegmentDistance(s2Vec2 p1, s2Vec2 q1, s2Vec2 p2, s2Vec2 q2)
+S2C_FN float s2cClampToUnit(float x)
 {
-	s2SegmentDistanceResult result;
-	result.fraction1 = 0.0f;
-	result.fraction2 = 0.0f;
+	return S2_CLAMP(x, 0.0f, 1.0f);
+}
 
-	s2Vec2 d1 = s2Sub(q1, p1);
-	s2Vec2 d2 = s2Sub(q2, p2);
-	s2Vec2 r = s2Sub(p1, p2);
-	float dd1 = s2Dot(d1, d1);
-	float dd2 = s2Dot(d2, d2);
-	float rd2 = s2Dot(r, d2);
-	float rd1 = s2Dot(r, d1);
+// Closest points of the segments a0-a1 and b0-b1 (behaviour and arithmetic of reference src/distance.c:14-98, the
+// clamped-projection scheme of Ericson 5.1.9). A: a0 + s u, B: b0 + t v with s, t in [0, 1] and w = a0 - b0; minimising
+// |w + s u - t v|^2 gives s = (uv wv - wu vv) / (uu vv - uv^2), t = (uv s + wv) / vv; whenever t leaves [0, 1] it is
+// pinned to the end it left through and s becomes the projection of that end point on A.
+S2C_FN s2SegmentDistanceResult s2cSegmentDistance(s2Vec2 a0, s2Vec2 a1, s2Vec2 b0, s2Vec2 b1)
+{
+	s2Vec2 u = s2Sub(a1, a0), v = s2Sub(b1, b0), w = s2Sub(a0, b0);
+	float uu = s2Dot(u, u), vv = s2Dot(v, v);
+	float wv = s2Dot(w, v), wu = s2Dot(w, u);
+	const float tiny = FLT_EPSILON * FLT_EPSILON;
+	bool aIsPoint = uu < tiny, bIsPoint = vv < tiny;
 
-	const float epsSqr = FLT_EPSILON * FLT_EPSILON;
-
-	if (dd1 < epsSqr || dd2 < epsSqr)
+	float sParam = 0.0f, tParam = 0.0f;
+	if (aIsPoint || bIsPoint)
 	{
-		if (dd1 >= epsSqr)
+		// point against segment (or point against point: both parameters stay 0)
+		if (aIsPoint == false)
 		{
-			result.fraction1 = S2_CLAMP(-rd1 / dd1, 0.0f, 1.0f);
-			result.fraction2 = 0.0f;
+			sParam = s2cClampToUnit(-wu / uu);
 		}
-		else if (dd2 >= epsSqr)
+		else if (bIsPoint == false)
 		{
-			result.fraction1 = 0.0f;
-			result.fraction2 = S2_CLAMP(rd2 / dd2, 0.0f, 1.0f);
+			tParam = s2cClampToUnit(wv / vv);
 		}
 	}
 	else
 	{
-		float d12 = s2Dot(d1, d2);
-		float denom = dd1 * dd2 - d12 * d12;
-		float f1 = 0.0f;
-		if (denom != 0.0f)
+		float uv = s2Dot(u, v);
+		float det = uu * vv - uv * uv; // zero: parallel, every s is as good, keep 0
+		if (det != 0.0f)
 		{
-			f1 = S2_CLAMP((d12 * rd2 - rd1 * dd2) / denom, 0.0f, 1.0f);
+			sParam = s2cClampToUnit((uv * wv - wu * vv) / det);
 		}
-		float f2 = (d12 * f1 + rd2) / dd2;
-		if (f2 < 0.0f)
+		tParam = (uv * sParam + wv) / vv;
+		if (tParam < 0.0f)
 		{
-			f2 = 0.0f;
-			f1 = S2_CLAMP(-rd1 / dd1, 0.0f, 1.0f);
+			tParam = 0.0f;
+			sParam = s2cClampToUnit(-wu / uu);
 		}
-		else if (f2 > 1.0f)
+		else if (tParam > 1.0f)
 		{
-			f2 = 1.0f;
-			f1 = S2_CLAMP((d12 - rd1) / dd1, 0.0f, 1.0f);
+			tParam = 1.0f;
+			sParam = s2cClampToUnit((uv - wu) / uu);
 		}
-		result.fraction1 = f1;
-		result.fraction2 = f2;
 	}
 
-	result.closest1 = s2MulAdd(p1, result.fraction1, d1);
-	result.closest2 = s2MulAdd(p2, result.fraction2, d2);
-	result.distanceSquared = s2DistanceSquared(result.closest1, result.closest2);
-	return result;
+	s2SegmentDistanceResult out;
+	out.fraction1 = sParam;
+	out.fraction2 = tParam;
+	out.closest1 = s2MulAdd(a0, sParam, u);
+	out.closest2 = s2MulAdd(b0, tParam, v);
+	out.distanceSquared = s2DistanceSquared(out.closest1, out.closest2);
+	return out;
 }
 
 // ---- manifolds (reference src/manifold.c) -----------------------------------------------------------------------
@@ -708,178 +699,161 @@ S2C_FN void s2cCollidePolygonAndCircle(s2Manifold* manifold, const s2Vec2* verti
 	}
 }
 
-// s2ClipPolygons (reference src/manifold.c:248-399): clip the incident edge against the side planes of the reference
-// edge; two points with feature ids. Everything is in polyA's frame.
+// anchors of the manifold's points expressed in shape B's frame (xf = frame of B seen from A). Literal point indices: on
+// the device the manifold then stays in registers.
+S2C_FN void s2cAnchorsIntoFrameB(s2Manifold* manifold, s2Transform xf)
+{
+	if (manifold->pointCount > 0)
+	{
+		manifold->points[0].localAnchorB = s2InvTransformPoint(xf, manifold->points[0].localAnchorA);
+	}
+	if (manifold->pointCount > 1)
+	{
+		manifold->points[1].localAnchorB = s2InvTransformPoint(xf, manifold->points[1].localAnchorA);
+	}
+}
+
+// next vertex of a polygon, cyclically
+S2C_FN int s2cNextIndex(const s2Polygon* poly, int i)
+{
+	return i + 1 < poly->count ? i + 1 : 0;
+}
+
+// Two-point manifold of a REFERENCE edge (the face that separates best) and the INCIDENT edge of the other polygon (the
+// one most anti-parallel to it), everything in polyA's frame (behaviour, arithmetic and feature ids of reference
+// src/manifold.c:248-399). `flip`: polyB owns the reference edge. The incident edge runs against the reference edge, so its
+// END vertex is the one near the reference edge's start; each end is cut back to the side plane through the corresponding
+// end of the reference edge if it sticks out, then moved to the mid surface of the two (rounded) polygons.
 S2C_FN void s2cClipPolygons(s2Manifold* manifold, const s2Polygon* polyA, const s2Polygon* polyB, int edgeA, int edgeB, bool flip)
 {
 	s2cClearManifold(manifold);
 
-	const s2Polygon* poly1;
-	const s2Polygon* poly2;
-	int i11, i12, i21, i22;
+	const s2Polygon* refPoly = flip ? polyB : polyA;
+	const s2Polygon* incPoly = flip ? polyA : polyB;
+	int refStart = flip ? edgeB : edgeA, incStart = flip ? edgeA : edgeB;
+	int refEnd = s2cNextIndex(refPoly, refStart), incEnd = s2cNextIndex(incPoly, incStart);
+
+	s2Vec2 normal = refPoly->normals[refStart];
+	s2Vec2 along = s2CrossSV(1.0f, normal);
+	s2Vec2 origin = refPoly->vertices[refStart];
+	s2Vec2 incFirst = incPoly->vertices[incStart], incSecond = incPoly->vertices[incEnd];
+
+	// positions along the reference edge (its start is 0)
+	float refSpan = s2Dot(s2Sub(refPoly->vertices[refEnd], origin), along);
+	float firstAt = s2Dot(s2Sub(incFirst, origin), along);
+	float secondAt = s2Dot(s2Sub(incSecond, origin), along);
+	bool cuttable = firstAt - secondAt > FLT_EPSILON; // a degenerate incident edge is not interpolated
+
+	s2Vec2 nearStart = incSecond, nearEnd = incFirst;
+	if (secondAt < 0.0f && cuttable)
+	{
+		nearStart = s2Lerp(incSecond, incFirst, (0.0f - secondAt) / (firstAt - secondAt));
+	}
+	if (firstAt > refSpan && cuttable)
+	{
+		nearEnd = s2Lerp(incSecond, incFirst, (refSpan - secondAt) / (firstAt - secondAt));
+	}
+
+	float gapAtStart = s2Dot(s2Sub(nearStart, origin), normal);
+	float gapAtEnd = s2Dot(s2Sub(nearEnd, origin), normal);
+
+	float refRadius = refPoly->radius, incRadius = incPoly->radius;
+	nearStart = s2MulAdd(nearStart, 0.5f * (refRadius - incRadius - gapAtStart), normal);
+	nearEnd = s2MulAdd(nearEnd, 0.5f * (refRadius - incRadius - gapAtEnd), normal);
+	float bothRadii = refRadius + incRadius;
+
+	// points are listed in polyA's edge direction; an id names (vertex of A, vertex of B)
+	s2ManifoldPoint* first = manifold->points + 0;
+	s2ManifoldPoint* second = manifold->points + 1;
 	if (flip)
 	{
-		poly1 = polyB;
-		poly2 = polyA;
-		i11 = edgeB;
-		i12 = edgeB + 1 < polyB->count ? edgeB + 1 : 0;
-		i21 = edgeA;
-		i22 = edgeA + 1 < polyA->count ? edgeA + 1 : 0;
+		manifold->normal = s2Neg(normal);
+		first->localAnchorA = nearEnd;
+		first->separation = gapAtEnd - bothRadii;
+		first->id = (uint16_t)S2_MAKE_ID(incStart, refEnd);
+		second->localAnchorA = nearStart;
+		second->separation = gapAtStart - bothRadii;
+		second->id = (uint16_t)S2_MAKE_ID(incEnd, refStart);
 	}
 	else
-	{
-		poly1 = polyA;
-		poly2 = polyB;
-		i11 = edgeA;
-		i12 = edgeA + 1 < polyA->count ? edgeA + 1 : 0;
-		i21 = edgeB;
-		i22 = edgeB + 1 < polyB->count ? edgeB + 1 : 0;
-	}
-
-	s2Vec2 normal = poly1->normals[i11];
-	s2Vec2 v11 = poly1->vertices[i11];
-	s2Vec2 v12 = poly1->vertices[i12];
-	s2Vec2 v21 = poly2->vertices[i21];
-	s2Vec2 v22 = poly2->vertices[i22];
-
-	s2Vec2 tangent = s2CrossSV(1.0f, normal);
-
-	float lower1 = 0.0f;
-	float upper1 = s2Dot(s2Sub(v12, v11), tangent);
-	float upper2 = s2Dot(s2Sub(v21, v11), tangent);
-	float lower2 = s2Dot(s2Sub(v22, v11), tangent);
-
-	s2Vec2 vLower;
-	if (lower2 < lower1 && upper2 - lower2 > FLT_EPSILON)
-	{
-		vLower = s2Lerp(v22, v21, (lower1 - lower2) / (upper2 - lower2));
-	}
-	else
-	{
-		vLower = v22;
-	}
-
-	s2Vec2 vUpper;
-	if (upper2 > upper1 && upper2 - lower2 > FLT_EPSILON)
-	{
-		vUpper = s2Lerp(v22, v21, (upper1 - lower2) / (upper2 - lower2));
-	}
-	else
-	{
-		vUpper = v21;
-	}
-
-	float separationLower = s2Dot(s2Sub(vLower, v11), normal);
-	float separationUpper = s2Dot(s2Sub(vUpper, v11), normal);
-
-	float r1 = poly1->radius;
-	float r2 = poly2->radius;
-
-	// contact points at the mid surface
-	vLower = s2MulAdd(vLower, 0.5f * (r1 - r2 - separationLower), normal);
-	vUpper = s2MulAdd(vUpper, 0.5f * (r1 - r2 - separationUpper), normal);
-
-	float radius = r1 + r2;
-
-	if (flip == false)
 	{
 		manifold->normal = normal;
-		manifold->points[0].localAnchorA = vLower;
-		manifold->points[0].separation = separationLower - radius;
-		manifold->points[0].id = (uint16_t)S2_MAKE_ID(i11, i22);
-		manifold->points[1].localAnchorA = vUpper;
-		manifold->points[1].separation = separationUpper - radius;
-		manifold->points[1].id = (uint16_t)S2_MAKE_ID(i12, i21);
-		manifold->pointCount = 2;
+		first->localAnchorA = nearStart;
+		first->separation = gapAtStart - bothRadii;
+		first->id = (uint16_t)S2_MAKE_ID(refStart, incEnd);
+		second->localAnchorA = nearEnd;
+		second->separation = gapAtEnd - bothRadii;
+		second->id = (uint16_t)S2_MAKE_ID(refEnd, incStart);
 	}
-	else
-	{
-		manifold->normal = s2Neg(normal);
-		manifold->points[0].localAnchorA = vUpper;
-		manifold->points[0].separation = separationUpper - radius;
-		manifold->points[0].id = (uint16_t)S2_MAKE_ID(i21, i12);
-		manifold->points[1].localAnchorA = vLower;
-		manifold->points[1].separation = separationLower - radius;
-		manifold->points[1].id = (uint16_t)S2_MAKE_ID(i22, i11);
-		manifold->pointCount = 2;
-	}
+	manifold->pointCount = 2;
 }
 
-// s2FindMaxSeparation (reference src/manifold.c:402-438)
-S2C_FN float s2cFindMaxSeparation(int* edgeIndex, const s2Polygon* poly1, const s2Polygon* poly2)
+// How far `other` stays outside the face (point `onFace`, outward normal `outward`): the signed distance of its deepest vertex.
+S2C_FN float s2cClearanceOfFace(s2Vec2 outward, s2Vec2 onFace, const s2Polygon* other)
 {
-	int count1 = poly1->count;
-	int count2 = poly2->count;
-	int bestIndex = 0;
-	float maxSeparation = -FLT_MAX;
-	for (int i = 0; i < count1; ++i)
+	float deepest = FLT_MAX;
+	for (int k = 0; k < other->count; ++k)
 	{
-		s2Vec2 n = poly1->normals[i];
-		s2Vec2 v1 = poly1->vertices[i];
-		float si = FLT_MAX;
-		for (int j = 0; j < count2; ++j)
-		{
-			float sij = s2Dot(n, s2Sub(poly2->vertices[j], v1));
-			if (sij < si)
-			{
-				si = sij;
-			}
-		}
-		if (si > maxSeparation)
-		{
-			maxSeparation = si;
-			bestIndex = i;
-		}
+		float d = s2Dot(outward, s2Sub(other->vertices[k], onFace));
+		deepest = d < deepest ? d : deepest;
 	}
-	*edgeIndex = bestIndex;
-	return maxSeparation;
+	return deepest;
 }
 
-// s2PolygonSAT (reference src/manifold.c:441-493): overlap assumed
+// The face of `poly` that keeps `other` furthest out (the first one on ties) and that clearance (behaviour of reference
+// src/manifold.c:402-438: the separating-axis search over the face normals of one polygon).
+S2C_FN float s2cFindMaxSeparation(int* edgeIndex, const s2Polygon* poly, const s2Polygon* other)
+{
+	int bestFace = 0;
+	float bestClearance = -FLT_MAX;
+	for (int face = 0; face < poly->count; ++face)
+	{
+		float clearance = s2cClearanceOfFace(poly->normals[face], poly->vertices[face], other);
+		if (clearance > bestClearance)
+		{
+			bestClearance = clearance;
+			bestFace = face;
+		}
+	}
+	*edgeIndex = bestFace;
+	return bestClearance;
+}
+
+// the edge of `poly` whose normal opposes `direction` most (the first one on ties)
+S2C_FN int s2cMostOpposedEdge(const s2Polygon* poly, s2Vec2 direction)
+{
+	int best = 0;
+	float least = FLT_MAX;
+	for (int k = 0; k < poly->count; ++k)
+	{
+		float alignment = s2Dot(direction, poly->normals[k]);
+		if (alignment < least)
+		{
+			least = alignment;
+			best = k;
+		}
+	}
+	return best;
+}
+
+// Manifold of two polygons known to overlap (or nearly): reference face = the face of either polygon with the largest
+// clearance (polyA's on ties), incident edge = the other polygon's edge most opposed to it (behaviour of reference
+// src/manifold.c:441-493).
 S2C_FN void s2cPolygonSAT(s2Manifold* manifold, const s2Polygon* polyA, const s2Polygon* polyB)
 {
-	int edgeA = 0;
-	float separationA = s2cFindMaxSeparation(&edgeA, polyA, polyB);
-	int edgeB = 0;
-	float separationB = s2cFindMaxSeparation(&edgeB, polyB, polyA);
-
-	bool flip;
-	if (separationB > separationA)
+	int faceA = 0, faceB = 0;
+	float clearanceA = s2cFindMaxSeparation(&faceA, polyA, polyB);
+	float clearanceB = s2cFindMaxSeparation(&faceB, polyB, polyA);
+	bool bOwnsReference = clearanceB > clearanceA;
+	if (bOwnsReference)
 	{
-		flip = true;
-		s2Vec2 searchDirection = polyB->normals[edgeB];
-		int count = polyA->count;
-		edgeA = 0;
-		float minDot = FLT_MAX;
-		for (int i = 0; i < count; ++i)
-		{
-			float dot = s2Dot(searchDirection, polyA->normals[i]);
-			if (dot < minDot)
-			{
-				minDot = dot;
-				edgeA = i;
-			}
-		}
+		faceA = s2cMostOpposedEdge(polyA, polyB->normals[faceB]);
 	}
 	else
 	{
-		flip = false;
-		s2Vec2 searchDirection = polyA->normals[edgeA];
-		int count = polyB->count;
-		edgeB = 0;
-		float minDot = FLT_MAX;
-		for (int i = 0; i < count; ++i)
-		{
-			float dot = s2Dot(searchDirection, polyB->normals[i]);
-			if (dot < minDot)
-			{
-				minDot = dot;
-				edgeB = i;
-			}
-		}
+		faceB = s2cMostOpposedEdge(polyB, polyA->normals[faceA]);
 	}
-
-	s2cClipPolygons(manifold, polyA, polyB, edgeA, edgeB, flip);
+	s2cClipPolygons(manifold, polyA, polyB, faceA, faceB, bOwnsReference);
 }
 
 // s2CollidePolygons (reference src/manifold.c:509-650): GJK closest features, SAT when (nearly) overlapping,
@@ -912,10 +886,7 @@ S2C_FN void s2cCollidePolygonsLocal(s2Manifold* manifold, const s2Polygon* polyA
 		if (manifold->pointCount > 0)
 		{
 			manifold->normal = s2RotateVector(xfA.q, manifold->normal);
-			for (int i = 0; i < manifold->pointCount; ++i)
-			{
-				manifold->points[i].localAnchorB = s2InvTransformPoint(xf, manifold->points[i].localAnchorA);
-			}
+			s2cAnchorsIntoFrameB(manifold, xf);
 		}
 		return;
 	}
@@ -982,10 +953,7 @@ S2C_FN void s2cCollidePolygonsLocal(s2Manifold* manifold, const s2Polygon* polyA
 	if (manifold->pointCount > 0)
 	{
 		manifold->normal = s2RotateVector(xfA.q, manifold->normal);
-		for (int i = 0; i < manifold->pointCount; ++i)
-		{
-			manifold->points[i].localAnchorB = s2InvTransformPoint(xf, manifold->points[i].localAnchorA);
-		}
+		s2cAnchorsIntoFrameB(manifold, xf);
 	}
 }
 
