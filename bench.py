@@ -196,13 +196,35 @@ def measure_field(args, P, dev, dist, rank: int, world_size: int, local_rank: in
     from solver2d_b200 import device, scenes
     L = P.lib
     mine = len(range(rank, args.field_count, world_size)) if shard else args.field_count
-    sc = scenes.pyramid_field(P, "TGS_Soft", count=mine, base_count=args.field_base, first=0)
-    dw = device.DeviceWorld.attach(dev, sc.world)
+    if shard and args.field_single_world and world_size > 1:
+        # ONE s2World holding every pile, sharded by ISLAND: every rank builds the whole world, asks the device for the islands
+        # of its constraint graph (s2b_download_islands) and keeps island k mod N == rank (static bodies stay everywhere)
+        sc = scenes.pyramid_field(P, "TGS_Soft", count=args.field_count, base_count=args.field_base, first=0)
+        sc.step(DT, args.substeps, args.relax, True)
+        dw = device.DeviceWorld.attach(dev, sc.world)
+        labels, _ = dw.islands()
+        ids = np.array([b.index for b in sc.bodies])
+        dynamic = np.array([P.s2Body_GetType(b) == 2 for b in sc.bodies])
+        roots = np.unique(labels[ids[dynamic]])
+        owner = {int(r): k % world_size for k, r in enumerate(roots)}
+        keep = []
+        for b, dyn in zip(sc.bodies, dynamic):
+            if dyn and owner[int(labels[b.index])] != rank:
+                P.s2DestroyBody(b)
+            else:
+                keep.append(b)
+        sc.bodies = keep
+        mine = int(sum(1 for r in roots if owner[int(r)] == rank))
+    else:
+        sc = scenes.pyramid_field(P, "TGS_Soft", count=mine, base_count=args.field_base, first=0)
+        dw = device.DeviceWorld.attach(dev, sc.world)
     nb = len(sc.bodies)
     gather_in = gather_out = ext_stream = side_stream = None
     state = {"done": None}
     if dist is not None and shard:
-        most = len(range(0, args.field_count, world_size)) * (args.field_base * (args.field_base + 1) // 2 + 1)
+        most_t = torch.tensor([nb], dtype=torch.int64, device="cuda")
+        dist.all_reduce(most_t, op=dist.ReduceOp.MAX)  # equal payload on every rank: the largest body count
+        most = int(most_t.item())
         gather_in = torch.zeros((most + 8) * 8, dtype=torch.float32, device="cuda")
         gather_out = torch.empty(world_size * (most + 8) * 8, dtype=torch.float32, device="cuda")
         L.s2b_get_stream.restype = C.c_void_p
@@ -258,7 +280,8 @@ def measure_field(args, P, dev, dist, rank: int, world_size: int, local_rank: in
     torch.cuda.synchronize()
     L.s2b_get_work(dw.h, out, 1)
     c = dw.counters()
-    res = (total_ms, int(out[0]), nb - mine, c.constraintCount, c.regionCount, c.cutCount)
+    boxes = sum(1 for b in sc.bodies if P.s2Body_GetType(b) == 2) if args.field_single_world else nb - mine
+    res = (total_ms, int(out[0]), boxes, c.constraintCount, c.regionCount, c.cutCount)
     sc.destroy()
     return res
 
@@ -581,6 +604,8 @@ def main():
                     help="pyramid = headline (replica per rank); field = config 5: --field-count worlds of --base rows, sharded over ranks")
     ap.add_argument("--field-count", type=int, default=256)
     ap.add_argument("--field-base", type=int, default=45, help="rows of each world of the sharded config-5 measurement (45 -> 1 035 boxes)")
+    ap.add_argument("--field-single-world", action="store_true",
+                    help="config 5 built as ONE s2World on every rank and sharded by island (s2b_download_islands) instead of by construction")
     ap.add_argument("--no-field", action="store_true", help="skip the sharded config-5 measurement attached as key 'field'")
     ap.add_argument("--no-field-n1", action="store_true", help="at N > 1: skip rank 0's single-GPU run of the whole field")
     ap.add_argument("--substeps", type=int, default=4)

@@ -90,6 +90,9 @@ void s2bFreeSolverScratch(s2bWorld* w)
 	s->incWork.release();
 	s->incList.release();
 	s->heavyBodies.release();
+	s->ovBodies.release();
+	s->longBodies.release();
+	s->ovBodySlot.release();
 	s->flow.release();
 	s->bodyTicket.release();
 	s->trace.release();
@@ -344,13 +347,28 @@ __global__ void s2bStoreColors(const int* counts, const int* jointSlots, const i
 // its constraints were coloured (a shape with density added to a massless body) makes constraints that share it conflict;
 // of two neighbours with the same colour the one with the larger index is uncoloured and picks again. Decided on the
 // colours as they were (two phases), so the outcome does not depend on thread timing.
+// abortAbove >= 0: give up as soon as any item would need a colour beyond it (the cut colouring: regions are only used when
+// the cut set needs few colours, so a long run of rounds for a hub's hundreds of mutually conflicting constraints would be
+// wasted) and leave CNT_CUT_ABORT set.
 __global__ void __launch_bounds__(256) s2bColorKernel(int* counts, const int2* itemBodies, const int* adjStart, const int* adj, int* color,
-													  int* tent, int maxColors, int indexRounds, int validate)
+													  int* tent, int maxColors, int indexRounds, int validate, int abortAbove, const int* hubs)
 {
 	cg::grid_group grid = cg::this_grid();
 	int n = counts[CNT_JOINTS] + counts[CNT_CONTACTS];
 	int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	int stride = gridDim.x * blockDim.x;
+
+	if (abortAbove >= 0 && hubs != nullptr && hubs[0] > 0)
+	{
+		// a hub body belongs to no region: its hundreds of constraints are all in the cut set and conflict with one another,
+		// so the cut set needs at least that many colours — regions are off, and every thread of every one of those
+		// constraints walking the hub's whole adjacency list round after round would cost milliseconds for nothing
+		if (tid == 0)
+		{
+			counts[CNT_CUT_ABORT] = 1;
+		}
+		return;
+	}
 
 	if (validate)
 	{
@@ -460,9 +478,17 @@ __global__ void __launch_bounds__(256) s2bColorKernel(int* counts, const int2* i
 			{
 				pick = S2B_OVERFLOW_KEY;
 			}
+			if (abortAbove >= 0 && pick > abortAbove)
+			{
+				counts[CNT_CUT_ABORT] = 1;
+			}
 			tent[i] = (round << 8) | pick;
 		}
 		grid.sync();
+		if (abortAbove >= 0 && *((volatile int*)(counts + CNT_CUT_ABORT)) != 0)
+		{
+			return; // uniform: read after the barrier by every thread
+		}
 
 		// phase B: commit unless a higher-priority neighbour took the same colour in this round
 		int* counter = counts + CNT_REMAINING + (round % 3);
@@ -917,13 +943,17 @@ __global__ void s2bMakeSortKeys(int* counts, const int* color, const int* itemRe
 {
 	int nJ = counts[CNT_JOINTS], nC = counts[CNT_CONTACTS];
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	bool regionsOn = regionCutLimit >= 0 && counts[CNT_CUT_COLORS] <= regionCutLimit;
+	bool regionsOn = regionCutLimit >= 0 && counts[CNT_CUT_ABORT] == 0 && counts[CNT_CUT_COLORS] <= regionCutLimit;
 	if (i == 0)
 	{
 		counts[CNT_REGIONS_ON] = regionsOn ? 1 : 0;
 		if (regionsOn == false)
 		{
 			counts[CNT_PRIMARY] = 0;
+		}
+		if (counts[CNT_CUT_ABORT] != 0)
+		{
+			counts[CNT_CUT_COLORS] = S2B_MAX_COLORS; // "more than regions are worth" (the colouring was not finished)
 		}
 	}
 	if (i >= nJ + nC)
@@ -1017,6 +1047,44 @@ __global__ void s2bFinishGroups(int* counts, const int* cOff, const int* jOff)
 	counts[CNT_OVERFLOW_J] = jOff[S2B_MAX_COLORS + 1] - jOff[S2B_MAX_COLORS];
 }
 
+// The distinct bodies the serial overflow group touches (movable or not), numbered in arrival order (the numbering is
+// only a cache layout: persistent.cuh stages these bodies in shared memory for the serial walk).
+__global__ void s2bOverflowBodiesKernel(const int* counts, const int* jGroupOff, const int* cGroupOff, const int* jPerm, const int* cPerm,
+										const int* jointSlots, const int* activeSlots, JointView joints, ContactView contacts, int* ovBodySlot,
+										int* ovBodies)
+{
+	int ovJ = counts[CNT_OVERFLOW_J], ovC = counts[CNT_OVERFLOW_C];
+	int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= ovJ + ovC)
+	{
+		return;
+	}
+	int a, b;
+	if (k < ovJ)
+	{
+		int4 head = joints.head[jointSlots[jPerm[jGroupOff[S2B_MAX_COLORS] + k]]];
+		a = head.y;
+		b = head.z;
+	}
+	else
+	{
+		int2 bo = contacts.bodies[activeSlots[cPerm[cGroupOff[S2B_MAX_COLORS] + (k - ovJ)]]];
+		a = bo.x;
+		b = bo.y;
+	}
+#pragma unroll
+	for (int side = 0; side < 2; ++side)
+	{
+		int body = side == 0 ? a : b;
+		if (body >= 0 && atomicCAS(ovBodySlot + body, -1, -2) == -1)
+		{
+			int slot = atomicAdd(ovBodies, 1);
+			ovBodies[1 + slot] = body;
+			ovBodySlot[body] = slot;
+		}
+	}
+}
+
 // src[t] = contact slot of the constraint at solve position t
 __global__ void s2bBuildSources(const int* counts, const int* cPerm, const int* activeSlots, int* src)
 {
@@ -1088,9 +1156,13 @@ __global__ void s2bItemOrderFromKeysKernel(const int* counts, const int* cPerm, 
 
 // Besides the sorted list this also hands every constraint its ORDINAL in the lists of its two bodies (k-th of d incident
 // items): what the ticketed Gauss-Seidel passes (solver.cu, "dataflow") wait on instead of a grid barrier.
+// lists longer than this are sorted by a whole block (s2bSortLongIncidenceKernel) instead of one thread
+#define S2B_LONG_LIST 24
+#define S2B_LONG_LIST_SHARED 2048
+
 __global__ void s2bSortIncidenceKernel(int bodyCapacity, const int* adjStart, const int* adj, const int2* itemBodies,
 									   const unsigned long long* itemVal, unsigned long long* work, int* incList, int2* cFlowA,
-									   int2* cFlowB, int2* jFlowA, int2* jFlowB, int* heavyBodies)
+									   int2* cFlowB, int2* jFlowA, int2* jFlowB, int* heavyBodies, int* longBodies)
 {
 	int b = blockIdx.x * blockDim.x + threadIdx.x;
 	if (b >= bodyCapacity)
@@ -1106,6 +1178,12 @@ __global__ void s2bSortIncidenceKernel(int bodyCapacity, const int* adjStart, co
 	if (heavyBodies != nullptr && n > S2B_HEAVY_DEGREE)
 	{
 		heavyBodies[1 + atomicAdd(heavyBodies, 1)] = b; // the list holds bodyCapacity entries
+	}
+	if (n > S2B_LONG_LIST)
+	{
+		// a hub body (container wall: hundreds of entries): one thread sorting it in global memory takes milliseconds
+		longBodies[1 + atomicAdd(longBodies, 1)] = b;
+		return;
 	}
 	if (n <= 8)
 	{
@@ -1260,6 +1338,148 @@ __global__ void s2bSortIncidenceKernel(int bodyCapacity, const int* adjStart, co
 				((e & S2B_INC_SIDE_B) ? jFlowB : jFlowA)[t] = ticket;
 			}
 		}
+	}
+}
+
+// Long incidence lists, one block per body: bitonic sort of the 64-bit values in shared memory (up to 2048 entries; longer
+// lists fall back to a heap sort by one thread), then the same outputs as s2bSortIncidenceKernel.
+__global__ void __launch_bounds__(256) s2bSortLongIncidenceKernel(const int* longBodies, const int* adjStart, const int* adj, const int2* itemBodies,
+																  const unsigned long long* itemVal, unsigned long long* work, int* incList, int2* cFlowA,
+																  int2* cFlowB, int2* jFlowA, int2* jFlowB)
+{
+	__shared__ unsigned long long sKeys[S2B_LONG_LIST_SHARED];
+	int count = longBodies[0];
+	for (int which = blockIdx.x; which < count; which += gridDim.x)
+	{
+		int b = longBodies[1 + which];
+		int begin = adjStart[b], end = adjStart[b + 1];
+		int n = end - begin;
+		unsigned long long* v = work + begin;
+		for (int k = threadIdx.x; k < n; k += blockDim.x)
+		{
+			int item = adj[begin + k];
+			unsigned long long val = itemVal[item];
+			if (itemBodies[item].x != b)
+			{
+				val |= S2B_INC_SIDE_B;
+			}
+			v[k] = val;
+		}
+		__syncthreads();
+		if (n <= S2B_LONG_LIST_SHARED)
+		{
+			int padded = 1;
+			while (padded < n)
+			{
+				padded <<= 1;
+			}
+			for (int k = threadIdx.x; k < padded; k += blockDim.x)
+			{
+				sKeys[k] = k < n ? v[k] : ~0ull;
+			}
+			__syncthreads();
+			for (int size = 2; size <= padded; size <<= 1)
+			{
+				for (int stride = size >> 1; stride > 0; stride >>= 1)
+				{
+					for (int k = threadIdx.x; k < padded; k += blockDim.x)
+					{
+						int partner = k ^ stride;
+						if (partner > k)
+						{
+							bool ascending = (k & size) == 0;
+							unsigned long long x = sKeys[k], y = sKeys[partner];
+							if ((x > y) == ascending)
+							{
+								sKeys[k] = y;
+								sKeys[partner] = x;
+							}
+						}
+					}
+					__syncthreads();
+				}
+			}
+			for (int k = threadIdx.x; k < n; k += blockDim.x)
+			{
+				v[k] = sKeys[k];
+			}
+			__syncthreads();
+		}
+		else if (threadIdx.x == 0)
+		{
+			// heap sort in global memory (lists beyond the shared-memory buffer: not seen in practice)
+			for (int start = n / 2 - 1; start >= 0; --start)
+			{
+				int root = start;
+				for (;;)
+				{
+					int child = 2 * root + 1;
+					if (child >= n)
+					{
+						break;
+					}
+					if (child + 1 < n && v[child] < v[child + 1])
+					{
+						child += 1;
+					}
+					if (v[root] >= v[child])
+					{
+						break;
+					}
+					unsigned long long tmp = v[root];
+					v[root] = v[child];
+					v[child] = tmp;
+					root = child;
+				}
+			}
+			for (int last = n - 1; last > 0; --last)
+			{
+				unsigned long long tmp = v[0];
+				v[0] = v[last];
+				v[last] = tmp;
+				int root = 0;
+				for (;;)
+				{
+					int child = 2 * root + 1;
+					if (child >= last)
+					{
+						break;
+					}
+					if (child + 1 < last && v[child] < v[child + 1])
+					{
+						child += 1;
+					}
+					if (v[root] >= v[child])
+					{
+						break;
+					}
+					unsigned long long t2 = v[root];
+					v[root] = v[child];
+					v[child] = t2;
+					root = child;
+				}
+			}
+		}
+		__syncthreads();
+		for (int k = threadIdx.x; k < n; k += blockDim.x)
+		{
+			int e = (int)(unsigned)(v[k] & 0xFFFFFFFFull);
+			incList[begin + k] = e;
+			if (cFlowA != nullptr)
+			{
+				int t = e >> 2;
+				int2 ticket = make_int2(k, n);
+				if (e & S2B_INC_CONTACT)
+				{
+					((e & S2B_INC_SIDE_B) ? cFlowB : cFlowA)[t] = ticket;
+				}
+				else
+				{
+					((e & S2B_INC_SIDE_B) ? jFlowB : jFlowA)[t] = ticket;
+				}
+			}
+		}
+		__syncthreads();
 	}
 }
 
@@ -1927,7 +2147,8 @@ static void planSolve(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 		if (w->solveGrid == 0 || w->solveGridSolver != solverType)
 		{
 			int blocksPerSm = 0;
-			S2B_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, s2bPersistentKernel(solverType), S2B_BLOCK, 0));
+			S2B_CHECK(cudaFuncSetAttribute(s2bPersistentKernel(solverType), cudaFuncAttributeMaxDynamicSharedMemorySize, S2B_OV_SHARED_BYTES));
+			S2B_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, s2bPersistentKernel(solverType), S2B_BLOCK, S2B_OV_SHARED_BYTES));
 			const char* env = getenv("S2B_SOLVE_BLOCKS_PER_SM");
 			int want = env != nullptr ? atoi(env) : 2;
 			w->solveGrid = w->smCount * std::min(std::max(blocksPerSm, 1), std::max(want, 1));
@@ -1974,6 +2195,9 @@ static void planSolve(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 	s->cPerm.reserve(nC, st, false);
 	s->jPerm.reserve(nJ, st, false);
 	s->heavyBodies.reserve((size_t)bodyCap + 2, st, false);
+	s->ovBodies.reserve((size_t)bodyCap + 2, st, false);
+	s->longBodies.reserve((size_t)bodyCap + 2, st, false);
+	s->ovBodySlot.reserve((size_t)bodyCap + 2, st, false);
 	if (pl.regions > 0)
 	{
 		s->bodyKeyIn.reserve((size_t)bodyCap + 1, st, false);
@@ -2059,7 +2283,8 @@ static void planSolve(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 	s->cubTemp.reserve(tempBytes + 256, st, false, false);
 }
 
-static void launchColorKernel(s2bWorld* w, SolverScratch* s, int maxItems, int* color, int maxColors, int indexRounds, int validate)
+static void launchColorKernel(s2bWorld* w, SolverScratch* s, int maxItems, int* color, int maxColors, int indexRounds, int validate,
+							  int abortAbove = -1, const int* hubs = nullptr)
 {
 	// work counters of the kernel (shared by the primary and the cut colouring)
 	S2B_CHECK(cudaMemsetAsync(s->counts.p + CNT_REMAINING, 0, sizeof(int) * 5, w->stream));
@@ -2075,7 +2300,7 @@ static void launchColorKernel(s2bWorld* w, SolverScratch* s, int maxItems, int* 
 	const int* as = s->adjStart.p;
 	const int* ad = s->adj.p;
 	int* tent = s->colorB.p;
-	void* args[] = {&countsPtr, &ib, &as, &ad, &color, &tent, &maxColors, &indexRounds, &validate};
+	void* args[] = {&countsPtr, &ib, &as, &ad, &color, &tent, &maxColors, &indexRounds, &validate, &abortAbove, &hubs};
 	S2B_CHECK(cudaLaunchCooperativeKernel((void*)s2bColorKernel, dim3(grid), dim3(256), args, 0, w->stream));
 	w->kernelLaunches += 1;
 }
@@ -2182,9 +2407,9 @@ static void enqueueSchedule(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 			if (pl.regions > 0)
 			{
 				// the cut set is coloured among itself, from scratch, with hashed priorities (a handful of rounds)
-				launchColorKernel(w, s, maxItems, s->colorC.p, S2B_MAX_COLORS, 0, 0);
-				S2B_LAUNCH(w, s2bCutColorCountKernel, gridFor(maxItems, 256), 256, 0, s->counts.p, s->colorC.p);
 				regionCutLimit = w->useRegions >= 2 ? S2B_MAX_COLORS : w->regionCutLimit;
+				launchColorKernel(w, s, maxItems, s->colorC.p, S2B_MAX_COLORS, 0, 0, regionCutLimit < S2B_MAX_COLORS ? regionCutLimit - 1 : -1, s->heavyBodies.p);
+				S2B_LAUNCH(w, s2bCutColorCountKernel, gridFor(maxItems, 256), 256, 0, s->counts.p, s->colorC.p);
 			}
 
 			// solve order: stable 16-bit radix sort of (key, natural index), joints and contacts separately
@@ -2216,6 +2441,11 @@ static void enqueueSchedule(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 			S2B_LAUNCH(w, s2bBuildTablesKernel, gridFor(entries, 256), 256, 0, pl.regions, jKeysOut, jointCap, cKeysOut, contactCount, s->jRegOff.p,
 					   s->cRegOff.p, s->jGroupOff.p, s->cGroupOff.p);
 			S2B_LAUNCH(w, s2bFinishGroups, 1, 1, 0, s->counts.p, s->cGroupOff.p, s->jGroupOff.p);
+			// bodies of the serial overflow group (hub bodies' constraints beyond the colour limit), for its shared-memory walk
+			S2B_CHECK(cudaMemsetAsync(s->ovBodySlot.p, 0xFF, sizeof(int) * ((size_t)bodyCap + 1), st));
+			S2B_CHECK(cudaMemsetAsync(s->ovBodies.p, 0, sizeof(int), st));
+			S2B_LAUNCH(w, s2bOverflowBodiesKernel, gridFor(maxItems, 256), 256, 0, s->counts.p, s->jGroupOff.p, s->cGroupOff.p, s->jPerm.p,
+					   s->cPerm.p, s->jointSlots.p, s->activeSlots.p, jointView(w), makeView(w->contacts[w->cur]), s->ovBodySlot.p, s->ovBodies.p);
 		}
 
 		if (needHostCounts)
@@ -2278,8 +2508,11 @@ static void enqueueSchedule(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 			}
 			// without regions the hub bodies (gathered by a whole block) are registered here; with regions s2bBodyKeysKernel did it
 			int* heavy = (pl.gatherWarm && pl.usePersistent && pl.regions == 0) ? s->heavyBodies.p : nullptr;
+			S2B_CHECK(cudaMemsetAsync(s->longBodies.p, 0, sizeof(int), st));
 			S2B_LAUNCH(w, s2bSortIncidenceKernel, gridFor(bodyCap, 128), 128, 0, bodyCap, s->adjStart.p, s->adj.p, s->itemBodies.p,
-					   s->itemVal.p, s->incWork.p, s->incList.p, cfa, cfb, jfa, jfb, heavy);
+					   s->itemVal.p, s->incWork.p, s->incList.p, cfa, cfb, jfa, jfb, heavy, s->longBodies.p);
+			S2B_LAUNCH(w, s2bSortLongIncidenceKernel, 64, 256, 0, s->longBodies.p, s->adjStart.p, s->adj.p, s->itemBodies.p, s->itemVal.p,
+					   s->incWork.p, s->incList.p, cfa, cfb, jfa, jfb);
 		}
 	}
 	else
@@ -2382,6 +2615,9 @@ static void enqueueIterate(s2bWorld* w, SolverScratch* s, SolvePlan& pl, bool ca
 	a.jRegOff = s->jRegOff.p;
 	a.cRegOff = s->cRegOff.p;
 	a.barrier = w->solveBarrier.p;
+	bool stagedOverflow = w->schedule == S2B_SCHEDULE_COLOR && pl.usePersistent && pl.maxItems > 0;
+	a.ovBodies = stagedOverflow ? s->ovBodies.p : nullptr;
+	a.ovBodySlot = stagedOverflow ? s->ovBodySlot.p : nullptr;
 	if (pl.dataflow)
 	{
 		S2B_CHECK(cudaMemsetAsync(s->bodyTicket.p, 0, sizeof(int) * ((size_t)bodyCap + 2), st));
@@ -2421,7 +2657,7 @@ static void enqueueIterate(s2bWorld* w, SolverScratch* s, SolvePlan& pl, bool ca
 		// (inside a capture the time stamps become external event-record nodes so that they are taken on every replay)
 		unsigned evFlags = capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
 		S2B_CHECK(cudaEventRecordWithFlags(w->solveKernelStart, st, evFlags));
-		S2B_CHECK(cudaLaunchCooperativeKernel(s2bPersistentKernel(solverType), dim3(pl.grid), dim3(pl.threads), args, 0, st));
+		S2B_CHECK(cudaLaunchCooperativeKernel(s2bPersistentKernel(solverType), dim3(pl.grid), dim3(pl.threads), args, S2B_OV_SHARED_BYTES, st));
 		S2B_CHECK(cudaEventRecordWithFlags(w->solveKernelEnd, st, evFlags));
 		w->solveKernelTimed = true;
 		w->kernelLaunches += 1;

@@ -34,6 +34,7 @@ enum
 	CNT_CUT = 13,		// constraints in the cut set (straddle two regions or touch a hub body)
 	CNT_CUT_COLORS = 14, // colours the cut set needed
 	CNT_REGIONS_ON = 15, // 1: the solve order is region-major (persistent.cuh); 0: one device-wide group per colour
+	CNT_CUT_ABORT = 20,	// the cut colouring gave up: it needs more colours than regions are worth
 	CNT_BOUNDS = 16,	// 4 slots: order-preserving keys of max x, max -x, max y, max -y over the bodies' centres
 	CNT_SIZE = 32
 };
@@ -58,6 +59,9 @@ struct SolveArgs
 	const int* jRegOff;		 // regions x (S2B_MAX_COLORS + 1): joint-constraint stream offsets of (region, colour)
 	const int* cRegOff;		 // same for contact constraints
 	unsigned* barrier;		 // [0] monotonic arrival counter of the grid barrier, [32] its value at the start of the next launch
+	// serial overflow group on a shared-memory copy of its bodies (persistent.cuh): the distinct bodies its constraints touch
+	const int* ovBodies;	 // [0] count, then body slots (null: walk in global memory)
+	const int* ovBodySlot;	 // per body: position in that list, or -1
 	// ticketed ("dataflow") Gauss-Seidel passes: null when the passes synchronise with grid barriers instead
 	int* bodyTicket;			   // per body: incident-item executions completed in this launch
 	const int2 *cFlowA, *cFlowB;   // per contact constraint and side: {ordinal in the body's incidence list, its degree} or -1
@@ -115,6 +119,8 @@ struct SolverScratch
 	DevArray<unsigned long long> itemVal, incWork; // warm-start gather: per-item sort value, per-body sort scratch
 	DevArray<int> incList;
 	DevArray<int> heavyBodies;
+	DevArray<int> longBodies;			// [0] count, then bodies whose incidence list is sorted by a whole block
+	DevArray<int> ovBodies, ovBodySlot; // bodies of the serial overflow group (SolveArgs::ovBodies)
 	DevArray<int2> flow;	  // cFlowA | cFlowB | jFlowA | jFlowB
 	DevArray<int> bodyTicket; // + 1 int error flag at the end
 	int flowErrorOffset = 0;
