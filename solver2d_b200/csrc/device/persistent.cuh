@@ -328,16 +328,42 @@ __device__ __forceinline__ void s2bGroupPass(int jointOp, int contactOp, const S
 		{
 			continue; // uniform: every thread reads the same table
 		}
-		s2bSyncBeforeGlobal(a, sync);
-		for (int t = tid; t < nj + nc; t += stride)
+		if (SOLVER == 7 && (contactOp == COP_TGS_SOFT_BIAS || contactOp == COP_TGS_SOFT_RELAX) && nj == 0)
 		{
-			if (t < nj)
+			// The headline op. Nothing in a thread's constraint row is written by another thread (the impulses by this very
+			// thread, one sweep ago), so the row is fetched BEFORE the barrier: what remains after it is the dependent part
+			// proper — the two bodies, the arithmetic, the stores (one L2 round trip less per device-wide step).
+			bool mine = tid < nc;
+			ContactStream cs;
+			if (mine)
 			{
-				s2bRunJointOpT<SOLVER>(jointOp, a, jBegin + t, p);
+				cs = s2bLoadContactStream(a, cBegin + tid);
 			}
-			else
+			s2bSyncBeforeGlobal(a, sync);
+			bool bias = contactOp == COP_TGS_SOFT_BIAS;
+			bool writeWarm = bias ? a.ctx.extraIterations == 0 : true;
+			if (mine)
 			{
-				s2bRunContactOpT<SOLVER>(contactOp, a, cBegin + (t - nj));
+				s2bSolveContactTgsSoftStream(a, cBegin + tid, cs, a.ctx.inv_h, bias, writeWarm);
+			}
+			for (int t = tid + stride; t < nc; t += stride)
+			{
+				s2bSolveContactTgsSoft(a, cBegin + t, a.ctx.inv_h, bias, writeWarm);
+			}
+		}
+		else
+		{
+			s2bSyncBeforeGlobal(a, sync);
+			for (int t = tid; t < nj + nc; t += stride)
+			{
+				if (t < nj)
+				{
+					s2bRunJointOpT<SOLVER>(jointOp, a, jBegin + t, p);
+				}
+				else
+				{
+					s2bRunContactOpT<SOLVER>(contactOp, a, cBegin + (t - nj));
+				}
 			}
 		}
 		sync.pending = S2B_PENDING_GLOBAL;

@@ -1510,9 +1510,10 @@ __global__ void __launch_bounds__(S2B_BLOCK) s2bTgsSoftColorKernel(SolveArgs a, 
 // stream column is one contiguous run, so one thread issues eight 1-D bulk copies (cp.async.bulk, completion counted on an
 // mbarrier) and the 256 threads then read their row from shared memory; only the gather of the two bodies and the final
 // stores go through the load/store units. Same arithmetic, same bits.
-#define S2B_BULK_ROWS (S2B_BLOCK + 2) // the slice may start one row early to keep 8-byte columns 16-byte aligned
+#define S2B_BULK_BLOCK 256
+#define S2B_BULK_ROWS (S2B_BULK_BLOCK + 2) // the slice may start one row early to keep 8-byte columns 16-byte aligned
 
-__global__ void __launch_bounds__(S2B_BLOCK) s2bTgsSoftColorKernelBulk(SolveArgs a, int cBegin, int cEnd, int useBias)
+__global__ void __launch_bounds__(S2B_BULK_BLOCK) s2bTgsSoftColorKernelBulk(SolveArgs a, int cBegin, int cEnd, int useBias)
 {
 	using BlockBarrier = cuda::barrier<cuda::thread_scope_block>;
 	__shared__ alignas(16) int2 sIdx[S2B_BULK_ROWS];
@@ -3148,7 +3149,7 @@ extern "C" float s2b_time_color_kernel(s2bWorld* w, const s2bStepContext* contex
 		S2B_CHECK(cudaEventRecord(e0, w->stream));
 		if (bulk)
 		{
-			S2B_LAUNCH(w, s2bTgsSoftColorKernelBulk, gridFor(bestCount, S2B_BLOCK), S2B_BLOCK, 0, a, cb, ce, 0);
+			S2B_LAUNCH(w, s2bTgsSoftColorKernelBulk, gridFor(bestCount, S2B_BULK_BLOCK), S2B_BULK_BLOCK, 0, a, cb, ce, 0);
 		}
 		else
 		{

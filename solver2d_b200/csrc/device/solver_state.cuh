@@ -5,7 +5,7 @@
 #include "s2b_internal.cuh"
 
 // threads per block of the solver kernels
-#define S2B_BLOCK 256
+#define S2B_BLOCK 512
 // colours of the constraint graph: 0..S2B_MAX_COLORS-1, or the serial overflow group
 #define S2B_MAX_COLORS 64
 #define S2B_OVERFLOW_KEY 255
