@@ -853,7 +853,16 @@ void s2bBroadphaseUpdatePairs(s2bWorld* w)
 	bool run = w->pairsDirty;
 	if (run == false)
 	{
-		S2B_CHECK(cudaStreamSynchronize(st));
+		// (wait for THAT copy only — not for whatever the caller has enqueued since: force uploads, row scatters — so that the
+		// kernels of this step can be queued behind them without the host idling)
+		if (w->movedEvent != nullptr)
+		{
+			S2B_CHECK(cudaEventSynchronize(w->movedEvent));
+		}
+		else
+		{
+			S2B_CHECK(cudaStreamSynchronize(st));
+		}
 		run = w->hostMail[MAIL_MOVED] > 0;
 	}
 	S2B_CHECK(cudaEventRecord(w->timer.ev[0], st));

@@ -115,4 +115,9 @@ void s2bFinalize(s2bWorld* w)
 	}
 	// publish the moved-proxy counter to the pinned mailbox; the next step reads it after this step has drained
 	S2B_CHECK(cudaMemcpyAsync(w->hostMail + MAIL_MOVED, w->dMovedFlag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+	if (w->movedEvent == nullptr)
+	{
+		S2B_CHECK(cudaEventCreateWithFlags(&w->movedEvent, cudaEventDisableTiming));
+	}
+	S2B_CHECK(cudaEventRecord(w->movedEvent, st));
 }

@@ -380,6 +380,7 @@ struct s2bWorld
 	cudaEvent_t solveKernelStart = nullptr, solveKernelEnd = nullptr;
 	bool solveKernelTimed = false;
 	cudaEvent_t markEvents[2] = {nullptr, nullptr};
+	cudaEvent_t movedEvent = nullptr; // recorded behind the D2H copy of the moved-proxy counter at the end of every step
 	StageTimer timer;
 	float stageMs[4] = {0, 0, 0, 0};
 

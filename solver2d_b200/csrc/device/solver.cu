@@ -761,14 +761,28 @@ __global__ void s2bBodyKeysKernel(BodyView bodies, int* counts, const int* degre
 	keys[i] = key;
 }
 
-// first rank of every island in the sorted order (at the island's label)
+// first rank of every island in the sorted order (at the island's label). Islands are runs of the sorted order (the island
+// is the major sort key), so only the first rank of a run has to post its position: a handful of atomics per island instead
+// of one per body — on a single 100 k-body island that was 100 k atomicMin on one address.
 __global__ void s2bIslandStartKernel(const int* counts, const int* sortedBodies, const int* island, int* islandStart)
 {
 	int k = blockIdx.x * blockDim.x + threadIdx.x;
 	if (k < counts[CNT_OWNED])
 	{
-		atomicMin(islandStart + island[sortedBodies[k]], k);
+		int label = island[sortedBodies[k]];
+		if (k == 0 || island[sortedBodies[k - 1]] != label)
+		{
+			atomicMin(islandStart + label, k);
+		}
 	}
+}
+
+// lanes of the warp that hold the same key as this one, and this lane's rank among them (warp-aggregated atomics)
+__device__ __forceinline__ unsigned s2bPeers(int key, bool active, int* rank)
+{
+	unsigned peers = __match_any_sync(0xFFFFFFFFu, active ? key : -1 - (int)(threadIdx.x & 31));
+	*rank = __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+	return peers;
 }
 
 // Region of every body. The owned bodies are cut into `regions` chunks of equal size along the sorted order; an island of
@@ -778,22 +792,28 @@ __global__ void s2bAssignRegionsKernel(const int* counts, int bodyCapacity, int 
 									   const int* islandStart, const int* islandSize, int* bodyRegion, int* regCount)
 {
 	int k = blockIdx.x * blockDim.x + threadIdx.x;
-	if (k >= bodyCapacity)
-	{
-		return;
-	}
 	int owned = counts[CNT_OWNED];
 	int chunk = max((owned + regions - 1) / regions, 1);
-	int body = sortedBodies[k];
 	int region = -1;
-	if (k < owned)
+	bool inRange = k < bodyCapacity;
+	int body = inRange ? sortedBodies[k] : 0;
+	if (inRange && k < owned)
 	{
 		int label = island[body];
 		int rank = islandSize[label] <= 2 * chunk ? islandStart[label] : k;
 		region = min(rank / chunk, regions - 1);
-		atomicAdd(regCount + region, 1);
 	}
-	bodyRegion[body] = region;
+	// neighbours in the sorted order mostly share a region: one atomic per (warp, region)
+	int lane;
+	unsigned peers = s2bPeers(region, region >= 0, &lane);
+	if (region >= 0 && lane == 0)
+	{
+		atomicAdd(regCount + region, __popc(peers));
+	}
+	if (inRange)
+	{
+		bodyRegion[body] = region;
+	}
 }
 
 // regBodyStart = exclusive scan of the region sizes (one block; regions <= 511); the cursors start at the same offsets
@@ -826,10 +846,20 @@ __global__ void __launch_bounds__(512) s2bRegionOffsetsKernel(int regions, const
 __global__ void s2bFillRegionBodiesKernel(const int* counts, const int* sortedBodies, const int* bodyRegion, int* regCursor, int* regBodies)
 {
 	int k = blockIdx.x * blockDim.x + threadIdx.x;
-	if (k < counts[CNT_OWNED])
+	bool active = k < counts[CNT_OWNED];
+	int body = active ? sortedBodies[k] : 0;
+	int region = active ? bodyRegion[body] : -1;
+	int lane;
+	unsigned peers = s2bPeers(region, active, &lane);
+	int base = 0;
+	if (active && lane == 0)
 	{
-		int body = sortedBodies[k];
-		regBodies[atomicAdd(regCursor + bodyRegion[body], 1)] = body;
+		base = atomicAdd(regCursor + region, __popc(peers));
+	}
+	base = __shfl_sync(0xFFFFFFFFu, base, __ffs(peers) - 1);
+	if (active)
+	{
+		regBodies[base + lane] = body;
 	}
 }
 

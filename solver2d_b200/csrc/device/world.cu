@@ -344,6 +344,11 @@ extern "C" s2bWorld* s2b_world_create(int cudaDevice, int solverType)
 		{
 			w->useGraph = atoi(env) != 0 ? 1 : 0;
 		}
+		env = getenv("S2B_PERSISTENT");
+		if (env != nullptr)
+		{
+			w->persistent = atoi(env) != 0 ? 1 : 0;
+		}
 		env = getenv("S2B_REGIONS");
 		if (env != nullptr)
 		{
@@ -433,6 +438,31 @@ extern "C" void s2b_world_destroy(s2bWorld* w)
 		cudaEventDestroy(w->solveKernelStart);
 		cudaEventDestroy(w->solveKernelEnd);
 	}
+	if (w->movedEvent != nullptr)
+	{
+		cudaEventDestroy(w->movedEvent);
+	}
+	for (int i = 0; i < 2; ++i)
+	{
+		if (w->markEvents[i] != nullptr)
+		{
+			cudaEventDestroy(w->markEvents[i]);
+		}
+		if (w->bulkEvent[i] != nullptr)
+		{
+			cudaEventDestroy(w->bulkEvent[i]);
+		}
+		if (w->bulkHost[i] != nullptr)
+		{
+			cudaFreeHost(w->bulkHost[i]);
+		}
+	}
+	if (w->hostXf != nullptr)
+	{
+		cudaFreeHost(w->hostXf);
+	}
+	w->dBulk.release();
+	w->dXf.release();
 	cudaFreeHost(w->hostMail);
 	cudaFree(w->devMail);
 	for (int i = 0; i < 5; ++i)
@@ -647,9 +677,16 @@ __global__ void s2bAddForcesKernel(const int* __restrict__ indices, const float2
 		return;
 	}
 	int i = indices[t];
+	// a body index may appear several times in one call (each entry adds, like repeated s2Body_ApplyForceToCenter calls):
+	// atomic adds; out-of-range or dead slots are ignored
+	if (i < 0 || i >= b.capacity || (b.flags[i] & S2B_BODY_VALID) == 0)
+	{
+		return;
+	}
 	float2 add = forces[t];
-	float4 f = b.frc[i];
-	b.frc[i] = make_float4(f.x + add.x, f.y + add.y, f.z, f.w);
+	float* f = reinterpret_cast<float*>(b.frc + i);
+	atomicAdd(f + 0, add.x);
+	atomicAdd(f + 1, add.y);
 }
 
 __global__ void s2bGatherTransforms(BodyView b, int count, float4* out)
