@@ -262,7 +262,13 @@ S2B_API void s2b_update_contacts(s2bWorld* world);
 S2B_API void s2b_solve(s2bWorld* world, int solverType, const s2bStepContext* context);
 // Stage 4: transforms, force reset, AABB refit, proxy enlarge + move buffering (reference src/world.c:258-301).
 S2B_API void s2b_finalize(s2bWorld* world);
-// All four in order.
+// Start the pair search of the NEXT step (hierarchy refit, queries of the moved proxies, survivors of the contact table)
+// behind this step's finalize, whose results are its inputs: the search's counters then reach the host together with the
+// end of the step, and the next s2b_update_pairs merges the result without a host synchronisation in the middle of the pass.
+// Optional (s2b_update_pairs does the whole pass itself when nothing was prefetched or rows were uploaded since); a no-op on
+// scenes where nothing moved in the previous pass.
+S2B_API void s2b_prefetch_pairs(s2bWorld* world);
+// All four in order, then s2b_prefetch_pairs.
 S2B_API void s2b_step(s2bWorld* world, int solverType, const s2bStepContext* context);
 
 // ---- device -> host (synchronising) ---------------------------------------------------------------------------

@@ -53,6 +53,15 @@ struct BroadScratch
 	DevArray<unsigned long long> pairHash;
 	unsigned long long hashMask = 0;
 	unsigned long long hashVersion = ~0ull; // contact table version the set was built from
+	// pair search started behind the previous step (s2bPrefetchPairSearch)
+	bool prefetched = false;	   // a search is in flight / finished and not consumed yet
+	bool lastPassRan = false;	   // the last pass found moved proxies (the scene is in motion)
+	bool searchTimed = false;
+	unsigned long long prefetchEpoch = 0, searchedVersion = 0;
+	int searchedCount = 0;
+	size_t prefetchTempBytes = 0;
+	cudaEvent_t evSearch[2] = {nullptr, nullptr};
+	cudaEvent_t searchDone = nullptr;
 };
 
 #define S2B_TREE_REUSE_LIMIT 16
@@ -97,6 +106,20 @@ void s2bFreeBroadScratch(s2bWorld* w)
 	b->mergeSrcIn.release();
 	b->mergeSrcOut.release();
 	b->cubTemp.release();
+	b->pairBox.release();
+	b->largeShapes.release();
+	b->pairHash.release();
+	for (int i = 0; i < 2; ++i)
+	{
+		if (b->evSearch[i] != nullptr)
+		{
+			cudaEventDestroy(b->evSearch[i]);
+		}
+	}
+	if (b->searchDone != nullptr)
+	{
+		cudaEventDestroy(b->searchDone);
+	}
 	delete b;
 	w->broad = nullptr;
 }
@@ -458,9 +481,11 @@ __global__ void s2bFlagMovedLeaves(ShapeView s, const int* leafShape, const int*
 {
 	int n = counters[BC_LEAVES];
 	int k = blockIdx.x * blockDim.x + threadIdx.x;
-	if (k < n)
+	if (k < s.capacity)
 	{
-		movedFlag[k] = (s.head[leafShape[sortedLeaf[k]]].x & S2B_SHAPE_MOVED) ? 1 : 0;
+		// (every slot the compaction below looks at is written: positions beyond the live leaves would otherwise keep the flag
+		// of whatever leaf sat there before shapes were destroyed, and a stale 1 queries some shape a second time)
+		movedFlag[k] = (k < n && (s.head[leafShape[sortedLeaf[k]]].x & S2B_SHAPE_MOVED)) ? 1 : 0;
 	}
 }
 
@@ -839,45 +864,15 @@ __global__ void s2bClearMovedFlags(ShapeView s, int* movedCounter)
 // host driver
 // ---------------------------------------------------------------------------------------------------------------
 
-void s2bBroadphaseUpdatePairs(s2bWorld* w)
+// mailbox slots of the pair pass (pinned host memory, written by asynchronous copies)
+#define MAIL_BC_BASE 16
+
+// scratch sizes of a pass (host only; the pass itself never allocates between its kernels)
+static size_t bpReserve(s2bWorld* w, BroadScratch* B)
 {
-	// scratch of this pass is not referenced by the solver's graph; a REPLACED contact table is, and shows up in the graph
-	// signature through w->cur / w->contactCount / w->contactTableVersion
-	S2bEpochFreeze freeze;
 	cudaStream_t st = w->stream;
-	BroadScratch* B = getBroad(w);
-	w->dMovedFlag.reserve(4, st, true);
-
-	// Did anything move in the last finalize? The counter was copied to the pinned mailbox at the end of the previous
-	// step; wait for that step to drain (normally long done) and read it.
-	bool run = w->pairsDirty;
-	if (run == false)
-	{
-		// (wait for THAT copy only — not for whatever the caller has enqueued since: force uploads, row scatters — so that the
-		// kernels of this step can be queued behind them without the host idling)
-		if (w->movedEvent != nullptr)
-		{
-			S2B_CHECK(cudaEventSynchronize(w->movedEvent));
-		}
-		else
-		{
-			S2B_CHECK(cudaStreamSynchronize(st));
-		}
-		run = w->hostMail[MAIL_MOVED] > 0;
-	}
-	S2B_CHECK(cudaEventRecord(w->timer.ev[0], st));
-	if (run == false || w->shapeCap == 0)
-	{
-		return;
-	}
-
 	int shapeCap = w->shapeCap;
 	int oldCount = w->contactCount;
-	ShapeView sv = shapeView(w);
-	BodyView bv = bodyView(w);
-	ContactColumns& cur = w->contacts[w->cur];
-	ContactColumns& nxt = w->contacts[w->cur ^ 1];
-
 	size_t nS = (size_t)shapeCap;
 	B->validFlag.reserve(nS, st, false);
 	B->leafShape.reserve(nS, st, false);
@@ -902,7 +897,6 @@ void s2bBroadphaseUpdatePairs(s2bWorld* w)
 	{
 		B->newPairCap = 8 * shapeCap + 1024;
 	}
-
 	size_t need = 0, tempBytes = 0;
 	cub::DeviceSelect::Flagged(nullptr, need, thrust::counting_iterator<int>(0), (int*)nullptr, (int*)nullptr, (int*)nullptr,
 							   std::max(shapeCap, oldCount), st);
@@ -910,127 +904,137 @@ void s2bBroadphaseUpdatePairs(s2bWorld* w)
 	cub::DeviceRadixSort::SortPairs(nullptr, need, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, shapeCap, 0,
 									32, st);
 	tempBytes = std::max(tempBytes, need);
+	B->newKey.reserve((size_t)B->newPairCap, st, false);
+	B->newShapes.reserve((size_t)B->newPairCap, st, false);
+	B->cubTemp.reserve(tempBytes + 256, st, false, false);
+	return tempBytes;
+}
 
-	for (int attempt = 0; attempt < 4; ++attempt)
+// First half of a pass, no host synchronisation: hierarchy (re-used or rebuilt) and refit, pair-key hash of the current
+// table, queries from the moved proxies -> candidate pairs (newKey / newShapes), survivors of the current table (keepSlots),
+// and the counters of all that copied to the pinned mailbox.
+static void bpSearch(s2bWorld* w, BroadScratch* B)
+{
+	cudaStream_t st = w->stream;
+	int shapeCap = w->shapeCap;
+	int oldCount = w->contactCount;
+	ShapeView sv = shapeView(w);
+	BodyView bv = bodyView(w);
+	ContactColumns& cur = w->contacts[w->cur];
+	size_t nS = (size_t)shapeCap;
+	int newCap = B->newPairCap;
+
+	bool reuseTree = B->treeValid && w->pairsDirty == false && B->treeShapeCap == shapeCap && B->treeReuses < S2B_TREE_REUSE_LIMIT;
+	if (reuseTree)
 	{
-		int newCap = B->newPairCap;
-		int mergeCap = oldCount + newCap;
-		(void)mergeCap;
-		B->newKey.reserve((size_t)newCap, st, false);
-		B->newShapes.reserve((size_t)newCap, st, false);
-		B->cubTemp.reserve(tempBytes + 256, st, false, false);
-		// (the merge buffers are reserved where the merge happens: most passes leave the table as it is, and a pass must
-		// not pay a cudaMalloc for buffers it will not use)
+		// keep BC_LEAVES (and the stale height); clear the per-pass counters
+		S2B_CHECK(cudaMemsetAsync(B->counters.p + BC_NEW_PAIRS, 0, sizeof(int) * (BC_SIZE - BC_NEW_PAIRS), st));
+		B->treeReuses += 1;
+	}
+	else
+	{
+		S2B_CHECK(cudaMemsetAsync(B->counters.p, 0, sizeof(int) * BC_SIZE, st));
 
-		bool reuseTree = B->treeValid && w->pairsDirty == false && B->treeShapeCap == shapeCap && B->treeReuses < S2B_TREE_REUSE_LIMIT;
-		if (reuseTree)
-		{
-			// keep BC_LEAVES (and the stale height); clear the per-pass counters
-			S2B_CHECK(cudaMemsetAsync(B->counters.p + BC_NEW_PAIRS, 0, sizeof(int) * (BC_SIZE - BC_NEW_PAIRS), st));
-			B->treeReuses += 1;
-		}
-		else
-		{
-			S2B_CHECK(cudaMemsetAsync(B->counters.p, 0, sizeof(int) * BC_SIZE, st));
-
-			// ---- leaves ----
-			S2B_LAUNCH(w, s2bFlagValidShapes, gridFor(shapeCap, 256), 256, 0, sv, B->validFlag.p);
-			size_t tb = B->cubTemp.cap;
-			cub::DeviceSelect::Flagged(B->cubTemp.p, tb, thrust::counting_iterator<int>(0), B->validFlag.p, B->leafShape.p,
-									   B->counters.p + BC_LEAVES, shapeCap, st);
-			w->kernelLaunches += 2;
-
-			// ---- Morton order ----
-			int initBounds[4] = {0x7F7FFFFF, 0x7F7FFFFF, (int)0x80800000, (int)0x80800000};
-			// ordered encoding: +FLT_MAX -> 0x7F7FFFFF, -FLT_MAX -> 0xFF7FFFFF ^ 0x7FFFFFFF = 0x80800000
-			S2B_CHECK(cudaMemcpyAsync(B->boundsBits.p, initBounds, sizeof(initBounds), cudaMemcpyHostToDevice, st));
-			S2B_LAUNCH(w, s2bSceneBounds, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->counters.p, B->boundsBits.p);
-			S2B_LAUNCH(w, s2bMortonCodes, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->counters.p, B->boundsBits.p,
-					   B->mortonIn.p, B->leafIn.p, shapeCap);
-			tb = B->cubTemp.cap;
-			cub::DeviceRadixSort::SortPairs(B->cubTemp.p, tb, B->mortonIn.p, B->mortonOut.p, B->leafIn.p, B->leafOut.p, shapeCap, 0, 32, st);
-			w->kernelLaunches += 5;
-
-			// ---- hierarchy ----
-			S2B_LAUNCH(w, s2bBuildRadixTree, gridFor(shapeCap, 256), 256, 0, B->mortonOut.p, B->counters.p, B->children.p, B->parent.p);
-			B->treeValid = true;
-			B->treeShapeCap = shapeCap;
-			B->treeReuses = 0;
-		}
-
-		// ---- refit ----
-		S2B_CHECK(cudaMemsetAsync(B->visit.p, 0, sizeof(int) * nS, st));
-		S2B_LAUNCH(w, s2bRefit, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->leafOut.p, B->counters.p, B->children.p,
-				   B->parent.p, B->nodeBox.p, B->pairBox.p, B->visit.p, B->nodeHeight.p, B->counters.p);
-
-		// ---- pair-key hash set of the current contact table (rebuilt only when the table changed) ----
-		if (B->hashVersion != w->contactTableVersion || B->pairHash.p == nullptr)
-		{
-			unsigned long long size = 1024;
-			while (size < 2ull * (unsigned long long)std::max(oldCount, 1))
-			{
-				size <<= 1;
-			}
-			B->pairHash.reserve((size_t)size, st, false, false);
-			B->hashMask = size - 1;
-			S2B_CHECK(cudaMemsetAsync(B->pairHash.p, 0xFF, sizeof(unsigned long long) * (size_t)size, st));
-			if (oldCount > 0)
-			{
-				S2B_LAUNCH(w, s2bBuildPairHash, gridFor(oldCount, 256), 256, 0, cur.key.p, oldCount, B->pairHash.p, B->hashMask);
-			}
-			B->hashVersion = w->contactTableVersion;
-		}
-
-		// ---- queries from moved proxies ----
-		S2B_LAUNCH(w, s2bFlagMovedLeaves, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->leafOut.p, B->counters.p,
-				   B->movedFlag.p);
-		S2B_LAUNCH(w, s2bSplitLargeMovers, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->leafOut.p, B->counters.p, B->nodeBox.p,
-				   B->movedFlag.p, B->largeShapes.p);
+		// ---- leaves ----
+		S2B_LAUNCH(w, s2bFlagValidShapes, gridFor(shapeCap, 256), 256, 0, sv, B->validFlag.p);
 		size_t tb = B->cubTemp.cap;
-		cub::DeviceSelect::Flagged(B->cubTemp.p, tb, thrust::counting_iterator<int>(0), B->movedFlag.p, B->movedLeaves.p,
-								   B->counters.p + BC_MOVED, shapeCap, st);
+		cub::DeviceSelect::Flagged(B->cubTemp.p, tb, thrust::counting_iterator<int>(0), B->validFlag.p, B->leafShape.p,
+								   B->counters.p + BC_LEAVES, shapeCap, st);
 		w->kernelLaunches += 2;
-		S2B_LAUNCH(w, s2bFindPairs, gridFor(shapeCap, 128), 128, 0, sv, bv, B->leafShape.p, B->leafOut.p, B->counters.p,
-				   B->movedLeaves.p, B->children.p, B->pairBox.p, B->pairHash.p, B->hashMask, w->jointPairKeys.p, w->jointPairCount,
-				   B->newKey.p, B->newShapes.p, newCap);
-		S2B_LAUNCH(w, s2bFindPairsLarge, gridFor(shapeCap, 256), 256, 0, sv, bv, B->leafShape.p, B->counters.p, B->largeShapes.p,
-				   B->pairHash.p, B->hashMask, w->jointPairKeys.p, w->jointPairCount, B->newKey.p, B->newShapes.p, newCap);
 
-		// ---- survivors ----
+		// ---- Morton order ----
+		int initBounds[4] = {0x7F7FFFFF, 0x7F7FFFFF, (int)0x80800000, (int)0x80800000};
+		// ordered encoding: +FLT_MAX -> 0x7F7FFFFF, -FLT_MAX -> 0xFF7FFFFF ^ 0x7FFFFFFF = 0x80800000
+		S2B_CHECK(cudaMemcpyAsync(B->boundsBits.p, initBounds, sizeof(initBounds), cudaMemcpyHostToDevice, st));
+		S2B_LAUNCH(w, s2bSceneBounds, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->counters.p, B->boundsBits.p);
+		S2B_LAUNCH(w, s2bMortonCodes, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->counters.p, B->boundsBits.p,
+				   B->mortonIn.p, B->leafIn.p, shapeCap);
+		tb = B->cubTemp.cap;
+		cub::DeviceRadixSort::SortPairs(B->cubTemp.p, tb, B->mortonIn.p, B->mortonOut.p, B->leafIn.p, B->leafOut.p, shapeCap, 0, 32, st);
+		w->kernelLaunches += 5;
+
+		// ---- hierarchy ----
+		S2B_LAUNCH(w, s2bBuildRadixTree, gridFor(shapeCap, 256), 256, 0, B->mortonOut.p, B->counters.p, B->children.p, B->parent.p);
+		B->treeValid = true;
+		B->treeShapeCap = shapeCap;
+		B->treeReuses = 0;
+	}
+
+	// ---- refit ----
+	S2B_CHECK(cudaMemsetAsync(B->visit.p, 0, sizeof(int) * nS, st));
+	S2B_LAUNCH(w, s2bRefit, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->leafOut.p, B->counters.p, B->children.p,
+			   B->parent.p, B->nodeBox.p, B->pairBox.p, B->visit.p, B->nodeHeight.p, B->counters.p);
+
+	// ---- pair-key hash set of the current contact table (rebuilt only when the table changed) ----
+	if (B->hashVersion != w->contactTableVersion || B->pairHash.p == nullptr)
+	{
+		unsigned long long size = 1024;
+		while (size < 2ull * (unsigned long long)std::max(oldCount, 1))
+		{
+			size <<= 1;
+		}
+		B->pairHash.reserve((size_t)size, st, false, false);
+		B->hashMask = size - 1;
+		S2B_CHECK(cudaMemsetAsync(B->pairHash.p, 0xFF, sizeof(unsigned long long) * (size_t)size, st));
 		if (oldCount > 0)
 		{
-			S2B_LAUNCH(w, s2bFlagKeptContacts, gridFor(oldCount, 256), 256, 0, makeView(cur), oldCount, sv, w->jointDestroyKeys.p,
-					   w->jointDestroyCount, B->keepFlag.p);
-			tb = B->cubTemp.cap;
-			cub::DeviceSelect::Flagged(B->cubTemp.p, tb, thrust::counting_iterator<int>(0), B->keepFlag.p, B->keepSlots.p,
-									   B->counters.p + BC_KEPT, oldCount, st);
-			w->kernelLaunches += 2;
+			S2B_LAUNCH(w, s2bBuildPairHash, gridFor(oldCount, 256), 256, 0, cur.key.p, oldCount, B->pairHash.p, B->hashMask);
 		}
+		B->hashVersion = w->contactTableVersion;
+	}
 
-		// the new table size has to be known on the host (column reservation): one small synchronising read-back,
-		// paid only on steps where the broad phase actually runs
-		int hostCounters[BC_SIZE];
-		S2B_CHECK(cudaMemcpyAsync(hostCounters, B->counters.p, sizeof(hostCounters), cudaMemcpyDeviceToHost, st));
-		S2B_CHECK(cudaStreamSynchronize(st));
-		int fresh = hostCounters[BC_NEW_PAIRS];
-		int kept = hostCounters[BC_KEPT];
-		if (fresh > newCap)
-		{
-			B->newPairCap = fresh + fresh / 2 + 1024;
-			continue; // rare: redo the pass with a larger pair buffer
-		}
-		w->treeHeight = hostCounters[BC_HEIGHT];
+	// ---- queries from moved proxies ----
+	S2B_LAUNCH(w, s2bFlagMovedLeaves, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->leafOut.p, B->counters.p,
+			   B->movedFlag.p);
+	S2B_LAUNCH(w, s2bSplitLargeMovers, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->leafOut.p, B->counters.p, B->nodeBox.p,
+			   B->movedFlag.p, B->largeShapes.p);
+	size_t tb = B->cubTemp.cap;
+	cub::DeviceSelect::Flagged(B->cubTemp.p, tb, thrust::counting_iterator<int>(0), B->movedFlag.p, B->movedLeaves.p,
+							   B->counters.p + BC_MOVED, shapeCap, st);
+	w->kernelLaunches += 2;
+	S2B_LAUNCH(w, s2bFindPairs, gridFor(shapeCap, 128), 128, 0, sv, bv, B->leafShape.p, B->leafOut.p, B->counters.p,
+			   B->movedLeaves.p, B->children.p, B->pairBox.p, B->pairHash.p, B->hashMask, w->jointPairKeys.p, w->jointPairCount,
+			   B->newKey.p, B->newShapes.p, newCap);
+	S2B_LAUNCH(w, s2bFindPairsLarge, gridFor(shapeCap, 256), 256, 0, sv, bv, B->leafShape.p, B->counters.p, B->largeShapes.p,
+			   B->pairHash.p, B->hashMask, w->jointPairKeys.p, w->jointPairCount, B->newKey.p, B->newShapes.p, newCap);
 
-		int total = kept + fresh;
-		if (fresh == 0 && kept == oldCount)
-		{
-			// the moved proxies still overlap exactly the shapes they overlapped before: the contact table stands as it is
-			// (the usual outcome on a slowly settling pile)
-			break;
-		}
+	// ---- survivors ----
+	if (oldCount > 0)
+	{
+		S2B_LAUNCH(w, s2bFlagKeptContacts, gridFor(oldCount, 256), 256, 0, makeView(cur), oldCount, sv, w->jointDestroyKeys.p,
+				   w->jointDestroyCount, B->keepFlag.p);
+		tb = B->cubTemp.cap;
+		cub::DeviceSelect::Flagged(B->cubTemp.p, tb, thrust::counting_iterator<int>(0), B->keepFlag.p, B->keepSlots.p,
+								   B->counters.p + BC_KEPT, oldCount, st);
+		w->kernelLaunches += 2;
+	}
+	S2B_CHECK(cudaMemcpyAsync(w->hostMail + MAIL_BC_BASE, B->counters.p, sizeof(int) * BC_SIZE, cudaMemcpyDeviceToHost, st));
+	B->searchedCount = oldCount;
+	B->searchedVersion = w->contactTableVersion;
+}
+
+// Second half: the host knows how many candidate pairs and survivors the search found. Merge them into the other column
+// set (or leave the table as it is), clear the MOVED / FRESH flags.
+static void bpCommit(s2bWorld* w, BroadScratch* B, int fresh, int kept, size_t tempBytes)
+{
+	cudaStream_t st = w->stream;
+	int shapeCap = w->shapeCap;
+	int oldCount = w->contactCount;
+	ShapeView sv = shapeView(w);
+	ContactColumns& cur = w->contacts[w->cur];
+	ContactColumns& nxt = w->contacts[w->cur ^ 1];
+	int total = kept + fresh;
+	if (fresh == 0 && kept == oldCount)
+	{
+		// the moved proxies still overlap exactly the shapes they overlapped before: the contact table stands as it is
+		// (the usual outcome on a slowly settling pile)
+	}
+	else
+	{
 		nxt.reserve((size_t)std::max(total, 1), st, w->sticky, false);
 		if (total > 0)
 		{
+			size_t need = 0;
 			B->mergeKeyIn.reserve((size_t)total, st, false);
 			B->mergeKeyOut.reserve((size_t)total, st, false);
 			B->mergeSrcIn.reserve((size_t)total, st, false);
@@ -1045,7 +1049,7 @@ void s2bBroadphaseUpdatePairs(s2bWorld* w)
 			}
 			S2B_LAUNCH(w, s2bMergeKeys, gridFor(total, 256), 256, 0, B->counters.p, B->keepSlots.p, cur.key.p, B->newKey.p,
 					   B->mergeKeyIn.p, B->mergeSrcIn.p, total, shapeBits);
-			tb = B->cubTemp.cap;
+			size_t tb = B->cubTemp.cap;
 			cub::DeviceRadixSort::SortPairs(B->cubTemp.p, tb, B->mergeKeyIn.p, B->mergeKeyOut.p, B->mergeSrcIn.p, B->mergeSrcOut.p,
 											total, 0, 2 * shapeBits, st);
 			w->kernelLaunches += 9;
@@ -1067,11 +1071,131 @@ void s2bBroadphaseUpdatePairs(s2bWorld* w)
 			}
 			B->pairHash.reserve((size_t)size, st, false, false);
 		}
-		break;
 	}
-
 	S2B_LAUNCH(w, s2bClearMovedFlags, gridFor(shapeCap, 256), 256, 0, sv, w->dMovedFlag.p);
 	w->hostMail[MAIL_MOVED] = 0;
 	w->pairsDirty = false;
 	w->pairPassCount += 1;
+}
+
+// Start the pair search of the NEXT step behind this one (called after finalize): its inputs — fat AABBs, MOVED flags, the
+// contact table — are final once finalize has run, and its counters then reach the host together with the end of the step,
+// which the caller waits for anyway before it reads results. The next s2b_update_pairs picks the result up without having to
+// stop in the middle of the pass. Anything the host uploads in between invalidates the search (uploadEpoch).
+void s2bPrefetchPairSearch(s2bWorld* w)
+{
+	S2bEpochFreeze freeze;
+	BroadScratch* B = getBroad(w);
+	B->prefetched = false;
+	// only scenes in motion: on a settled scene nothing is enqueued and the next pass is skipped from the moved counter alone
+	if (w->prefetchPairs == 0 || w->shapeCap == 0 || B->lastPassRan == false || w->pairsDirty)
+	{
+		return;
+	}
+	if (B->evSearch[0] == nullptr)
+	{
+		S2B_CHECK(cudaEventCreate(&B->evSearch[0]));
+		S2B_CHECK(cudaEventCreate(&B->evSearch[1]));
+		S2B_CHECK(cudaEventCreateWithFlags(&B->searchDone, cudaEventDisableTiming));
+	}
+	B->prefetchTempBytes = bpReserve(w, B);
+	S2B_CHECK(cudaEventRecord(B->evSearch[0], w->stream));
+	bpSearch(w, B);
+	S2B_CHECK(cudaEventRecord(B->evSearch[1], w->stream));
+	S2B_CHECK(cudaEventRecord(B->searchDone, w->stream));
+	B->prefetched = true;
+	B->prefetchEpoch = w->uploadEpoch;
+	B->searchTimed = true;
+}
+
+float s2bLastPairSearchMs(s2bWorld* w)
+{
+	BroadScratch* B = w->broad;
+	if (B == nullptr || B->searchTimed == false)
+	{
+		return 0.0f;
+	}
+	float ms = 0.0f;
+	if (cudaEventQuery(B->evSearch[1]) == cudaSuccess)
+	{
+		cudaEventElapsedTime(&ms, B->evSearch[0], B->evSearch[1]);
+	}
+	return ms;
+}
+
+void s2bBroadphaseUpdatePairs(s2bWorld* w)
+{
+	// scratch of this pass is not referenced by the solver's graph; a REPLACED contact table is, and shows up in the graph
+	// signature through w->cur / w->contactCount / w->contactTableVersion
+	S2bEpochFreeze freeze;
+	cudaStream_t st = w->stream;
+	BroadScratch* B = getBroad(w);
+	w->dMovedFlag.reserve(4, st, true);
+
+	// ---- the search was started behind the previous step: its counters are (about to be) in the mailbox ----
+	if (B->prefetched)
+	{
+		B->prefetched = false;
+		bool valid = w->pairsDirty == false && B->prefetchEpoch == w->uploadEpoch && B->searchedVersion == w->contactTableVersion &&
+					 B->searchedCount == w->contactCount && w->prefetchPairs == 1; // (2: search but never use the result — debugging)
+		if (valid)
+		{
+			S2B_CHECK(cudaEventSynchronize(B->searchDone));
+			S2B_CHECK(cudaEventRecord(w->timer.ev[0], st));
+			const int* hc = w->hostMail + MAIL_BC_BASE;
+			int fresh = hc[BC_NEW_PAIRS], kept = hc[BC_KEPT];
+			if (fresh <= B->newPairCap)
+			{
+				w->treeHeight = hc[BC_HEIGHT];
+				B->lastPassRan = hc[BC_MOVED] > 0 || hc[BC_LARGE] > 0;
+				bpCommit(w, B, fresh, kept, B->prefetchTempBytes);
+				return;
+			}
+			B->newPairCap = fresh + fresh / 2 + 1024; // rare: redo the pass below with a larger pair buffer
+		}
+		// (something was uploaded since: the search is stale — e.g. new shapes — and is redone)
+	}
+
+	// Did anything move in the last finalize? The counter was copied to the pinned mailbox at the end of the previous
+	// step; wait for that copy (normally long done) and read it.
+	bool run = w->pairsDirty;
+	if (run == false)
+	{
+		// (wait for THAT copy only — not for whatever the caller has enqueued since: force uploads, row scatters — so that the
+		// kernels of this step can be queued behind them without the host idling)
+		if (w->movedEvent != nullptr)
+		{
+			S2B_CHECK(cudaEventSynchronize(w->movedEvent));
+		}
+		else
+		{
+			S2B_CHECK(cudaStreamSynchronize(st));
+		}
+		run = w->hostMail[MAIL_MOVED] > 0;
+	}
+	S2B_CHECK(cudaEventRecord(w->timer.ev[0], st));
+	B->lastPassRan = run && w->shapeCap > 0;
+	if (run == false || w->shapeCap == 0)
+	{
+		return;
+	}
+
+	for (int attempt = 0; attempt < 4; ++attempt)
+	{
+		size_t tempBytes = bpReserve(w, B);
+		bpSearch(w, B);
+		// the new table size has to be known on the host (column reservation): one small synchronising read-back, paid only
+		// when the search could not be started behind the previous step (first steps, after uploads, settled scenes)
+		S2B_CHECK(cudaStreamSynchronize(st));
+		const int* hc = w->hostMail + MAIL_BC_BASE;
+		int fresh = hc[BC_NEW_PAIRS], kept = hc[BC_KEPT];
+		if (fresh > B->newPairCap)
+		{
+			B->newPairCap = fresh + fresh / 2 + 1024;
+			continue; // rare: redo the pass with a larger pair buffer
+		}
+		w->treeHeight = hc[BC_HEIGHT];
+		bpCommit(w, B, fresh, kept, tempBytes);
+		break;
+	}
 }

@@ -358,6 +358,8 @@ struct s2bWorld
 
 	// broad phase
 	bool pairsDirty = true; // host-side structural change
+	unsigned long long uploadEpoch = 0; // bumped by every row upload: a pair search started before it is stale
+	int prefetchPairs = 1;	// start the pair search of the next step behind finalize (S2B_PREFETCH_PAIRS=0: off)
 	DevArray<int> dMovedFlag; // [0] = number of proxies moved in last finalize (device counter)
 	int pairPassCount = 0;
 	int treeHeight = 0;
@@ -461,6 +463,8 @@ inline int gridFor(int n, int block)
 
 // stage entry points implemented in the other translation units
 void s2bBroadphaseUpdatePairs(s2bWorld* w);
+void s2bPrefetchPairSearch(s2bWorld* w);
+float s2bLastPairSearchMs(s2bWorld* w);
 void s2bNarrowphaseUpdate(s2bWorld* w);
 void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctx);
 void s2bFinalize(s2bWorld* w);

@@ -344,6 +344,11 @@ extern "C" s2bWorld* s2b_world_create(int cudaDevice, int solverType)
 		{
 			w->useGraph = atoi(env) != 0 ? 1 : 0;
 		}
+		env = getenv("S2B_PREFETCH_PAIRS");
+		if (env != nullptr)
+		{
+			w->prefetchPairs = atoi(env);
+		}
 		env = getenv("S2B_PERSISTENT");
 		if (env != nullptr)
 		{
@@ -582,6 +587,7 @@ extern "C" void s2b_upload_bodies(s2bWorld* w, const s2bBodyRow* rows, int count
 	{
 		return;
 	}
+	w->uploadEpoch += 1; // rows changed: a pair search started behind the previous step is stale now
 	s2bBodyRow* d = (s2bBodyRow*)stageRows(w, rows, sizeof(s2bBodyRow) * (size_t)count);
 	S2B_LAUNCH(w, s2bScatterBodies, gridFor(count, 128), 128, 0, d, count, bodyView(w), w->schedDirty.p);
 	S2B_CHECK(cudaFreeAsync(d, w->stream));
@@ -597,6 +603,7 @@ extern "C" void s2b_upload_shapes(s2bWorld* w, const s2bShapeRow* rows, int coun
 	{
 		return;
 	}
+	w->uploadEpoch += 1; // rows changed: a pair search started behind the previous step is stale now
 	s2bShapeRow* d = (s2bShapeRow*)stageRows(w, rows, sizeof(s2bShapeRow) * (size_t)count);
 	S2B_LAUNCH(w, s2bScatterShapes, gridFor(count, 128), 128, 0, d, count, shapeView(w));
 	S2B_CHECK(cudaFreeAsync(d, w->stream));
@@ -612,6 +619,7 @@ extern "C" void s2b_upload_joints(s2bWorld* w, const s2bJointRow* rows, int coun
 	{
 		return;
 	}
+	w->uploadEpoch += 1; // rows changed: a pair search started behind the previous step is stale now
 	s2bJointRow* d = (s2bJointRow*)stageRows(w, rows, sizeof(s2bJointRow) * (size_t)count);
 	S2B_LAUNCH(w, s2bScatterJoints, gridFor(count, 128), 128, 0, d, count, jointView(w), w->schedDirty.p);
 	S2B_CHECK(cudaFreeAsync(d, w->stream));
@@ -620,6 +628,7 @@ extern "C" void s2b_upload_joints(s2bWorld* w, const s2bJointRow* rows, int coun
 
 extern "C" void s2b_upload_contacts(s2bWorld* w, const s2bContactRow* rows, int count)
 {
+	w->uploadEpoch += 1; // a pair search started behind the previous step is stale now
 	S2B_CHECK(cudaSetDevice(w->device));
 	ContactColumns& c = w->contacts[w->cur];
 	c.reserve((size_t)(count > 0 ? count : 1), w->stream, w->sticky, false);
@@ -638,6 +647,7 @@ extern "C" void s2b_upload_contacts(s2bWorld* w, const s2bContactRow* rows, int 
 extern "C" void s2b_upload_joint_pairs(s2bWorld* w, const uint64_t* blockKeys, int blockCount, const uint64_t* destroyKeys,
 									   int destroyCount)
 {
+	w->uploadEpoch += 1; // a pair search started behind the previous step is stale now
 	S2B_CHECK(cudaSetDevice(w->device));
 	w->jointPairKeys.reserve((size_t)(blockCount > 0 ? blockCount : 1), w->stream, false);
 	w->jointDestroyKeys.reserve((size_t)(destroyCount > 0 ? destroyCount : 1), w->stream, false);
@@ -1035,12 +1045,19 @@ extern "C" void s2b_finalize(s2bWorld* w)
 	w->timer.recorded = true;
 }
 
+extern "C" void s2b_prefetch_pairs(s2bWorld* w)
+{
+	S2B_CHECK(cudaSetDevice(w->device));
+	s2bPrefetchPairSearch(w);
+}
+
 extern "C" void s2b_step(s2bWorld* w, int solverType, const s2bStepContext* context)
 {
 	s2b_update_pairs(w);
 	s2b_update_contacts(w);
 	s2b_solve(w, solverType, context);
 	s2b_finalize(w);
+	s2b_prefetch_pairs(w);
 }
 
 extern "C" void s2b_last_stage_ms(s2bWorld* w, float out[4])
@@ -1059,6 +1076,8 @@ extern "C" void s2b_last_stage_ms(s2bWorld* w, float out[4])
 	{
 		S2B_CHECK(cudaEventElapsedTime(out + i, w->timer.ev[i], w->timer.ev[i + 1]));
 	}
+	// the search half of the pair pass runs behind finalize (s2b_prefetch_pairs): the last finished one is charged to "pairs"
+	out[0] += s2bLastPairSearchMs(w);
 }
 
 extern "C" float s2b_timed_steps(s2bWorld* w, int solverType, const s2bStepContext* context, int steps)

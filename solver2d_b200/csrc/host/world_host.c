@@ -621,6 +621,9 @@ void s2World_Step(s2WorldId worldId, float timeStep, int32_t velIters, int32_t p
 
 	// stage 4 (reference src/world.c:258-301); also zeroes the applied forces on the device
 	s2b_finalize(world->device);
+	// the pair search of the NEXT step (reference src/broad_phase.c:309-367: s2UpdateBroadPhasePairs) only needs what finalize
+	// has just produced: start it now, so that the next step finds its counters waiting instead of stopping mid-pass
+	s2b_prefetch_pairs(world->device);
 
 	// forces are consumed by the step (reference src/world.c:275-276)
 	world->stateFresh = false;
