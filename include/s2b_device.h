@@ -180,7 +180,7 @@ typedef struct s2bCounters
 	int32_t regionCount;	 // region-local schedule: regions (= blocks of the persistent kernel) of the last solve, 0 = off
 	int32_t cutCount;		 // constraints that straddle two regions (solved in device-wide steps)
 	int32_t cutGroupCount;	 // colours of the cut set = device-wide steps per Gauss-Seidel sweep
-	int32_t reserved0;
+	int32_t recolouredCount; /* constraints moved out of a sparse top colour by Kempe chains so far (colouring) */
 } s2bCounters;
 
 // ---- lifecycle ------------------------------------------------------------------------------------------------

@@ -319,12 +319,14 @@ struct ContactStream
 	float4 nf;
 	float4 la0, la1, pm0, pm1;
 	float2 l0, l1;
+	int slot; // contact slot of the row (only loaded by the sweep that also stores the impulses to the manifold)
 };
 
-__device__ __forceinline__ ContactStream s2bLoadContactStream(const SolveArgs& a, int t)
+__device__ __forceinline__ ContactStream s2bLoadContactStream(const SolveArgs& a, int t, bool withSlot = false)
 {
 	const ConstraintView& cc = a.cc;
 	ContactStream cs;
+	cs.slot = withSlot ? cc.src[t] : -1;
 	cs.idx = cc.idx[t];
 	cs.nf = cc.nf[t];
 	cs.la0 = cc.anchor[0][t];
@@ -336,8 +338,11 @@ __device__ __forceinline__ ContactStream s2bLoadContactStream(const SolveArgs& a
 	return cs;
 }
 
+// storeManifold: this is the last sweep of the step — the accumulated impulses also go to the persistent manifold
+// (s2StoreContactImpulses, reference src/solve_common.c:396-410, folded into the sweep: the values are in registers here and
+// a separate pass would cost a device-wide barrier plus a dependent slot -> manifold round trip per constraint).
 __device__ __forceinline__ void s2bSolveContactTgsSoftStream(const SolveArgs& a, int t, const ContactStream& cs, float inv_h, bool useBias,
-															 bool writeWarm = false)
+															 bool writeWarm = false, bool storeManifold = false)
 {
 	const ConstraintView& cc = a.cc;
 	int2 idx = cs.idx;
@@ -451,15 +456,29 @@ __device__ __forceinline__ void s2bSolveContactTgsSoftStream(const SolveArgs& a,
 	{
 		s2bWriteWarmImpulses(a, t, normal, tangent, pointCount, lam[0], lam[1]);
 	}
+	if (storeManifold)
+	{
+		// (.x separation and .w stay as the narrow phase left them: two scalar stores instead of a read-modify-write)
+		float* m0 = reinterpret_cast<float*>(a.contacts.impulse[0] + cs.slot);
+		m0[1] = lam[0].x;
+		m0[2] = lam[0].y;
+		if (pointCount == 2)
+		{
+			float* m1 = reinterpret_cast<float*>(a.contacts.impulse[1] + cs.slot);
+			m1[1] = lam[1].x;
+			m1[2] = lam[1].y;
+		}
+	}
 	BodyPair bp = {ia, ib, velA, velB, (mA != 0.0f) || (iA != 0.0f), (mB != 0.0f) || (iB != 0.0f)};
 	s2bStoreVelocities(a, bp, vA, wA, vB, wB);
 }
 
 // writeWarm: this is the last pass that changes the impulses before the next sub-step's warm-start gather
-__device__ __forceinline__ void s2bSolveContactTgsSoft(const SolveArgs& a, int t, float inv_h, bool useBias, bool writeWarm = false)
+__device__ __forceinline__ void s2bSolveContactTgsSoft(const SolveArgs& a, int t, float inv_h, bool useBias, bool writeWarm = false,
+													   bool storeManifold = false)
 {
-	ContactStream cs = s2bLoadContactStream(a, t);
-	s2bSolveContactTgsSoftStream(a, t, cs, inv_h, useBias, writeWarm);
+	ContactStream cs = s2bLoadContactStream(a, t, storeManifold);
+	s2bSolveContactTgsSoftStream(a, t, cs, inv_h, useBias, writeWarm, storeManifold);
 }
 
 // ===============================================================================================================

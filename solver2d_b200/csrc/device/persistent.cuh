@@ -328,27 +328,28 @@ __device__ __forceinline__ void s2bGroupPass(int jointOp, int contactOp, const S
 		{
 			continue; // uniform: every thread reads the same table
 		}
-		if (SOLVER == 7 && (contactOp == COP_TGS_SOFT_BIAS || contactOp == COP_TGS_SOFT_RELAX) && nj == 0)
+		if (SOLVER == 7 && (contactOp == COP_TGS_SOFT_BIAS || contactOp == COP_TGS_SOFT_RELAX || contactOp == COP_TGS_SOFT_RELAX_STORE) && nj == 0)
 		{
 			// The headline op. Nothing in a thread's constraint row is written by another thread (the impulses by this very
 			// thread, one sweep ago), so the row is fetched BEFORE the barrier: what remains after it is the dependent part
 			// proper — the two bodies, the arithmetic, the stores (one L2 round trip less per device-wide step).
 			bool mine = tid < nc;
+			bool store = contactOp == COP_TGS_SOFT_RELAX_STORE;
 			ContactStream cs;
 			if (mine)
 			{
-				cs = s2bLoadContactStream(a, cBegin + tid);
+				cs = s2bLoadContactStream(a, cBegin + tid, store);
 			}
 			s2bSyncBeforeGlobal(a, sync);
 			bool bias = contactOp == COP_TGS_SOFT_BIAS;
 			bool writeWarm = bias ? a.ctx.extraIterations == 0 : true;
 			if (mine)
 			{
-				s2bSolveContactTgsSoftStream(a, cBegin + tid, cs, a.ctx.inv_h, bias, writeWarm);
+				s2bSolveContactTgsSoftStream(a, cBegin + tid, cs, a.ctx.inv_h, bias, writeWarm, store);
 			}
 			for (int t = tid + stride; t < nc; t += stride)
 			{
-				s2bSolveContactTgsSoft(a, cBegin + t, a.ctx.inv_h, bias, writeWarm);
+				s2bSolveContactTgsSoft(a, cBegin + t, a.ctx.inv_h, bias, writeWarm, store);
 			}
 		}
 		else
@@ -696,6 +697,10 @@ template <int SOLVER> __global__ void __launch_bounds__(S2B_BLOCK) s2bPersistent
 						sync.pending = S2B_PENDING_GLOBAL;
 						sync.code = code;
 					}
+				}
+				else if ((pass.jointOp == JOP_NONE || li.nJ == 0) && (pass.contactOp == COP_NONE || li.nC == 0))
+				{
+					// nothing to do for anybody (the counts are grid-uniform): no barrier either
 				}
 				else
 				{

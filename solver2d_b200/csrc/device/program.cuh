@@ -67,6 +67,7 @@ enum ContactOp
 	COP_BLOCK_POSITION,
 	COP_STORE,
 	COP_STORE_SCALED, // XPBD stores impulse * inv_h
+	COP_TGS_SOFT_RELAX_STORE, // the LAST relax sweep of TGS_Soft: also writes the impulses to the manifolds (no separate store pass)
 };
 
 enum JointOp
@@ -162,6 +163,7 @@ __host__ __device__ constexpr bool s2bUsesContactOp(int solver, int op)
 			return solver == 3 || solver == 5;
 		case COP_TGS_SOFT_BIAS:
 		case COP_TGS_SOFT_RELAX:
+		case COP_TGS_SOFT_RELAX_STORE:
 			return solver == 7;
 		case COP_PGS_BAUMGARTE:
 			return solver == 1;
@@ -368,6 +370,12 @@ template <int SOLVER> __device__ __forceinline__ void s2bRunContactOpT(int op, c
 			if constexpr (s2bUsesContactOp(SOLVER, COP_TGS_SOFT_RELAX))
 			{
 				s2bSolveContactTgsSoft(a, t, inv_h, false, true);
+			}
+			break;
+		case COP_TGS_SOFT_RELAX_STORE:
+			if constexpr (s2bUsesContactOp(SOLVER, COP_TGS_SOFT_RELAX_STORE))
+			{
+				s2bSolveContactTgsSoft(a, t, inv_h, false, true, true);
 			}
 			break;
 		case COP_PGS_BAUMGARTE:

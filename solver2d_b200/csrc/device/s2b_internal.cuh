@@ -360,6 +360,8 @@ struct s2bWorld
 	bool pairsDirty = true; // host-side structural change
 	unsigned long long uploadEpoch = 0; // bumped by every row upload: a pair search started before it is stale
 	int prefetchPairs = 1;	// start the pair search of the next step behind finalize (S2B_PREFETCH_PAIRS=0: off)
+	int kempe = 1;		// empty a sparse top colour by Kempe chains after colouring (S2B_KEMPE=0 disables)
+	int kempeGrid = 0;
 	DevArray<int> dMovedFlag; // [0] = number of proxies moved in last finalize (device counter)
 	int pairPassCount = 0;
 	int treeHeight = 0;

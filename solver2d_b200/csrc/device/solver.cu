@@ -62,6 +62,9 @@ void s2bFreeSolverScratch(s2bWorld* w)
 	s->colorA.release();
 	s->colorB.release();
 	s->colorC.release();
+	s->kempeState.release();
+	s->kempeClaim.release();
+	s->kempePath.release();
 	s->itemRegion.release();
 	s->sortKeyIn.release();
 	s->sortKeyOut.release();
@@ -548,6 +551,359 @@ __global__ void __launch_bounds__(256) s2bColorKernel(int* counts, const int2* i
 		{
 			break;
 		}
+	}
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Emptying a sparse top colour (Kempe chains).
+//
+// Greedy colouring of a regular contact lattice ends with a handful of stragglers in one colour too many (36 of the 299 490
+// constraints of the 100 k-box pyramid sit alone in a 7th colour; every box touches 6 others, so 6 is the optimum) — and
+// every colour costs the solver one device-wide step per sweep, however few constraints it holds. A straggler e = (u, v)
+// of the top colour has a colour `alpha` free at u and a colour `beta` free at v (its bodies have fewer neighbours than
+// there are colours below), just never the same one. The constraints coloured alpha or beta form paths that alternate
+// between the two; swapping the two colours along the path that starts at v frees alpha at v as well — unless that path
+// ends at u — and e takes alpha (Vizing's argument for edge colourings; ours is one: constraints are the edges of the body
+// graph). Static bodies end a path: they constrain nothing.
+//
+// One block per straggler walks its path (read-only, recorded); then every walker claims the bodies of its path
+// (atomicMin of its rank, rank = order of the item indices, so the winners do not depend on timing); the walkers that own
+// all their bodies swap. Paths of different winners share no body, hence no constraint, and what a walk read is still true
+// when it is applied. Losers walk again next round. The walks are long dependent chains (up to S2B_KEMPE_MAX_HOPS hops of
+// a few L2 round trips each — milliseconds), paid once: colours persist, and a top colour that could not be emptied is
+// left alone for the next S2B_KEMPE_BACKOFF rebuilds.
+// ---------------------------------------------------------------------------------------------------------------
+#define S2B_KEMPE_MAX_ITEMS 64
+#define S2B_KEMPE_MAX_HOPS 4096
+#define S2B_KEMPE_ROUNDS 6
+#define S2B_KEMPE_MAX_DEGREE 32
+#define S2B_KEMPE_BACKOFF 32
+
+enum
+{
+	KS_BACKOFF = 0, // rebuilds to sit out (persists from launch to launch)
+	KS_RUNS = 1,	// statistics: launches that walked, stragglers recoloured
+	KS_FIXED = 2,
+	KS_HIST = 8,	  // 64: items per colour
+	KS_CURSOR = 72,	  // fill cursor of the straggler list
+	KS_PROGRESS = 80, // 8: stragglers recoloured in round r
+	KS_REMAINING = 88, // 8: stragglers still in the top colour after round r
+	KS_LIST = 96,	   // 64: the stragglers (item indices)
+	KS_LENGTH = 160,   // 64: recorded path length, -1 no usable path, -2 no longer a straggler
+	KS_ALPHA = 224,	   // 64
+	KS_BETA = 288,	   // 64
+	KS_SIZE = 352
+};
+
+// colours held by the items around `body` (every item but `skip`); *hub is raised when the body has too many to bother
+__device__ __forceinline__ unsigned long long s2bColoursAround(const int* adjStart, const int* adj, const int* color, int body, int skip, bool* hub)
+{
+	int begin = adjStart[body], end = adjStart[body + 1];
+	if (end - begin > S2B_KEMPE_MAX_DEGREE)
+	{
+		*hub = true;
+		return ~0ull;
+	}
+	unsigned long long used = 0ull;
+	for (int k = begin; k < end; ++k)
+	{
+		int j = adj[k];
+		int c = color[j];
+		if (j != skip && c >= 0 && c < S2B_MAX_COLORS)
+		{
+			used |= 1ull << c;
+		}
+	}
+	return used;
+}
+
+// the alpha/beta path from v for straggler `item` = (u, v); records its constraints; returns the length or -1
+__device__ __forceinline__ int s2bKempeWalk(const int2* itemBodies, const int* adjStart, const int* adj, const int* color, int item, int u, int v,
+											 int alpha, int beta, int* path)
+{
+	int body = v, want = alpha, length = 0;
+	for (;;)
+	{
+		int begin = adjStart[body], end = adjStart[body + 1];
+		if (end - begin > S2B_KEMPE_MAX_DEGREE)
+		{
+			return -1;
+		}
+		int next = -1;
+		for (int k = begin; k < end; ++k)
+		{
+			int j = adj[k];
+			if (j != item && color[j] == want)
+			{
+				next = j;
+			}
+		}
+		if (next < 0)
+		{
+			return length; // dead end: `want` is free here
+		}
+		if (length == S2B_KEMPE_MAX_HOPS)
+		{
+			return -1;
+		}
+		path[length++] = next;
+		int2 e = itemBodies[next];
+		int other = e.x == body ? e.y : e.x;
+		if (other < 0)
+		{
+			return length; // a body that cannot move ends the path
+		}
+		if (other == u)
+		{
+			return -1; // the swap would take alpha away from u
+		}
+		body = other;
+		want = want == alpha ? beta : alpha;
+	}
+}
+
+__global__ void __launch_bounds__(256) s2bKempeKernel(const int* counts, const int2* itemBodies, const int* adjStart, const int* adj, int* color,
+													  int* state, int* claim, int* paths, int bodyCapacity)
+{
+	cg::grid_group grid = cg::this_grid();
+	// only when the colouring kernel had something to colour (a settled scene costs this launch and nothing else)
+	if (counts[CNT_UNCOLOURED] == 0)
+	{
+		return;
+	}
+	int tid = blockIdx.x * blockDim.x + threadIdx.x;
+	int stride = gridDim.x * blockDim.x;
+	int n = counts[CNT_JOINTS] + counts[CNT_CONTACTS];
+	int backoff = *((volatile int*)(state + KS_BACKOFF));
+	grid.sync(); // (everybody has read the word before thread 0 changes it)
+	if (backoff > 0)
+	{
+		if (tid == 0)
+		{
+			state[KS_BACKOFF] = backoff - 1;
+		}
+		return;
+	}
+
+	__shared__ int hist[S2B_MAX_COLORS];
+	for (int attempt = 0; attempt < 2; ++attempt)
+	{
+		for (int k = tid; k < KS_SIZE - KS_HIST; k += stride)
+		{
+			state[KS_HIST + k] = 0;
+		}
+		if (threadIdx.x < S2B_MAX_COLORS)
+		{
+			hist[threadIdx.x] = 0;
+		}
+		__syncthreads();
+		grid.sync();
+		for (int i = tid; i < n; i += stride)
+		{
+			int c = color[i];
+			if (c >= 0 && c < S2B_MAX_COLORS)
+			{
+				atomicAdd(&hist[c], 1);
+			}
+		}
+		__syncthreads();
+		if (threadIdx.x < S2B_MAX_COLORS && hist[threadIdx.x] > 0)
+		{
+			atomicAdd(state + KS_HIST + threadIdx.x, hist[threadIdx.x]);
+		}
+		grid.sync();
+		int top = -1;
+		for (int c = S2B_MAX_COLORS - 1; c >= 0; --c)
+		{
+			if (*((volatile int*)(state + KS_HIST + c)) > 0)
+			{
+				top = c;
+				break;
+			}
+		}
+		int nTop = top >= 0 ? *((volatile int*)(state + KS_HIST + top)) : 0;
+		if (top < 2 || nTop > S2B_KEMPE_MAX_ITEMS)
+		{
+			return; // uniform. Nothing sparse on top: the colouring stands
+		}
+		for (int i = tid; i < n; i += stride)
+		{
+			if (color[i] == top)
+			{
+				state[KS_LIST + atomicAdd(state + KS_CURSOR, 1)] = i;
+			}
+		}
+		if (tid == 0)
+		{
+			state[KS_RUNS] += 1;
+		}
+		__threadfence();
+		grid.sync();
+
+		bool emptied = false;
+		for (int round = 0; round < S2B_KEMPE_ROUNDS; ++round)
+		{
+			for (int b = tid; b <= bodyCapacity; b += stride)
+			{
+				claim[b] = 0x7FFFFFFF;
+			}
+			// ---- walk (one thread of a block per straggler) ----
+			if (threadIdx.x == 0)
+			{
+				for (int q = blockIdx.x; q < nTop; q += gridDim.x)
+				{
+					int item = state[KS_LIST + q];
+					int* path = paths + (size_t)q * S2B_KEMPE_MAX_HOPS;
+					int length = -1, alphaOut = -1, betaOut = -1;
+					if (color[item] != top)
+					{
+						length = -2;
+					}
+					else
+					{
+						int2 e = itemBodies[item];
+						bool hub = false;
+						if (e.x >= 0 && e.y >= 0)
+						{
+							unsigned long long below = (1ull << top) - 1ull;
+							unsigned long long freeU = ~s2bColoursAround(adjStart, adj, color, e.x, item, &hub) & below;
+							unsigned long long freeV = ~s2bColoursAround(adjStart, adj, color, e.y, item, &hub) & below;
+							if (hub == false && (freeU & freeV) != 0ull)
+							{
+								// (earlier swaps around it left a common colour)
+								alphaOut = __ffsll((long long)(freeU & freeV)) - 1;
+								betaOut = alphaOut;
+								length = 0;
+							}
+							else if (hub == false)
+							{
+								for (unsigned long long fu = freeU; fu != 0ull && length < 0; fu &= fu - 1ull)
+								{
+									int alpha = __ffsll((long long)fu) - 1;
+									for (unsigned long long fv = freeV; fv != 0ull && length < 0; fv &= fv - 1ull)
+									{
+										int beta = __ffsll((long long)fv) - 1;
+										length = s2bKempeWalk(itemBodies, adjStart, adj, color, item, e.x, e.y, alpha, beta, path);
+										alphaOut = alpha;
+										betaOut = beta;
+									}
+								}
+							}
+						}
+					}
+					state[KS_LENGTH + q] = length;
+					state[KS_ALPHA + q] = alphaOut;
+					state[KS_BETA + q] = betaOut;
+				}
+			}
+			__threadfence();
+			grid.sync();
+			// ---- claim ----
+			if (threadIdx.x == 0)
+			{
+				for (int q = blockIdx.x; q < nTop; q += gridDim.x)
+				{
+					int length = state[KS_LENGTH + q];
+					if (length < 0)
+					{
+						continue;
+					}
+					int item = state[KS_LIST + q];
+					int rank = 0;
+					for (int k = 0; k < nTop; ++k)
+					{
+						rank += state[KS_LIST + k] < item ? 1 : 0;
+					}
+					const int* path = paths + (size_t)q * S2B_KEMPE_MAX_HOPS;
+					int2 e = itemBodies[item];
+					atomicMin(claim + e.x, rank);
+					atomicMin(claim + e.y, rank);
+					for (int k = 0; k < length; ++k)
+					{
+						int2 pe = itemBodies[path[k]];
+						if (pe.x >= 0)
+						{
+							atomicMin(claim + pe.x, rank);
+						}
+						if (pe.y >= 0)
+						{
+							atomicMin(claim + pe.y, rank);
+						}
+					}
+				}
+			}
+			__threadfence();
+			grid.sync();
+			// ---- swap where every body of the path is ours ----
+			if (threadIdx.x == 0)
+			{
+				for (int q = blockIdx.x; q < nTop; q += gridDim.x)
+				{
+					int length = state[KS_LENGTH + q];
+					if (length == -2)
+					{
+						continue;
+					}
+					bool mine = length >= 0;
+					int item = state[KS_LIST + q];
+					const int* path = paths + (size_t)q * S2B_KEMPE_MAX_HOPS;
+					if (mine)
+					{
+						int rank = 0;
+						for (int k = 0; k < nTop; ++k)
+						{
+							rank += state[KS_LIST + k] < item ? 1 : 0;
+						}
+						int2 e = itemBodies[item];
+						mine = claim[e.x] == rank && claim[e.y] == rank;
+						for (int k = 0; k < length && mine; ++k)
+						{
+							int2 pe = itemBodies[path[k]];
+							mine = (pe.x < 0 || claim[pe.x] == rank) && (pe.y < 0 || claim[pe.y] == rank);
+						}
+					}
+					if (mine)
+					{
+						int alpha = state[KS_ALPHA + q], beta = state[KS_BETA + q];
+						for (int k = 0; k < length; ++k)
+						{
+							int j = path[k];
+							color[j] = color[j] == alpha ? beta : alpha;
+						}
+						color[item] = alpha;
+						atomicAdd(state + KS_PROGRESS + round, 1);
+						atomicAdd(state + KS_FIXED, 1);
+					}
+					else
+					{
+						atomicAdd(state + KS_REMAINING + round, 1);
+					}
+				}
+			}
+			__threadfence();
+			grid.sync();
+			int progress = *((volatile int*)(state + KS_PROGRESS + round));
+			int remaining = *((volatile int*)(state + KS_REMAINING + round));
+			if (remaining == 0)
+			{
+				emptied = true;
+				break;
+			}
+			if (progress == 0)
+			{
+				break;
+			}
+		}
+		if (emptied == false)
+		{
+			if (tid == 0)
+			{
+				state[KS_BACKOFF] = S2B_KEMPE_BACKOFF;
+			}
+			return;
+		}
+		grid.sync(); // (the state words are reset at the top of the next attempt)
 	}
 }
 
@@ -1723,28 +2079,35 @@ static Program buildProgram(int solverType, const s2bStepContext& ctx, bool gath
 			bool softStep = solverType == 5;
 			b.segment(1);
 			b.add(flatPass(JOP_PREPARE_SOFT_WARM, COP_PREPARE));
-			b.segment(S);
-			if (warm && gatherWarm)
+			// TGS_Soft with relax sweeps: the last sub-step's relax sweep also writes the impulses to the manifolds
+			// (COP_TGS_SOFT_RELAX_STORE), so the closing store pass only has the joints left
+			bool foldStore = softStep == false && E > 0 && S > 0;
+			for (int part = 0; part < (foldStore ? 2 : 1); ++part)
 			{
-				b.add(bodyPass(softStep ? BOP_INTEGRATE_VELOCITIES_WARM_FIXED : BOP_INTEGRATE_VELOCITIES_WARM));
-			}
-			else
-			{
-				b.add(bodyPass(BOP_INTEGRATE_VELOCITIES));
-				if (warm)
+				bool last = foldStore && part == 1;
+				b.segment(foldStore ? (last ? 1 : S - 1) : S);
+				if (warm && gatherWarm)
 				{
-					b.add(groupPass(JOP_WARM_START, softStep ? COP_WARM_START_FIXED : COP_WARM_START));
+					b.add(bodyPass(softStep ? BOP_INTEGRATE_VELOCITIES_WARM_FIXED : BOP_INTEGRATE_VELOCITIES_WARM));
 				}
-			}
-			b.add(groupPass(JOP_SOFT_BIAS, softStep ? COP_SOFTSTEP_BIAS : COP_TGS_SOFT_BIAS));
-			b.add(bodyPass(BOP_INTEGRATE_POSITIONS));
-			if (E > 0)
-			{
-				b.add(groupPass(JOP_SOFT_RELAX, softStep ? COP_SOFTSTEP_RELAX : COP_TGS_SOFT_RELAX));
+				else
+				{
+					b.add(bodyPass(BOP_INTEGRATE_VELOCITIES));
+					if (warm)
+					{
+						b.add(groupPass(JOP_WARM_START, softStep ? COP_WARM_START_FIXED : COP_WARM_START));
+					}
+				}
+				b.add(groupPass(JOP_SOFT_BIAS, softStep ? COP_SOFTSTEP_BIAS : COP_TGS_SOFT_BIAS));
+				b.add(bodyPass(BOP_INTEGRATE_POSITIONS));
+				if (E > 0)
+				{
+					b.add(groupPass(JOP_SOFT_RELAX, softStep ? COP_SOFTSTEP_RELAX : (last ? COP_TGS_SOFT_RELAX_STORE : COP_TGS_SOFT_RELAX)));
+				}
 			}
 			b.segment(1);
 			b.add(bodyPass(BOP_FINALIZE_POSITIONS));
-			b.add(flatPass(JOP_STORE, COP_STORE));
+			b.add(flatPass(JOP_STORE, foldStore ? COP_NONE : COP_STORE));
 			*countedPasses = S * (1 + (E > 0 ? 1 : 0));
 			break;
 		}
@@ -2216,6 +2579,9 @@ static void planSolve(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 	s->colorA.reserve(nI, st, false);
 	s->colorB.reserve(nI, st, false);
 	s->colorC.reserve(nI, st, false);
+	s->kempeState.reserve(KS_SIZE, st, false, true);
+	s->kempeClaim.reserve((size_t)bodyCap + 1, st, false, false);
+	s->kempePath.reserve((size_t)S2B_KEMPE_MAX_ITEMS * S2B_KEMPE_MAX_HOPS, st, false, false);
 	s->itemRegion.reserve(nI, st, false);
 	s->sortKeyIn.reserve(2 * nI, st, false);
 	s->sortKeyOut.reserve(2 * nI, st, false);
@@ -2336,6 +2702,28 @@ static void launchColorKernel(s2bWorld* w, SolverScratch* s, int maxItems, int* 
 	w->kernelLaunches += 1;
 }
 
+static void launchKempeKernel(s2bWorld* w, SolverScratch* s, int bodyCap)
+{
+	if (w->kempeGrid == 0)
+	{
+		int blocksPerSm = 0;
+		S2B_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, s2bKempeKernel, 256, 0));
+		w->kempeGrid = w->smCount * std::min(std::max(blocksPerSm, 1), 2);
+	}
+	int grid = w->kempeGrid;
+	const int* countsPtr = s->counts.p;
+	const int2* ib = s->itemBodies.p;
+	const int* as = s->adjStart.p;
+	const int* ad = s->adj.p;
+	int* color = s->colorA.p;
+	int* state = s->kempeState.p;
+	int* claim = s->kempeClaim.p;
+	int* paths = s->kempePath.p;
+	void* args[] = {&countsPtr, &ib, &as, &ad, &color, &state, &claim, &paths, &bodyCap};
+	S2B_CHECK(cudaLaunchCooperativeKernel((void*)s2bKempeKernel, dim3(grid), dim3(256), args, 0, w->stream));
+	w->kernelLaunches += 1;
+}
+
 // gather + schedule: from the contact / joint tables to the solve order, the group tables, the regions and the incidence
 // lists. Everything here depends only on WHICH constraints are live (and on the settings in the graph signature), not on
 // their values: while that set stands, a replayed graph skips all of it (see s2bSolve).
@@ -2404,6 +2792,10 @@ static void enqueueSchedule(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 			S2B_LAUNCH(w, s2bSeedColors, gridFor(maxItems, 256), 256, 0, s->counts.p, s->jointSlots.p, s->activeSlots.p, w->jColor.p,
 					   w->contacts[w->cur].color.p, s->colorA.p, w->maxColors);
 			launchColorKernel(w, s, maxItems, s->colorA.p, w->maxColors, S2B_INDEX_PRIORITY_ROUNDS, 1);
+			if (w->kempe != 0)
+			{
+				launchKempeKernel(w, s, bodyCap);
+			}
 			S2B_LAUNCH(w, s2bStoreColors, gridFor(maxItems, 256), 256, 0, s->counts.p, s->jointSlots.p, s->activeSlots.p, w->jColor.p,
 					   w->contacts[w->cur].color.p, s->colorA.p);
 
@@ -3083,6 +3475,12 @@ extern "C" void s2b_get_counters(s2bWorld* w, s2bCounters* out)
 		out->cutCount = w->scratch->regions > 0 ? counts[CNT_CUT] : 0;
 		out->regionCount = counts[CNT_REGIONS_ON] != 0 ? w->scratch->regions : 0;
 		out->overflowCount = counts[CNT_OVERFLOW_C] + counts[CNT_OVERFLOW_J];
+		if (w->scratch->kempeState.p != nullptr)
+		{
+			int ks[4];
+			S2B_CHECK(cudaMemcpy(ks, w->scratch->kempeState.p, sizeof(ks), cudaMemcpyDeviceToHost));
+			out->recolouredCount = ks[KS_FIXED];
+		}
 		if (w->scratch->bodyTicket.p != nullptr && w->scratch->flowErrorOffset > 0)
 		{
 			int flag = 0;

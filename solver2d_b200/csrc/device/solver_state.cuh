@@ -97,6 +97,7 @@ struct SolverScratch
 	DevArray<int> adj;			  // 2 * items
 	DevArray<int> colorA, colorB; // per item: colour, tentative colour of the speculative rounds
 	DevArray<int> colorC;		  // per item: colour inside the cut set
+	DevArray<int> kempeState, kempeClaim, kempePath; // s2bKempeKernel: KS_* words, per-body claims, recorded chains
 	DevArray<int> itemRegion;	  // per item: region it is interior to, or -1 (cut set)
 	DevArray<unsigned short> sortKeyIn, sortKeyOut; // solve-order keys (region x colour | cut colour | overflow), see s2bMakeSortKeys
 	// regions

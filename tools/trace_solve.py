@@ -40,4 +40,4 @@ for key, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
 print("sequence (us):", [round(float(d) / 1e3, 2) for d in dt[:60]])
 c = dw.counters()
 print("constraints", c.constraintCount, "colours", c.groupCount, "overflow", c.overflowCount, "regions", c.regionCount, "cut", c.cutCount,
-      "cut colours", c.cutGroupCount, "stage ms", dw.stage_ms(), "kernel ms", dev.lib.s2b_last_solve_kernel_ms(dw.h) if hasattr(dev.lib, "s2b_last_solve_kernel_ms") else None)
+      "cut colours", c.cutGroupCount, "recoloured", c.recolouredCount, "stage ms", dw.stage_ms(), "kernel ms", dev.lib.s2b_last_solve_kernel_ms(dw.h) if hasattr(dev.lib, "s2b_last_solve_kernel_ms") else None)
