@@ -320,12 +320,14 @@ struct ContactStream
 	float4 la0, la1, pm0, pm1;
 	float2 l0, l1;
 	int slot; // contact slot of the row (only loaded by the sweep that also stores the impulses to the manifold)
+	int last; // ConstraintView::lastTouch bits (only loaded by a bias sweep that also integrates positions)
 };
 
 __device__ __forceinline__ ContactStream s2bLoadContactStream(const SolveArgs& a, int t, bool withSlot = false)
 {
 	const ConstraintView& cc = a.cc;
 	ContactStream cs;
+	cs.last = 0;
 	cs.slot = withSlot ? cc.src[t] : -1;
 	cs.idx = cc.idx[t];
 	cs.nf = cc.nf[t];
@@ -471,6 +473,22 @@ __device__ __forceinline__ void s2bSolveContactTgsSoftStream(const SolveArgs& a,
 	}
 	BodyPair bp = {ia, ib, velA, velB, (mA != 0.0f) || (iA != 0.0f), (mB != 0.0f) || (iB != 0.0f)};
 	s2bStoreVelocities(a, bp, vA, wA, vB, wB);
+	// s2IntegratePositions (reference src/solve_common.c:47-68) of the bodies this constraint is the last of the sweep to
+	// touch: the same arithmetic on the values just stored as s2bIntegratePosition applies after a device-wide barrier
+	// (cs.last is only ever non-zero in a bias sweep of the persistent kernel that folds the position pass; marked bodies
+	// are movable, hence valid and not static)
+	if (cs.last & 1)
+	{
+		s2Vec2 dp = s2MulAdd(dcA, a.ctx.h, vA);
+		s2Rot q = s2IntegrateRot(qA, a.ctx.h * wA);
+		a.bodies.pose[ia] = make_float4(dp.x, dp.y, q.s, q.c);
+	}
+	if (cs.last & 2)
+	{
+		s2Vec2 dp = s2MulAdd(dcB, a.ctx.h, vB);
+		s2Rot q = s2IntegrateRot(qB, a.ctx.h * wB);
+		a.bodies.pose[ib] = make_float4(dp.x, dp.y, q.s, q.c);
+	}
 }
 
 // writeWarm: this is the last pass that changes the impulses before the next sub-step's warm-start gather

@@ -126,6 +126,7 @@ struct S2bLaunchInfo
 	int hubs;		  // hub bodies (body passes run over them grid-wide)
 	int bodyBegin, bodyEnd; // this block's range of regBodies
 	bool regions;
+	bool foldPositions; // TGS_Soft: the bias sweep integrates positions (ConstraintView::lastTouch), the body pass is skipped
 };
 
 template <int SOLVER> __device__ __forceinline__ void s2bBodyPass(int bodyOp, const SolveArgs& a, const S2bLaunchInfo& li)
@@ -158,10 +159,21 @@ template <int SOLVER> __device__ __forceinline__ void s2bBodyPass(int bodyOp, co
 		}
 		return;
 	}
-	int stride = gridDim.x * blockDim.x;
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.bodies.capacity; i += stride)
+	if (s2bUsesBodyOp(SOLVER, BOP_INTEGRATE_VELOCITIES_WARM) && bodyOp == BOP_INTEGRATE_VELOCITIES_WARM)
 	{
-		s2bRunBodyOpT<SOLVER>(bodyOp, a, i);
+		s2bIntegrateVelocityWarmAll<false>(a, a.ctx.h, li.foldPositions);
+	}
+	else if (s2bUsesBodyOp(SOLVER, BOP_INTEGRATE_VELOCITIES_WARM_FIXED) && bodyOp == BOP_INTEGRATE_VELOCITIES_WARM_FIXED)
+	{
+		s2bIntegrateVelocityWarmAll<true>(a, a.ctx.h);
+	}
+	else
+	{
+		int stride = gridDim.x * blockDim.x;
+		for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.bodies.capacity; i += stride)
+		{
+			s2bRunBodyOpT<SOLVER>(bodyOp, a, i);
+		}
 	}
 	if (a.heavyBodies != nullptr)
 	{
@@ -335,13 +347,15 @@ __device__ __forceinline__ void s2bGroupPass(int jointOp, int contactOp, const S
 			// proper — the two bodies, the arithmetic, the stores (one L2 round trip less per device-wide step).
 			bool mine = tid < nc;
 			bool store = contactOp == COP_TGS_SOFT_RELAX_STORE;
+			bool bias = contactOp == COP_TGS_SOFT_BIAS;
+			bool fold = bias && li.foldPositions;
 			ContactStream cs;
 			if (mine)
 			{
 				cs = s2bLoadContactStream(a, cBegin + tid, store);
+				cs.last = fold ? a.cc.lastTouch[cBegin + tid] : 0;
 			}
 			s2bSyncBeforeGlobal(a, sync);
-			bool bias = contactOp == COP_TGS_SOFT_BIAS;
 			bool writeWarm = bias ? a.ctx.extraIterations == 0 : true;
 			if (mine)
 			{
@@ -349,7 +363,9 @@ __device__ __forceinline__ void s2bGroupPass(int jointOp, int contactOp, const S
 			}
 			for (int t = tid + stride; t < nc; t += stride)
 			{
-				s2bSolveContactTgsSoft(a, cBegin + t, a.ctx.inv_h, bias, writeWarm, store);
+				ContactStream more = s2bLoadContactStream(a, cBegin + t, store);
+				more.last = fold ? a.cc.lastTouch[cBegin + t] : 0;
+				s2bSolveContactTgsSoftStream(a, cBegin + t, more, a.ctx.inv_h, bias, writeWarm, store);
 			}
 		}
 		else
@@ -630,6 +646,11 @@ template <int SOLVER> __global__ void __launch_bounds__(S2B_BLOCK) s2bPersistent
 	li.ovC = a.counts[CNT_OVERFLOW_C];
 	li.regions = a.regions > 0 && a.counts[CNT_REGIONS_ON] != 0;
 	li.hubs = (li.regions && a.heavyBodies != nullptr) ? a.heavyBodies[0] : 0;
+	// s2IntegratePositions folded into the TGS_Soft bias sweep: only in the plain colour schedule of a scene without joints,
+	// hub bodies or an overflow group (every movable body with a constraint then has a CONTACT as its last toucher, and
+	// every bias step runs through the branch below that looks at the marks); all of it is grid-uniform
+	li.foldPositions = SOLVER == 7 && a.cc.lastTouch != nullptr && li.regions == false && li.nJ == 0 && li.ovC + li.ovJ == 0 &&
+					   (a.heavyBodies == nullptr || a.heavyBodies[0] == 0) && a.bodyTicket == nullptr && li.nC > 0;
 	li.bodyBegin = li.bodyEnd = 0;
 	if (li.regions)
 	{
@@ -679,6 +700,10 @@ template <int SOLVER> __global__ void __launch_bounds__(S2B_BLOCK) s2bPersistent
 						s2bGroupPass<SOLVER>(pass.jointOp, pass.contactOp, a, p, li, sync, sRegJ, sRegC, groupsInShared ? sGroupJ : nullptr,
 											 groupsInShared ? sGroupC : nullptr);
 					}
+				}
+				else if (pass.kind == PASS_BODY && li.foldPositions && pass.bodyOp == BOP_INTEGRATE_POSITIONS)
+				{
+					// done by the bias sweep before it (and by the velocity pass for bodies without constraints)
 				}
 				else if (pass.kind == PASS_BODY)
 				{

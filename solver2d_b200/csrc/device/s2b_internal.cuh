@@ -215,6 +215,10 @@ struct ConstraintView
 	// prepare-time world anchors for SoftStep). Null when the variant does not gather.
 	float4* warmP;
 	float4* warmAnchor;
+	// per constraint: bit 0 / bit 1 = this constraint is the LAST one of the solve order that touches its body A / B. The
+	// TGS_Soft bias sweep then integrates that body's position itself (s2IntegratePositions folded into the sweep, one
+	// device-wide step less per sub-step; persistent.cuh). Null: positions are integrated by their own body pass.
+	const int* lastTouch;
 	// sticky extras
 	float4* fanchor[2]; // COM-relative local friction anchors A.xy B.xy
 	float2* tsep[2];	// tangentSeparation, spare
@@ -361,6 +365,7 @@ struct s2bWorld
 	unsigned long long uploadEpoch = 0; // bumped by every row upload: a pair search started before it is stale
 	int prefetchPairs = 1;	// start the pair search of the next step behind finalize (S2B_PREFETCH_PAIRS=0: off)
 	int kempe = 1;		// empty a sparse top colour by Kempe chains after colouring (S2B_KEMPE=0 disables)
+	int fusePositions = 1; // TGS_Soft: s2IntegratePositions folded into the bias sweep (S2B_FUSE_POSITIONS=0 disables)
 	int kempeGrid = 0;
 	DevArray<int> dMovedFlag; // [0] = number of proxies moved in last finalize (device counter)
 	int pairPassCount = 0;

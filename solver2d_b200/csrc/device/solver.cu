@@ -92,6 +92,7 @@ void s2bFreeSolverScratch(s2bWorld* w)
 	s->itemVal.release();
 	s->incWork.release();
 	s->incList.release();
+	s->lastTouch.release();
 	s->heavyBodies.release();
 	s->ovBodies.release();
 	s->longBodies.release();
@@ -1869,6 +1870,27 @@ __global__ void __launch_bounds__(256) s2bSortLongIncidenceKernel(const int* lon
 	}
 }
 
+// ConstraintView::lastTouch from the sorted incidence lists: the last entry of a body's list is the last constraint of the
+// solve order that touches it. Bit 2 marks a constraint row as such for side A (bit 0) / B (bit 1); a body whose last
+// toucher is a joint gets no mark at all (the persistent kernel only folds when there are no joints).
+__global__ void s2bLastTouchKernel(int bodyCapacity, const int* incStart, const int* incList, int* lastTouch)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= bodyCapacity)
+	{
+		return;
+	}
+	int begin = incStart[i], end = incStart[i + 1];
+	if (end > begin)
+	{
+		int e = incList[end - 1];
+		if (e & S2B_INC_CONTACT)
+		{
+			atomicOr(lastTouch + (e >> 2), (e & S2B_INC_SIDE_B) ? 2 : 1);
+		}
+	}
+}
+
 // ---- launch-by-launch kernels (profiling / cross-check path) ----------------------------------------------------
 
 __global__ void __launch_bounds__(S2B_BLOCK) s2bBodyPassKernel(SolveArgs a, int bodyOp)
@@ -1946,6 +1968,8 @@ __global__ void __launch_bounds__(S2B_BULK_BLOCK) s2bTgsSoftColorKernelBulk(Solv
 	{
 		int r = t - ta;
 		ContactStream cs;
+		cs.slot = -1;
+		cs.last = 0;
 		cs.idx = sIdx[r];
 		cs.nf = sNf[r];
 		cs.la0 = sAnchor[0][r];
@@ -2617,6 +2641,7 @@ static void planSolve(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 		s->itemVal.reserve(nI, st, false);
 		s->incWork.reserve(2 * nI, st, false);
 		s->incList.reserve(2 * nI, st, false);
+		s->lastTouch.reserve(nC + 2, st, false);
 	}
 	if (pl.dataflow)
 	{
@@ -2936,6 +2961,11 @@ static void enqueueSchedule(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 					   s->itemVal.p, s->incWork.p, s->incList.p, cfa, cfb, jfa, jfb, heavy, s->longBodies.p);
 			S2B_LAUNCH(w, s2bSortLongIncidenceKernel, 64, 256, 0, s->longBodies.p, s->adjStart.p, s->adj.p, s->itemBodies.p, s->itemVal.p,
 					   s->incWork.p, s->incList.p, cfa, cfb, jfa, jfb);
+			if (contactCount > 0)
+			{
+				S2B_CHECK(cudaMemsetAsync(s->lastTouch.p, 0, sizeof(int) * (size_t)contactCount, st));
+				S2B_LAUNCH(w, s2bLastTouchKernel, gridFor(bodyCap, 256), 256, 0, bodyCap, s->adjStart.p, s->incList.p, s->lastTouch.p);
+			}
 		}
 	}
 	else
@@ -2978,6 +3008,7 @@ static void enqueueIterate(s2bWorld* w, SolverScratch* s, SolvePlan& pl, bool ca
 	a.cc.src = s->src.p;
 	a.cc.warmP = pl.gatherWarm ? s->warmP.p : nullptr;
 	a.cc.warmAnchor = pl.gatherWarm ? s->warmAnchor.p : nullptr;
+	a.cc.lastTouch = (pl.gatherWarm && pl.solverType == 7 && w->fusePositions != 0 && pl.dataflow == false) ? s->lastTouch.p : nullptr;
 	for (int p = 0; p < 2; ++p)
 	{
 		a.cc.anchor[p] = s->anchor[p].p;

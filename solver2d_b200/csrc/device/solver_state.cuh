@@ -119,6 +119,7 @@ struct SolverScratch
 	DevArray<char> cubTemp;
 	DevArray<unsigned long long> itemVal, incWork; // warm-start gather: per-item sort value, per-body sort scratch
 	DevArray<int> incList;
+	DevArray<int> lastTouch; // ConstraintView::lastTouch
 	DevArray<int> heavyBodies;
 	DevArray<int> longBodies;			// [0] count, then bodies whose incidence list is sorted by a whole block
 	DevArray<int> ovBodies, ovBodySlot; // bodies of the serial overflow group (SolveArgs::ovBodies)

@@ -102,17 +102,77 @@ __device__ __forceinline__ GatherTerms s2bGatherTermsOf(const SolveArgs& a, int 
 	return g;
 }
 
+// what the gather needs of a body before it can look at its incidence list: loaded in one go (and, in the grid-stride loop
+// of the body pass, one body AHEAD: the next body's first round trip overlaps this body's dependent chain)
+struct GatherHead
+{
+	unsigned f;
+	float4 vel, prm, frc, pose;
+	int begin, end;
+};
+
+__device__ __forceinline__ GatherHead s2bLoadGatherHead(const SolveArgs& a, int i)
+{
+	GatherHead hd;
+	hd.f = a.bodies.flags[i];
+	hd.vel = a.bodies.vel[i];
+	hd.prm = a.bodies.prm[i];
+	hd.frc = a.bodies.frc[i];
+	hd.pose = a.bodies.pose[i];
+	hd.begin = a.incStart[i];
+	hd.end = a.incStart[i + 1];
+	return hd;
+}
+
+// four incidence entries: their (independent) load chains — entry -> constraint row — in flight together, then added to
+// v, w in list order (same float operations, same order as the constraint-by-constraint pass, and the same code as the
+// block-wide hub gather below)
+template <bool FIXED>
+__device__ __forceinline__ void s2bGatherFour(const SolveArgs& a, const int (&e)[4], s2Rot q, float invMass, float invI, s2Vec2& v, float& w)
+{
+	GatherTerms g[4];
+#pragma unroll
+	for (int u = 0; u < 4; ++u)
+	{
+		g[u].np = 0;
+		g[u].tw0 = g[u].tw1 = 0.0f;
+		g[u].tv0 = g[u].tv1 = V2(0.0f, 0.0f);
+		if (e[u] != -1)
+		{
+			g[u] = s2bGatherTermsOf<FIXED>(a, e[u], q, invMass, invI);
+		}
+	}
+#pragma unroll
+	for (int u = 0; u < 4; ++u)
+	{
+		if (g[u].np >= 1)
+		{
+			w = w + g[u].tw0;
+			v = V2(v.x + g[u].tv0.x, v.y + g[u].tv0.y);
+		}
+		if (g[u].np == 2)
+		{
+			w = w + g[u].tw1;
+			v = V2(v.x + g[u].tv1.x, v.y + g[u].tv1.y);
+		}
+	}
+}
+
 // FIXED = false: anchors rotated by the current rotation (s2WarmStartContacts, reference src/solve_common.c:276-326)
 // FIXED = true : prepare-time anchors (s2WarmStartContacts_Fixed, reference src/solve_soft_step.c:16-63)
-template <bool FIXED> __device__ __forceinline__ void s2bIntegrateVelocityWarm(const SolveArgs& a, int i, float h)
+// alsoPosition: the bias sweep integrates the positions of the bodies it touches (ConstraintView::lastTouch); a body
+// without any constraint is touched by nobody, so its position is integrated here, right after its velocity (nothing in
+// between changes either)
+template <bool FIXED>
+__device__ __forceinline__ void s2bIntegrateVelocityWarmHead(const SolveArgs& a, int i, float h, const GatherHead& hd, bool alsoPosition = false)
 {
-	unsigned f = a.bodies.flags[i];
+	unsigned f = hd.f;
 	if ((f & S2B_BODY_VALID) == 0)
 	{
 		return;
 	}
-	float4 vel = a.bodies.vel[i];
-	float4 prm = a.bodies.prm[i];
+	float4 vel = hd.vel;
+	float4 prm = hd.prm;
 	float invMass = vel.w, invI = prm.w;
 	s2Vec2 v = V2(vel.x, vel.y);
 	float w = vel.z;
@@ -121,7 +181,7 @@ template <bool FIXED> __device__ __forceinline__ void s2bIntegrateVelocityWarm(c
 	// s2IntegrateVelocities (reference src/solve_common.c:10-45)
 	if (dynamic)
 	{
-		float4 frc = a.bodies.frc[i];
+		float4 frc = hd.frc;
 		s2Vec2 gravity = V2(a.gravity.x, a.gravity.y);
 		v = s2Add(v, s2MulSV(h * invMass, s2MulAdd(V2(frc.x, frc.y), frc.w * prm.z, gravity)));
 		w = w + h * invI * frc.z;
@@ -129,12 +189,19 @@ template <bool FIXED> __device__ __forceinline__ void s2bIntegrateVelocityWarm(c
 		w *= 1.0f / (1.0f + h * prm.y);
 	}
 
-	int begin = a.incStart[i], end = a.incStart[i + 1];
+	int begin = hd.begin, end = hd.end;
 	if (begin == end)
 	{
 		if (dynamic)
 		{
 			a.bodies.vel[i] = make_float4(v.x, v.y, w, invMass);
+		}
+		if (alsoPosition && S2B_BODY_TYPE(f) != S2B_BODY_STATIC)
+		{
+			// s2IntegratePositions (reference src/solve_common.c:47-68)
+			s2Vec2 dp = s2MulAdd(V2(hd.pose.x, hd.pose.y), h, v);
+			s2Rot qn = s2IntegrateRot(R2(hd.pose.z, hd.pose.w), h * w);
+			a.bodies.pose[i] = make_float4(dp.x, dp.y, qn.s, qn.c);
 		}
 		return;
 	}
@@ -143,12 +210,21 @@ template <bool FIXED> __device__ __forceinline__ void s2bIntegrateVelocityWarm(c
 		return; // a hub body (container wall ...): gathered by a whole block, s2bGatherHeavyBodies
 	}
 
-	float4 pose = a.bodies.pose[i];
-	s2Rot q = R2(pose.z, pose.w);
-	// The terms do not depend on v, w: four entries at a time, their (independent) load chains — incidence entry ->
-	// constraint row — in flight together, then added to v, w in list order (same float operations, same order as the
-	// constraint-by-constraint pass, and the same code as the block-wide hub gather below).
-	for (int k0 = begin; k0 < end; k0 += 4)
+	s2Rot q = R2(hd.pose.z, hd.pose.w);
+	// the first eight entries of the list in one round trip (a box in a pile has six neighbours), then four at a time
+	int e0[4], e1[4];
+#pragma unroll
+	for (int u = 0; u < 4; ++u)
+	{
+		e0[u] = begin + u < end ? a.incList[begin + u] : -1;
+		e1[u] = begin + 4 + u < end ? a.incList[begin + 4 + u] : -1;
+	}
+	s2bGatherFour<FIXED>(a, e0, q, invMass, invI, v, w);
+	if (end - begin > 4)
+	{
+		s2bGatherFour<FIXED>(a, e1, q, invMass, invI, v, w);
+	}
+	for (int k0 = begin + 8; k0 < end; k0 += 4)
 	{
 		int e[4];
 #pragma unroll
@@ -156,34 +232,36 @@ template <bool FIXED> __device__ __forceinline__ void s2bIntegrateVelocityWarm(c
 		{
 			e[u] = k0 + u < end ? a.incList[k0 + u] : -1;
 		}
-		GatherTerms g[4];
-#pragma unroll
-		for (int u = 0; u < 4; ++u)
-		{
-			g[u].np = 0;
-			g[u].tw0 = g[u].tw1 = 0.0f;
-			g[u].tv0 = g[u].tv1 = V2(0.0f, 0.0f);
-			if (e[u] != -1)
-			{
-				g[u] = s2bGatherTermsOf<FIXED>(a, e[u], q, invMass, invI);
-			}
-		}
-#pragma unroll
-		for (int u = 0; u < 4; ++u)
-		{
-			if (g[u].np >= 1)
-			{
-				w = w + g[u].tw0;
-				v = V2(v.x + g[u].tv0.x, v.y + g[u].tv0.y);
-			}
-			if (g[u].np == 2)
-			{
-				w = w + g[u].tw1;
-				v = V2(v.x + g[u].tv1.x, v.y + g[u].tv1.y);
-			}
-		}
+		s2bGatherFour<FIXED>(a, e, q, invMass, invI, v, w);
 	}
 	a.bodies.vel[i] = make_float4(v.x, v.y, w, invMass);
+}
+
+template <bool FIXED> __device__ __forceinline__ void s2bIntegrateVelocityWarm(const SolveArgs& a, int i, float h)
+{
+	s2bIntegrateVelocityWarmHead<FIXED>(a, i, h, s2bLoadGatherHead(a, i));
+}
+
+// the body pass of the persistent kernel without regions: every body slot, grid-stride, the next body's head loaded ahead
+template <bool FIXED> __device__ __forceinline__ void s2bIntegrateVelocityWarmAll(const SolveArgs& a, float h, bool alsoPosition = false)
+{
+	int stride = gridDim.x * blockDim.x;
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= a.bodies.capacity)
+	{
+		return;
+	}
+	GatherHead hd = s2bLoadGatherHead(a, i);
+	for (; i < a.bodies.capacity; i += stride)
+	{
+		GatherHead next = hd;
+		if (i + stride < a.bodies.capacity)
+		{
+			next = s2bLoadGatherHead(a, i + stride);
+		}
+		s2bIntegrateVelocityWarmHead<FIXED>(a, i, h, hd, alsoPosition);
+		hd = next;
+	}
 }
 
 // ---- hub bodies -----------------------------------------------------------------------------------------------------

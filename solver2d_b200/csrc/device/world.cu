@@ -349,6 +349,11 @@ extern "C" s2bWorld* s2b_world_create(int cudaDevice, int solverType)
 		{
 			w->prefetchPairs = atoi(env);
 		}
+		env = getenv("S2B_FUSE_POSITIONS");
+		if (env != nullptr)
+		{
+			w->fusePositions = atoi(env);
+		}
 		env = getenv("S2B_KEMPE");
 		if (env != nullptr)
 		{
