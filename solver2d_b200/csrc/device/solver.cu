@@ -354,8 +354,13 @@ __global__ void s2bStoreColors(const int* counts, const int* jointSlots, const i
 // abortAbove >= 0: give up as soon as any item would need a colour beyond it (the cut colouring: regions are only used when
 // the cut set needs few colours, so a long run of rounds for a hub's hundreds of mutually conflicting constraints would be
 // wasted) and leave CNT_CUT_ABORT set.
+// hubDegree > 0: a constraint that touches a body with more incident constraints than that goes straight to the serial
+// overflow group. All constraints of such a body conflict with one another, so each would need a colour of its own — a
+// device-wide step (~2.8 us) for what the serial walk does in ~0.5 us — and the rest of the scene would be dragged through
+// those steps as well (10 k-box tumbler: 24 colours with the drum's constraints coloured, 9 without).
 __global__ void __launch_bounds__(256) s2bColorKernel(int* counts, const int2* itemBodies, const int* adjStart, const int* adj, int* color,
-													  int* tent, int maxColors, int indexRounds, int validate, int abortAbove, const int* hubs)
+													  int* tent, int maxColors, int indexRounds, int validate, int abortAbove, const int* hubs,
+													  int hubDegree)
 {
 	cg::grid_group grid = cg::this_grid();
 	int n = counts[CNT_JOINTS] + counts[CNT_CONTACTS];
@@ -392,6 +397,11 @@ __global__ void __launch_bounds__(256) s2bColorKernel(int* counts, const int2* i
 						continue;
 					}
 					int begin = adjStart[body], end = adjStart[body + 1];
+					if (hubDegree > 0 && end - begin > hubDegree)
+					{
+						keep = 0; // the body has become a hub since this constraint was coloured
+						continue;
+					}
 					for (int k = begin; k < end; ++k)
 					{
 						int j = adj[k];
@@ -467,6 +477,11 @@ __global__ void __launch_bounds__(256) s2bColorKernel(int* counts, const int2* i
 					continue;
 				}
 				int begin = adjStart[body], end = adjStart[body + 1];
+				if (hubDegree > 0 && end - begin > hubDegree)
+				{
+					forbidden = ~0ull; // serial overflow group
+					continue;
+				}
 				for (int k = begin; k < end; ++k)
 				{
 					int cj = color[adj[k]];
@@ -575,7 +590,7 @@ __global__ void __launch_bounds__(256) s2bColorKernel(int* counts, const int2* i
 // a few L2 round trips each — milliseconds), paid once: colours persist, and a top colour that could not be emptied is
 // left alone for the next S2B_KEMPE_BACKOFF rebuilds.
 // ---------------------------------------------------------------------------------------------------------------
-#define S2B_KEMPE_MAX_ITEMS 64
+#define S2B_KEMPE_MAX_ITEMS 512
 #define S2B_KEMPE_MAX_HOPS 4096
 #define S2B_KEMPE_ROUNDS 6
 #define S2B_KEMPE_MAX_DEGREE 32
@@ -590,11 +605,11 @@ enum
 	KS_CURSOR = 72,	  // fill cursor of the straggler list
 	KS_PROGRESS = 80, // 8: stragglers recoloured in round r
 	KS_REMAINING = 88, // 8: stragglers still in the top colour after round r
-	KS_LIST = 96,	   // 64: the stragglers (item indices)
-	KS_LENGTH = 160,   // 64: recorded path length, -1 no usable path, -2 no longer a straggler
-	KS_ALPHA = 224,	   // 64
-	KS_BETA = 288,	   // 64
-	KS_SIZE = 352
+	KS_LIST = 96,								// the stragglers (item indices)
+	KS_LENGTH = KS_LIST + S2B_KEMPE_MAX_ITEMS,	// recorded path length, -1 no usable path, -2 no longer a straggler
+	KS_ALPHA = KS_LENGTH + S2B_KEMPE_MAX_ITEMS,
+	KS_BETA = KS_ALPHA + S2B_KEMPE_MAX_ITEMS,
+	KS_SIZE = KS_BETA + S2B_KEMPE_MAX_ITEMS
 };
 
 // colours held by the items around `body` (every item but `skip`); *hub is raised when the body has too many to bother
@@ -724,7 +739,8 @@ __global__ void __launch_bounds__(256) s2bKempeKernel(const int* counts, const i
 			}
 		}
 		int nTop = top >= 0 ? *((volatile int*)(state + KS_HIST + top)) : 0;
-		if (top < 2 || nTop > S2B_KEMPE_MAX_ITEMS)
+		// sparse = a small fraction of an average colour (and few enough to walk)
+		if (top < 2 || nTop > S2B_KEMPE_MAX_ITEMS || (long long)nTop * 16 * (top + 1) > (long long)n)
 		{
 			return; // uniform. Nothing sparse on top: the colouring stands
 		}
@@ -2706,7 +2722,7 @@ static void planSolve(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 }
 
 static void launchColorKernel(s2bWorld* w, SolverScratch* s, int maxItems, int* color, int maxColors, int indexRounds, int validate,
-							  int abortAbove = -1, const int* hubs = nullptr)
+							  int abortAbove = -1, const int* hubs = nullptr, int hubDegree = 0)
 {
 	// work counters of the kernel (shared by the primary and the cut colouring)
 	S2B_CHECK(cudaMemsetAsync(s->counts.p + CNT_REMAINING, 0, sizeof(int) * 5, w->stream));
@@ -2722,7 +2738,7 @@ static void launchColorKernel(s2bWorld* w, SolverScratch* s, int maxItems, int* 
 	const int* as = s->adjStart.p;
 	const int* ad = s->adj.p;
 	int* tent = s->colorB.p;
-	void* args[] = {&countsPtr, &ib, &as, &ad, &color, &tent, &maxColors, &indexRounds, &validate, &abortAbove, &hubs};
+	void* args[] = {&countsPtr, &ib, &as, &ad, &color, &tent, &maxColors, &indexRounds, &validate, &abortAbove, &hubs, &hubDegree};
 	S2B_CHECK(cudaLaunchCooperativeKernel((void*)s2bColorKernel, dim3(grid), dim3(256), args, 0, w->stream));
 	w->kernelLaunches += 1;
 }
@@ -2816,7 +2832,7 @@ static void enqueueSchedule(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 			// colours: start from the persisted ones; only constraints that appeared this step are uncoloured
 			S2B_LAUNCH(w, s2bSeedColors, gridFor(maxItems, 256), 256, 0, s->counts.p, s->jointSlots.p, s->activeSlots.p, w->jColor.p,
 					   w->contacts[w->cur].color.p, s->colorA.p, w->maxColors);
-			launchColorKernel(w, s, maxItems, s->colorA.p, w->maxColors, S2B_INDEX_PRIORITY_ROUNDS, 1);
+			launchColorKernel(w, s, maxItems, s->colorA.p, w->maxColors, S2B_INDEX_PRIORITY_ROUNDS, 1, -1, nullptr, w->hubDegree);
 			if (w->kempe != 0)
 			{
 				launchKempeKernel(w, s, bodyCap);

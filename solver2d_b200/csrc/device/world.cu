@@ -354,6 +354,11 @@ extern "C" s2bWorld* s2b_world_create(int cudaDevice, int solverType)
 		{
 			w->fusePositions = atoi(env);
 		}
+		env = getenv("S2B_HUB_DEGREE");
+		if (env != nullptr)
+		{
+			w->hubDegree = atoi(env);
+		}
 		env = getenv("S2B_KEMPE");
 		if (env != nullptr)
 		{

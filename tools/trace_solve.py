@@ -9,7 +9,12 @@ scene = sys.argv[2] if len(sys.argv) > 2 else "pyramid"
 warm = int(sys.argv[3]) if len(sys.argv) > 3 else 12
 P = capi.Solver2D(device.LIB_PATH)
 dev = device.Device()
-sc = scenes.pyramid(P, "TGS_Soft", base_count=base) if scene == "pyramid" else scenes.tumbler(P, "TGS_Soft", grid=base)
+if scene == "pyramid":
+    sc = scenes.pyramid(P, "TGS_Soft", base_count=base)
+elif scene == "field":
+    sc = scenes.pyramid_field(P, "TGS_Soft", count=base, base_count=45)  # `base` = number of 1 035-box piles
+else:
+    sc = scenes.tumbler(P, "TGS_Soft", grid=base)
 dw = device.DeviceWorld.attach(dev, sc.world)
 L = dev.lib
 L.s2b_set_solve_trace.argtypes = [C.c_void_p, C.c_int]
