@@ -454,6 +454,7 @@ enum
 	MAIL_JOINTS = 6,
 	MAIL_UNCOLORED = 7,
 	MAIL_PAIR_OVERFLOW = 8,
+	MAIL_REGIONS_ON = 9, // CNT_REGIONS_ON of the last schedule built outside a graph with regions on trial (a hint, read a step later)
 	MAIL_COUNT = 64
 };
 

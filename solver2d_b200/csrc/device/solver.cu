@@ -595,12 +595,15 @@ __global__ void __launch_bounds__(256) s2bColorKernel(int* counts, const int2* i
 #define S2B_KEMPE_ROUNDS 6
 #define S2B_KEMPE_MAX_DEGREE 32
 #define S2B_KEMPE_BACKOFF 32
+#define S2B_KEMPE_QUIET_STEPS 8
+#define S2B_REGION_RETRY 32
 
 enum
 {
 	KS_BACKOFF = 0, // rebuilds to sit out (persists from launch to launch)
 	KS_RUNS = 1,	// statistics: launches that walked, stragglers recoloured
 	KS_FIXED = 2,
+	KS_EVER = 3,	// a schedule has been built before
 	KS_HIST = 8,	  // 64: items per colour
 	KS_CURSOR = 72,	  // fill cursor of the straggler list
 	KS_PROGRESS = 80, // 8: stragglers recoloured in round r
@@ -679,12 +682,17 @@ __device__ __forceinline__ int s2bKempeWalk(const int2* itemBodies, const int* a
 	}
 }
 
+// sched = the words of s2bScheduleGate. The pass runs on the first schedule ever built and on rebuilds that follow
+// S2B_KEMPE_QUIET_STEPS steps without one: a scene whose constraints change every step (a pile still falling) would pay
+// the walks again and again for colours that do not last.
 __global__ void __launch_bounds__(256) s2bKempeKernel(const int* counts, const int2* itemBodies, const int* adjStart, const int* adj, int* color,
-													  int* state, int* claim, int* paths, int bodyCapacity)
+													  int* state, int* claim, int* paths, int bodyCapacity, int* sched)
 {
 	cg::grid_group grid = cg::this_grid();
-	// only when the colouring kernel had something to colour (a settled scene costs this launch and nothing else)
-	if (counts[CNT_UNCOLOURED] == 0)
+	// only when the colouring kernel had something to colour, or a skipped pass is owed (a settled scene costs this launch
+	// and nothing else)
+	int owed = *((volatile int*)(sched + 2));
+	if (counts[CNT_UNCOLOURED] == 0 && owed == 0)
 	{
 		return;
 	}
@@ -692,7 +700,20 @@ __global__ void __launch_bounds__(256) s2bKempeKernel(const int* counts, const i
 	int stride = gridDim.x * blockDim.x;
 	int n = counts[CNT_JOINTS] + counts[CNT_CONTACTS];
 	int backoff = *((volatile int*)(state + KS_BACKOFF));
-	grid.sync(); // (everybody has read the word before thread 0 changes it)
+	int ever = *((volatile int*)(state + KS_EVER));
+	int quiet = *((volatile int*)(sched + 3));
+	bool churning = ever != 0 && quiet < S2B_KEMPE_QUIET_STEPS;
+	grid.sync(); // (everybody has read the words before thread 0 changes them)
+	if (tid == 0)
+	{
+		state[KS_EVER] = 1;
+		sched[2] = churning ? 1 : 0;
+		sched[3] = 0;
+	}
+	if (churning)
+	{
+		return;
+	}
 	if (backoff > 0)
 	{
 		if (tid == 0)
@@ -2507,10 +2528,30 @@ static void buildWavefront(s2bWorld* w, SolverScratch* s, int nJ, int nC, HostPl
 // constraints changed since it was last built (flag raised by the narrow phase when a manifold gains its first or loses
 // its last point, by body rows whose validity / movability changed, by joint uploads; anything the host knows about —
 // a replaced contact table, other settings — changes the graph signature instead and is rebuilt eagerly).
+// The same word block also carries what the Kempe pass (s2bKempeKernel) wants to know about the scene's recent past:
+// [1] replays since the last rebuild, [2] a rebuild skipped the pass because the scene was churning, [3] the value of [1]
+// when the rebuild that is about to run was asked for. A scene that has gone quiet with a skipped pass still owed gets ONE
+// rebuild of its own, so that it does not keep the extra colours for good.
 __global__ void s2bScheduleGate(cudaGraphConditionalHandle handle, int* dirty)
 {
-	int v = *dirty;
-	*dirty = 0;
+	int v = dirty[0];
+	dirty[0] = 0;
+	if (v != 0)
+	{
+		dirty[3] = dirty[1];
+		dirty[1] = 0;
+	}
+	else
+	{
+		int quiet = dirty[1] + 1;
+		dirty[1] = quiet;
+		if (quiet == S2B_KEMPE_QUIET_STEPS && dirty[2] != 0)
+		{
+			v = 1;
+			dirty[3] = quiet;
+			dirty[1] = 0;
+		}
+	}
 	cudaGraphSetConditional(handle, v != 0 ? 1u : 0u);
 }
 
@@ -2599,6 +2640,23 @@ static void planSolve(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 	pl.regions = (w->schedule == S2B_SCHEDULE_COLOR && pl.usePersistent && w->useRegions != 0 && pl.dataflow == false && maxItems > 0)
 					 ? pl.grid
 					 : 0;
+	if (w->useRegions == 1 && pl.regions > 0)
+	{
+		if (s->regionVerdictPending)
+		{
+			// (the copy was enqueued a step ago, behind a schedule the host has long waited past; a stale word is only a hint)
+			s->regionVerdictPending = false;
+			if (w->hostMail[MAIL_REGIONS_ON] == 0)
+			{
+				s->regionSkip = S2B_REGION_RETRY;
+			}
+		}
+		if (s->regionSkip > 0)
+		{
+			s->regionSkip -= 1;
+			pl.regions = 0;
+		}
+	}
 
 	// ---- reserve scratch (sizes are upper bounds known on the host: no synchronisation) ----
 	size_t nC = (size_t)std::max(contactCount, 1), nJ = (size_t)std::max(jointCap, 1), nI = (size_t)std::max(maxItems, 1);
@@ -2760,7 +2818,8 @@ static void launchKempeKernel(s2bWorld* w, SolverScratch* s, int bodyCap)
 	int* state = s->kempeState.p;
 	int* claim = s->kempeClaim.p;
 	int* paths = s->kempePath.p;
-	void* args[] = {&countsPtr, &ib, &as, &ad, &color, &state, &claim, &paths, &bodyCap};
+	int* sched = w->schedDirty.p;
+	void* args[] = {&countsPtr, &ib, &as, &ad, &color, &state, &claim, &paths, &bodyCap, &sched};
 	S2B_CHECK(cudaLaunchCooperativeKernel((void*)s2bKempeKernel, dim3(grid), dim3(256), args, 0, w->stream));
 	w->kernelLaunches += 1;
 }
@@ -3193,6 +3252,7 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 				s->scheduleSig = sig;
 			}
 			S2B_CHECK(cudaGraphLaunch(s->graphExec, st));
+			s->stepsSinceEager += 1;
 			w->kernelLaunches += s->graphLaunches;
 			w->solveKernelTimed = true;
 			s->hostCountsValid = false;
@@ -3232,10 +3292,19 @@ void s2bSolve(s2bWorld* w, int solverType, const s2bStepContext* ctxIn)
 	s->scheduleSig = sig;
 	if (capturing == false)
 	{
+		// (no gate in front of this rebuild: the host says how quiet the scene has been — every byte 0 or 0x7F)
+		S2B_CHECK(cudaMemsetAsync(w->schedDirty.p + 3, s->stepsSinceEager >= S2B_KEMPE_QUIET_STEPS ? 0x7F : 0, sizeof(int), st));
+		s->stepsSinceEager = 0;
 		enqueueSchedule(w, s, pl);
+		if (w->useRegions == 1 && pl.regions > 0)
+		{
+			S2B_CHECK(cudaMemcpyAsync(w->hostMail + MAIL_REGIONS_ON, s->counts.p + CNT_REGIONS_ON, sizeof(int), cudaMemcpyDeviceToHost, st));
+			s->regionVerdictPending = true;
+		}
 		enqueueIterate(w, s, pl, false);
 		return;
 	}
+	s->stepsSinceEager += 1;
 
 	// ---- build the graph: gate -> IF (gather + schedule) -> iterate ----
 	if (s->graphExec != nullptr)

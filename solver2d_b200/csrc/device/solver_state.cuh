@@ -151,6 +151,11 @@ struct SolverScratch
 	int graphLaunches = 0;
 	bool graphDisabled = false;
 	int graphReplays = 0, graphCaptures = 0;
+	// regions on trial (useRegions == 1) and found useless (hub bodies, a cut set that needs too many colours): the rebuilds
+	// of the next S2B_REGION_RETRY schedules do not build islands, Hilbert keys and the cut colouring only to drop them
+	int regionSkip = 0;
+	bool regionVerdictPending = false;
+	int stepsSinceEager = 0; // solves since the last one that rebuilt the schedule outside the graph (how quiet the scene is)
 
 	// argument block of the last solve (the per-colour kernel probe re-launches one of its passes)
 	SolveArgs lastArgs;
