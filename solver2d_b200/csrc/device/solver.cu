@@ -219,17 +219,20 @@ __global__ void s2bItemEndpoints(const int* counts, const int* jointSlots, const
 		a = bo.x;
 		b = bo.y;
 	}
+	// -1: cannot be moved by a constraint and does not move by itself either; -2: cannot be moved by a constraint but its
+	// pose changes every sub-step (a kinematic body) — no conflict, but whoever reads it has to stay in step with the pass
+	// that integrates it (s2bClassifyItemsKernel keeps such constraints out of the region-local phases)
 	if (a >= 0)
 	{
 		bool movable = bodies.vel[a].w != 0.0f || bodies.prm[a].w != 0.0f;
-		a = movable ? a : -1;
+		a = movable ? a : (S2B_BODY_TYPE(bodies.flags[a]) == S2B_BODY_STATIC ? -1 : -2);
 	}
 	if (b >= 0)
 	{
 		bool movable = bodies.vel[b].w != 0.0f || bodies.prm[b].w != 0.0f;
-		b = movable ? b : -1;
+		b = movable ? b : (S2B_BODY_TYPE(bodies.flags[b]) == S2B_BODY_STATIC ? -1 : -2);
 	}
-	if (a == b)
+	if (a == b && a >= 0)
 	{
 		b = -1;
 	}
@@ -1272,14 +1275,24 @@ __global__ void s2bClassifyItemsKernel(int* counts, const int2* itemBodies, cons
 		if (useRegions)
 		{
 			int2 e = itemBodies[i];
-			if (e.x < 0 && e.y < 0)
+			if (e.x == -1 && e.y == -1)
 			{
 				region = 0; // touches no movable body: conflicts with nothing
+			}
+			else if (e.x < 0 && e.y < 0)
+			{
+				region = -1; // (a kinematic body among them: see below)
 			}
 			else
 			{
 				int ra = e.x >= 0 ? bodyRegion[e.x] : -2, rb = e.y >= 0 ? bodyRegion[e.y] : -2;
-				if (ra == -2)
+				if (e.x == -2 || e.y == -2)
+				{
+					// the other body is kinematic: its pose is integrated by the block that owns it, so this constraint runs
+					// in the device-wide steps, which are ordered against every block's body passes
+					region = -1;
+				}
+				else if (ra == -2)
 				{
 					region = rb;
 				}

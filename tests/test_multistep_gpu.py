@@ -48,7 +48,7 @@ def _load_bodies_into_ref(R, wid, rows):
     R.load_body_state(wid, bf)
 
 
-def _run(R, P, dev, recipe, solver, steps, vel, pos, kw, min_replays=0):
+def _run(R, P, dev, recipe, solver, steps, vel, pos, kw, min_replays=0, setup=None):
     O = port.load()
     sr = recipe(R, solver, **kw)
     sp = recipe(P, solver, **kw)
@@ -57,6 +57,8 @@ def _run(R, P, dev, recipe, solver, steps, vel, pos, kw, min_replays=0):
     dev.lib.s2World_Flush.argtypes = [capi.WorldId]
     dev.lib.s2World_Flush(sp.world)
     dw = device.DeviceWorld.attach(dev, sp.world)
+    if setup is not None:
+        setup(dw)
     ctx = device.make_context(solver, DT, vel, pos, True)
     worst = {}
     for step in range(steps):
@@ -177,3 +179,41 @@ def test_falling_boxes_every_step_bit_exact(reference, product, dev):
         return sc
     c = _run(reference, product, dev, recipe, "TGS_Soft", 120, 4, 2, {})
     assert c.pairPassCount > 5
+
+
+def test_kinematic_platforms_under_regions_every_step_bit_exact(reference, product, dev):
+    """Piles standing on KINEMATIC platforms that slide sideways, region-local schedule forced. A kinematic body conflicts
+    with nothing (no constraint moves it) but its pose changes every sub-step, integrated by the block that owns it: a
+    constraint that reads it from another block's region-local phase would race with that pass. Such constraints have to
+    run in the device-wide steps (s2bClassifyItemsKernel)."""
+    def recipe(lib, solver, **kw):
+        import ctypes as C
+        world = lib.create_world(solver)
+        sc = scenes.Scene(lib, world, name="kinematic_platforms")
+        h, base = 0.5, 16
+        box = lib.s2MakeSquare(h)
+        sd = scenes.default_shape_def()
+        sd.density = 1.0
+        for k in range(4):
+            x0 = k * 30.0
+            bd = scenes.default_body_def()
+            bd.type = capi.KINEMATIC_BODY
+            bd.position = capi.Vec2(x0, -1.0)
+            bd.linearVelocity = capi.Vec2(0.6 if k % 2 == 0 else -0.4, 0.0)
+            gid = lib.s2CreateBody(world, C.byref(bd))
+            plat = lib.s2MakeBox(0.5 * base + 2.0, 1.0)
+            lib.s2CreatePolygonShape(gid, C.byref(sd), C.byref(plat))
+            sc.bodies.append(gid)
+            bd = scenes.default_body_def()
+            bd.type = capi.DYNAMIC_BODY
+            for i in range(base):
+                y = (2.0 * i + 1.0) * h
+                for j in range(i, base):
+                    x = (i + 1.0) * h + 2.0 * (j - i) * h - h * base
+                    bd.position = capi.Vec2(x0 + x, y)
+                    bid = lib.s2CreateBody(world, C.byref(bd))
+                    lib.s2CreatePolygonShape(bid, C.byref(sd), C.byref(box))
+                    sc.bodies.append(bid)
+        return sc
+    c = _run(reference, product, dev, recipe, "TGS_Soft", 40, 4, 2, {}, setup=lambda dw: dw.set_regions(2))
+    assert c.regionCount >= 3 and c.cutCount >= 40
