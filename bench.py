@@ -325,6 +325,9 @@ def run_ours(args, rank: int, world_size: int, local_rank: int):
         import torch.distributed as dist_mod
         dist = dist_mod
         torch.cuda.set_device(local_rank)
+        # (NCCL prints its version banner to STDOUT at this level; the one line this script owes the driver is JSON)
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     else:
         torch.cuda.set_device(local_rank)

@@ -214,6 +214,19 @@ __device__ __forceinline__ void s2bPrefetchL1(const void* ptr)
 	asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
 }
 
+// the TGS_Soft row of a contact constraint (what s2bLoadContactStream reads)
+__device__ __forceinline__ void s2bTouchContactRow(const SolveArgs& a, int t)
+{
+	s2bPrefetchL1(a.cc.idx + t);
+	s2bPrefetchL1(a.cc.nf + t);
+	s2bPrefetchL1(a.cc.anchor[0] + t);
+	s2bPrefetchL1(a.cc.pm[0] + t);
+	s2bPrefetchL1(a.cc.lambda[0] + t);
+	s2bPrefetchL1(a.cc.anchor[1] + t);
+	s2bPrefetchL1(a.cc.pm[1] + t);
+	s2bPrefetchL1(a.cc.lambda[1] + t);
+}
+
 __device__ __forceinline__ void s2bTouchBody(const SolveArgs& a, int i)
 {
 	s2bPrefetchL1(a.bodies.vel + i);
@@ -299,6 +312,40 @@ __device__ __forceinline__ void s2bGroupPass(int jointOp, int contactOp, const S
 			if (nj + nc == 0)
 			{
 				continue; // uniform within the block
+			}
+			if (SOLVER == 7 && (contactOp == COP_TGS_SOFT_BIAS || contactOp == COP_TGS_SOFT_RELAX || contactOp == COP_TGS_SOFT_RELAX_STORE))
+			{
+				// The headline op, region-local: a thread's rows are private to it, so the row of its first constraint of this
+				// colour is requested (prefetch into L1: no registers held) BEFORE the block barrier that ends the previous
+				// colour, and the row of its next constraint while the current one is being solved: what stays on the dependent
+				// chain of a round is the two bodies, the arithmetic and the stores. (Holding the next row in registers instead
+				// pushed the kernel over 128 registers.)
+				bool store = contactOp == COP_TGS_SOFT_RELAX_STORE;
+				bool bias = contactOp == COP_TGS_SOFT_BIAS;
+				bool writeWarm = bias ? a.ctx.extraIterations == 0 : true;
+				int t = threadIdx.x;
+				if (t < nc)
+				{
+					s2bTouchContactRow(a, cBegin + t);
+				}
+				if (first == false)
+				{
+					__syncthreads();
+				}
+				first = false;
+				for (int tj = threadIdx.x; tj < nj; tj += blockDim.x)
+				{
+					s2bRunJointOpT<SOLVER>(jointOp, a, jBegin + tj, p);
+				}
+				for (; t < nc; t += blockDim.x)
+				{
+					if (t + (int)blockDim.x < nc)
+					{
+						s2bTouchContactRow(a, cBegin + t + blockDim.x);
+					}
+					s2bSolveContactTgsSoft(a, cBegin + t, a.ctx.inv_h, bias, writeWarm, store);
+				}
+				continue;
 			}
 			if (first == false)
 			{
