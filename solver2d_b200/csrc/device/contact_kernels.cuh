@@ -146,7 +146,14 @@ template <int KIND> __device__ __forceinline__ void s2bPrepareContact(const Solv
 	{
 		flags |= S2B_CF_TWO_POINTS;
 	}
-	cc.idx[t] = make_int2(bodies.x, (int)((unsigned)bodies.y | flags));
+	int rowA = bodies.x, rowB = bodies.y;
+	if (a.bodyLocal != nullptr && a.counts[CNT_RESIDENT] != 0)
+	{
+		// resident regions: the sweeps address the bodies through the region's shared-memory copy
+		rowA = (mA != 0.0f || iA != 0.0f) ? a.bodyLocal[rowA] : (rowA | S2B_RES_GLOBAL);
+		rowB = (mB != 0.0f || iB != 0.0f) ? a.bodyLocal[rowB] : (rowB | S2B_RES_GLOBAL);
+	}
+	cc.idx[t] = make_int2(rowA, (int)((unsigned)rowB | flags));
 	cc.nf[t] = make_float4(normal.x, normal.y, mnf.z, iA);
 	float2 warmLam[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
 	float4 warmAnchor[2] = {make_float4(0.0f, 0.0f, 0.0f, 0.0f), make_float4(0.0f, 0.0f, 0.0f, 0.0f)};
@@ -343,9 +350,16 @@ __device__ __forceinline__ ContactStream s2bLoadContactStream(const SolveArgs& a
 // storeManifold: this is the last sweep of the step — the accumulated impulses also go to the persistent manifold
 // (s2StoreContactImpulses, reference src/solve_common.c:396-410, folded into the sweep: the values are in registers here and
 // a separate pass would cost a device-wide barrier plus a dependent slot -> manifold round trip per constraint).
+// RES: resident regions — a.bodies.vel / .pose point at the region's shared-memory copy and the row's indices are positions
+// in it, except indices flagged S2B_RES_GLOBAL, which are body slots of the global arrays gVel / gPose (immovable bodies).
+template <bool RES = false>
 __device__ __forceinline__ void s2bSolveContactTgsSoftStream(const SolveArgs& a, int t, const ContactStream& cs, float inv_h, bool useBias,
-															 bool writeWarm = false, bool storeManifold = false)
+															 bool writeWarm = false, bool storeManifold = false, const float4* gVel = nullptr,
+															 const float4* gPose = nullptr, float4* lVel = nullptr, float4* lPose = nullptr)
 {
+	// (RES: the region's copy is addressed through lVel / lPose, handed over as plain arguments)
+	float4* velRows = RES ? lVel : a.bodies.vel;
+	float4* poseRows = RES ? lPose : a.bodies.pose;
 	const ConstraintView& cc = a.cc;
 	int2 idx = cs.idx;
 	int ia = idx.x, ib = idx.y & S2B_CF_INDEX_MASK;
@@ -358,8 +372,29 @@ __device__ __forceinline__ void s2bSolveContactTgsSoftStream(const SolveArgs& a,
 	float4 la1 = cs.la1, pm1 = cs.pm1;
 	float2 l1 = cs.l1;
 
-	float4 velA = a.bodies.vel[ia], velB = a.bodies.vel[ib];
-	float4 poseA = a.bodies.pose[ia], poseB = a.bodies.pose[ib];
+	float4 velA, velB, poseA, poseB;
+	if (RES && (ia & S2B_RES_GLOBAL))
+	{
+		ia &= ~S2B_RES_GLOBAL;
+		velA = gVel[ia];
+		poseA = gPose[ia];
+	}
+	else
+	{
+		velA = velRows[ia];
+		poseA = poseRows[ia];
+	}
+	if (RES && (ib & S2B_RES_GLOBAL))
+	{
+		ib &= ~S2B_RES_GLOBAL;
+		velB = gVel[ib];
+		poseB = gPose[ib];
+	}
+	else
+	{
+		velB = velRows[ib];
+		poseB = poseRows[ib];
+	}
 
 	float mA = velA.w, mB = velB.w, iA = nf.w, iB = pm0.w;
 	s2Vec2 vA = V2(velA.x, velA.y), vB = V2(velB.x, velB.y);
@@ -471,8 +506,15 @@ __device__ __forceinline__ void s2bSolveContactTgsSoftStream(const SolveArgs& a,
 			m1[2] = lam[1].y;
 		}
 	}
-	BodyPair bp = {ia, ib, velA, velB, (mA != 0.0f) || (iA != 0.0f), (mB != 0.0f) || (iB != 0.0f)};
-	s2bStoreVelocities(a, bp, vA, wA, vB, wB);
+	// bodies of infinite mass and inertia are never written (s2bStoreVelocities)
+	if ((mA != 0.0f) || (iA != 0.0f))
+	{
+		velRows[ia] = make_float4(vA.x, vA.y, wA, velA.w);
+	}
+	if ((mB != 0.0f) || (iB != 0.0f))
+	{
+		velRows[ib] = make_float4(vB.x, vB.y, wB, velB.w);
+	}
 	// s2IntegratePositions (reference src/solve_common.c:47-68) of the bodies this constraint is the last of the sweep to
 	// touch: the same arithmetic on the values just stored as s2bIntegratePosition applies after a device-wide barrier
 	// (cs.last is only ever non-zero in a bias sweep of the persistent kernel that folds the position pass; marked bodies
@@ -481,13 +523,13 @@ __device__ __forceinline__ void s2bSolveContactTgsSoftStream(const SolveArgs& a,
 	{
 		s2Vec2 dp = s2MulAdd(dcA, a.ctx.h, vA);
 		s2Rot q = s2IntegrateRot(qA, a.ctx.h * wA);
-		a.bodies.pose[ia] = make_float4(dp.x, dp.y, q.s, q.c);
+		poseRows[ia] = make_float4(dp.x, dp.y, q.s, q.c);
 	}
 	if (cs.last & 2)
 	{
 		s2Vec2 dp = s2MulAdd(dcB, a.ctx.h, vB);
 		s2Rot q = s2IntegrateRot(qB, a.ctx.h * wB);
-		a.bodies.pose[ib] = make_float4(dp.x, dp.y, q.s, q.c);
+		poseRows[ib] = make_float4(dp.x, dp.y, q.s, q.c);
 	}
 }
 

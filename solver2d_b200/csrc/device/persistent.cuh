@@ -23,6 +23,12 @@
 #define S2B_OV_MAX_CONTACTS 2048
 #define S2B_OV_MAX_JOINTS 256
 #define S2B_OV_SHARED_BYTES (S2B_OV_MAX_BODIES * 48 + S2B_OV_MAX_CONTACTS * 8 + S2B_OV_MAX_JOINTS * 16)
+// Resident regions: when nothing has to be solved device-wide (no cut set, no overflow group, no hub, no joints — batched
+// independent worlds, a small scene) every block keeps the velocity and pose rows of its region's bodies in shared memory from
+// prepare to finalize: 32 B per body in the same dynamic shared memory (the overflow staging is not needed then).
+#define S2B_RES_MAX_BODIES 3072
+#define S2B_RES_SHARED_BYTES (S2B_RES_MAX_BODIES * 32)
+#define S2B_DYN_SHARED_BYTES (S2B_RES_SHARED_BYTES > S2B_OV_SHARED_BYTES ? S2B_RES_SHARED_BYTES : S2B_OV_SHARED_BYTES)
 
 // stride of the per-region offset tables: entry c = first stream row of (region, colour c), entry S2B_MAX_COLORS = end
 #define S2B_REG_STRIDE (S2B_MAX_COLORS + 1)
@@ -127,6 +133,7 @@ struct S2bLaunchInfo
 	int bodyBegin, bodyEnd; // this block's range of regBodies
 	bool regions;
 	bool foldPositions; // TGS_Soft: the bias sweep integrates positions (ConstraintView::lastTouch), the body pass is skipped
+	bool resident;		// TGS_Soft: the region's velocity / pose rows live in shared memory for the whole launch
 };
 
 template <int SOLVER> __device__ __forceinline__ void s2bBodyPass(int bodyOp, const SolveArgs& a, const S2bLaunchInfo& li)
@@ -225,6 +232,97 @@ __device__ __forceinline__ void s2bTouchContactRow(const SolveArgs& a, int t)
 	s2bPrefetchL1(a.cc.anchor[1] + t);
 	s2bPrefetchL1(a.cc.pm[1] + t);
 	s2bPrefetchL1(a.cc.lambda[1] + t);
+}
+
+// ---- resident regions (TGS_Soft) -------------------------------------------------------------------------------------
+// sVel / sPose = the region's copy; body k of the region is body slot regBodies[bodyBegin + k] of the world.
+
+// body passes of the TGS_Soft program on the region's copy
+__device__ __forceinline__ void s2bResidentBodyPass(int bodyOp, const SolveArgs& a, const S2bLaunchInfo& li, float4* sVel, float4* sPose)
+{
+	int nb = li.bodyEnd - li.bodyBegin;
+	for (int k = threadIdx.x; k < nb; k += blockDim.x)
+	{
+		int i = a.regBodies[li.bodyBegin + k];
+		if (bodyOp == BOP_INTEGRATE_VELOCITIES_WARM)
+		{
+			GatherHead hd;
+			hd.f = a.bodies.flags[i];
+			hd.prm = a.bodies.prm[i];
+			hd.frc = a.bodies.frc[i];
+			hd.begin = a.incStart[i];
+			hd.end = a.incStart[i + 1];
+			hd.vel = sVel[k];
+			hd.pose = sPose[k];
+			s2bIntegrateVelocityWarmHead<false>(a, i, a.ctx.h, hd, false, sVel + k);
+		}
+		else if (bodyOp == BOP_INTEGRATE_POSITIONS)
+		{
+			// s2IntegratePositions (reference src/solve_common.c:47-68)
+			unsigned f = a.bodies.flags[i];
+			if ((f & S2B_BODY_VALID) != 0 && S2B_BODY_TYPE(f) != S2B_BODY_STATIC)
+			{
+				float4 vel = sVel[k];
+				float4 pose = sPose[k];
+				s2Vec2 dp = s2MulAdd(V2(pose.x, pose.y), a.ctx.h, V2(vel.x, vel.y));
+				s2Rot q = s2IntegrateRot(R2(pose.z, pose.w), a.ctx.h * vel.z);
+				sPose[k] = make_float4(dp.x, dp.y, q.s, q.c);
+			}
+		}
+		else if (bodyOp == BOP_FINALIZE_POSITIONS)
+		{
+			// s2FinalizePositions (reference src/solve_common.c:70-91) + the copy goes home
+			unsigned f = a.bodies.flags[i];
+			if ((f & S2B_BODY_VALID) != 0 && S2B_BODY_TYPE(f) != S2B_BODY_STATIC)
+			{
+				float4 pos = a.bodies.pos[i];
+				float4 pose = sPose[k];
+				s2Vec2 pn = s2Add(V2(pos.x, pos.y), V2(pose.x, pose.y));
+				a.bodies.pos[i] = make_float4(pn.x, pn.y, pos.z, pos.w);
+				a.bodies.pose[i] = make_float4(0.0f, 0.0f, pose.z, pose.w);
+				a.bodies.vel[i] = sVel[k];
+			}
+		}
+	}
+}
+
+// one Gauss-Seidel sweep over the region's constraints, colour by colour, on the region's copy
+template <int SOLVER>
+__device__ __forceinline__ void s2bResidentSweep(int contactOp, const SolveArgs& a, float4* sVel, float4* sPose, const S2bLaunchInfo& li,
+												 const int* sRegC)
+{
+	bool store = contactOp == COP_TGS_SOFT_RELAX_STORE;
+	bool bias = contactOp == COP_TGS_SOFT_BIAS;
+	bool writeWarm = bias ? a.ctx.extraIterations == 0 : true;
+	bool first = true;
+	for (int c = 0; c < li.primary; ++c)
+	{
+		int cBegin = sRegC[c];
+		int nc = sRegC[c + 1] - cBegin;
+		if (nc == 0)
+		{
+			continue; // uniform within the block
+		}
+		int t = threadIdx.x;
+		if (t < nc)
+		{
+			s2bTouchContactRow(a, cBegin + t);
+		}
+		if (first == false)
+		{
+			__syncthreads();
+		}
+		first = false;
+		for (; t < nc; t += blockDim.x)
+		{
+			if (t + (int)blockDim.x < nc)
+			{
+				s2bTouchContactRow(a, cBegin + t + blockDim.x);
+			}
+			ContactStream cs = s2bLoadContactStream(a, cBegin + t, store);
+			s2bSolveContactTgsSoftStream<true>(a, cBegin + t, cs, a.ctx.inv_h, bias, writeWarm, store, a.bodies.vel, a.bodies.pose, sVel, sPose);
+		}
+	}
 }
 
 __device__ __forceinline__ void s2bTouchBody(const SolveArgs& a, int i)
@@ -698,6 +796,7 @@ template <int SOLVER> __global__ void __launch_bounds__(S2B_BLOCK) s2bPersistent
 	// every bias step runs through the branch below that looks at the marks); all of it is grid-uniform
 	li.foldPositions = SOLVER == 7 && a.cc.lastTouch != nullptr && li.regions == false && li.nJ == 0 && li.ovC + li.ovJ == 0 &&
 					   (a.heavyBodies == nullptr || a.heavyBodies[0] == 0) && a.bodyTicket == nullptr && li.nC > 0;
+	li.resident = SOLVER == 7 && li.regions && a.bodyLocal != nullptr && a.counts[CNT_RESIDENT] != 0 && a.bodyTicket == nullptr;
 	li.bodyBegin = li.bodyEnd = 0;
 	if (li.regions)
 	{
@@ -719,6 +818,19 @@ template <int SOLVER> __global__ void __launch_bounds__(S2B_BLOCK) s2bPersistent
 			sGroupC[c] = a.cGroupOff[c];
 		}
 	}
+	// resident regions: the block's copy of its bodies (nothing has changed them yet: prepare, the first pass, only reads)
+	extern __shared__ __align__(16) unsigned char s2bDynShared[];
+	float4* sVel = reinterpret_cast<float4*>(s2bDynShared);
+	float4* sPose = sVel + S2B_RES_MAX_BODIES;
+	if (li.resident)
+	{
+		for (int k = li.bodyBegin + threadIdx.x; k < li.bodyEnd; k += blockDim.x)
+		{
+			int i = a.regBodies[k];
+			sVel[k - li.bodyBegin] = a.bodies.vel[i];
+			sPose[k - li.bodyBegin] = a.bodies.pose[i];
+		}
+	}
 	__syncthreads();
 
 	bool flow = a.bodyTicket != nullptr;
@@ -730,7 +842,22 @@ template <int SOLVER> __global__ void __launch_bounds__(S2B_BLOCK) s2bPersistent
 			for (int k = 0; k < prog.passCount[s]; ++k)
 			{
 				PassDesc pass = prog.passes[s][k];
-				if (pass.kind == PASS_GROUP)
+				if (li.resident && pass.kind == PASS_GROUP)
+				{
+					// (a resident launch has no joints, no device-wide groups and no overflow group: the sweep is the region's own)
+					s2bSyncBeforeLocal(a, sync);
+					s2bResidentSweep<SOLVER>(pass.contactOp, a, sVel, sPose, li, sRegC);
+					sync.pending = S2B_PENDING_LOCAL;
+					sync.code = (PASS_GROUP << 8) | pass.contactOp;
+				}
+				else if (li.resident && pass.kind == PASS_BODY)
+				{
+					s2bSyncBeforeLocal(a, sync);
+					s2bResidentBodyPass(pass.bodyOp, a, li, sVel, sPose);
+					sync.pending = S2B_PENDING_LOCAL;
+					sync.code = (PASS_BODY << 8) | pass.bodyOp;
+				}
+				else if (pass.kind == PASS_GROUP)
 				{
 					if (flow)
 					{

@@ -227,6 +227,9 @@ struct ConstraintView
 #define S2B_CF_TWO_POINTS 0x40000000
 #define S2B_CF_STATIC_SOFT 0x80000000u
 #define S2B_CF_INDEX_MASK 0x3FFFFFFF
+// resident regions (persistent.cuh): body indices of a row are positions in the region's shared-memory copy; an index with
+// this bit set is a body slot in global memory instead (a body no constraint can move: read only)
+#define S2B_RES_GLOBAL 0x20000000
 
 // view of the body columns
 struct BodyView
@@ -365,6 +368,7 @@ struct s2bWorld
 	unsigned long long uploadEpoch = 0; // bumped by every row upload: a pair search started before it is stale
 	int prefetchPairs = 1;	// start the pair search of the next step behind finalize (S2B_PREFETCH_PAIRS=0: off)
 	int kempe = 1;		// empty a sparse top colour by Kempe chains after colouring (S2B_KEMPE=0 disables)
+	int residentRegions = 1; // TGS_Soft: regions with nothing device-wide to solve keep their bodies in shared memory (S2B_RESIDENT=0 disables)
 	int hubDegree = 48; // constraints of a body with more incident constraints go to the serial overflow group uncoloured (S2B_HUB_DEGREE, 0 = colour them)
 	int fusePositions = 1; // TGS_Soft: s2IntegratePositions folded into the bias sweep (S2B_FUSE_POSITIONS=0 disables)
 	int kempeGrid = 0;

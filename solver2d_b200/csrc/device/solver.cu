@@ -79,6 +79,7 @@ void s2bFreeSolverScratch(s2bWorld* w)
 	s->regCount.release();
 	s->regBodies.release();
 	s->bodyRegion.release();
+	s->bodyLocal.release();
 	s->regBodyStart.release();
 	s->cRegOff.release();
 	s->jRegOff.release();
@@ -1214,7 +1215,7 @@ __global__ void s2bAssignRegionsKernel(const int* counts, int bodyCapacity, int 
 }
 
 // regBodyStart = exclusive scan of the region sizes (one block; regions <= 511); the cursors start at the same offsets
-__global__ void __launch_bounds__(512) s2bRegionOffsetsKernel(int regions, const int* regCount, int* regBodyStart, int* regCursor)
+__global__ void __launch_bounds__(512) s2bRegionOffsetsKernel(int regions, const int* regCount, int* regBodyStart, int* regCursor, int* counts)
 {
 	__shared__ int s[512];
 	int t = threadIdx.x;
@@ -1232,6 +1233,7 @@ __global__ void __launch_bounds__(512) s2bRegionOffsetsKernel(int regions, const
 		int begin = s[t] - regCount[t];
 		regBodyStart[t] = begin;
 		regCursor[t] = begin;
+		atomicMax(counts + CNT_MAX_REGION, regCount[t]);
 		if (t == regions - 1)
 		{
 			regBodyStart[regions] = s[t];
@@ -1240,7 +1242,8 @@ __global__ void __launch_bounds__(512) s2bRegionOffsetsKernel(int regions, const
 }
 
 // body lists of the regions (order inside a region is irrelevant: body passes treat every body on its own)
-__global__ void s2bFillRegionBodiesKernel(const int* counts, const int* sortedBodies, const int* bodyRegion, int* regCursor, int* regBodies)
+__global__ void s2bFillRegionBodiesKernel(const int* counts, const int* sortedBodies, const int* bodyRegion, int* regCursor, int* regBodies,
+										  const int* regBodyStart, int* bodyLocal)
 {
 	int k = blockIdx.x * blockDim.x + threadIdx.x;
 	bool active = k < counts[CNT_OWNED];
@@ -1257,6 +1260,7 @@ __global__ void s2bFillRegionBodiesKernel(const int* counts, const int* sortedBo
 	if (active)
 	{
 		regBodies[base + lane] = body;
+		bodyLocal[body] = base + lane - regBodyStart[region];
 	}
 }
 
@@ -1468,7 +1472,9 @@ __global__ void s2bBuildTablesKernel(int regions, const unsigned short* jSorted,
 	}
 }
 
-__global__ void s2bFinishGroups(int* counts, const int* cOff, const int* jOff)
+// + whether the regions can run out of shared memory (persistent.cuh, resident regions): regions on, nothing device-wide to
+// solve (no cut set, no overflow group, no hub), no joints, every region small enough
+__global__ void s2bFinishGroups(int* counts, const int* cOff, const int* jOff, const int* heavyBodies, int residentCapacity)
 {
 	// number of device-wide groups actually used (largest non-empty one + 1)
 	int groups = 0;
@@ -1482,6 +1488,10 @@ __global__ void s2bFinishGroups(int* counts, const int* cOff, const int* jOff)
 	counts[CNT_GROUPS] = groups;
 	counts[CNT_OVERFLOW_C] = cOff[S2B_MAX_COLORS + 1] - cOff[S2B_MAX_COLORS];
 	counts[CNT_OVERFLOW_J] = jOff[S2B_MAX_COLORS + 1] - jOff[S2B_MAX_COLORS];
+	bool resident = residentCapacity > 0 && counts[CNT_REGIONS_ON] != 0 && groups == 0 && counts[CNT_OVERFLOW_C] + counts[CNT_OVERFLOW_J] == 0 &&
+					counts[CNT_JOINTS] == 0 && counts[CNT_CONTACTS] > 0 && counts[CNT_MAX_REGION] <= residentCapacity &&
+					(heavyBodies == nullptr || heavyBodies[0] == 0);
+	counts[CNT_RESIDENT] = resident ? 1 : 0;
 }
 
 // The distinct bodies the serial overflow group touches (movable or not), numbered in arrival order (the numbering is
@@ -2635,8 +2645,8 @@ static void planSolve(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 		if (w->solveGrid == 0 || w->solveGridSolver != solverType)
 		{
 			int blocksPerSm = 0;
-			S2B_CHECK(cudaFuncSetAttribute(s2bPersistentKernel(solverType), cudaFuncAttributeMaxDynamicSharedMemorySize, S2B_OV_SHARED_BYTES));
-			S2B_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, s2bPersistentKernel(solverType), S2B_BLOCK, S2B_OV_SHARED_BYTES));
+			S2B_CHECK(cudaFuncSetAttribute(s2bPersistentKernel(solverType), cudaFuncAttributeMaxDynamicSharedMemorySize, S2B_DYN_SHARED_BYTES));
+			S2B_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, s2bPersistentKernel(solverType), S2B_BLOCK, S2B_DYN_SHARED_BYTES));
 			const char* env = getenv("S2B_SOLVE_BLOCKS_PER_SM");
 			int want = env != nullptr ? atoi(env) : 2;
 			w->solveGrid = w->smCount * std::min(std::max(blocksPerSm, 1), std::max(want, 1));
@@ -2718,6 +2728,7 @@ static void planSolve(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 		s->islandStart.reserve((size_t)bodyCap + 1, st, false);
 		s->regCount.reserve(1024, st, false);
 		s->regBodies.reserve((size_t)bodyCap + 1, st, false);
+		s->bodyLocal.reserve((size_t)bodyCap + 1, st, false);
 		s->bodyRegion.reserve((size_t)bodyCap + 1, st, false);
 		s->regBodyStart.reserve((size_t)pl.regions + 2, st, false);
 		s->cRegOff.reserve((size_t)pl.regions * S2B_REG_STRIDE, st, false);
@@ -2932,9 +2943,9 @@ static void enqueueSchedule(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 				S2B_LAUNCH(w, s2bIslandStartKernel, gridFor(bodyCap, 256), 256, 0, s->counts.p, s->bodySorted.p, s->island.p, s->islandStart.p);
 				S2B_LAUNCH(w, s2bAssignRegionsKernel, gridFor(bodyCap, 256), 256, 0, s->counts.p, bodyCap, pl.regions, s->bodySorted.p, s->island.p,
 						   s->islandStart.p, s->islandSize.p, s->bodyRegion.p, s->regCount.p);
-				S2B_LAUNCH(w, s2bRegionOffsetsKernel, 1, 512, 0, pl.regions, s->regCount.p, s->regBodyStart.p, s->regCount.p + 512);
+				S2B_LAUNCH(w, s2bRegionOffsetsKernel, 1, 512, 0, pl.regions, s->regCount.p, s->regBodyStart.p, s->regCount.p + 512, s->counts.p);
 				S2B_LAUNCH(w, s2bFillRegionBodiesKernel, gridFor(bodyCap, 256), 256, 0, s->counts.p, s->bodySorted.p, s->bodyRegion.p,
-						   s->regCount.p + 512, s->regBodies.p);
+						   s->regCount.p + 512, s->regBodies.p, s->regBodyStart.p, s->bodyLocal.p);
 				s->regions = pl.regions;
 			}
 			S2B_LAUNCH(w, s2bClassifyItemsKernel, gridFor(maxItems, 256), 256, 0, s->counts.p, s->itemBodies.p, s->bodyRegion.p, s->colorA.p,
@@ -2976,7 +2987,8 @@ static void enqueueSchedule(s2bWorld* w, SolverScratch* s, SolvePlan& pl)
 			int entries = pl.regions * S2B_REG_STRIDE + S2B_MAX_COLORS + 2;
 			S2B_LAUNCH(w, s2bBuildTablesKernel, gridFor(entries, 256), 256, 0, pl.regions, jKeysOut, jointCap, cKeysOut, contactCount, s->jRegOff.p,
 					   s->cRegOff.p, s->jGroupOff.p, s->cGroupOff.p);
-			S2B_LAUNCH(w, s2bFinishGroups, 1, 1, 0, s->counts.p, s->cGroupOff.p, s->jGroupOff.p);
+			S2B_LAUNCH(w, s2bFinishGroups, 1, 1, 0, s->counts.p, s->cGroupOff.p, s->jGroupOff.p, s->heavyBodies.p,
+					   (pl.regions > 0 && pl.solverType == 7 && pl.gatherWarm && w->residentRegions != 0) ? S2B_RES_MAX_BODIES : 0);
 			// bodies of the serial overflow group (hub bodies' constraints beyond the colour limit), for its shared-memory walk
 			S2B_CHECK(cudaMemsetAsync(s->ovBodySlot.p, 0xFF, sizeof(int) * ((size_t)bodyCap + 1), st));
 			S2B_CHECK(cudaMemsetAsync(s->ovBodies.p, 0, sizeof(int), st));
@@ -3152,6 +3164,7 @@ static void enqueueIterate(s2bWorld* w, SolverScratch* s, SolvePlan& pl, bool ca
 	// hub bodies: with regions the list drives their body passes (every variant); without, only the block-wide gather
 	a.heavyBodies = (pl.regions > 0 || (pl.gatherWarm && pl.maxItems > 0 && pl.usePersistent)) ? s->heavyBodies.p : nullptr;
 	a.regions = pl.regions;
+	a.bodyLocal = (pl.regions > 0 && pl.solverType == 7 && pl.gatherWarm && w->residentRegions != 0) ? s->bodyLocal.p : nullptr;
 	a.regBodyStart = s->regBodyStart.p;
 	a.regBodies = s->regBodies.p;
 	a.jRegOff = s->jRegOff.p;
@@ -3199,7 +3212,7 @@ static void enqueueIterate(s2bWorld* w, SolverScratch* s, SolvePlan& pl, bool ca
 		// (inside a capture the time stamps become external event-record nodes so that they are taken on every replay)
 		unsigned evFlags = capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
 		S2B_CHECK(cudaEventRecordWithFlags(w->solveKernelStart, st, evFlags));
-		S2B_CHECK(cudaLaunchCooperativeKernel(s2bPersistentKernel(solverType), dim3(pl.grid), dim3(pl.threads), args, S2B_OV_SHARED_BYTES, st));
+		S2B_CHECK(cudaLaunchCooperativeKernel(s2bPersistentKernel(solverType), dim3(pl.grid), dim3(pl.threads), args, S2B_DYN_SHARED_BYTES, st));
 		S2B_CHECK(cudaEventRecordWithFlags(w->solveKernelEnd, st, evFlags));
 		w->solveKernelTimed = true;
 		w->kernelLaunches += 1;

@@ -34,6 +34,8 @@ enum
 	CNT_CUT = 13,		// constraints in the cut set (straddle two regions or touch a hub body)
 	CNT_CUT_COLORS = 14, // colours the cut set needed
 	CNT_REGIONS_ON = 15, // 1: the solve order is region-major (persistent.cuh); 0: one device-wide group per colour
+	CNT_MAX_REGION = 21, // bodies in the largest region
+	CNT_RESIDENT = 22,	 // 1: every region runs out of shared memory (persistent.cuh, "resident regions"); decided by s2bFinishGroups
 	CNT_CUT_ABORT = 20,	// the cut colouring gave up: it needs more colours than regions are worth
 	CNT_BOUNDS = 16,	// 4 slots: order-preserving keys of max x, max -x, max y, max -y over the bodies' centres
 	CNT_SIZE = 32
@@ -58,6 +60,7 @@ struct SolveArgs
 	const int* regBodies;	 // body slots sorted by region (Hilbert order of their centres)
 	const int* jRegOff;		 // regions x (S2B_MAX_COLORS + 1): joint-constraint stream offsets of (region, colour)
 	const int* cRegOff;		 // same for contact constraints
+	const int* bodyLocal;	 // per body: its position in its region's slice of regBodies (resident regions); null: not offered
 	unsigned* barrier;		 // [0] monotonic arrival counter of the grid barrier, [32] its value at the start of the next launch
 	// serial overflow group on a shared-memory copy of its bodies (persistent.cuh): the distinct bodies its constraints touch
 	const int* ovBodies;	 // [0] count, then body slots (null: walk in global memory)
@@ -109,6 +112,7 @@ struct SolverScratch
 	DevArray<int> islandSize, islandStart;	  // per label: bodies in the island, its first rank in the sorted order
 	DevArray<int> regCount;					  // [0, 512): bodies per region; [512, 1024): fill cursors
 	DevArray<int> bodyRegion;				  // per body: region or -1 (hub, invalid)
+	DevArray<int> bodyLocal;				  // per body: position in its region's list (SolveArgs::bodyLocal)
 	DevArray<int> regBodyStart;				  // regions + 1
 	DevArray<int> cRegOff, jRegOff;			  // regions x (S2B_MAX_COLORS + 1)
 	int regions = 0;						  // regions of the last schedule (0: none)

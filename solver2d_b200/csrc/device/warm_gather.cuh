@@ -163,9 +163,12 @@ __device__ __forceinline__ void s2bGatherFour(const SolveArgs& a, const int (&e)
 // alsoPosition: the bias sweep integrates the positions of the bodies it touches (ConstraintView::lastTouch); a body
 // without any constraint is touched by nobody, so its position is integrated here, right after its velocity (nothing in
 // between changes either)
+// velOut: where the new velocity goes (the region's shared-memory copy in a resident launch); null = the body's row
 template <bool FIXED>
-__device__ __forceinline__ void s2bIntegrateVelocityWarmHead(const SolveArgs& a, int i, float h, const GatherHead& hd, bool alsoPosition = false)
+__device__ __forceinline__ void s2bIntegrateVelocityWarmHead(const SolveArgs& a, int i, float h, const GatherHead& hd, bool alsoPosition = false,
+															 float4* velOut = nullptr)
 {
+	float4* out = velOut != nullptr ? velOut : a.bodies.vel + i;
 	unsigned f = hd.f;
 	if ((f & S2B_BODY_VALID) == 0)
 	{
@@ -194,7 +197,7 @@ __device__ __forceinline__ void s2bIntegrateVelocityWarmHead(const SolveArgs& a,
 	{
 		if (dynamic)
 		{
-			a.bodies.vel[i] = make_float4(v.x, v.y, w, invMass);
+			*out = make_float4(v.x, v.y, w, invMass);
 		}
 		if (alsoPosition && S2B_BODY_TYPE(f) != S2B_BODY_STATIC)
 		{
@@ -234,7 +237,7 @@ __device__ __forceinline__ void s2bIntegrateVelocityWarmHead(const SolveArgs& a,
 		}
 		s2bGatherFour<FIXED>(a, e, q, invMass, invI, v, w);
 	}
-	a.bodies.vel[i] = make_float4(v.x, v.y, w, invMass);
+	*out = make_float4(v.x, v.y, w, invMass);
 }
 
 template <bool FIXED> __device__ __forceinline__ void s2bIntegrateVelocityWarm(const SolveArgs& a, int i, float h)

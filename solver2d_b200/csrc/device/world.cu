@@ -359,6 +359,11 @@ extern "C" s2bWorld* s2b_world_create(int cudaDevice, int solverType)
 		{
 			w->hubDegree = atoi(env);
 		}
+		env = getenv("S2B_RESIDENT");
+		if (env != nullptr)
+		{
+			w->residentRegions = atoi(env);
+		}
 		env = getenv("S2B_KEMPE");
 		if (env != nullptr)
 		{
