@@ -477,16 +477,63 @@ __global__ void s2bRefit(ShapeView s, const int* leafShape, const int* sortedLea
 // pair queries
 // ---------------------------------------------------------------------------------------------------------------
 
-__global__ void s2bFlagMovedLeaves(ShapeView s, const int* leafShape, const int* sortedLeaf, const int* counters, int* movedFlag)
+// append `value` to list[] (length in *count) for every lane with take == true: one atomic per warp
+__device__ __forceinline__ void s2bWarpAppend(bool take, int value, int* list, int* count)
+{
+	unsigned takers = __ballot_sync(0xFFFFFFFFu, take);
+	if (takers == 0u)
+	{
+		return;
+	}
+	int lane = threadIdx.x & 31;
+	int leader = __ffs(takers) - 1;
+	int base = 0;
+	if (lane == leader)
+	{
+		base = atomicAdd(count, __popc(takers));
+	}
+	base = __shfl_sync(0xFFFFFFFFu, base, leader);
+	if (take)
+	{
+		list[base + __popc(takers & ((1u << lane) - 1u))] = value;
+	}
+}
+
+// The queries of this pass: the sorted-leaf indices of the proxies that moved (BC_MOVED, movedLeaves) — neighbours in Morton
+// order stay neighbours in the list, a warp's queries walk the same part of the tree — except up to S2B_MAX_LARGE_MOVERS
+// proxies with LARGE boxes (a container wall spanning the scene overlaps thousands of leaves: one thread walking them all
+// takes milliseconds), which go to largeShapes (BC_LARGE) and are tested the other way round: every leaf against that short
+// list (s2bFindPairsLarge). One kernel, one atomic per warp (round 1: flag array + split + cub select).
+#define S2B_MAX_LARGE_MOVERS 64
+
+__global__ void s2bCollectMovers(ShapeView s, const int* leafShape, const int* sortedLeaf, int* counters, const float4* nodeBox, int* movedLeaves,
+								 int* largeShapes)
 {
 	int n = counters[BC_LEAVES];
 	int k = blockIdx.x * blockDim.x + threadIdx.x;
-	if (k < s.capacity)
+	bool moved = false;
+	if (k < n)
 	{
-		// (every slot the compaction below looks at is written: positions beyond the live leaves would otherwise keep the flag
-		// of whatever leaf sat there before shapes were destroyed, and a stale 1 queries some shape a second time)
-		movedFlag[k] = (k < n && (s.head[leafShape[sortedLeaf[k]]].x & S2B_SHAPE_MOVED)) ? 1 : 0;
+		int shape = leafShape[sortedLeaf[k]];
+		moved = (s.head[shape].x & S2B_SHAPE_MOVED) != 0;
+		if (moved && n >= 256)
+		{
+			float4 root = nodeBox[0];
+			float4 box = s.fat[shape];
+			float area = (box.z - box.x) * (box.w - box.y);
+			float sceneArea = (root.z - root.x) * (root.w - root.y);
+			if (area * 256.0f > sceneArea)
+			{
+				int slot = atomicAdd(counters + BC_LARGE, 1);
+				if (slot < S2B_MAX_LARGE_MOVERS)
+				{
+					largeShapes[slot] = shape;
+					moved = false;
+				}
+			}
+		}
 	}
+	s2bWarpAppend(moved, k, movedLeaves, counters + BC_MOVED);
 }
 
 // what the query of proxy Q does with an overlapping proxy `other` (reference s2PairQueryCallback, src/broad_phase.c:166-258)
@@ -534,7 +581,7 @@ __device__ __forceinline__ void s2bConsiderPair(const PairQuery& q, int other, c
 	unsigned long long hi = (unsigned long long)(other < shapeQ ? shapeQ : other);
 	unsigned long long pairKey = (lo << 32) | hi;
 	// "this pair already has a contact" — unless one of the shapes was (re)created since the table was built: the table's
-	// contact then belongs to the shape that used to live in that slot and is dropped by this very pass (s2bFlagKeptContacts),
+	// contact then belongs to the shape that used to live in that slot and is dropped by this very pass (s2bCollectKeptContacts),
 	// so the pair has to be reported again (the reference removes the key from its pair set when the old shape is destroyed,
 	// src/contact.c:231-292, and creates the contact on the next update)
 	bool recreated = ((q.headQ.x | headO.x) & S2B_SHAPE_FRESH) != 0;
@@ -680,36 +727,8 @@ __global__ void __launch_bounds__(128) s2bFindPairs(ShapeView s, BodyView b, con
 	}
 }
 
-// Moved proxies with LARGE boxes (a container wall spanning the scene overlaps thousands of leaves: one thread walking
-// them all takes milliseconds) are taken out of the walk above and tested the other way round: every leaf against the short
-// list of large movers. Same rules, same pairs; the order new pairs are emitted in never matters (they are sorted).
-#define S2B_MAX_LARGE_MOVERS 64
-
-__global__ void s2bSplitLargeMovers(ShapeView s, const int* leafShape, const int* sortedLeaf, int* counters, const float4* nodeBox,
-									int* movedFlag, int* largeShapes)
-{
-	int n = counters[BC_LEAVES];
-	int k = blockIdx.x * blockDim.x + threadIdx.x;
-	if (k >= n || movedFlag[k] == 0 || n < 256)
-	{
-		return;
-	}
-	float4 root = nodeBox[0];
-	int shape = leafShape[sortedLeaf[k]];
-	float4 box = s.fat[shape];
-	float area = (box.z - box.x) * (box.w - box.y);
-	float sceneArea = (root.z - root.x) * (root.w - root.y);
-	if (area * 256.0f > sceneArea)
-	{
-		int slot = atomicAdd(counters + BC_LARGE, 1);
-		if (slot < S2B_MAX_LARGE_MOVERS)
-		{
-			largeShapes[slot] = shape;
-			movedFlag[k] = 0;
-		}
-	}
-}
-
+// every leaf against the short list of large movers (s2bCollectMovers). Same rules, same pairs; the order new pairs are
+// emitted in never matters (they are sorted).
 __global__ void s2bFindPairsLarge(ShapeView s, BodyView b, const int* leafShape, int* counters, const int* largeShapes,
 								  const unsigned long long* pairHash, unsigned long long hashMask, const unsigned long long* jointKeys,
 								  int jointKeyCount, unsigned long long* newKey, int2* newShapes, int newCap)
@@ -740,19 +759,20 @@ __global__ void s2bFindPairsLarge(ShapeView s, BodyView b, const int* leafShape,
 
 // survivors: both shapes alive and not re-created, fat AABBs still overlap (reference src/world.c:149-166), and no joint
 // created since forbids the pair (reference src/joint.c:214-217)
-__global__ void s2bFlagKeptContacts(ContactView c, int contactCount, ShapeView s, const unsigned long long* jointKeys,
-									int jointKeyCount, int* keepFlag)
+// The survivors' slots are appended to keepSlots (BC_KEPT): their order does not matter, the merged table is sorted by pair key.
+__global__ void s2bCollectKeptContacts(ContactView c, int contactCount, ShapeView s, const unsigned long long* jointKeys, int jointKeyCount,
+									   int* keepSlots, int* counters)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= contactCount)
+	bool keep = false;
+	if (i < contactCount)
 	{
-		return;
+		int2 sh = c.shapes[i];
+		int4 ha = s.head[sh.x], hb = s.head[sh.y];
+		bool alive = (ha.x & S2B_ROW_VALID) && (hb.x & S2B_ROW_VALID) && (ha.x & S2B_SHAPE_FRESH) == 0 && (hb.x & S2B_SHAPE_FRESH) == 0;
+		keep = alive && s2bBoxesOverlap(s.fat[sh.x], s.fat[sh.y]) && s2bJointOverride(jointKeys, jointKeyCount, ha.y, hb.y) == false;
 	}
-	int2 sh = c.shapes[i];
-	int4 ha = s.head[sh.x], hb = s.head[sh.y];
-	bool alive = (ha.x & S2B_ROW_VALID) && (hb.x & S2B_ROW_VALID) && (ha.x & S2B_SHAPE_FRESH) == 0 && (hb.x & S2B_SHAPE_FRESH) == 0;
-	bool keep = alive && s2bBoxesOverlap(s.fat[sh.x], s.fat[sh.y]) && s2bJointOverride(jointKeys, jointKeyCount, ha.y, hb.y) == false;
-	keepFlag[i] = keep ? 1 : 0;
+	s2bWarpAppend(keep, i, keepSlots, counters + BC_KEPT);
 }
 
 // The sort key is the pair key squeezed to 2 x shapeBits bits (lo << shapeBits | hi) so the radix sort runs only over
@@ -984,14 +1004,8 @@ static void bpSearch(s2bWorld* w, BroadScratch* B)
 	}
 
 	// ---- queries from moved proxies ----
-	S2B_LAUNCH(w, s2bFlagMovedLeaves, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->leafOut.p, B->counters.p,
-			   B->movedFlag.p);
-	S2B_LAUNCH(w, s2bSplitLargeMovers, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->leafOut.p, B->counters.p, B->nodeBox.p,
-			   B->movedFlag.p, B->largeShapes.p);
-	size_t tb = B->cubTemp.cap;
-	cub::DeviceSelect::Flagged(B->cubTemp.p, tb, thrust::counting_iterator<int>(0), B->movedFlag.p, B->movedLeaves.p,
-							   B->counters.p + BC_MOVED, shapeCap, st);
-	w->kernelLaunches += 2;
+	S2B_LAUNCH(w, s2bCollectMovers, gridFor(shapeCap, 256), 256, 0, sv, B->leafShape.p, B->leafOut.p, B->counters.p, B->nodeBox.p,
+			   B->movedLeaves.p, B->largeShapes.p);
 	S2B_LAUNCH(w, s2bFindPairs, gridFor(shapeCap, 128), 128, 0, sv, bv, B->leafShape.p, B->leafOut.p, B->counters.p,
 			   B->movedLeaves.p, B->children.p, B->pairBox.p, B->pairHash.p, B->hashMask, w->jointPairKeys.p, w->jointPairCount,
 			   B->newKey.p, B->newShapes.p, newCap);
@@ -1001,12 +1015,8 @@ static void bpSearch(s2bWorld* w, BroadScratch* B)
 	// ---- survivors ----
 	if (oldCount > 0)
 	{
-		S2B_LAUNCH(w, s2bFlagKeptContacts, gridFor(oldCount, 256), 256, 0, makeView(cur), oldCount, sv, w->jointDestroyKeys.p,
-				   w->jointDestroyCount, B->keepFlag.p);
-		tb = B->cubTemp.cap;
-		cub::DeviceSelect::Flagged(B->cubTemp.p, tb, thrust::counting_iterator<int>(0), B->keepFlag.p, B->keepSlots.p,
-								   B->counters.p + BC_KEPT, oldCount, st);
-		w->kernelLaunches += 2;
+		S2B_LAUNCH(w, s2bCollectKeptContacts, gridFor(oldCount, 256), 256, 0, makeView(cur), oldCount, sv, w->jointDestroyKeys.p,
+				   w->jointDestroyCount, B->keepSlots.p, B->counters.p);
 	}
 	S2B_CHECK(cudaMemcpyAsync(w->hostMail + MAIL_BC_BASE, B->counters.p, sizeof(int) * BC_SIZE, cudaMemcpyDeviceToHost, st));
 	B->searchedCount = oldCount;

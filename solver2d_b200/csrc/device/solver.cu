@@ -831,6 +831,18 @@ __global__ void __launch_bounds__(256) s2bKempeKernel(const int* counts, const i
 										betaOut = beta;
 									}
 								}
+								// the same from the other end: a colour free at v, the path that starts at u
+								for (unsigned long long fv = freeV; fv != 0ull && length < 0; fv &= fv - 1ull)
+								{
+									int alpha = __ffsll((long long)fv) - 1;
+									for (unsigned long long fu = freeU; fu != 0ull && length < 0; fu &= fu - 1ull)
+									{
+										int beta = __ffsll((long long)fu) - 1;
+										length = s2bKempeWalk(itemBodies, adjStart, adj, color, item, e.y, e.x, alpha, beta, path);
+										alphaOut = alpha;
+										betaOut = beta;
+									}
+								}
 							}
 						}
 					}
