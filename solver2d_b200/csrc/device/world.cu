@@ -364,6 +364,11 @@ extern "C" s2bWorld* s2b_world_create(int cudaDevice, int solverType)
 		{
 			w->residentRegions = atoi(env);
 		}
+		env = getenv("S2B_SIDE_COPIES");
+		if (env != nullptr)
+		{
+			w->sideCopies = atoi(env);
+		}
 		env = getenv("S2B_KEMPE");
 		if (env != nullptr)
 		{
@@ -462,6 +467,11 @@ extern "C" void s2b_world_destroy(s2bWorld* w)
 	{
 		cudaEventDestroy(w->solveKernelStart);
 		cudaEventDestroy(w->solveKernelEnd);
+	}
+	if (w->copyStream != nullptr)
+	{
+		cudaStreamDestroy(w->copyStream);
+		w->copyStream = nullptr;
 	}
 	if (w->movedEvent != nullptr)
 	{
@@ -602,6 +612,7 @@ static void reserveJoints(s2bWorld* w, int cap)
 extern "C" void s2b_upload_bodies(s2bWorld* w, const s2bBodyRow* rows, int count, int bodyCapacity)
 {
 	S2B_CHECK(cudaSetDevice(w->device));
+	w->xfSeq += 1; // (rows or the columns themselves may change: the next transform read-back orders itself behind this stream)
 	reserveBodies(w, bodyCapacity);
 	if (count <= 0)
 	{
@@ -816,16 +827,31 @@ extern "C" void s2b_download_transforms(s2bWorld* w, float* out, int count)
 		w->hostXfFloats = floats + floats / 2;
 		S2B_CHECK(cudaMallocHost((void**)&w->hostXf, sizeof(float) * w->hostXfFloats));
 	}
+	// finalize was the last writer of the transforms (nothing uploaded, no solver stage since): gather and copy on the side
+	// stream, behind finalize only — not behind what the world's stream has queued after it
+	bool side = w->sideCopies != 0 && w->movedEvent != nullptr && w->finalizeSeq == w->xfSeq && w->dXf.cap >= (size_t)count;
 	w->dXf.reserve((size_t)count, w->stream, false, false);
-	S2B_LAUNCH(w, s2bGatherTransforms, gridFor(count, 256), 256, 0, bodyView(w), count, w->dXf.p);
+	cudaStream_t cs = w->stream;
+	if (side)
+	{
+		if (w->copyStream == nullptr)
+		{
+			S2B_CHECK(cudaStreamCreateWithFlags(&w->copyStream, cudaStreamNonBlocking));
+		}
+		cs = w->copyStream;
+		S2B_CHECK(cudaStreamWaitEvent(cs, w->movedEvent, 0));
+	}
+	s2bGatherTransforms<<<gridFor(count, 256), 256, 0, cs>>>(bodyView(w), count, w->dXf.p);
+	S2B_CHECK(cudaGetLastError());
+	w->kernelLaunches += 1;
 	// a page-locked destination (s2b_host_alloc / cudaHostRegister) takes the DMA directly; pageable memory goes through the
 	// world's own pinned buffer and one host copy
 	cudaPointerAttributes attr;
 	bool pinned = cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
 	(void)cudaGetLastError();
 	float* dst = pinned ? out : w->hostXf;
-	S2B_CHECK(cudaMemcpyAsync(dst, w->dXf.p, sizeof(float) * floats, cudaMemcpyDeviceToHost, w->stream));
-	S2B_CHECK(cudaStreamSynchronize(w->stream));
+	S2B_CHECK(cudaMemcpyAsync(dst, w->dXf.p, sizeof(float) * floats, cudaMemcpyDeviceToHost, cs));
+	S2B_CHECK(cudaStreamSynchronize(cs));
 	if (pinned == false)
 	{
 		memcpy(out, w->hostXf, sizeof(float) * floats);
@@ -1052,6 +1078,7 @@ extern "C" void s2b_update_contacts(s2bWorld* w)
 extern "C" void s2b_solve(s2bWorld* w, int solverType, const s2bStepContext* context)
 {
 	S2B_CHECK(cudaSetDevice(w->device));
+	w->xfSeq += 1;
 	S2B_CHECK(cudaEventRecord(w->timer.ev[2], w->stream));
 	s2bSolve(w, solverType, context);
 }
@@ -1061,6 +1088,8 @@ extern "C" void s2b_finalize(s2bWorld* w)
 	S2B_CHECK(cudaSetDevice(w->device));
 	S2B_CHECK(cudaEventRecord(w->timer.ev[3], w->stream));
 	s2bFinalize(w);
+	w->xfSeq += 1;
+	w->finalizeSeq = w->xfSeq;
 	S2B_CHECK(cudaEventRecord(w->timer.ev[4], w->stream));
 	w->timer.recorded = true;
 }
