@@ -369,6 +369,11 @@ extern "C" s2bWorld* s2b_world_create(int cudaDevice, int solverType)
 		{
 			w->sideCopies = atoi(env);
 		}
+		env = getenv("S2B_WHOLE_ISLAND");
+		if (env != nullptr)
+		{
+			w->wholeIslandBodies = atoi(env);
+		}
 		env = getenv("S2B_KEMPE");
 		if (env != nullptr)
 		{
