@@ -477,25 +477,35 @@ __global__ void s2bRefit(ShapeView s, const int* leafShape, const int* sortedLea
 // pair queries
 // ---------------------------------------------------------------------------------------------------------------
 
-// append `value` to list[] (length in *count) for every lane with take == true: one atomic per warp
-__device__ __forceinline__ void s2bWarpAppend(bool take, int value, int* list, int* count)
+// append `value` to list[] (length in *count) for every thread with take == true: one atomic per BLOCK, and the block's
+// entries keep their thread order (every thread of the block has to call this)
+__device__ __forceinline__ void s2bBlockAppend(bool take, int value, int* list, int* count)
 {
+	__shared__ int warpOffset[32];
+	__shared__ int blockBase;
 	unsigned takers = __ballot_sync(0xFFFFFFFFu, take);
-	if (takers == 0u)
+	int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (lane == 0)
 	{
-		return;
+		warpOffset[warp] = __popc(takers);
 	}
-	int lane = threadIdx.x & 31;
-	int leader = __ffs(takers) - 1;
-	int base = 0;
-	if (lane == leader)
+	__syncthreads();
+	if (threadIdx.x == 0)
 	{
-		base = atomicAdd(count, __popc(takers));
+		int total = 0;
+		int warps = (blockDim.x + 31) >> 5;
+		for (int k = 0; k < warps; ++k)
+		{
+			int c = warpOffset[k];
+			warpOffset[k] = total;
+			total += c;
+		}
+		blockBase = total > 0 ? atomicAdd(count, total) : 0;
 	}
-	base = __shfl_sync(0xFFFFFFFFu, base, leader);
+	__syncthreads();
 	if (take)
 	{
-		list[base + __popc(takers & ((1u << lane) - 1u))] = value;
+		list[blockBase + warpOffset[warp] + __popc(takers & ((1u << lane) - 1u))] = value;
 	}
 }
 
@@ -503,7 +513,7 @@ __device__ __forceinline__ void s2bWarpAppend(bool take, int value, int* list, i
 // order stay neighbours in the list, a warp's queries walk the same part of the tree — except up to S2B_MAX_LARGE_MOVERS
 // proxies with LARGE boxes (a container wall spanning the scene overlaps thousands of leaves: one thread walking them all
 // takes milliseconds), which go to largeShapes (BC_LARGE) and are tested the other way round: every leaf against that short
-// list (s2bFindPairsLarge). One kernel, one atomic per warp (round 1: flag array + split + cub select).
+// list (s2bFindPairsLarge). One kernel, one atomic per block (round 1: flag array + split + cub select).
 #define S2B_MAX_LARGE_MOVERS 64
 
 __global__ void s2bCollectMovers(ShapeView s, const int* leafShape, const int* sortedLeaf, int* counters, const float4* nodeBox, int* movedLeaves,
@@ -533,7 +543,7 @@ __global__ void s2bCollectMovers(ShapeView s, const int* leafShape, const int* s
 			}
 		}
 	}
-	s2bWarpAppend(moved, k, movedLeaves, counters + BC_MOVED);
+	s2bBlockAppend(moved, k, movedLeaves, counters + BC_MOVED);
 }
 
 // what the query of proxy Q does with an overlapping proxy `other` (reference s2PairQueryCallback, src/broad_phase.c:166-258)
@@ -772,7 +782,7 @@ __global__ void s2bCollectKeptContacts(ContactView c, int contactCount, ShapeVie
 		bool alive = (ha.x & S2B_ROW_VALID) && (hb.x & S2B_ROW_VALID) && (ha.x & S2B_SHAPE_FRESH) == 0 && (hb.x & S2B_SHAPE_FRESH) == 0;
 		keep = alive && s2bBoxesOverlap(s.fat[sh.x], s.fat[sh.y]) && s2bJointOverride(jointKeys, jointKeyCount, ha.y, hb.y) == false;
 	}
-	s2bWarpAppend(keep, i, keepSlots, counters + BC_KEPT);
+	s2bBlockAppend(keep, i, keepSlots, counters + BC_KEPT);
 }
 
 // The sort key is the pair key squeezed to 2 x shapeBits bits (lo << shapeBits | hi) so the radix sort runs only over
